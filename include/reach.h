@@ -1,0 +1,226 @@
+/* reach.h -- C ABI of libreach_cuda.so
+ *
+ * B200-native (sm_100a) implementation of the linear set-propagation hot path of
+ * ReachabilityAnalysis.jl: the LGG09 template support-function recurrence and the GLGM06
+ * zonotope flowpipe.  The reference has no FFI for this path (it is pure Julia); the seam this
+ * library replaces is the inside of the four loops below, which become `ccall`s:
+ *
+ *   reach_lgg09 / reach_lgg09_plan_*  <-  reach_homog_LGG09!   src/Algorithms/LGG09/reach_homog.jl:6-33,49-62
+ *                                         reach_inhomog_LGG09! src/Algorithms/LGG09/reach_inhomog.jl:5-33,49-81
+ *                                         (invariant variants reach_homog.jl:382-424, reach_inhomog.jl:174-218)
+ *   reach_glgm06 / reach_glgm06_plan_* <- reach_homog_GLGM06!   src/Algorithms/GLGM06/reach_homog.jl:33-73
+ *                                         reach_inhomog_GLGM06! src/Algorithms/GLGM06/reach_inhomog.jl:6-43
+ *                                         reduce_order(., GIR05) call sites GLGM06/post.jl:26, reach_inhomog.jl:30,36
+ *                                         linear_map_minkowski_sum src/Continuous/setops.jl:7-25
+ *   reach_*_max_over_steps / fetch     <- rho(d, fp)  src/Flowpipes/AbstractFlowpipe.jl:35-37,
+ *                                         support_function_matrix src/Flowpipes/Flowpipe.jl:304-306
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, no C++/torch types.  All matrices are Float64, COLUMN-MAJOR
+ *     (Julia layout) unless stated.
+ *   - every function returns 0 on success or a negative REACH_E* code; the message is available
+ *     from reach_last_error().  The library never aborts and has no CPU fallback: without a
+ *     usable CUDA device reach_create fails.
+ *   - host pointers are borrowed for the duration of the call only.
+ *   - one reach_ctx per calling thread (or lock externally); a ctx owns one device + one stream.
+ *   - time stamps (dt, dt0), TemplateReachSet / ReachSet construction and the :sfmat dictionary
+ *     stay on the caller's side.
+ */
+#ifndef REACH_H
+#define REACH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REACH_OK            0
+#define REACH_EINVAL      (-1)  /* bad argument (maps to ArgumentError)            */
+#define REACH_ECUDA       (-2)  /* CUDA runtime / driver error                      */
+#define REACH_ENOMEM      (-3)  /* host or device allocation failed                 */
+#define REACH_EUNSUPPORTED (-4) /* valid request the device path does not implement */
+#define REACH_ESTATE      (-5)  /* call order violated (e.g. fetch before run)      */
+
+typedef struct reach_ctx reach_ctx;
+
+int         reach_version(void);                          /* 10000*major + 100*minor + patch */
+int         reach_device_count(void);                     /* <0 on error                      */
+int         reach_create(reach_ctx** out, int device);
+void        reach_destroy(reach_ctx* ctx);
+const char* reach_last_error(const reach_ctx* ctx);       /* ctx may be NULL: last create error */
+int         reach_device_name(const reach_ctx* ctx, char* buf, size_t len);
+int         reach_sm_count(const reach_ctx* ctx);
+/* stream the ctx launches on (a cudaStream_t), for callers that interleave their own work */
+void*       reach_stream(const reach_ctx* ctx);
+int         reach_synchronize(reach_ctx* ctx);
+
+/* ---------------------------------------------------------------------------------------------
+ * Flattened support-function program.
+ *
+ * The lazy set trees that `discretize` hands to `post` (ConvexHull / MinkowskiSum / LinearMap of
+ * Hyperrectangle, BallInf, Interval, Singleton, ZeroSet, Zonotope -- ForwardModule.jl:137-164)
+ * are flattened by the caller into
+ *
+ *      rho(r_k; Omega0) = max over alternatives a of  sum over terms t in a of  term_t
+ *      rho(r_k; V)      =                             sum over terms t       of  term_t
+ *
+ * Each term is evaluated at d = r_k (which = 0) or d = r_{k+1} = Phi' r_k (which = 1, i.e. the
+ * term sat under `LinearMap(Phi, .)`), optionally after a further linear map d' = M' d:
+ *
+ *      REACH_TERM_BOX  : sum_i d'_i c_i + |d'_i| r_i            (c, r may be NULL = 0)
+ *      REACH_TERM_ZONO : d'.c + sum_j |g_j . d'|                (G is dim x p, column-major)
+ *
+ * An alternative with zero terms evaluates to 0 (Omega0 = ZeroSet, reach_inhomog.jl:66-81).
+ * ------------------------------------------------------------------------------------------- */
+#define REACH_TERM_BOX  0
+#define REACH_TERM_ZONO 1
+
+typedef struct {
+    int32_t kind;        /* REACH_TERM_BOX | REACH_TERM_ZONO                                  */
+    int32_t which;       /* 0: r_k, 1: r_{k+1}; must be 0 inside V                            */
+    int32_t q;           /* 0: the set lives in R^n; >0: it lives in R^q and M is n x q       */
+    int32_t p;           /* REACH_TERM_ZONO: number of generators                             */
+    const double* M;     /* n x q column-major, or NULL when q == 0                            */
+    const double* c;     /* centre, length (q ? q : n), or NULL                                */
+    const double* r;     /* REACH_TERM_BOX radius, length (q ? q : n), or NULL                 */
+    const double* G;     /* REACH_TERM_ZONO generators, (q ? q : n) x p column-major          */
+} reach_term;
+
+typedef struct {
+    int32_t           nalt;     /* >= 1                                                        */
+    const int32_t*    alt_len;  /* nalt entries; terms of alternative a follow those of a-1    */
+    const reach_term* terms;    /* sum(alt_len) entries                                        */
+} reach_setexpr;
+
+/* Invariant for the early-terminating variants (the `X` argument of reach_*_LGG09!):
+ *   REACH_INV_NONE      Universe
+ *   REACH_INV_HALFSPACE {x : a.x <= b}
+ *   REACH_INV_BOX       [lo, hi]
+ * Disjointness of the template reach-set from X is decided from the template's own support
+ * values (exact when the needed +-a / +-e_i directions are in the template; otherwise no step
+ * is ever reported disjoint). */
+#define REACH_INV_NONE      0
+#define REACH_INV_HALFSPACE 1
+#define REACH_INV_BOX       2
+typedef struct {
+    int32_t kind;
+    const double* a;   /* HALFSPACE: normal (n)      BOX: lo (n) */
+    const double* b;   /* HALFSPACE: offset (1)      BOX: hi (n) */
+} reach_invariant;
+
+typedef struct {
+    int32_t time_block;   /* S: steps advanced per device pass via the power stack (Phi')^1..S.
+                             0 = choose automatically; 1 = strictly sequential chain (the
+                             reference's association, r_{k+1} = Phi' r_k)                     */
+    int32_t share_negated;/* 1 (default when zeroed struct is NOT used: see reach_lgg09_default_opts):
+                             directions l and -l share the chain (Phi')^k l
+                             (noted at reach_homog.jl:108-110); results are bit-identical     */
+    int32_t tile_m;       /* 0 = auto; else force the direction-tile size (testing)           */
+    int32_t tile_n;       /* 0 = auto; else force the row-tile size (testing)                 */
+    int32_t reserved[4];
+} reach_lgg09_opts;
+
+void reach_lgg09_default_opts(reach_lgg09_opts* o);
+
+typedef struct reach_lgg09_plan reach_lgg09_plan;
+
+/* One-shot, host buffers in, host buffer out: what `reach_homog_LGG09!` / `reach_inhomog_LGG09!`
+ * become.  rho_host is ndirs x nsteps column-major: rho_host[j + ndirs*k] = rho_l[j+1, k+1].
+ * V == NULL  <=>  homogeneous.  inv == NULL <=> Universe.  *nsteps_done (may be NULL) receives
+ * the number of valid columns (< nsteps only if an invariant stopped the run early; the column
+ * that triggered the stop is not counted, as `resize!(F, k-1)` drops it). */
+int reach_lgg09(reach_ctx* ctx, int n, int ndirs, int64_t nsteps,
+                const double* Phi,              /* n x n column-major, NOT transposed          */
+                const double* dirs,             /* n x ndirs column-major; row order of output */
+                const reach_setexpr* Omega0, const reach_setexpr* V,
+                const reach_invariant* inv, const reach_lgg09_opts* opts,
+                double* rho_host, int64_t* nsteps_done);
+
+/* Plan API: device-resident inputs and outputs (device-resident Flowpipe storage). */
+int  reach_lgg09_plan_create(reach_ctx* ctx, int n, int ndirs, int64_t nsteps,
+                             const reach_lgg09_opts* opts, reach_lgg09_plan** out);
+int  reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, const double* dirs,
+                             const reach_setexpr* Omega0, const reach_setexpr* V,
+                             const reach_invariant* inv);
+/* If set before run, rho is written to this caller-owned DEVICE buffer (ndirs x nsteps doubles,
+ * column-major) instead of the plan's own; lets a caller hand in memory it will feed to NCCL. */
+int  reach_lgg09_plan_set_output(reach_lgg09_plan* p, void* rho_device);
+int  reach_lgg09_plan_run(reach_lgg09_plan* p);            /* asynchronous on the ctx stream  */
+int  reach_lgg09_plan_sync(reach_lgg09_plan* p);           /* waits; reports device faults    */
+int  reach_lgg09_plan_fetch(reach_lgg09_plan* p, int64_t step0, int64_t nsteps, double* rho_host);
+int  reach_lgg09_plan_nsteps_done(reach_lgg09_plan* p, int64_t* out);
+/* rho(d_j, flowpipe) = max over steps of row j (AbstractFlowpipe.jl:35-37), reduced on device */
+int  reach_lgg09_plan_max_over_steps(reach_lgg09_plan* p, double* max_host /* ndirs */,
+                                     int64_t* argmax_host /* ndirs, may be NULL */);
+void* reach_lgg09_plan_device_rho(reach_lgg09_plan* p);    /* device pointer, ndirs x nsteps   */
+/* CUDA-event time of the last run (ms), the number of kernels it launched, and the launch
+ * configuration chosen; any out pointer may be NULL */
+int  reach_lgg09_plan_stats(reach_lgg09_plan* p, double* ms, int64_t* launches,
+                            int32_t* time_block, int32_t* tile_m, int32_t* tile_n,
+                            int32_t* nchains, double* gemm_ms, int64_t* gemm_launches);
+void reach_lgg09_plan_destroy(reach_lgg09_plan* p);
+
+/* ---------------------------------------------------------------------------------------------
+ * GLGM06: zonotope flowpipes for a batch of initial sets ("splits") that share Phi and U.
+ *
+ *   homogeneous   (pU < 0):  Z_k = Phi Z_{k-1}                       (reach_homog.jl:33-73)
+ *   inhomogeneous (pU >= 0): R_k = reduce(P_{k-1} Omega0 (+) W_k),  W_{k+1} = reduce(P_{k-1} U (+) W_k),
+ *                            P_k = P_{k-1} Phi                       (reach_inhomog.jl:6-43)
+ *
+ * with reduce = reduce_order(., max_order, GIR05()).  Step 1 is Omega0 itself, after the initial
+ * reduce_order of post.jl:26 (done on the device as well).
+ *
+ * Device-resident storage: per (split, step) the reduced zonotope [kept generators in sorted
+ * order | n x n diagonal] is stored as the centre (n), the split's own mapped generators
+ * P_{k-1} G0 (n x p0), the shared input generators W_k (once per step, not per split), the
+ * selection (indices into [own | shared], sorted order) and the diagonal (n).  fetch materialises
+ * the dense n x p matrix of one (split, step) exactly as the reference would hold it.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct reach_glgm06_plan reach_glgm06_plan;
+
+int  reach_glgm06_plan_create(reach_ctx* ctx, int n, int64_t nsteps, int nsplits, int max_order,
+                              int p0, int pU /* <0: homogeneous */, reach_glgm06_plan** out);
+int  reach_glgm06_plan_upload(reach_glgm06_plan* p, const double* Phi,
+                              const double* c0 /* n x nsplits */,
+                              const double* G0 /* n x p0 x nsplits */,
+                              const double* cU /* n, or NULL */, const double* GU /* n x pU, or NULL */);
+int  reach_glgm06_plan_run(reach_glgm06_plan* p);
+int  reach_glgm06_plan_sync(reach_glgm06_plan* p);
+/* number of generators of the (split, step) zonotope; step is 0-based (step 0 = Omega0) */
+int  reach_glgm06_plan_ngens(reach_glgm06_plan* p, int split, int64_t step, int* out);
+/* materialise one zonotope: c (n), G (n x ngens column-major).  sel (may be NULL, capacity
+ * ngens) receives for each output column the index of the source generator in [own | shared]
+ * numbering of the un-reduced zonotope, or -1 for the diagonal columns. */
+int  reach_glgm06_plan_fetch(reach_glgm06_plan* p, int split, int64_t step,
+                             double* c_host, double* G_host, int32_t* sel);
+/* rho(d, Z_{split,step}) for all splits and steps on the device: out is nsplits x nsteps
+ * column-major (split fastest) */
+int  reach_glgm06_plan_support(reach_glgm06_plan* p, const double* d /* n */, double* out_host);
+int  reach_glgm06_plan_stats(reach_glgm06_plan* p, double* ms, int64_t* launches,
+                             int64_t* bytes_stored);
+void reach_glgm06_plan_destroy(reach_glgm06_plan* p);
+
+/* One-shot form (single problem or batch), host buffers out.  G_host is laid out with a fixed
+ * stride of gcap columns per zonotope: zonotope (split s, step k) starts at
+ * G_host + ((k*nsplits + s) * gcap) * n, and ngens_host[k*nsplits + s] columns of it are valid.
+ * gcap >= max(p0_reduced, max_order*n).  Any output pointer may be NULL. */
+int reach_glgm06(reach_ctx* ctx, int n, int64_t nsteps, int nsplits, int max_order,
+                 const double* Phi, const double* c0, const double* G0, int p0,
+                 const double* cU, const double* GU, int pU,
+                 double* c_host, double* G_host, int gcap, int32_t* ngens_host);
+
+/* reduce_order(Zonotope(c, G), r, GIR05()) on the device for one zonotope (post.jl:26 and tests):
+ * G n x p in, Gred n x pred out (capacity p columns), *pred the new count, sel as above. */
+int reach_reduce_order_gir05(reach_ctx* ctx, int n, int p, int max_order, const double* G,
+                             double* Gred, int* pred, int32_t* sel);
+
+/* FP64 GEMM throughput probe with this library's own DMMA kernel on an m x n x k problem
+ * (C[m x n] = X[m x k] * Y[n x k]'), returns achieved TFLOP/s; used by bench.py beside cuBLAS. */
+int reach_dgemm_probe(reach_ctx* ctx, int m, int n, int k, int iters, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REACH_H */

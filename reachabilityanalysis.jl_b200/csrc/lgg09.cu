@@ -1,0 +1,798 @@
+// lgg09.cu -- host side of the LGG09 device path: flattening of the support program into
+// feature rows, direction-chain sharing, the (Phi')^s row stack, launch configuration and the
+// C ABI entry points declared in include/reach.h.
+//
+// Replaces the inside of reach_homog_LGG09! (src/Algorithms/LGG09/reach_homog.jl:6-33,49-62) and
+// reach_inhomog_LGG09! (reach_inhomog.jl:5-33,49-81); the invariant variants
+// (reach_homog.jl:382-424, reach_inhomog.jl:174-218) are served by the same pass plus a
+// first-disjoint-step reduction.
+#include "reach_common.cuh"
+#include "lgg09_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace reach;
+
+namespace {
+
+// ---- launch configurations ------------------------------------------------------------------
+struct TileCfg {
+    int id, TM, TN, occ;     // occ: CTAs that fit one SM (registers / shared memory)
+};
+//                         id  TM   TN  occ
+const TileCfg kCfgs[] = {{0, 128, 128, 1},    // 2x4 warps, 64x32 warp tile  (large blocks)
+                         {1, 64, 64, 2},      // 2x2 warps, 32x32 warp tile  (small n / stack build)
+                         {2, 16, 128, 2},     // 1x4 warps, 16x32 warp tile  (a handful of directions)
+                         {3, 64, 128, 1}};    // 2x4 warps, 32x32 warp tile
+constexpr int kNumCfgs = 4;
+
+template <class Epi>
+cudaError_t launch_cfg(int cfg, const GemmOperands& g, const Epi& epi, cudaStream_t st) {
+    switch (cfg) {
+        case 0: return launch_nt_dgemm<2, 4, 8, 4, 4>(g, epi, st);
+        case 1: return launch_nt_dgemm<2, 2, 4, 4, 4>(g, epi, st);
+        case 2: return launch_nt_dgemm<1, 4, 2, 4, 4>(g, epi, st);
+        case 3: return launch_nt_dgemm<2, 4, 4, 4, 4>(g, epi, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// ---- flattened support program -> features --------------------------------------------------
+struct Feature {
+    std::vector<double> a, b;          // direct weights on r (length n)
+    std::map<int, std::pair<double, double>> rows;   // mapped row -> (lin, abs) weight
+    bool empty() const {
+        for (double v : a) if (v != 0.0) return false;
+        for (double v : b) if (v != 0.0) return false;
+        return rows.empty();
+    }
+    bool operator==(const Feature& o) const { return a == o.a && b == o.b && rows == o.rows; }
+};
+
+struct Program {
+    int n = 0;
+    std::vector<std::vector<double>> erows;          // mapped rows E (each length n)
+    std::map<std::string, int> erow_index;
+    std::vector<Feature> feats;
+    Lgg09Program dev{};
+    bool need_next = false;                          // some term is evaluated at r_{k+1}
+
+    int add_row(const double* v) {
+        std::vector<double> row(v, v + n);
+        for (double& x : row) x += 0.0;              // -0.0 -> +0.0 so equal rows compare equal
+        std::string key(reinterpret_cast<const char*>(row.data()), sizeof(double) * n);
+        auto it = erow_index.find(key);
+        if (it != erow_index.end()) return it->second;
+        int id = int(erows.size());
+        erows.push_back(std::move(row));
+        erow_index.emplace(std::move(key), id);
+        return id;
+    }
+    int add_feature(const Feature& f) {
+        for (size_t i = 0; i < feats.size(); ++i)
+            if (feats[i] == f) return int(i);
+        feats.push_back(f);
+        return int(feats.size()) - 1;
+    }
+};
+
+// contribution of one direction-space vector v (a column of M, a generator, ...) with weights
+// (wl, wa): a single-entry vector folds into the direct weights, anything else becomes a mapped row
+void add_vector(Program& P, Feature& f, const double* v, double wl, double wa) {
+    int nz = 0, at = -1;
+    for (int i = 0; i < P.n; ++i)
+        if (v[i] != 0.0) { ++nz; at = i; }
+    if (nz == 0) return;
+    if (nz == 1) {
+        f.a[at] += v[at] * wl;
+        f.b[at] += std::fabs(v[at]) * wa;
+        return;
+    }
+    int id = P.add_row(v);
+    auto& w = f.rows[id];
+    w.first += wl;
+    w.second += wa;
+}
+
+int add_term(reach_ctx* ctx, Program& P, Feature& f, const reach_term& t) {
+    const int n = P.n;
+    const int d = t.q > 0 ? t.q : n;
+    if (t.q < 0) return set_error(ctx, REACH_EINVAL, "term: q < 0");
+    if (t.q > 0 && !t.M) return set_error(ctx, REACH_EINVAL, "term: q > 0 but M is NULL");
+    if (t.kind == REACH_TERM_BOX) {
+        if (t.q == 0) {
+            for (int i = 0; i < n; ++i) {
+                if (t.c) f.a[i] += t.c[i];
+                if (t.r) {
+                    if (t.r[i] < 0) return set_error(ctx, REACH_EINVAL, "term: negative radius");
+                    f.b[i] += t.r[i];
+                }
+            }
+        } else {
+            for (int j = 0; j < d; ++j) {
+                const double wl = t.c ? t.c[j] : 0.0, wa = t.r ? t.r[j] : 0.0;
+                if (wa < 0) return set_error(ctx, REACH_EINVAL, "term: negative radius");
+                if (wl == 0.0 && wa == 0.0) continue;
+                add_vector(P, f, t.M + size_t(j) * n, wl, wa);
+            }
+        }
+        return REACH_OK;
+    }
+    if (t.kind == REACH_TERM_ZONO) {
+        if (t.p < 0 || (t.p > 0 && !t.G)) return set_error(ctx, REACH_EINVAL, "term: bad generators");
+        if (t.c) {
+            if (t.q == 0) {
+                for (int i = 0; i < n; ++i) f.a[i] += t.c[i];
+            } else {
+                for (int j = 0; j < d; ++j)
+                    if (t.c[j] != 0.0) add_vector(P, f, t.M + size_t(j) * n, t.c[j], 0.0);
+            }
+        }
+        std::vector<double> v(n);
+        for (int g = 0; g < t.p; ++g) {
+            const double* col = t.G + size_t(g) * d;
+            if (t.q == 0) {
+                add_vector(P, f, col, 0.0, 1.0);
+            } else {                                   // v = M g
+                std::fill(v.begin(), v.end(), 0.0);
+                for (int j = 0; j < d; ++j) {
+                    const double gj = col[j];
+                    if (gj == 0.0) continue;
+                    const double* mc = t.M + size_t(j) * n;
+                    for (int i = 0; i < n; ++i) v[i] += mc[i] * gj;
+                }
+                add_vector(P, f, v.data(), 0.0, 1.0);
+            }
+        }
+        return REACH_OK;
+    }
+    return set_error(ctx, REACH_EINVAL, "term: unknown kind %d", t.kind);
+}
+
+int build_program(reach_ctx* ctx, int n, const reach_setexpr* O, const reach_setexpr* V, Program& P) {
+    P.n = n;
+    if (!O || O->nalt < 1) return set_error(ctx, REACH_EINVAL, "Omega0 must have at least one alternative");
+    if (O->nalt > LGG09_MAX_ALTS)
+        return set_error(ctx, REACH_EUNSUPPORTED, "Omega0 has %d alternatives (max %d)", O->nalt, LGG09_MAX_ALTS);
+    P.dev.nalt = O->nalt;
+    P.dev.qV = -1;
+    const reach_term* t = O->terms;
+    for (int a = 0; a < O->nalt; ++a) {
+        Feature f[2];
+        for (auto& x : f) { x.a.assign(n, 0.0); x.b.assign(n, 0.0); }
+        const int len = O->alt_len ? O->alt_len[a] : 0;
+        if (len < 0) return set_error(ctx, REACH_EINVAL, "negative alt_len");
+        for (int i = 0; i < len; ++i, ++t) {
+            if (t->which != 0 && t->which != 1) return set_error(ctx, REACH_EINVAL, "term: which must be 0 or 1");
+            REACH_TRY(add_term(ctx, P, f[t->which], *t));
+        }
+        P.dev.q0[a] = f[0].empty() ? int8_t(-1) : int8_t(P.add_feature(f[0]));
+        P.dev.q1[a] = f[1].empty() ? int8_t(-1) : int8_t(P.add_feature(f[1]));
+        if (P.dev.q1[a] >= 0) P.need_next = true;
+    }
+    if (V) {
+        if (V->nalt != 1) return set_error(ctx, REACH_EINVAL, "V must be a single sum of terms (nalt == 1)");
+        Feature f;
+        f.a.assign(n, 0.0);
+        f.b.assign(n, 0.0);
+        const int len = V->alt_len ? V->alt_len[0] : 0;
+        for (int i = 0; i < len; ++i) {
+            if (V->terms[i].which != 0) return set_error(ctx, REACH_EINVAL, "V terms must have which == 0");
+            REACH_TRY(add_term(ctx, P, f, V->terms[i]));
+        }
+        // an all-zero V still is an input: s stays 0, identical to the reference adding zeros
+        P.dev.qV = int8_t(P.add_feature(f));
+    }
+    if (int(P.feats.size()) > LGG09_MAX_FEATS)
+        return set_error(ctx, REACH_EUNSUPPORTED, "support program needs %zu features (max %d)",
+                         P.feats.size(), LGG09_MAX_FEATS);
+    return REACH_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+struct reach_lgg09_plan {
+    reach_ctx* ctx = nullptr;
+    int n = 0, ndirs = 0;
+    int64_t nsteps = 0;
+    reach_lgg09_opts opts{};
+
+    // derived sizes
+    int Kp = 0;            // n padded to BK
+    int mu = 0, mu_pad = 0;
+    int ne = 0, nbe = 0;   // mapped rows, rows per stack block
+    int nq = 0;
+    int S = 1;
+    int cfg = 0, TM = 0, TN = 0, tpb = 0;
+    int nq_pad = 0;        // rows of the Q (row-major power) buffers
+    bool uploaded = false, ran = false;
+    Program prog;
+
+    DevBuf stack;          // [(S+1)*nbe][Kp]
+    DevBuf Qbuf[2];        // [nq_pad][Kp] : Phi^s row-major, ping-pong
+    DevBuf L0, Lbuf[2];    // [mu_pad][Kp]
+    DevBuf Wl, Wa;         // [nq][nbe]
+    DevBuf tile_mask;      // [tpb] uint32
+    DevBuf featpart;       // [(S+1)*tpb][nq][2][mu_pad]
+    DevBuf carry;          // [nq][2][mu_pad]
+    DevBuf s_pos, s_neg;   // [mu_pad]
+    DevBuf row_pos, row_neg;   // [mu] int
+    DevBuf rho_own;        // ndirs x nsteps
+    double* rho = nullptr; // rho_own or caller-provided
+    DevBuf checks;         // InvCheck[]
+    int nchecks = 0;
+    DevBuf first_bad;      // unsigned long long
+    int64_t nsteps_done = 0;
+    DevBuf phi_cm;         // n x n column-major copy of Phi (source of the transpose)
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaEvent_t> gemm_ev;   // pairs around sampled main-loop GEMM launches
+    int gemm_sampled = 0;
+    int64_t gemm_total = 0;
+    int64_t launches = 0;
+    double last_ms = 0.0, gemm_ms = 0.0;
+
+    ~reach_lgg09_plan() {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        for (auto e : gemm_ev) cudaEventDestroy(e);
+    }
+};
+
+namespace {
+
+// Cost model (SM cycles per time step) used to pick the tile shape and the time block S.
+double step_cost(const reach_lgg09_plan& p, const TileCfg& c, int S, int mu, int nrows, int sms) {
+    const int mu_pad = round_up(mu, c.TM);
+    const int nbe = round_up(nrows, c.TN);
+    const double tiles = double(mu_pad / c.TM) * (double(S) * nbe / c.TN);
+    const double slots = double(sms) * c.occ;
+    const double waves = std::ceil(tiles / slots);
+    const double mma = double(c.TM) * c.TN * p.Kp / 64.0 * c.occ;          // 64 FP64 FMA/clk/SM
+    const double mem = double(c.TM + c.TN) * p.Kp * 8.0 / 40.0 * c.occ;    // ~40 B/clk/SM from L2
+    const double tile = std::max(mma, mem) + 3000.0;
+    const double launch = 16000.0;                                         // two launches, ~8 us
+    return (waves * tile + launch) / S;
+}
+
+int choose_config(reach_lgg09_plan& p) {
+    reach_ctx* ctx = p.ctx;
+    const int nrows = p.n + p.ne;
+    int smax = 1;
+    while (smax * 2 <= 256 && int64_t(smax) * 2 <= std::max<int64_t>(1, p.nsteps)) smax *= 2;
+    int best_cfg = -1, best_S = 1;
+    double best = 1e300;
+    for (int ci = 0; ci < kNumCfgs; ++ci) {
+        const TileCfg& c = kCfgs[ci];
+        if (p.opts.tile_m && p.opts.tile_m != c.TM) continue;
+        if (p.opts.tile_n && p.opts.tile_n != c.TN) continue;
+        for (int S = 1; S <= smax; S *= 2) {
+            if (p.opts.time_block > 0 && S != p.opts.time_block) continue;
+            const int nbe = round_up(nrows, c.TN);
+            const int mu_pad = round_up(p.mu, c.TM);
+            const double stack_bytes = double(S + 1) * nbe * p.Kp * 8.0;
+            const double feat_bytes = double(S + 1) * (nbe / c.TN) * std::max(1, p.nq) * 2.0 * mu_pad * 8.0;
+            if (S > 1 && (stack_bytes > 3e9 || feat_bytes > 1e9)) continue;
+            const double cost = step_cost(p, c, S, p.mu, nrows, ctx->sm_count);
+            if (cost < best * 0.98) { best = cost; best_cfg = ci; best_S = S; }
+        }
+    }
+    if (best_cfg < 0)
+        return set_error(ctx, REACH_EINVAL,
+                         "no launch configuration matches time_block=%d tile_m=%d tile_n=%d "
+                         "(time_block must be a power of two <= min(256, nsteps); tiles 128x128, 64x64, 16x128, 64x128)",
+                         p.opts.time_block, p.opts.tile_m, p.opts.tile_n);
+    p.cfg = best_cfg;
+    p.S = best_S;
+    p.TM = kCfgs[best_cfg].TM;
+    p.TN = kCfgs[best_cfg].TN;
+    return REACH_OK;
+}
+
+}  // namespace
+
+extern "C" void reach_lgg09_default_opts(reach_lgg09_opts* o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->time_block = 0;
+    o->share_negated = 1;
+}
+
+extern "C" int reach_lgg09_plan_create(reach_ctx* ctx, int n, int ndirs, int64_t nsteps,
+                                       const reach_lgg09_opts* opts, reach_lgg09_plan** out) {
+    if (!ctx) return set_error(nullptr, REACH_EINVAL, "ctx is NULL");
+    if (!out) return set_error(ctx, REACH_EINVAL, "out is NULL");
+    *out = nullptr;
+    if (n < 1) return set_error(ctx, REACH_EINVAL, "state dimension must be >= 1, got %d", n);
+    if (ndirs < 1) return set_error(ctx, REACH_EINVAL, "need at least one template direction, got %d", ndirs);
+    if (nsteps < 1) return set_error(ctx, REACH_EINVAL, "NSTEPS must be >= 1, got %lld", (long long)nsteps);
+    if (opts && opts->time_block < 0) return set_error(ctx, REACH_EINVAL, "time_block < 0");
+    if (opts && opts->time_block > 0 && (opts->time_block & (opts->time_block - 1)))
+        return set_error(ctx, REACH_EINVAL, "time_block must be a power of two, got %d", opts->time_block);
+    reach_lgg09_plan* p = new (std::nothrow) reach_lgg09_plan;
+    if (!p) return set_error(ctx, REACH_ENOMEM, "out of host memory");
+    p->ctx = ctx;
+    p->n = n;
+    p->ndirs = ndirs;
+    p->nsteps = nsteps;
+    if (opts) p->opts = *opts; else reach_lgg09_default_opts(&p->opts);
+    p->Kp = round_up(n, BK);
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e == cudaSuccess) e = cudaEventCreate(&p->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&p->ev1);
+    if (e != cudaSuccess) {
+        delete p;
+        return set_error(ctx, REACH_ECUDA, "plan_create: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return REACH_OK;
+}
+
+extern "C" void reach_lgg09_plan_destroy(reach_lgg09_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->ctx->stream);
+    delete p;
+}
+
+extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, const double* dirs,
+                                       const reach_setexpr* Omega0, const reach_setexpr* V,
+                                       const reach_invariant* inv) {
+    if (!p) return REACH_EINVAL;
+    reach_ctx* ctx = p->ctx;
+    if (!Phi || !dirs) return set_error(ctx, REACH_EINVAL, "Phi and dirs must not be NULL");
+    REACH_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int n = p->n, Kp = p->Kp, ndirs = p->ndirs;
+    for (size_t i = 0; i < size_t(n) * n; ++i)
+        if (!std::isfinite(Phi[i])) return set_error(ctx, REACH_EINVAL, "Phi contains a non-finite entry");
+
+    // ---- support program ----
+    p->prog = Program();
+    REACH_TRY(build_program(ctx, n, Omega0, V, p->prog));
+    p->ne = int(p->prog.erows.size());
+    p->nq = int(p->prog.feats.size());
+
+    // ---- direction chains: l and -l share (Phi')^k l (reach_homog.jl:108-110) ----
+    std::vector<int> row_pos, row_neg;
+    std::vector<std::vector<double>> chains;
+    {
+        std::map<std::string, int> index;
+        std::vector<double> canon(n);
+        for (int j = 0; j < ndirs; ++j) {
+            const double* d = dirs + size_t(j) * n;
+            double sign = 1.0;
+            for (int i = 0; i < n; ++i) {
+                if (!std::isfinite(d[i])) return set_error(ctx, REACH_EINVAL, "direction %d is not finite", j);
+            }
+            if (p->opts.share_negated)
+                for (int i = 0; i < n; ++i)
+                    if (d[i] != 0.0) { sign = d[i] < 0 ? -1.0 : 1.0; break; }
+            for (int i = 0; i < n; ++i) canon[i] = sign * d[i] + 0.0;
+            int c = -1;
+            if (p->opts.share_negated) {
+                std::string key(reinterpret_cast<const char*>(canon.data()), sizeof(double) * n);
+                auto it = index.find(key);
+                if (it != index.end()) {
+                    c = it->second;
+                    int& slot = sign > 0 ? row_pos[c] : row_neg[c];
+                    if (slot >= 0) c = -1;          // duplicate direction: give it its own chain
+                    else slot = j;
+                }
+                if (c < 0) {
+                    c = int(chains.size());
+                    chains.push_back(canon);
+                    row_pos.push_back(sign > 0 ? j : -1);
+                    row_neg.push_back(sign > 0 ? -1 : j);
+                    index[key] = c;
+                }
+            } else {
+                chains.push_back(canon);
+                row_pos.push_back(j);
+                row_neg.push_back(-1);
+            }
+        }
+    }
+    p->mu = int(chains.size());
+
+    REACH_TRY(choose_config(*p));
+    const int TM = p->TM, TN = p->TN, S = p->S;
+    p->mu_pad = round_up(p->mu, TM);
+    p->nbe = round_up(n + p->ne, TN);
+    p->tpb = p->nbe / TN;
+    p->nq_pad = round_up(n, 128);
+    const int nbe = p->nbe, mu_pad = p->mu_pad, nq = p->nq;
+
+    // ---- device buffers ----
+    REACH_TRY(p->stack.alloc(ctx, size_t(S + 1) * nbe * Kp * sizeof(double)));
+    REACH_TRY(p->Qbuf[0].alloc(ctx, size_t(p->nq_pad) * Kp * sizeof(double)));
+    REACH_TRY(p->Qbuf[1].alloc(ctx, size_t(p->nq_pad) * Kp * sizeof(double)));
+    REACH_TRY(p->L0.alloc(ctx, size_t(mu_pad) * Kp * sizeof(double)));
+    REACH_TRY(p->Lbuf[0].alloc(ctx, size_t(mu_pad) * Kp * sizeof(double)));
+    REACH_TRY(p->Lbuf[1].alloc(ctx, size_t(mu_pad) * Kp * sizeof(double)));
+    REACH_TRY(p->Wl.alloc(ctx, size_t(std::max(1, nq)) * nbe * sizeof(double)));
+    REACH_TRY(p->Wa.alloc(ctx, size_t(std::max(1, nq)) * nbe * sizeof(double)));
+    REACH_TRY(p->tile_mask.alloc(ctx, size_t(p->tpb) * sizeof(uint32_t)));
+    REACH_TRY(p->featpart.alloc(ctx, size_t(S + 1) * p->tpb * std::max(1, nq) * 2 * mu_pad * sizeof(double)));
+    REACH_TRY(p->carry.alloc(ctx, size_t(std::max(1, nq)) * 2 * mu_pad * sizeof(double)));
+    REACH_TRY(p->s_pos.alloc(ctx, size_t(mu_pad) * sizeof(double)));
+    REACH_TRY(p->s_neg.alloc(ctx, size_t(mu_pad) * sizeof(double)));
+    REACH_TRY(p->row_pos.alloc(ctx, size_t(p->mu) * sizeof(int)));
+    REACH_TRY(p->row_neg.alloc(ctx, size_t(p->mu) * sizeof(int)));
+    REACH_TRY(p->phi_cm.alloc(ctx, size_t(n) * n * sizeof(double), false));
+    REACH_TRY(p->first_bad.alloc(ctx, sizeof(unsigned long long)));
+    if (!p->rho) {
+        REACH_TRY(p->rho_own.alloc(ctx, size_t(ndirs) * p->nsteps * sizeof(double), false));
+        p->rho = p->rho_own.as<double>();
+    }
+
+    // ---- host staging + H2D ----
+    // Phi: column-major n x n.  Row k of the row-major Phi (the seed Q_1) is produced on the
+    // device by a transpose at run time; here we only ship the matrix.
+    REACH_CUDA(ctx, cudaMemcpyAsync(p->phi_cm.p, Phi, size_t(n) * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    {   // block 0 of the stack = [I ; E] (rows of length Kp)
+        std::vector<double> b0(size_t(nbe) * Kp, 0.0);
+        for (int i = 0; i < n; ++i) b0[size_t(i) * Kp + i] = 1.0;
+        for (int e = 0; e < p->ne; ++e)
+            std::memcpy(&b0[size_t(n + e) * Kp], p->prog.erows[e].data(), sizeof(double) * n);
+        REACH_CUDA(ctx, cudaMemcpyAsync(p->stack.p, b0.data(), b0.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        REACH_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    {   // direction chains, one row each
+        std::vector<double> l0(size_t(mu_pad) * Kp, 0.0);
+        for (int c = 0; c < p->mu; ++c) std::memcpy(&l0[size_t(c) * Kp], chains[c].data(), sizeof(double) * n);
+        REACH_CUDA(ctx, cudaMemcpyAsync(p->L0.p, l0.data(), l0.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        REACH_CUDA(ctx, cudaMemcpyAsync(p->row_pos.p, row_pos.data(), sizeof(int) * p->mu, cudaMemcpyHostToDevice, st));
+        REACH_CUDA(ctx, cudaMemcpyAsync(p->row_neg.p, row_neg.data(), sizeof(int) * p->mu, cudaMemcpyHostToDevice, st));
+        REACH_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    {   // per-row feature weights and the per-tile activity masks
+        std::vector<double> wl(size_t(std::max(1, nq)) * nbe, 0.0), wa(size_t(std::max(1, nq)) * nbe, 0.0);
+        std::vector<uint32_t> mask(p->tpb, 0u);
+        for (int q = 0; q < nq; ++q) {
+            const Feature& f = p->prog.feats[q];
+            for (int i = 0; i < n; ++i) { wl[size_t(q) * nbe + i] = f.a[i]; wa[size_t(q) * nbe + i] = f.b[i]; }
+            for (auto& kv : f.rows) {
+                wl[size_t(q) * nbe + n + kv.first] = kv.second.first;
+                wa[size_t(q) * nbe + n + kv.first] = kv.second.second;
+            }
+            for (int r = 0; r < nbe; ++r)
+                if (wl[size_t(q) * nbe + r] != 0.0 || wa[size_t(q) * nbe + r] != 0.0) mask[r / TN] |= 1u << q;
+        }
+        REACH_CUDA(ctx, cudaMemcpyAsync(p->Wl.p, wl.data(), wl.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        REACH_CUDA(ctx, cudaMemcpyAsync(p->Wa.p, wa.data(), wa.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        REACH_CUDA(ctx, cudaMemcpyAsync(p->tile_mask.p, mask.data(), mask.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        REACH_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+
+    // ---- invariant -> support-value checks on template rows ----
+    p->nchecks = 0;
+    if (inv && inv->kind != REACH_INV_NONE) {
+        std::vector<InvCheck> checks;
+        if (inv->kind == REACH_INV_HALFSPACE) {
+            if (!inv->a || !inv->b) return set_error(ctx, REACH_EINVAL, "half-space invariant needs a and b");
+            for (int j = 0; j < ndirs; ++j) {
+                const double* d = dirs + size_t(j) * n;
+                int at = -1;
+                for (int i = 0; i < n; ++i) if (inv->a[i] != 0.0) { at = i; break; }
+                if (at < 0) break;
+                const double lam = -d[at] / inv->a[at];
+                if (!(lam > 0)) continue;
+                bool same = true;
+                for (int i = 0; i < n && same; ++i) same = (d[i] == -lam * inv->a[i]);
+                if (same) checks.push_back({j, +1, -lam, inv->b[0]});     // -rho/lam > b
+            }
+        } else if (inv->kind == REACH_INV_BOX) {
+            if (!inv->a || !inv->b) return set_error(ctx, REACH_EINVAL, "box invariant needs lo and hi");
+            for (int j = 0; j < ndirs; ++j) {
+                const double* d = dirs + size_t(j) * n;
+                int nz = 0, at = -1;
+                for (int i = 0; i < n; ++i) if (d[i] != 0.0) { ++nz; at = i; }
+                if (nz != 1) continue;
+                if (d[at] > 0) checks.push_back({j, -1, d[at], inv->a[at]});   // rho/d_i < lo_i
+                else checks.push_back({j, +1, d[at], inv->b[at]});             // rho/d_i > hi_i
+            }
+        } else {
+            return set_error(ctx, REACH_EUNSUPPORTED, "invariant kind %d is not supported on the device", inv->kind);
+        }
+        p->nchecks = int(checks.size());
+        if (p->nchecks) {
+            REACH_TRY(p->checks.alloc(ctx, checks.size() * sizeof(InvCheck), false));
+            REACH_CUDA(ctx, cudaMemcpyAsync(p->checks.p, checks.data(), checks.size() * sizeof(InvCheck), cudaMemcpyHostToDevice, st));
+            REACH_CUDA(ctx, cudaStreamSynchronize(st));
+        }
+    }
+    p->uploaded = true;
+    p->ran = false;
+    return REACH_OK;
+}
+
+extern "C" int reach_lgg09_plan_set_output(reach_lgg09_plan* p, void* rho_device) {
+    if (!p) return REACH_EINVAL;
+    if (!rho_device) return set_error(p->ctx, REACH_EINVAL, "rho_device is NULL");
+    p->rho = static_cast<double*>(rho_device);
+    p->rho_own.release();
+    return REACH_OK;
+}
+
+extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
+    if (!p) return REACH_EINVAL;
+    reach_ctx* ctx = p->ctx;
+    if (!p->uploaded) return set_error(ctx, REACH_ESTATE, "plan_run before plan_upload");
+    REACH_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int n = p->n, Kp = p->Kp, nbe = p->nbe, S = p->S, TM = p->TM, TN = p->TN, mu_pad = p->mu_pad;
+    double* stack = p->stack.as<double>();
+    auto block = [&](int b) { return stack + size_t(b) * nbe * Kp; };
+    p->launches = 0;
+    p->gemm_total = 0;
+    p->gemm_sampled = 0;
+
+    REACH_CUDA(ctx, cudaEventRecord(p->ev0, st));
+
+    // state reset so a plan can be re-run
+    REACH_CUDA(ctx, cudaMemcpyAsync(p->Lbuf[0].p, p->L0.p, size_t(mu_pad) * Kp * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    REACH_CUDA(ctx, cudaMemsetAsync(p->s_pos.p, 0, p->s_pos.bytes, st));
+    REACH_CUDA(ctx, cudaMemsetAsync(p->s_neg.p, 0, p->s_neg.bytes, st));
+
+    // ---- row stack: block_b = [I;E] (Phi')^b, b = 0..S.  block_0 was uploaded. ----
+    {   // Q_1 = Phi row-major: Q[k][l] = Phi(k,l) = phi_cm[k + n l]
+        dim3 grid((n + 31) / 32, (n + 31) / 32), blk(32, 8);
+        transpose_kernel<<<grid, blk, 0, st>>>(p->phi_cm.as<double>(), n, p->Qbuf[0].as<double>(), Kp, n);
+        REACH_CUDA(ctx, cudaGetLastError());
+        ++p->launches;
+    }
+    auto plain_gemm = [&](const double* X, int mrows, const double* Y, int yrows, double* out, int m_valid) -> int {
+        GemmOperands g{X, Y, Kp, Kp, Kp, round_up(mrows, 64) / 64, round_up(yrows, 64) / 64};
+        StoreEpi epi{out, Kp, m_valid, n};
+        REACH_CUDA(ctx, (launch_cfg(1, g, epi, st)));
+        ++p->launches;
+        return REACH_OK;
+    };
+    // block_1 = block_0 * P_1   (Y[k][l] = P_1[l][k] = Phi(k,l) = Q_1)
+    REACH_TRY(plain_gemm(block(0), nbe, p->Qbuf[0].as<double>(), n, block(1), nbe));
+    int qcur = 0;
+    for (int s = 1; s < S; s *= 2) {
+        // Q_{2s} = Q_s Q_s : X = Q_s rows, Y[b][l] = Q_s[l][b] = P_s[b][l] = first n rows of block_s
+        REACH_TRY(plain_gemm(p->Qbuf[qcur].as<double>(), n, block(s), n, p->Qbuf[1 - qcur].as<double>(), n));
+        // blocks s+1..2s = blocks 1..s * P_s : Y = Q_s
+        REACH_TRY(plain_gemm(block(1), s * nbe, p->Qbuf[qcur].as<double>(), n, block(s + 1), s * nbe));
+        qcur ^= 1;
+    }
+
+    // ---- main loop over super-steps ----
+    const int64_t Kmax = p->nsteps - 1 + (p->prog.need_next ? 1 : 0);
+    const int64_t T = (Kmax + S - 1) / S;
+    Lgg09Epi epi{};
+    epi.ldl = Kp;
+    epi.n = n;
+    epi.nbe = nbe;
+    epi.Wl = p->Wl.as<double>();
+    epi.Wa = p->Wa.as<double>();
+    epi.tile_mask = p->tile_mask.as<uint32_t>();
+    epi.nq = p->nq;
+    epi.featpart = p->featpart.as<double>();
+    epi.mu_pad = mu_pad;
+
+    Lgg09Combine cmb{};
+    cmb.prog = p->prog.dev;
+    cmb.featpart = p->featpart.as<double>();
+    cmb.tile_mask = p->tile_mask.as<uint32_t>();
+    cmb.tpb = p->tpb;
+    cmb.nq = p->nq;
+    cmb.mu_pad = mu_pad;
+    cmb.mu = p->mu;
+    cmb.nsteps = p->nsteps;
+    cmb.carry = p->carry.as<double>();
+    cmb.s_pos = p->s_pos.as<double>();
+    cmb.s_neg = p->s_neg.as<double>();
+    cmb.row_pos = p->row_pos.as<int>();
+    cmb.row_neg = p->row_neg.as<int>();
+    cmb.rho = p->rho;
+    cmb.ndirs = p->ndirs;
+    const int cthreads = 128, cblocks = (p->mu + cthreads - 1) / cthreads;
+
+    // sample at most 512 main-loop GEMM launches with event pairs
+    const int64_t sample_every = std::max<int64_t>(1, (T + 511) / 512);
+    const size_t want_ev = size_t(2) * size_t((T + sample_every - 1) / sample_every + 1);
+    while (p->gemm_ev.size() < want_ev) {
+        cudaEvent_t e;
+        REACH_CUDA(ctx, cudaEventCreate(&e));
+        p->gemm_ev.push_back(e);
+    }
+
+    int cur = 0;
+    if (T == 0) {
+        // NSTEPS == 1 and nothing is evaluated at r_1: only the features of r_0 are needed
+        GemmOperands g{p->Lbuf[cur].as<double>(), block(0), Kp, Kp, Kp, mu_pad / TM, nbe / TN};
+        epi.Lnext = p->Lbuf[1 - cur].as<double>();
+        epi.block0 = 0;
+        epi.store_block = -1;
+        REACH_CUDA(ctx, (launch_cfg(p->cfg, g, epi, st)));
+        ++p->launches;
+        cmb.b_lo = 0; cmb.b_hi = 0; cmb.has_carry = 0; cmb.tail = 1; cmb.k0 = 0;
+        lgg09_combine_kernel<<<cblocks, cthreads, 0, st>>>(cmb);
+        REACH_CUDA(ctx, cudaGetLastError());
+        ++p->launches;
+    }
+    for (int64_t t = 0; t < T; ++t) {
+        const int b_lo = t == 0 ? 0 : 1;
+        GemmOperands g{p->Lbuf[cur].as<double>(), block(b_lo), Kp, Kp, Kp, mu_pad / TM, (S + 1 - b_lo) * nbe / TN};
+        epi.Lnext = p->Lbuf[1 - cur].as<double>();
+        epi.block0 = b_lo;
+        epi.store_block = S;
+        const bool sample = (t % sample_every) == 0;
+        if (sample) REACH_CUDA(ctx, cudaEventRecord(p->gemm_ev[2 * p->gemm_sampled], st));
+        REACH_CUDA(ctx, (launch_cfg(p->cfg, g, epi, st)));
+        if (sample) {
+            REACH_CUDA(ctx, cudaEventRecord(p->gemm_ev[2 * p->gemm_sampled + 1], st));
+            ++p->gemm_sampled;
+        }
+        ++p->launches;
+        ++p->gemm_total;
+        cmb.b_lo = b_lo; cmb.b_hi = S; cmb.has_carry = t > 0; cmb.tail = 0; cmb.k0 = t * S;
+        lgg09_combine_kernel<<<cblocks, cthreads, 0, st>>>(cmb);
+        REACH_CUDA(ctx, cudaGetLastError());
+        ++p->launches;
+        cur ^= 1;
+    }
+    if (T > 0 && T * S < p->nsteps) {
+        // one step left whose support values only need the carried features of r_{T S}
+        cmb.b_lo = 1; cmb.b_hi = 0; cmb.has_carry = 1; cmb.tail = 1; cmb.k0 = T * S;
+        lgg09_combine_kernel<<<cblocks, cthreads, 0, st>>>(cmb);
+        REACH_CUDA(ctx, cudaGetLastError());
+        ++p->launches;
+    }
+
+    // ---- invariant: first step certified disjoint ----
+    if (p->nchecks > 0) {
+        REACH_CUDA(ctx, cudaMemsetAsync(p->first_bad.p, 0xFF, sizeof(unsigned long long), st));
+        const int th = 256;
+        const unsigned blocks = unsigned((p->nsteps + th - 1) / th);
+        first_disjoint_kernel<<<blocks, th, 0, st>>>(p->rho, p->ndirs, p->nsteps, p->checks.as<InvCheck>(),
+                                                      p->nchecks, p->first_bad.as<unsigned long long>());
+        REACH_CUDA(ctx, cudaGetLastError());
+        ++p->launches;
+    }
+    REACH_CUDA(ctx, cudaEventRecord(p->ev1, st));
+    p->ran = true;
+    return REACH_OK;
+}
+
+extern "C" int reach_lgg09_plan_sync(reach_lgg09_plan* p) {
+    if (!p) return REACH_EINVAL;
+    reach_ctx* ctx = p->ctx;
+    if (!p->ran) return set_error(ctx, REACH_ESTATE, "plan_sync before plan_run");
+    REACH_CUDA(ctx, cudaSetDevice(ctx->device));
+    REACH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    REACH_CUDA(ctx, cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+    p->last_ms = ms;
+    double acc = 0.0;
+    for (int i = 0; i < p->gemm_sampled; ++i) {
+        float t = 0.f;
+        REACH_CUDA(ctx, cudaEventElapsedTime(&t, p->gemm_ev[2 * i], p->gemm_ev[2 * i + 1]));
+        acc += t;
+    }
+    p->gemm_ms = p->gemm_sampled ? acc / p->gemm_sampled : 0.0;   // mean per launch
+    p->nsteps_done = p->nsteps;
+    if (p->nchecks > 0) {
+        unsigned long long fb = 0;
+        REACH_CUDA(ctx, cudaMemcpy(&fb, p->first_bad.p, sizeof(fb), cudaMemcpyDeviceToHost));
+        if (fb != ~0ull && int64_t(fb) < p->nsteps) p->nsteps_done = int64_t(fb);
+    }
+    return REACH_OK;
+}
+
+extern "C" int reach_lgg09_plan_fetch(reach_lgg09_plan* p, int64_t step0, int64_t nsteps, double* rho_host) {
+    if (!p) return REACH_EINVAL;
+    reach_ctx* ctx = p->ctx;
+    if (!p->ran) return set_error(ctx, REACH_ESTATE, "plan_fetch before plan_run");
+    if (!rho_host) return set_error(ctx, REACH_EINVAL, "rho_host is NULL");
+    if (step0 < 0 || nsteps < 0 || step0 + nsteps > p->nsteps)
+        return set_error(ctx, REACH_EINVAL, "fetch range [%lld, %lld) outside [0, %lld)", (long long)step0,
+                         (long long)(step0 + nsteps), (long long)p->nsteps);
+    REACH_CUDA(ctx, cudaSetDevice(ctx->device));
+    REACH_CUDA(ctx, cudaMemcpyAsync(rho_host, p->rho + size_t(step0) * p->ndirs,
+                                    size_t(nsteps) * p->ndirs * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    REACH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return REACH_OK;
+}
+
+extern "C" int reach_lgg09_plan_nsteps_done(reach_lgg09_plan* p, int64_t* out) {
+    if (!p || !out) return REACH_EINVAL;
+    if (!p->ran) return set_error(p->ctx, REACH_ESTATE, "nsteps_done before plan_run");
+    *out = p->nsteps_done;
+    return REACH_OK;
+}
+
+extern "C" int reach_lgg09_plan_max_over_steps(reach_lgg09_plan* p, double* max_host, int64_t* argmax_host) {
+    if (!p) return REACH_EINVAL;
+    reach_ctx* ctx = p->ctx;
+    if (!p->ran) return set_error(ctx, REACH_ESTATE, "max_over_steps before plan_run");
+    if (!max_host) return set_error(ctx, REACH_EINVAL, "max_host is NULL");
+    REACH_CUDA(ctx, cudaSetDevice(ctx->device));
+    DevBuf vmax, amax;
+    REACH_TRY(vmax.alloc(ctx, sizeof(double) * p->ndirs, false));
+    REACH_TRY(amax.alloc(ctx, sizeof(long long) * p->ndirs, false));
+    const int th = 128;
+    max_over_steps_kernel<<<(p->ndirs + th - 1) / th, th, 0, ctx->stream>>>(
+        p->rho, p->ndirs, p->nsteps_done > 0 ? p->nsteps_done : p->nsteps, vmax.as<double>(), amax.as<long long>());
+    REACH_CUDA(ctx, cudaGetLastError());
+    REACH_CUDA(ctx, cudaMemcpyAsync(max_host, vmax.p, sizeof(double) * p->ndirs, cudaMemcpyDeviceToHost, ctx->stream));
+    if (argmax_host) {
+        static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+        REACH_CUDA(ctx, cudaMemcpyAsync(argmax_host, amax.p, sizeof(int64_t) * p->ndirs, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    REACH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return REACH_OK;
+}
+
+extern "C" void* reach_lgg09_plan_device_rho(reach_lgg09_plan* p) { return p ? p->rho : nullptr; }
+
+extern "C" int reach_lgg09_plan_stats(reach_lgg09_plan* p, double* ms, int64_t* launches, int32_t* time_block,
+                                      int32_t* tile_m, int32_t* tile_n, int32_t* nchains, double* gemm_ms,
+                                      int64_t* gemm_launches) {
+    if (!p) return REACH_EINVAL;
+    if (ms) *ms = p->last_ms;
+    if (launches) *launches = p->launches;
+    if (time_block) *time_block = p->S;
+    if (tile_m) *tile_m = p->TM;
+    if (tile_n) *tile_n = p->TN;
+    if (nchains) *nchains = p->mu;
+    if (gemm_ms) *gemm_ms = p->gemm_ms;
+    if (gemm_launches) *gemm_launches = p->gemm_total;
+    return REACH_OK;
+}
+
+extern "C" int reach_lgg09(reach_ctx* ctx, int n, int ndirs, int64_t nsteps, const double* Phi, const double* dirs,
+                           const reach_setexpr* Omega0, const reach_setexpr* V, const reach_invariant* inv,
+                           const reach_lgg09_opts* opts, double* rho_host, int64_t* nsteps_done) {
+    reach_lgg09_plan* p = nullptr;
+    REACH_TRY(reach_lgg09_plan_create(ctx, n, ndirs, nsteps, opts, &p));
+    int rc = reach_lgg09_plan_upload(p, Phi, dirs, Omega0, V, inv);
+    if (rc == REACH_OK) rc = reach_lgg09_plan_run(p);
+    if (rc == REACH_OK) rc = reach_lgg09_plan_sync(p);
+    if (rc == REACH_OK && rho_host) rc = reach_lgg09_plan_fetch(p, 0, nsteps, rho_host);
+    if (rc == REACH_OK && nsteps_done) *nsteps_done = p->nsteps_done;
+    reach_lgg09_plan_destroy(p);
+    return rc;
+}
+
+// FP64 throughput probe of the DMMA kernel on an m x n x k problem (128x128 tiles).
+extern "C" int reach_dgemm_probe(reach_ctx* ctx, int m, int n, int k, int iters, double* tflops) {
+    if (!ctx || !tflops) return REACH_EINVAL;
+    if (m < 1 || n < 1 || k < 1 || iters < 1) return set_error(ctx, REACH_EINVAL, "probe sizes must be positive");
+    REACH_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int mp = round_up(m, 128), np = round_up(n, 128), kp = round_up(k, BK);
+    DevBuf X, Y, C;
+    REACH_TRY(X.alloc(ctx, size_t(mp) * kp * 8));
+    REACH_TRY(Y.alloc(ctx, size_t(np) * kp * 8));
+    REACH_TRY(C.alloc(ctx, size_t(mp) * np * 8));
+    std::vector<double> h(size_t(std::max(mp, np)) * kp);
+    for (size_t i = 0; i < h.size(); ++i) h[i] = double((i * 2654435761u) % 1000) / 1000.0 - 0.5;
+    REACH_CUDA(ctx, cudaMemcpy(X.p, h.data(), size_t(mp) * kp * 8, cudaMemcpyHostToDevice));
+    REACH_CUDA(ctx, cudaMemcpy(Y.p, h.data(), size_t(np) * kp * 8, cudaMemcpyHostToDevice));
+    GemmOperands g{X.as<double>(), Y.as<double>(), kp, kp, kp, mp / 128, np / 128};
+    StoreEpi epi{C.as<double>(), np, mp, np};
+    cudaEvent_t e0, e1;
+    REACH_CUDA(ctx, cudaEventCreate(&e0));
+    REACH_CUDA(ctx, cudaEventCreate(&e1));
+    for (int i = 0; i < 2; ++i) REACH_CUDA(ctx, (launch_cfg(0, g, epi, ctx->stream)));
+    REACH_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    for (int i = 0; i < iters; ++i) REACH_CUDA(ctx, (launch_cfg(0, g, epi, ctx->stream)));
+    REACH_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    REACH_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    REACH_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = 2.0 * m * double(n) * k * iters / (ms * 1e-3) / 1e12;
+    return REACH_OK;
+}

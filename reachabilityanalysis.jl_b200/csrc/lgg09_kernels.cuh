@@ -1,0 +1,270 @@
+// lgg09_kernels.cuh -- device side of the LGG09 support-function recurrence.
+//
+// Reference loop (src/Algorithms/LGG09/reach_inhomog.jl:49-64), per direction l:
+//     r_0 = l;   rho[j,i] = rho(r_i, Omega0) + s_i;   s_{i+1} = s_i + rho(r_i, U);   r_{i+1} = Phi' r_i
+//
+// Device formulation.  Every support term of the flattened Omega0 / V program is a "feature"
+//     F_q(r) = lin_q(r) + abs_q(r),   lin_q(r) = sum_i a_q[i] y_i,   abs_q(r) = sum_i b_q[i] |y_i|
+// over the rows y = [I ; E] r (E = the mapped rows M' / G' of LinearMap / Zonotope terms).  One
+// pass of nt_dgemm over the row stack [I;E](Phi')^s, s = 1..S, yields y for S consecutive steps
+// of every direction chain; the epilogue below reduces the accumulator tile to per-row-tile
+// partial (lin, abs) sums, and stores the s = S block as the next direction block.  The combine
+// kernel then walks the S steps sequentially per chain: alternatives (max), Minkowski terms
+// (sum), the running input sum s_i, and the +l / -l outputs of a shared chain
+// (rho(-r) = -lin + abs).
+#pragma once
+
+#include "nt_dgemm.cuh"
+
+namespace reach {
+
+constexpr int LGG09_MAX_FEATS = 16;
+constexpr int LGG09_MAX_ALTS = 16;
+
+struct Lgg09Epi {
+    double* Lnext;              // [mu_pad][ldl]: rows = chains; written from the store block
+    int ldl;
+    int n;                      // state dimension (columns < n of the store block are stored)
+    int nbe;                    // rows per stack block (multiple of TN)
+    int block0;                 // absolute index of the first block of this launch (0 or 1)
+    int store_block;            // absolute block index whose C tile is L_{k0+S}; -1: none
+    const double* Wl;           // [nq][nbe] linear weights per stack-block row
+    const double* Wa;           // [nq][nbe] absolute-value weights
+    const uint32_t* tile_mask;  // [nbe/TN] features with a non-zero weight in that row tile
+    int nq;
+    double* featpart;           // [blocks][nbe/TN][nq][2][mu_pad]
+    int mu_pad;
+
+    template <int MT, int NT, int WN, class TC>
+    __device__ __forceinline__ void run(double (&acc)[MT][NT][2], const TC& tc, double* smem) const {
+        constexpr int TM = TC::TM, TN = TC::TN;
+        const int row0 = tc.tn * TN;                 // row inside this launch's stack slice
+        const int blk = block0 + row0 / nbe;         // absolute block
+        const int rib0 = row0 % nbe;                 // row in block of the tile's first row
+        const int tib = rib0 / TN;                   // tile in block
+        const int tpb = nbe / TN;
+
+        if (blk == store_block) {
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                const int m = tc.tm * TM + tc.wm0 + i * 8 + tc.g4;
+                double* o = Lnext + size_t(m) * ldl;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const int c = rib0 + tc.wn0 + j * 8 + 2 * tc.t4;
+                    if (c + 1 < n) {
+                        *reinterpret_cast<double2*>(o + c) = make_double2(acc[i][j][0], acc[i][j][1]);
+                    } else if (c < n) {
+                        o[c] = acc[i][j][0];
+                    }
+                }
+            }
+        }
+
+        const uint32_t mask = tile_mask[tib];
+        if (mask == 0u) return;
+        // red[q'][wn][part][TM] for the active features q' (compacted)
+        double* red = smem;
+        const int wn = tc.wn0 / (NT * 8);
+        int qa = 0;
+        for (int q = 0; q < nq; ++q) {
+            if (!((mask >> q) & 1u)) continue;
+            double wl[NT][2], wa[NT][2];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int c = rib0 + tc.wn0 + j * 8 + 2 * tc.t4;
+                const double2 l2 = *reinterpret_cast<const double2*>(Wl + size_t(q) * nbe + c);
+                const double2 a2 = *reinterpret_cast<const double2*>(Wa + size_t(q) * nbe + c);
+                wl[j][0] = l2.x; wl[j][1] = l2.y;
+                wa[j][0] = a2.x; wa[j][1] = a2.y;
+            }
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                double lin = 0.0, ab = 0.0;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    lin = fma(wl[j][0], acc[i][j][0], lin);
+                    lin = fma(wl[j][1], acc[i][j][1], lin);
+                    ab = fma(wa[j][0], fabs(acc[i][j][0]), ab);
+                    ab = fma(wa[j][1], fabs(acc[i][j][1]), ab);
+                }
+                lin += __shfl_xor_sync(0xffffffffu, lin, 1);
+                ab += __shfl_xor_sync(0xffffffffu, ab, 1);
+                lin += __shfl_xor_sync(0xffffffffu, lin, 2);
+                ab += __shfl_xor_sync(0xffffffffu, ab, 2);
+                if (tc.t4 == 0) {
+                    const int m = tc.wm0 + i * 8 + tc.g4;
+                    red[((qa * WN + wn) * 2 + 0) * TM + m] = lin;
+                    red[((qa * WN + wn) * 2 + 1) * TM + m] = ab;
+                }
+            }
+            ++qa;
+        }
+        __syncthreads();
+        // fixed-order sum over the WN warps that share a direction row -> deterministic
+        const int nact = qa;
+        for (int idx = tc.tid; idx < nact * 2 * TM; idx += tc.nthr) {
+            const int m = idx % TM;
+            const int part = (idx / TM) & 1;
+            const int qi = idx / (2 * TM);
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < WN; ++w) s += red[((qi * WN + w) * 2 + part) * TM + m];
+            // map compacted index back to the feature id
+            int q = 0, seen = 0;
+            for (; q < nq; ++q)
+                if ((mask >> q) & 1u) {
+                    if (seen == qi) break;
+                    ++seen;
+                }
+            featpart[(((size_t(blk) * tpb + tib) * nq + q) * 2 + part) * mu_pad + tc.tm * TM + m] = s;
+        }
+    }
+};
+
+struct Lgg09Program {
+    int nalt;
+    int qV;                         // feature of rho(., V), -1 when homogeneous
+    int8_t q0[LGG09_MAX_ALTS];      // per alternative: feature evaluated at r_k     (-1: none)
+    int8_t q1[LGG09_MAX_ALTS];      // per alternative: feature evaluated at r_{k+1} (-1: none)
+};
+
+struct Lgg09Combine {
+    Lgg09Program prog;
+    const double* featpart;         // [blocks][tpb][nq][2][mu_pad]
+    const uint32_t* tile_mask;      // [tpb]
+    int tpb, nq, mu_pad, mu;
+    int b_lo, b_hi;                 // blocks present in featpart for this pass (inclusive)
+    int has_carry;                  // F(r_{k0}) comes from `carry` instead of block b_lo
+    int tail;                       // also emit step k0 + b_hi from the last features alone
+    long long k0;                   // r index of block 0 of this pass
+    long long nsteps;
+    double* carry;                  // [nq][2][mu_pad]
+    double* s_pos;                  // [mu_pad] running input sums of the +chain / -chain outputs
+    double* s_neg;
+    const int* row_pos;             // [mu] output row of +chain (-1: absent)
+    const int* row_neg;             // [mu] output row of -chain (-1: absent)
+    double* rho;                    // ndirs x nsteps column-major
+    int ndirs;
+};
+
+__device__ __forceinline__ void lgg09_emit(const Lgg09Combine& c, long long k, const double (*Fp)[2],
+                                           const double (*Fc)[2], int rp, int rn, double& sp, double& sn) {
+    double vp = 0.0, vn = 0.0;
+    for (int a = 0; a < c.prog.nalt; ++a) {
+        double ap = 0.0, an = 0.0;
+        const int q0 = c.prog.q0[a], q1 = c.prog.q1[a];
+        if (q0 >= 0) { ap += Fp[q0][0] + Fp[q0][1]; an += Fp[q0][1] - Fp[q0][0]; }
+        if (q1 >= 0) { ap += Fc[q1][0] + Fc[q1][1]; an += Fc[q1][1] - Fc[q1][0]; }
+        if (a == 0) { vp = ap; vn = an; } else { vp = fmax(vp, ap); vn = fmax(vn, an); }
+    }
+    if (rp >= 0) c.rho[size_t(k) * c.ndirs + rp] = vp + sp;
+    if (rn >= 0) c.rho[size_t(k) * c.ndirs + rn] = vn + sn;
+    if (c.prog.qV >= 0) {
+        const int q = c.prog.qV;
+        sp += Fp[q][0] + Fp[q][1];
+        sn += Fp[q][1] - Fp[q][0];
+    }
+}
+
+__device__ __forceinline__ void lgg09_block_features(const Lgg09Combine& c, int blk, int j, double (*F)[2]) {
+    for (int q = 0; q < c.nq; ++q) { F[q][0] = 0.0; F[q][1] = 0.0; }
+    for (int t = 0; t < c.tpb; ++t) {            // fixed order over row tiles
+        const uint32_t mask = c.tile_mask[t];
+        for (int q = 0; q < c.nq; ++q) {
+            if (!((mask >> q) & 1u)) continue;
+            const size_t base = (((size_t(blk) * c.tpb + t) * c.nq + q) * 2) * c.mu_pad + j;
+            F[q][0] += c.featpart[base];
+            F[q][1] += c.featpart[base + c.mu_pad];
+        }
+    }
+}
+
+__global__ void lgg09_combine_kernel(const Lgg09Combine c) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= c.mu) return;
+    double Fa[LGG09_MAX_FEATS][2], Fb[LGG09_MAX_FEATS][2];
+    double (*Fp)[2] = Fa;
+    double (*Fc)[2] = Fb;
+    const int rp = c.row_pos[j], rn = c.row_neg[j];
+    double sp = c.s_pos[j], sn = c.s_neg[j];
+    int b = c.b_lo;
+    if (c.has_carry) {
+        for (int q = 0; q < c.nq; ++q) {
+            Fp[q][0] = c.carry[(size_t(q) * 2 + 0) * c.mu_pad + j];
+            Fp[q][1] = c.carry[(size_t(q) * 2 + 1) * c.mu_pad + j];
+        }
+    } else {
+        lgg09_block_features(c, b, j, Fp);
+        ++b;
+    }
+    for (; b <= c.b_hi; ++b) {
+        lgg09_block_features(c, b, j, Fc);
+        const long long k = c.k0 + b - 1;
+        if (k < c.nsteps) lgg09_emit(c, k, Fp, Fc, rp, rn, sp, sn);
+        double (*t)[2] = Fp; Fp = Fc; Fc = t;
+    }
+    if (c.tail) {
+        const long long k = c.k0 + c.b_hi;
+        if (k < c.nsteps) lgg09_emit(c, k, Fp, Fp, rp, rn, sp, sn);
+    }
+    for (int q = 0; q < c.nq; ++q) {
+        c.carry[(size_t(q) * 2 + 0) * c.mu_pad + j] = Fp[q][0];
+        c.carry[(size_t(q) * 2 + 1) * c.mu_pad + j] = Fp[q][1];
+    }
+    c.s_pos[j] = sp;
+    c.s_neg[j] = sn;
+}
+
+// out[r][c] = in[c][r] for an n x n block (in: ld_in, out: ld_out); used once per run to get
+// the row-major copy of Phi that seeds the power stack.
+__global__ void transpose_kernel(const double* __restrict__ in, int ld_in, double* __restrict__ out,
+                                 int ld_out, int n) {
+    __shared__ double tile[32][33];
+    int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 32 + threadIdx.y;
+    for (int dy = 0; dy < 32; dy += 8)
+        if (x < n && y + dy < n) tile[threadIdx.y + dy][threadIdx.x] = in[size_t(y + dy) * ld_in + x];
+    __syncthreads();
+    x = blockIdx.y * 32 + threadIdx.x;
+    y = blockIdx.x * 32 + threadIdx.y;
+    for (int dy = 0; dy < 32; dy += 8)
+        if (x < n && y + dy < n) out[size_t(y + dy) * ld_out + x] = tile[threadIdx.x][threadIdx.y + dy];
+}
+
+// rho(d_j, flowpipe) = max_k rho[j,k]  (Flowpipes/AbstractFlowpipe.jl:35-37); first maximiser.
+__global__ void max_over_steps_kernel(const double* __restrict__ rho, int ndirs, long long nsteps,
+                                      double* __restrict__ vmax, long long* __restrict__ amax) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= ndirs) return;
+    double best = -INFINITY;
+    long long at = -1;
+    for (long long k = 0; k < nsteps; ++k) {
+        const double v = rho[size_t(k) * ndirs + j];
+        if (v > best || at < 0) { best = v; at = k; }
+    }
+    vmax[j] = best;
+    if (amax) amax[j] = at;
+}
+
+// Early termination (reach_homog.jl:418, reach_inhomog.jl:210): first step whose template
+// reach-set is certified disjoint from the invariant by one of its own support values.
+struct InvCheck {
+    int row;        // output row whose support value is tested
+    int sense;      // +1: violated if value > bound; -1: violated if value < bound
+    double div;     // value = rho / div
+    double bound;
+};
+__global__ void first_disjoint_kernel(const double* __restrict__ rho, int ndirs, long long nsteps,
+                                      const InvCheck* __restrict__ checks, int nchecks,
+                                      unsigned long long* __restrict__ first) {
+    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= nsteps) return;
+    bool bad = false;
+    for (int i = 0; i < nchecks && !bad; ++i) {
+        const double v = rho[size_t(k) * ndirs + checks[i].row] / checks[i].div;
+        bad = checks[i].sense > 0 ? (v > checks[i].bound) : (v < checks[i].bound);
+    }
+    if (bad) atomicMin(first, (unsigned long long)k);
+}
+
+}  // namespace reach

@@ -1,0 +1,212 @@
+"""Result containers: TemplateReachSet, ReachSet, Flowpipe, MixedFlowpipe.
+
+Mirrors src/ReachSets/TemplateReachSet.jl:32-37,97-115, src/ReachSets/ReachSet.jl:24-27,
+src/Flowpipes/Flowpipe.jl:22-25,97-128,304-331, AbstractFlowpipe.jl:35-37 and
+MixedFlowpipe.jl:20-23,66-68 -- with the difference this build is about: the support-value
+matrix / the zonotope generators live in device memory (the plan object) and are only brought
+to the host when asked for; `rho(d, fp)` over a template direction is a device reduction.
+Time stamps stay on the host exactly as in the reference (`Δt += δ`, reach_homog.jl:26-30).
+"""
+import numpy as np
+
+
+class TimeInterval(tuple):
+    def __new__(cls, lo, hi):
+        return super().__new__(cls, (float(lo), float(hi)))
+
+    lo = property(lambda s: s[0])
+    hi = property(lambda s: s[1])
+
+    def __add__(self, other):
+        if isinstance(other, TimeInterval):
+            return TimeInterval(self[0] + other[0], self[1] + other[1])
+        return TimeInterval(self[0] + other, self[1] + other)
+
+    def __contains__(self, t):
+        return self[0] <= t <= self[1]
+
+
+zeroT = TimeInterval(0.0, 0.0)
+
+
+class TemplateReachSet:
+    """(dirs, sf, Δt): sf is a view into column k of the ndirs × NSTEPS matrix."""
+
+    def __init__(self, dirs, sf, dt):
+        self.dirs, self.sf, self.dt = dirs, sf, dt
+
+    tspan = property(lambda s: s.dt)
+    tstart = property(lambda s: s.dt.lo)
+    tend = property(lambda s: s.dt.hi)
+    dim = property(lambda s: s.dirs.n)
+
+    def support_functions(self, i=None):
+        return self.sf if i is None else self.sf[i]
+
+    def rho(self, d):
+        """TemplateReachSet.jl:97-115: exact match, then positive multiple; no LP fallback."""
+        d = np.asarray(d, dtype=np.float64)
+        D = self.dirs.matrix()
+        for i in range(D.shape[1]):
+            if np.array_equal(d, D[:, i]):
+                return float(self.sf[i])
+        for i in range(D.shape[1]):
+            ok, k = samedir(d, D[:, i])
+            if ok:
+                return float(self.sf[i]) * k
+        raise NotImplementedError("ρ(d, TemplateReachSet) for a non-template direction needs an LP "
+                                  "(out of scope of the device path)")
+
+
+def samedir(u, v):
+    """(True, k) iff u = k·v with k > 0."""
+    nz = np.flatnonzero(v)
+    if len(nz) == 0:
+        return False, 0.0
+    k = u[nz[0]] / v[nz[0]]
+    if k > 0 and np.allclose(u, k * v, rtol=1e-12, atol=0.0):
+        return True, float(k)
+    return False, 0.0
+
+
+class ReachSet:
+    """(set, Δt) with set = (centre, generators) of a zonotope."""
+
+    def __init__(self, Z, dt):
+        self.set, self.dt = Z, dt
+
+    tspan = property(lambda s: s.dt)
+    tstart = property(lambda s: s.dt.lo)
+    tend = property(lambda s: s.dt.hi)
+
+    def rho(self, d):
+        c, G = self.set.center, self.set.generators
+        d = np.asarray(d, dtype=np.float64)
+        return float(d @ c + np.abs(G.T @ d).sum())
+
+
+class Flowpipe:
+    """Indexable sequence of reach-sets + `ext` dictionary (Flowpipe.jl:22-25).
+
+    `make(k)` materialises reach-set k on demand; `nsets` is their number."""
+
+    def __init__(self, nsets, make, delta, dt0=zeroT, ext=None, device=None):
+        self._n = int(nsets)
+        self._make = make
+        self.delta = float(delta)
+        self.dt0 = dt0
+        self.ext = ext if ext is not None else {}
+        self.device = device            # the plan wrapper holding the device-resident data
+        # Δt_k by repeated addition, as the reference does
+        self._t = None
+
+    def _times(self):
+        if self._t is None:
+            lo = np.empty(self._n)
+            hi = np.empty(self._n)
+            dt = TimeInterval(0.0, self.delta) + self.dt0
+            for k in range(self._n):
+                lo[k], hi[k] = dt
+                dt = dt + self.delta
+            self._t = (lo, hi)
+        return self._t
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(self._n))]
+        if k < 0:
+            k += self._n
+        if not 0 <= k < self._n:
+            raise IndexError(k)
+        lo, hi = self._times()
+        return self._make(k, TimeInterval(lo[k], hi[k]))
+
+    def __iter__(self):
+        return (self[k] for k in range(self._n))
+
+    @property
+    def tstart(self):
+        return self._times()[0][0]
+
+    @property
+    def tend(self):
+        return self._times()[1][-1]
+
+    @property
+    def tspan(self):
+        return TimeInterval(self.tstart, self.tend)
+
+    def __call__(self, t):
+        """Flowpipe.jl:97-128: the reach-set(s) whose time span contains t."""
+        lo, hi = self._times()
+        if np.isscalar(t):
+            idx = np.flatnonzero((lo <= t) & (t <= hi))
+            if len(idx) == 0:
+                raise ValueError("time %s does not belong to the time span %s" % (t, tuple(self.tspan)))
+            sets = [self[i] for i in idx]
+            return sets[0] if len(sets) == 1 else sets
+        t0, t1 = t
+        idx = np.flatnonzero((hi >= t0) & (lo <= t1))
+        if len(idx) == 0:
+            raise ValueError("time interval %s does not intersect the time span" % (t,))
+        return [self[i] for i in idx]
+
+    def support_function_matrix(self):
+        """Flowpipe.jl:304-306."""
+        return self.ext["sfmat"]() if callable(self.ext.get("sfmat")) else self.ext["sfmat"]
+
+    def rho(self, d):
+        """ρ(d, fp) = max_k ρ(d, F[k]) (AbstractFlowpipe.jl:35-37)."""
+        if self.device is not None and hasattr(self.device, "rho_flowpipe"):
+            return self.device.rho_flowpipe(d)
+        return max(R.rho(d) for R in self)
+
+
+class MixedFlowpipe:
+    """Vector of flowpipes, one per initial-set split (MixedFlowpipe.jl:20-23); ρ = max (:66-68)."""
+
+    def __init__(self, flowpipes, ext=None):
+        self.flowpipes = list(flowpipes)
+        self.ext = ext if ext is not None else {}
+
+    def __len__(self):
+        return len(self.flowpipes)
+
+    def __getitem__(self, i):
+        return self.flowpipes[i]
+
+    def __iter__(self):
+        return iter(self.flowpipes)
+
+    def rho(self, d):
+        return max(fp.rho(d) for fp in self.flowpipes)
+
+
+class ReachSolution:
+    """(F, alg, ext) (Flowpipes/solutions.jl:60-64); forwards the flowpipe interface."""
+
+    def __init__(self, F, alg, ext=None):
+        self.F, self.alg, self.ext = F, alg, ext if ext is not None else {}
+
+    def __getattr__(self, name):
+        return getattr(self.F, name)
+
+    def __len__(self):
+        return len(self.F)
+
+    def __getitem__(self, k):
+        return self.F[k]
+
+    def __iter__(self):
+        return iter(self.F)
+
+    def __call__(self, t):
+        return self.F(t)
+
+
+def rho(d, X):
+    """ρ(d, ·) for reach-sets, flowpipes and solutions."""
+    return X.rho(d)

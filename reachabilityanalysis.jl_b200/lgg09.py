@@ -1,0 +1,252 @@
+"""LGG09 (Le Guernic–Girard support-function algorithm): host-side mirror of the reference's
+operator interface over the device path.
+
+  struct / constructor : src/Algorithms/LGG09/LGG09.jl:46-103
+  discrete `post`      : src/Algorithms/LGG09/post.jl:4-50
+  reach_homog_LGG09!   : src/Algorithms/LGG09/reach_homog.jl:6-33   (-> reach_lgg09_plan_*)
+  reach_inhomog_LGG09! : src/Algorithms/LGG09/reach_inhomog.jl:5-33 (-> reach_lgg09_plan_*)
+
+`threaded`, `sparse`, `cache` and `static` are accepted for drop-in compatibility and ignored
+by the device path (the reference itself ignores `static`, post.jl:34): every direction runs in
+one batched pass, so there is nothing to thread or cache.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib as L
+from . import sets as S
+from .directions import AbstractDirections, get_template, template_from_vars
+from .flowpipe import Flowpipe, TemplateReachSet, zeroT, samedir
+from .support_program import flatten, to_c, invariant_to_c
+
+
+class Forward:
+    name = "Forward"
+
+    def __init__(self, sih="concrete", exp="base", setops="lazy"):
+        self.sih, self.exp, self.setops = sih, exp, setops
+
+
+class NoBloating:
+    name = "NoBloating"
+
+    def __init__(self, exp="base", setops="lazy"):
+        self.exp, self.setops = exp, setops
+
+
+class FirstOrderZonotope:
+    name = "FirstOrderZonotope"
+
+    def __init__(self, exp="base"):
+        self.exp = exp
+
+
+@dataclass
+class LGG09:
+    δ: float
+    approx_model: object
+    template: AbstractDirections
+    static: bool
+    threaded: bool
+    sparse: bool
+    cache: bool
+    vars: object
+    # device knobs (no counterpart in the reference)
+    time_block: int = 0
+    share_negated: bool = True
+
+    def __init__(self, *, δ=None, delta=None, approx_model=None, template=None, dirs=None, vars=None,
+                 n=None, dim=None, static=False, threaded=False, sparse=False, cache=True,
+                 time_block=0, share_negated=True):
+        if δ is None:
+            δ = delta
+        if δ is None:
+            raise TypeError("LGG09: the step size `δ` is required")
+        _n = n if n is not None else dim
+        _template = dirs if dirs is not None else template
+        if vars is not None:
+            if _n is None:
+                raise ValueError("the ambient dimension, `n` (or `dim`), should be specified")
+            directions = template_from_vars(vars, _n)
+        elif _template is not None:
+            directions = get_template(_template, _n)
+        else:
+            raise ValueError("either `vars`, `dirs` or `template` should be specified")
+        self.δ = float(δ)
+        self.approx_model = approx_model if approx_model is not None else Forward()
+        self.template = directions
+        self.static, self.threaded, self.sparse, self.cache = static, threaded, sparse, cache
+        self.vars = vars
+        self.time_block = int(time_block)
+        self.share_negated = bool(share_negated)
+
+    @property
+    def delta(self):
+        return self.δ
+
+
+def step_size(alg):
+    return alg.δ
+
+
+class Lgg09Plan:
+    """Device-resident LGG09 run: owns a `reach_lgg09_plan` (inputs, ρ matrix, statistics)."""
+
+    def __init__(self, ctx, n, ndirs, nsteps, time_block=0, share_negated=True, tile_m=0, tile_n=0):
+        self.ctx, self.lib = ctx, ctx.lib
+        self.n, self.ndirs, self.nsteps = int(n), int(ndirs), int(nsteps)
+        opts = L.reach_lgg09_opts()
+        self.lib.reach_lgg09_default_opts(C.byref(opts))
+        opts.time_block, opts.share_negated = int(time_block), int(bool(share_negated))
+        opts.tile_m, opts.tile_n = int(tile_m), int(tile_n)
+        self.handle = C.c_void_p()
+        ctx.check(self.lib.reach_lgg09_plan_create(ctx.handle, self.n, self.ndirs, self.nsteps,
+                                                   C.byref(opts), C.byref(self.handle)))
+        self._dirs = None
+        self._sfmat = None
+
+    def upload(self, Phi, dirs, Omega0, V=None, X=None):
+        """Flatten the sets and copy the inputs to the device (host→device traffic only)."""
+        n = self.n
+        Phi = L.fmat(Phi)
+        dirs = L.fmat(dirs)
+        if Phi.shape != (n, n):
+            raise ValueError("Φ is %s, expected (%d, %d)" % (Phi.shape, n, n))
+        if dirs.shape != (n, self.ndirs):
+            raise ValueError("the problem's dimension %d doesn't match the dimension of the template "
+                             "directions, %d" % (n, dirs.shape[0]))
+        if S.dim(Omega0) != n:
+            raise ValueError("Ω₀ has dimension %d, expected %d" % (S.dim(Omega0), n))
+        om = to_c(flatten(Omega0, Phi), n)
+        v = to_c(flatten(V, Phi), n) if V is not None else None
+        if v is not None and v.expr.nalt != 1:
+            raise NotImplementedError("input sets containing a convex hull are not supported")
+        inv, keep = invariant_to_c(X, n)
+        self._keep = (Phi, dirs, om, v, inv, keep)
+        self.ctx.check(self.lib.reach_lgg09_plan_upload(
+            self.handle, L.dptr(Phi), L.dptr(dirs), om.ptr(), v.ptr() if v is not None else None,
+            C.byref(inv) if inv is not None else None))
+        self._dirs = dirs
+        self._sfmat = None
+        self.h2d_bytes = Phi.nbytes + dirs.nbytes
+        return self
+
+    def set_output(self, device_ptr):
+        self.ctx.check(self.lib.reach_lgg09_plan_set_output(self.handle, C.c_void_p(int(device_ptr))))
+
+    def run(self, sync=True):
+        self.ctx.check(self.lib.reach_lgg09_plan_run(self.handle))
+        self._sfmat = None
+        if sync:
+            self.sync()
+        return self
+
+    def sync(self):
+        self.ctx.check(self.lib.reach_lgg09_plan_sync(self.handle))
+
+    @property
+    def nsteps_done(self):
+        out = C.c_int64()
+        self.ctx.check(self.lib.reach_lgg09_plan_nsteps_done(self.handle, C.byref(out)))
+        return out.value
+
+    def fetch(self, step0=0, nsteps=None):
+        """ρℓ[:, step0:step0+nsteps] as an (ndirs, nsteps) array (device→host copy)."""
+        nsteps = self.nsteps - step0 if nsteps is None else nsteps
+        out = np.empty((self.ndirs, nsteps), order="F")
+        self.ctx.check(self.lib.reach_lgg09_plan_fetch(self.handle, step0, nsteps, L.dptr(out)))
+        return out
+
+    def sfmat(self):
+        if self._sfmat is None:
+            self._sfmat = self.fetch(0, self.nsteps)[:, :self.nsteps_done]
+        return self._sfmat
+
+    def max_over_steps(self):
+        vmax = np.empty(self.ndirs)
+        amax = np.empty(self.ndirs, dtype=np.int64)
+        self.ctx.check(self.lib.reach_lgg09_plan_max_over_steps(
+            self.handle, L.dptr(vmax), amax.ctypes.data_as(L.c_int64_p)))
+        return vmax, amax
+
+    def rho_flowpipe(self, d):
+        """ρ(d, fp) = max over steps, reduced on the device when d is (a positive multiple of) a
+        template direction (TemplateReachSet.jl:97-115 + AbstractFlowpipe.jl:35-37)."""
+        d = np.asarray(d, dtype=np.float64)
+        D = self._dirs
+        for i in range(D.shape[1]):
+            if np.array_equal(d, D[:, i]):
+                return float(self.max_over_steps()[0][i])
+        for i in range(D.shape[1]):
+            ok, k = samedir(d, D[:, i])
+            if ok:
+                return float(self.max_over_steps()[0][i]) * k
+        raise NotImplementedError("ρ(d, flowpipe) for a non-template direction needs an LP")
+
+    @property
+    def device_rho(self):
+        return self.lib.reach_lgg09_plan_device_rho(self.handle)
+
+    def stats(self):
+        ms, gms = C.c_double(), C.c_double()
+        launches, gl = C.c_int64(), C.c_int64()
+        S_, tm, tn, mu = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        self.ctx.check(self.lib.reach_lgg09_plan_stats(
+            self.handle, C.byref(ms), C.byref(launches), C.byref(S_), C.byref(tm), C.byref(tn),
+            C.byref(mu), C.byref(gms), C.byref(gl)))
+        return dict(ms=ms.value, launches=launches.value, time_block=S_.value, tile_m=tm.value,
+                    tile_n=tn.value, nchains=mu.value, gemm_ms=gms.value, gemm_launches=gl.value)
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.reach_lgg09_plan_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def reach_homog_LGG09(dirs, Omega0, Phi, NSTEPS, X=None, ctx=None, **opts):
+    """`reach_homog_LGG09!` (reach_homog.jl:6-33): returns the device-resident plan; `.sfmat()`
+    is the ndirs × NSTEPS matrix ρℓ."""
+    return reach_inhomog_LGG09(dirs, Omega0, Phi, NSTEPS, X, None, ctx=ctx, **opts)
+
+
+def reach_inhomog_LGG09(dirs, Omega0, Phi, NSTEPS, X=None, U=None, ctx=None, **opts):
+    """`reach_inhomog_LGG09!` (reach_inhomog.jl:5-33)."""
+    ctx = ctx or L.default_context()
+    D = dirs.matrix() if isinstance(dirs, AbstractDirections) else np.asarray(dirs, dtype=np.float64)
+    Phi = np.asarray(Phi, dtype=np.float64)
+    plan = Lgg09Plan(ctx, Phi.shape[0], D.shape[1], NSTEPS, **opts)
+    plan.upload(Phi, D, Omega0, U, X)
+    plan.run()
+    return plan
+
+
+def post(alg, ivp, NSTEPS=None, Δt0=zeroT, ctx=None, **kwargs):
+    """Discrete `post(alg::LGG09, ivp::IVP{<:AbstractDiscreteSystem}, NSTEPS; Δt0)` (post.jl:4-50).
+
+    `ivp` is a `discretization.DiscreteIVP` (Φ, Ω₀, V, X).  Returns a Flowpipe of
+    TemplateReachSets whose `ext` holds `:sfmat` (fetched lazily) and `:alg_vars`."""
+    template = alg.template
+    if ivp.n != template.n:
+        raise AssertionError("the problems' dimension %d doesn't match the dimension of the template "
+                             "directions, %d" % (ivp.n, template.n))
+    if NSTEPS is None:
+        NSTEPS = kwargs.get("NSTEPS")
+        if NSTEPS is None:
+            raise ValueError("`NSTEPS` not specified")
+    plan = reach_inhomog_LGG09(template, ivp.Omega0, ivp.Phi, NSTEPS, ivp.X, ivp.V, ctx=ctx,
+                               time_block=alg.time_block, share_negated=alg.share_negated)
+    nsets = plan.nsteps_done
+
+    def make(k, dt):
+        return TemplateReachSet(template, plan.sfmat()[:, k], dt)
+
+    ext = {"sfmat": plan.sfmat, "alg_vars": alg.vars}
+    return Flowpipe(nsets, make, alg.δ, Δt0, ext, device=plan)

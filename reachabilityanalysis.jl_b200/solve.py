@@ -1,0 +1,81 @@
+"""`solve` for linear systems: the caller of the hot path.
+
+Mirrors src/Continuous/solve.jl:49-117 (argument handling, NSTEPS = ceil(T/δ) :284-289,
+vector-of-initial-sets form :84-117) and src/Algorithms/linear_post.jl:2-22
+(normalize → discretize → discrete post).  Everything here is host code that stays Julia in
+the reference; only `post` touches the device."""
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import sets as S
+from . import discretization as D
+from .flowpipe import ReachSolution, MixedFlowpipe, zeroT
+from . import lgg09 as _lgg09
+
+
+@dataclass
+class IVP:
+    """x' = A x + B u, u ∈ U, x ∈ X, x(0) ∈ X0  (B, U, X optional)."""
+    A: object
+    X0: object
+    B: object = None
+    U: object = None
+    X: object = None
+
+
+def _nsteps(T, delta):
+    return int(math.ceil(T / delta - 1e-12))
+
+
+def discretize(ivp, delta, model):
+    """`discretize(ivp, δ, approx_model)` for the models the hot path consumes."""
+    U = D.normalize_input(ivp.B, ivp.U) if ivp.U is not None else None
+    name = getattr(model, "name", type(model).__name__)
+    if name == "Forward":
+        f = D.forward_zono if getattr(model, "setops", "lazy") == "zono" else D.forward
+        return f(ivp.A, ivp.X0, delta, U, ivp.X)
+    if name == "NoBloating":
+        return D.no_bloating(ivp.A, ivp.X0, delta, U, ivp.X)
+    if name == "FirstOrderZonotope":
+        return D.first_order_zonotope(ivp.A, ivp.X0, delta, U, ivp.X)
+    raise NotImplementedError("approximation model %s" % name)
+
+
+def post_continuous(alg, ivp, T=None, NSTEPS=None, Δt0=zeroT, ctx=None):
+    """linear_post.jl:2-22."""
+    from . import glgm06 as _glgm06
+    delta = alg.δ
+    if NSTEPS is None:
+        if T is None:
+            raise ValueError("the time horizon `T` (or `NSTEPS`) should be specified")
+        NSTEPS = _nsteps(T, delta)
+    divp = discretize(ivp, delta, alg.approx_model)
+    mod = _lgg09 if isinstance(alg, _lgg09.LGG09) else _glgm06
+    return mod.post(alg, divp, NSTEPS, Δt0=Δt0, ctx=ctx)
+
+
+def solve(ivp, T=None, alg=None, NSTEPS=None, tspan=None, algorithm=None, opC=None, threading=False,
+          ctx=None):
+    """`solve(ivp; T, alg)` (solve.jl:49-76); a list of initial sets runs every split through the
+    same Φ / input chain in one batch (`_solve_distributed`, solve.jl:103-117) and returns a
+    MixedFlowpipe."""
+    alg = alg or algorithm or opC
+    if alg is None:
+        raise ValueError("an algorithm (`alg=LGG09(...)` or `alg=GLGM06(...)`) is required")
+    if tspan is not None:
+        T = tspan[1] - tspan[0]
+        dt0 = zeroT + tspan[0]
+    else:
+        dt0 = zeroT
+    if isinstance(ivp.X0, (list, tuple)):
+        from . import glgm06 as _glgm06
+        if isinstance(alg, _glgm06.GLGM06):
+            F = _glgm06.post_batch(alg, ivp, T=T, NSTEPS=NSTEPS, Δt0=dt0, ctx=ctx)
+        else:
+            F = MixedFlowpipe([post_continuous(alg, IVP(ivp.A, X0, ivp.B, ivp.U, ivp.X), T, NSTEPS, dt0, ctx)
+                               for X0 in ivp.X0])
+        return ReachSolution(F, alg)
+    F = post_continuous(alg, ivp, T, NSTEPS, dt0, ctx)
+    return ReachSolution(F, alg)

@@ -1,0 +1,207 @@
+"""Parity of the CUDA LGG09 path (through the C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+
+import reach_b200 as rb
+from reach_b200 import discretization as D
+from reach_b200.lgg09 import reach_inhomog_LGG09, reach_homog_LGG09, post
+from oracle import lgg09_oracle as LO
+from conftest import building_problem, iss_problem, assert_support_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def stable_system(n, seed, delta=0.05):
+    rng = np.random.default_rng(seed)
+    A = -np.eye(n) + (0.5 / np.sqrt(n)) * rng.standard_normal((n, n))
+    import scipy.linalg
+    return A, scipy.linalg.expm(A * delta)
+
+
+def random_sets(n, seed):
+    rng = np.random.default_rng(seed + 1000)
+    X0 = rb.Hyperrectangle(rng.uniform(-1, 1, n), 0.1 * rng.uniform(0, 1, n))
+    q = max(1, n // 3)
+    Bm = rng.standard_normal((n, q))
+    U0 = rb.Hyperrectangle(rng.uniform(-0.2, 0.2, q), 0.05 * rng.uniform(0, 1, q))
+    Z = rb.Zonotope(rng.uniform(-1, 1, n), 0.1 * rng.standard_normal((n, n + 3)))
+    return X0, rb.LinearMap(Bm, U0), Z
+
+
+@pytest.mark.parametrize("n,ndirs,nsteps", [(1, 2, 7), (5, 10, 40), (13, 7, 33), (48, 96, 64), (100, 37, 50)])
+@pytest.mark.parametrize("S", [1, 4])
+def test_random_forward_inhomog(ctx, n, ndirs, nsteps, S):
+    A, _ = stable_system(n, n)
+    X0, U, _ = random_sets(n, n)
+    ivp = D.forward(A, X0, 0.05, U)
+    rng = np.random.default_rng(7)
+    dirs = np.hstack([np.eye(n), -np.eye(n)])[:, :ndirs] if ndirs <= 2 * n else rng.standard_normal((n, ndirs))
+    if ndirs % 2:
+        dirs = np.hstack([dirs[:, :-1], rng.standard_normal((n, 1))])
+    ref = LO.reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, nsteps, ivp.V)
+    plan = reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, nsteps, None, ivp.V, ctx=ctx, time_block=S)
+    assert plan.stats()["time_block"] == S
+    assert_support_parity(plan.sfmat(), ref)
+
+
+@pytest.mark.parametrize("tile", [(128, 128), (64, 64), (16, 128), (64, 128)])
+@pytest.mark.parametrize("share", [True, False])
+def test_tile_configs_and_chain_sharing(ctx, tile, share):
+    n, nsteps = 70, 45
+    A, _ = stable_system(n, 3)
+    X0, U, _ = random_sets(n, 3)
+    ivp = D.forward(A, X0, 0.05, U)
+    rng = np.random.default_rng(11)
+    dirs = np.hstack([np.eye(n), -np.eye(n), rng.standard_normal((n, 5))])
+    ref = LO.reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, nsteps, ivp.V)
+    plan = reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, nsteps, None, ivp.V, ctx=ctx, time_block=2,
+                               tile_m=tile[0], tile_n=tile[1], share_negated=share)
+    st = plan.stats()
+    assert (st["tile_m"], st["tile_n"]) == tile
+    assert st["nchains"] == (n + 5 if share else 2 * n + 5)
+    assert_support_parity(plan.sfmat(), ref)
+
+
+def test_chain_sharing_is_bit_identical(ctx):
+    n, nsteps = 33, 60
+    A, _ = stable_system(n, 5)
+    X0, U, _ = random_sets(n, 5)
+    ivp = D.forward(A, X0, 0.05, U)
+    dirs = np.hstack([np.eye(n), -np.eye(n)])
+    a = reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, nsteps, None, ivp.V, ctx=ctx, time_block=1, share_negated=True).sfmat()
+    b = reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, nsteps, None, ivp.V, ctx=ctx, time_block=1, share_negated=False).sfmat()
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("S", [1, 8])
+def test_homogeneous_set_types(ctx, S):
+    n, nsteps = 20, 50
+    A, Phi = stable_system(n, 9)
+    X0, U, Z = random_sets(n, 9)
+    dirs = rb.OctDirections(4).matrix()
+    dirs = np.vstack([dirs, np.zeros((n - 4, dirs.shape[1]))])
+    cases = {
+        "zonotope": Z,
+        "box": X0,
+        "ballinf": rb.BallInf(np.arange(n) / n, 0.3),
+        "singleton": rb.Singleton(np.linspace(-1, 1, n)),
+        "forward_homog": D.forward(A, X0, 0.05).Omega0,
+        "ch_of_zono_and_mapped_zono": rb.ConvexHull(Z, rb.MinkowskiSum(rb.LinearMap(Phi, Z), X0)),
+        "cartesian": rb.CartesianProduct(rb.Interval(-1, 2), rb.Hyperrectangle(np.zeros(n - 1), np.ones(n - 1))),
+        "scaled_mapped": rb.Scale(0.5, rb.LinearMap(np.random.default_rng(1).standard_normal((n, n)), Z)),
+    }
+    for name, Om in cases.items():
+        ref = LO.reach_homog_LGG09(dirs, Om, Phi, nsteps)
+        got = reach_homog_LGG09(dirs, Om, Phi, nsteps, ctx=ctx, time_block=S).sfmat()
+        assert_support_parity(got, ref), name
+
+
+def test_zero_initial_set_and_nsteps_one(ctx):
+    n = 6
+    A, Phi = stable_system(n, 2)
+    X0, U, Z = random_sets(n, 2)
+    dirs = np.hstack([np.eye(n), -np.eye(n)])
+    ref = LO.reach_inhomog_LGG09(dirs, rb.ZeroSet(n), Phi, 30, U)
+    got = reach_inhomog_LGG09(dirs, rb.ZeroSet(n), Phi, 30, None, U, ctx=ctx).sfmat()
+    assert_support_parity(got, ref)
+    for Om, V in ((X0, None), (X0, U), (D.forward(A, X0, 0.05, U).Omega0, D.forward(A, X0, 0.05, U).V)):
+        ref = LO.reach_inhomog_LGG09(dirs, Om, Phi, 1, V) if V is not None else LO.reach_homog_LGG09(dirs, Om, Phi, 1)
+        got = reach_inhomog_LGG09(dirs, Om, Phi, 1, None, V, ctx=ctx).sfmat()
+        assert_support_parity(got, ref)
+
+
+def test_building_bldf01_reference_assertions(ctx):
+    """test/models/generated/Building.jl:41-47 (Forward, δ=0.004) and :49-55 (NoBloating, δ=0.01)."""
+    prob = building_problem()
+    x25 = np.zeros(48)
+    x25[24] = 1.0
+    sol = rb.solve(prob, T=20.0, alg=rb.LGG09(δ=0.004, vars=(25,), n=48), ctx=ctx)
+    assert len(sol) == 5000 and sol.F.support_function_matrix().shape == (2, 5000)
+    assert rb.rho(x25, sol) <= 5.1e-3
+    assert not (rb.rho(x25, sol) <= 4e-3)
+    assert not (rb.rho(x25, sol(20.0)) <= -0.78e-3)
+    ivp = D.forward(prob.A, prob.X0, 0.004, D.normalize_input(prob.B, prob.U))
+    ref = LO.reach_inhomog_LGG09(LO.vars_directions(25, 48), ivp.Omega0, ivp.Phi, 5000, ivp.V)
+    assert_support_parity(sol.F.support_function_matrix(), ref)
+    assert abs(rb.rho(x25, sol) - 4.8602388967852826e-3) < 1e-12
+
+    sol = rb.solve(prob, T=20.0, alg=rb.LGG09(δ=0.01, vars=(25,), n=48, approx_model=rb.NoBloating()), ctx=ctx)
+    assert rb.rho(x25, sol) <= 5.1e-3
+    assert not (rb.rho(x25, sol) <= 4e-3)
+    assert not (rb.rho(x25, sol(20.0)) <= -0.78e-3)
+
+
+def test_building_box_template_c1(ctx):
+    """BASELINE config C1: BLDF01, box template (96 dirs), δ=0.002, 10^4 steps; oracle on the
+    first 2000 steps, all time-block settings agree on the rest."""
+    prob = building_problem()
+    ivp = D.forward(prob.A, prob.X0, 0.002, D.normalize_input(prob.B, prob.U))
+    dirs = rb.BoxDirections(48).matrix()
+    ref = LO.reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, 2000, ivp.V)
+    full = {}
+    for S in (1, 0):
+        plan = reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, 10000, None, ivp.V, ctx=ctx, time_block=S)
+        full[S] = plan.sfmat()
+        assert_support_parity(full[S][:, :2000], ref)
+    assert_support_parity(full[0], full[1])
+
+
+def test_iss_issf01_two_directions(ctx):
+    """examples/ISS/ISS.jl:117-120: template ±C₃, δ=6e-4 (first 3000 steps against the oracle)."""
+    prob, Cm = iss_problem()
+    ivp = D.forward(prob.A, prob.X0, 6e-4, D.normalize_input(prob.B, prob.U))
+    dirs = np.stack([Cm[2], -Cm[2]], axis=1)
+    ref = LO.reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, 3000, ivp.V)
+    got = reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, 3000, None, ivp.V, ctx=ctx).sfmat()
+    assert_support_parity(got, ref)
+
+
+def test_invariant_early_termination(ctx):
+    n = 4
+    A = np.diag([-1.0, -2.0, -0.5, -1.5])
+    import scipy.linalg
+    Phi = scipy.linalg.expm(A * 0.1)
+    X0 = rb.Hyperrectangle(np.full(n, 5.0), np.full(n, 0.5))
+    dirs = rb.BoxDirections(n).matrix()
+    inv = rb.HalfSpace(-np.eye(n)[0], -2.0)          # x1 >= 2
+    ref, k = LO.reach_LGG09_invariant(dirs, X0, Phi, 100, inv)
+    plan = reach_homog_LGG09(dirs, X0, Phi, 100, X=inv, ctx=ctx)
+    assert plan.nsteps_done == k and 0 < k < 100
+    assert_support_parity(plan.sfmat(), ref)
+    box = rb.Hyperrectangle(np.full(n, 4.0), np.full(n, 3.0))   # x_i in [1, 7]
+    ref, k = LO.reach_LGG09_invariant(dirs, X0, Phi, 100, box)
+    plan = reach_homog_LGG09(dirs, X0, Phi, 100, X=box, ctx=ctx)
+    assert plan.nsteps_done == k and 0 < k < 100
+
+
+def test_post_api_and_template_reach_set(ctx):
+    """test/algorithms/LGG09.jl:62-117,151-170 (shapes) and test/reachsets/reachsets.jl:20-29."""
+    A, _ = stable_system(5, 1)
+    X0 = rb.BallInf(np.ones(5), 0.1)
+    for tmpl in ("box", "oct"):
+        sol = rb.solve(rb.IVP(A, X0), T=1.0, alg=rb.LGG09(δ=0.01, template=tmpl, n=5), ctx=ctx)
+        assert len(sol) == 100 and sol[0].dim == 5
+        assert sol.F.support_function_matrix().shape == (10 if tmpl == "box" else 50, 100)
+    R = sol[3]
+    d = rb.BoxDirections(5).matrix()[:, 1]
+    assert R.rho(2 * d) == 2 * R.rho(d)
+    assert abs(sol.tend - 1.0) < 1e-9 and sol.tstart == 0.0
+    with pytest.raises(AssertionError):
+        post(rb.LGG09(δ=0.01, template="box", n=4), D.no_bloating(A, X0, 0.01), 10, ctx=ctx)
+    with pytest.raises(ValueError):
+        post(rb.LGG09(δ=0.01, template="box", n=5), D.no_bloating(A, X0, 0.01), ctx=ctx)
+
+
+def test_error_behaviour(ctx):
+    A, Phi = stable_system(3, 1)
+    X0 = rb.BallInf(np.zeros(3), 1.0)
+    with pytest.raises(ValueError):
+        reach_homog_LGG09(np.eye(3), X0, Phi, 0, ctx=ctx)
+    with pytest.raises(ValueError):
+        reach_homog_LGG09(np.eye(3), rb.Universe(3), Phi, 5, ctx=ctx)
+    with pytest.raises(ValueError):
+        reach_homog_LGG09(np.eye(3), X0, Phi, 5, ctx=ctx, time_block=3)
+    bad = Phi.copy()
+    bad[0, 0] = np.nan
+    with pytest.raises(ValueError):
+        reach_homog_LGG09(np.eye(3), X0, bad, 5, ctx=ctx)
