@@ -45,15 +45,16 @@ def discretize(ivp, delta, model):
 
 def post_continuous(alg, ivp, T=None, NSTEPS=None, Δt0=zeroT, ctx=None):
     """linear_post.jl:2-22."""
-    from . import glgm06 as _glgm06
     delta = alg.δ
     if NSTEPS is None:
         if T is None:
             raise ValueError("the time horizon `T` (or `NSTEPS`) should be specified")
         NSTEPS = _nsteps(T, delta)
     divp = discretize(ivp, delta, alg.approx_model)
-    mod = _lgg09 if isinstance(alg, _lgg09.LGG09) else _glgm06
-    return mod.post(alg, divp, NSTEPS, Δt0=Δt0, ctx=ctx)
+    if isinstance(alg, _lgg09.LGG09):
+        return _lgg09.post(alg, divp, NSTEPS, Δt0=Δt0, ctx=ctx)
+    from . import glgm06 as _glgm06
+    return _glgm06.post(alg, divp, NSTEPS, Δt0=Δt0, ctx=ctx)
 
 
 def solve(ivp, T=None, alg=None, NSTEPS=None, tspan=None, algorithm=None, opC=None, threading=False,
@@ -70,8 +71,8 @@ def solve(ivp, T=None, alg=None, NSTEPS=None, tspan=None, algorithm=None, opC=No
     else:
         dt0 = zeroT
     if isinstance(ivp.X0, (list, tuple)):
-        from . import glgm06 as _glgm06
-        if isinstance(alg, _glgm06.GLGM06):
+        if not isinstance(alg, _lgg09.LGG09):
+            from . import glgm06 as _glgm06
             F = _glgm06.post_batch(alg, ivp, T=T, NSTEPS=NSTEPS, Δt0=dt0, ctx=ctx)
         else:
             F = MixedFlowpipe([post_continuous(alg, IVP(ivp.A, X0, ivp.B, ivp.U, ivp.X), T, NSTEPS, dt0, ctx)
