@@ -220,7 +220,9 @@ struct reach_lgg09_plan {
     DevBuf Wl, Wa;         // [nq][nbe]
     DevBuf tile_mask;      // [tpb] uint32
     DevBuf featpart;       // [(S+1)*tpb][nq][2][mu_pad]
-    DevBuf carry;          // [nq][2][mu_pad]
+    DevBuf ftot;           // [(S+1)][nq][2][mu_pad] per-block feature totals
+    DevBuf carry[2];       // [nq][2][mu_pad], ping-pong between passes
+    DevBuf dv;             // [S+2][2][mu_pad] rho(r_k; V) per emit slot of a pass
     DevBuf s_pos, s_neg;   // [mu_pad]
     DevBuf row_pos, row_neg;   // [mu] int
     DevBuf rho_own;        // ndirs x nsteps
@@ -248,17 +250,29 @@ struct reach_lgg09_plan {
 namespace {
 
 // Cost model (SM cycles per time step) used to pick the tile shape and the time block S.
+// Calibrated on B200: a 128x128x2000 tile takes ~0.31 ms (~55 FP64 FMA/clk/SM sustained); smaller
+// tiles lose a little to shared-memory traffic; every pass costs two launches; building the row
+// stack costs about S + 2 log2(S) passes of an n x n x n product, amortised over the run.
 double step_cost(const reach_lgg09_plan& p, const TileCfg& c, int S, int mu, int nrows, int sms) {
+    static const double eff[kNumCfgs] = {1.0, 0.85, 0.9, 0.92};
     const int mu_pad = round_up(mu, c.TM);
     const int nbe = round_up(nrows, c.TN);
-    const double tiles = double(mu_pad / c.TM) * (double(S) * nbe / c.TN);
     const double slots = double(sms) * c.occ;
-    const double waves = std::ceil(tiles / slots);
-    const double mma = double(c.TM) * c.TN * p.Kp / 64.0 * c.occ;          // 64 FP64 FMA/clk/SM
-    const double mem = double(c.TM + c.TN) * p.Kp * 8.0 / 40.0 * c.occ;    // ~40 B/clk/SM from L2
-    const double tile = std::max(mma, mem) + 3000.0;
-    const double launch = 16000.0;                                         // two launches, ~8 us
-    return (waves * tile + launch) / S;
+    auto pass = [&](double tiles) {
+        const double waves = std::ceil(tiles / slots);
+        const double mma = double(c.TM) * c.TN * p.Kp / (55.0 * eff[c.id]) * c.occ;
+        const double mem = double(c.TM + c.TN) * p.Kp * 8.0 / 40.0 * c.occ;   // ~40 B/clk/SM from L2
+        return waves * (std::max(mma, mem) + 4000.0);
+    };
+    const double launch = 12000.0;                                            // ~6 us per pass
+    double cost = (pass(double(mu_pad / c.TM) * (double(S) * nbe / c.TN)) + launch) / S;
+    // stack build (64x64 tiles, occupancy 2), amortised
+    int lg = 0;
+    for (int s = 1; s < S; s *= 2) ++lg;
+    const double nn_tiles = std::ceil(nbe / 64.0) * std::ceil(p.n / 64.0);
+    const double nn_pass = std::ceil(nn_tiles / (sms * 2.0)) * (64.0 * 64.0 * p.Kp / (55.0 * 0.85) * 2 + 4000.0) + 6000.0;
+    cost += (double(S) + 2.0 * lg) * nn_pass / double(std::max<int64_t>(1, p.nsteps));
+    return cost;
 }
 
 int choose_config(reach_lgg09_plan& p) {
@@ -280,7 +294,8 @@ int choose_config(reach_lgg09_plan& p) {
             const double feat_bytes = double(S + 1) * (nbe / c.TN) * std::max(1, p.nq) * 2.0 * mu_pad * 8.0;
             if (S > 1 && (stack_bytes > 3e9 || feat_bytes > 1e9)) continue;
             const double cost = step_cost(p, c, S, p.mu, nrows, ctx->sm_count);
-            if (cost < best * 0.98) { best = cost; best_cfg = ci; best_S = S; }
+            // prefer the earlier (larger-tile, smaller-S) candidate unless clearly beaten
+            if (cost < best * 0.97) { best = cost; best_cfg = ci; best_S = S; }
         }
     }
     if (best_cfg < 0)
@@ -420,7 +435,10 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
     REACH_TRY(p->Wa.alloc(ctx, size_t(std::max(1, nq)) * nbe * sizeof(double)));
     REACH_TRY(p->tile_mask.alloc(ctx, size_t(p->tpb) * sizeof(uint32_t)));
     REACH_TRY(p->featpart.alloc(ctx, size_t(S + 1) * p->tpb * std::max(1, nq) * 2 * mu_pad * sizeof(double)));
-    REACH_TRY(p->carry.alloc(ctx, size_t(std::max(1, nq)) * 2 * mu_pad * sizeof(double)));
+    REACH_TRY(p->ftot.alloc(ctx, size_t(S + 1) * std::max(1, nq) * 2 * mu_pad * sizeof(double)));
+    REACH_TRY(p->carry[0].alloc(ctx, size_t(std::max(1, nq)) * 2 * mu_pad * sizeof(double)));
+    REACH_TRY(p->carry[1].alloc(ctx, size_t(std::max(1, nq)) * 2 * mu_pad * sizeof(double)));
+    REACH_TRY(p->dv.alloc(ctx, size_t(S + 2) * 2 * mu_pad * sizeof(double)));
     REACH_TRY(p->s_pos.alloc(ctx, size_t(mu_pad) * sizeof(double)));
     REACH_TRY(p->s_neg.alloc(ctx, size_t(mu_pad) * sizeof(double)));
     REACH_TRY(p->row_pos.alloc(ctx, size_t(p->mu) * sizeof(int)));
@@ -589,14 +607,48 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     cmb.mu_pad = mu_pad;
     cmb.mu = p->mu;
     cmb.nsteps = p->nsteps;
-    cmb.carry = p->carry.as<double>();
     cmb.s_pos = p->s_pos.as<double>();
     cmb.s_neg = p->s_neg.as<double>();
     cmb.row_pos = p->row_pos.as<int>();
     cmb.row_neg = p->row_neg.as<int>();
     cmb.rho = p->rho;
     cmb.ndirs = p->ndirs;
-    const int cthreads = 128, cblocks = (p->mu + cthreads - 1) / cthreads;
+    const int cthreads = 64, cblocks = (p->mu + cthreads - 1) / cthreads;
+    double* ftot = p->ftot.as<double>();
+    int carry_cur = 0;
+    auto combine = [&](const Lgg09Combine& c) -> int {
+        const int nblk = c.b_hi - c.b_lo + 1;
+        if (nblk > 0) {
+            dim3 grid(cblocks, nblk);
+            lgg09_tilesum_kernel<<<grid, cthreads, 0, st>>>(c, ftot);
+            REACH_CUDA(ctx, cudaGetLastError());
+            ++p->launches;
+        }
+        const int npair = c.has_carry ? nblk : (nblk > 0 ? nblk - 1 : 0);
+        const int nslots = npair + (c.tail ? 1 : 0);
+        if (nslots <= 0) {
+            // nothing to emit (cannot happen for the passes issued below, kept for safety)
+            return REACH_OK;
+        }
+        const double* cin = p->carry[carry_cur].as<double>();
+        double* cout = p->carry[1 - carry_cur].as<double>();
+        double* dv = p->dv.as<double>();
+        dim3 grid(cblocks, nslots);
+        if (c.nq <= 4) lgg09_eval_kernel<4><<<grid, cthreads, 0, st>>>(c, ftot, cin, cout, dv);
+        else if (c.nq <= 8) lgg09_eval_kernel<8><<<grid, cthreads, 0, st>>>(c, ftot, cin, cout, dv);
+        else lgg09_eval_kernel<LGG09_MAX_FEATS><<<grid, cthreads, 0, st>>>(c, ftot, cin, cout, dv);
+        REACH_CUDA(ctx, cudaGetLastError());
+        ++p->launches;
+        carry_cur ^= 1;
+        if (c.prog.qV >= 0) {
+            // first step emitted by this pass
+            const long long kfirst = c.has_carry ? c.k0 + c.b_lo - 1 : (nblk > 0 ? c.k0 + c.b_lo : c.k0);
+            lgg09_prefix_kernel<<<cblocks, cthreads, 0, st>>>(c, dv, nslots, kfirst);
+            REACH_CUDA(ctx, cudaGetLastError());
+            ++p->launches;
+        }
+        return REACH_OK;
+    };
 
     // sample at most 512 main-loop GEMM launches with event pairs
     const int64_t sample_every = std::max<int64_t>(1, (T + 511) / 512);
@@ -617,9 +669,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         REACH_CUDA(ctx, (launch_cfg(p->cfg, g, epi, st)));
         ++p->launches;
         cmb.b_lo = 0; cmb.b_hi = 0; cmb.has_carry = 0; cmb.tail = 1; cmb.k0 = 0;
-        lgg09_combine_kernel<<<cblocks, cthreads, 0, st>>>(cmb);
-        REACH_CUDA(ctx, cudaGetLastError());
-        ++p->launches;
+        REACH_TRY(combine(cmb));
     }
     for (int64_t t = 0; t < T; ++t) {
         const int b_lo = t == 0 ? 0 : 1;
@@ -637,17 +687,13 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         ++p->launches;
         ++p->gemm_total;
         cmb.b_lo = b_lo; cmb.b_hi = S; cmb.has_carry = t > 0; cmb.tail = 0; cmb.k0 = t * S;
-        lgg09_combine_kernel<<<cblocks, cthreads, 0, st>>>(cmb);
-        REACH_CUDA(ctx, cudaGetLastError());
-        ++p->launches;
+        REACH_TRY(combine(cmb));
         cur ^= 1;
     }
     if (T > 0 && T * S < p->nsteps) {
         // one step left whose support values only need the carried features of r_{T S}
         cmb.b_lo = 1; cmb.b_hi = 0; cmb.has_carry = 1; cmb.tail = 1; cmb.k0 = T * S;
-        lgg09_combine_kernel<<<cblocks, cthreads, 0, st>>>(cmb);
-        REACH_CUDA(ctx, cudaGetLastError());
-        ++p->launches;
+        REACH_TRY(combine(cmb));
     }
 
     // ---- invariant: first step certified disjoint ----

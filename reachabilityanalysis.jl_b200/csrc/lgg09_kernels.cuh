@@ -139,7 +139,6 @@ struct Lgg09Combine {
     int tail;                       // also emit step k0 + b_hi from the last features alone
     long long k0;                   // r index of block 0 of this pass
     long long nsteps;
-    double* carry;                  // [nq][2][mu_pad]
     double* s_pos;                  // [mu_pad] running input sums of the +chain / -chain outputs
     double* s_neg;
     const int* row_pos;             // [mu] output row of +chain (-1: absent)
@@ -148,69 +147,138 @@ struct Lgg09Combine {
     int ndirs;
 };
 
-__device__ __forceinline__ void lgg09_emit(const Lgg09Combine& c, long long k, const double (*Fp)[2],
-                                           const double (*Fc)[2], int rp, int rn, double& sp, double& sn) {
-    double vp = 0.0, vn = 0.0;
-    for (int a = 0; a < c.prog.nalt; ++a) {
-        double ap = 0.0, an = 0.0;
-        const int q0 = c.prog.q0[a], q1 = c.prog.q1[a];
-        if (q0 >= 0) { ap += Fp[q0][0] + Fp[q0][1]; an += Fp[q0][1] - Fp[q0][0]; }
-        if (q1 >= 0) { ap += Fc[q1][0] + Fc[q1][1]; an += Fc[q1][1] - Fc[q1][0]; }
-        if (a == 0) { vp = ap; vn = an; } else { vp = fmax(vp, ap); vn = fmax(vn, an); }
-    }
-    if (rp >= 0) c.rho[size_t(k) * c.ndirs + rp] = vp + sp;
-    if (rn >= 0) c.rho[size_t(k) * c.ndirs + rn] = vn + sn;
-    if (c.prog.qV >= 0) {
-        const int q = c.prog.qV;
-        sp += Fp[q][0] + Fp[q][1];
-        sn += Fp[q][1] - Fp[q][0];
+// ---- combine, phase A: per-block feature totals -----------------------------------------------
+// Ftot[b][q][part][j] = sum over the row tiles of block b of the per-tile partials, in fixed tile
+// order (deterministic).  One thread per (chain j, block b).
+__global__ void lgg09_tilesum_kernel(const Lgg09Combine c, double* __restrict__ ftot) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = c.b_lo + blockIdx.y;
+    if (j >= c.mu || b > c.b_hi) return;
+    for (int q = 0; q < c.nq; ++q) {
+        double lin = 0.0, ab = 0.0;
+        for (int t = 0; t < c.tpb; ++t) {
+            if (!((c.tile_mask[t] >> q) & 1u)) continue;
+            const size_t base = (((size_t(b) * c.tpb + t) * c.nq + q) * 2) * c.mu_pad + j;
+            lin += c.featpart[base];
+            ab += c.featpart[base + c.mu_pad];
+        }
+        ftot[((size_t(b) * c.nq + q) * 2 + 0) * c.mu_pad + j] = lin;
+        ftot[((size_t(b) * c.nq + q) * 2 + 1) * c.mu_pad + j] = ab;
     }
 }
 
-__device__ __forceinline__ void lgg09_block_features(const Lgg09Combine& c, int blk, int j, double (*F)[2]) {
-    for (int q = 0; q < c.nq; ++q) { F[q][0] = 0.0; F[q][1] = 0.0; }
-    for (int t = 0; t < c.tpb; ++t) {            // fixed order over row tiles
-        const uint32_t mask = c.tile_mask[t];
-        for (int q = 0; q < c.nq; ++q) {
-            if (!((mask >> q) & 1u)) continue;
-            const size_t base = (((size_t(blk) * c.tpb + t) * c.nq + q) * 2) * c.mu_pad + j;
-            F[q][0] += c.featpart[base];
-            F[q][1] += c.featpart[base + c.mu_pad];
+// ---- combine, phase B: support values of Omega0 and V per (chain, step), fully parallel --------
+// Emit slot e of a pass pairs the features of r_k ("prev") with those of r_{k+1} ("cur"):
+//   has_carry: slot 0 = (carry, block b_lo), slot e = (block b_lo+e-1, block b_lo+e)
+//   otherwise: slot e = (block b_lo+e, block b_lo+e+1)
+//   tail     : one more slot (last, last) for a final step that needs nothing at r_{k+1}
+// rho(r_k; Omega0) goes straight into the output matrix; rho(r_k; V) into dv[e][2][mu_pad] for
+// the running-sum pass.  The thread of the last slot also writes the next pass's carry.
+template <int NQ>
+__global__ void lgg09_eval_kernel(const Lgg09Combine c, const double* __restrict__ ftot,
+                                  const double* __restrict__ carry_in, double* __restrict__ carry_out,
+                                  double* __restrict__ dv) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = blockIdx.y;
+    if (j >= c.mu) return;
+    const int nblk = c.b_hi - c.b_lo + 1;                       // may be 0
+    const int npair = c.has_carry ? nblk : (nblk > 0 ? nblk - 1 : 0);
+    const bool is_tail = (e == npair);                          // only launched when c.tail
+    int bp, bc;                                                 // block ids; -1 = carry
+    if (is_tail) {
+        bp = bc = (nblk > 0 ? c.b_hi : -1);
+    } else if (c.has_carry) {
+        bp = e == 0 ? -1 : c.b_lo + e - 1;
+        bc = c.b_lo + e;
+    } else {
+        bp = c.b_lo + e;
+        bc = c.b_lo + e + 1;
+    }
+    const long long k = is_tail ? c.k0 + c.b_hi : c.k0 + bc - 1;
+    double Fp[NQ][2], Fc[NQ][2];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        Fp[q][0] = Fp[q][1] = Fc[q][0] = Fc[q][1] = 0.0;
+        if (q < c.nq) {
+            const double* sp = bp < 0 ? carry_in + (size_t(q) * 2) * c.mu_pad
+                                      : ftot + ((size_t(bp) * c.nq + q) * 2) * c.mu_pad;
+            const double* sc = bc < 0 ? carry_in + (size_t(q) * 2) * c.mu_pad
+                                      : ftot + ((size_t(bc) * c.nq + q) * 2) * c.mu_pad;
+            Fp[q][0] = sp[j]; Fp[q][1] = sp[c.mu_pad + j];
+            Fc[q][0] = sc[j]; Fc[q][1] = sc[c.mu_pad + j];
         }
     }
+    if (k < c.nsteps) {
+        double vp = 0.0, vn = 0.0;
+        for (int a = 0; a < c.prog.nalt; ++a) {
+            double ap = 0.0, an = 0.0;
+            const int q0 = c.prog.q0[a], q1 = c.prog.q1[a];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (q == q0) { ap += Fp[q][0] + Fp[q][1]; an += Fp[q][1] - Fp[q][0]; }
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (q == q1) { ap += Fc[q][0] + Fc[q][1]; an += Fc[q][1] - Fc[q][0]; }
+            if (a == 0) { vp = ap; vn = an; } else { vp = fmax(vp, ap); vn = fmax(vn, an); }
+        }
+        const int rp = c.row_pos[j], rn = c.row_neg[j];
+        if (rp >= 0) c.rho[size_t(k) * c.ndirs + rp] = vp;
+        if (rn >= 0) c.rho[size_t(k) * c.ndirs + rn] = vn;
+        const int qv = c.prog.qV;
+        if (qv >= 0) {
+            double dp = 0.0, dn = 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (q == qv) { dp = Fp[q][0] + Fp[q][1]; dn = Fp[q][1] - Fp[q][0]; }
+            dv[(size_t(e) * 2 + 0) * c.mu_pad + j] = dp;
+            dv[(size_t(e) * 2 + 1) * c.mu_pad + j] = dn;
+        }
+    }
+    // the features of the last r of this pass seed the next one
+    const int nslots = npair + (c.tail ? 1 : 0);
+    if (e == nslots - 1) {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+            if (q < c.nq) {
+                carry_out[(size_t(q) * 2 + 0) * c.mu_pad + j] = Fc[q][0];
+                carry_out[(size_t(q) * 2 + 1) * c.mu_pad + j] = Fc[q][1];
+            }
+    }
 }
 
-__global__ void lgg09_combine_kernel(const Lgg09Combine c) {
+// ---- combine, phase C: running input sum, strictly in step order ---------------------------------
+// rho[j,k] = rho(r_k; Omega0) + s_k ;  s_{k+1} = s_k + rho(r_k; V)   (reach_inhomog.jl:56-57).
+// One thread per chain; loads are issued CH steps ahead of the dependent adds.
+__global__ void lgg09_prefix_kernel(const Lgg09Combine c, const double* __restrict__ dv, int nslots,
+                                    long long kfirst) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= c.mu) return;
-    double Fa[LGG09_MAX_FEATS][2], Fb[LGG09_MAX_FEATS][2];
-    double (*Fp)[2] = Fa;
-    double (*Fc)[2] = Fb;
+    constexpr int CH = 16;
     const int rp = c.row_pos[j], rn = c.row_neg[j];
     double sp = c.s_pos[j], sn = c.s_neg[j];
-    int b = c.b_lo;
-    if (c.has_carry) {
-        for (int q = 0; q < c.nq; ++q) {
-            Fp[q][0] = c.carry[(size_t(q) * 2 + 0) * c.mu_pad + j];
-            Fp[q][1] = c.carry[(size_t(q) * 2 + 1) * c.mu_pad + j];
+    for (int e0 = 0; e0 < nslots; e0 += CH) {
+        double dp[CH], dn[CH], vp[CH], vn[CH];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int e = e0 + i;
+            const long long k = kfirst + e;
+            const bool ok = e < nslots && k < c.nsteps;
+            dp[i] = ok ? dv[(size_t(e) * 2 + 0) * c.mu_pad + j] : 0.0;
+            dn[i] = ok ? dv[(size_t(e) * 2 + 1) * c.mu_pad + j] : 0.0;
+            vp[i] = (ok && rp >= 0) ? c.rho[size_t(k) * c.ndirs + rp] : 0.0;
+            vn[i] = (ok && rn >= 0) ? c.rho[size_t(k) * c.ndirs + rn] : 0.0;
         }
-    } else {
-        lgg09_block_features(c, b, j, Fp);
-        ++b;
-    }
-    for (; b <= c.b_hi; ++b) {
-        lgg09_block_features(c, b, j, Fc);
-        const long long k = c.k0 + b - 1;
-        if (k < c.nsteps) lgg09_emit(c, k, Fp, Fc, rp, rn, sp, sn);
-        double (*t)[2] = Fp; Fp = Fc; Fc = t;
-    }
-    if (c.tail) {
-        const long long k = c.k0 + c.b_hi;
-        if (k < c.nsteps) lgg09_emit(c, k, Fp, Fp, rp, rn, sp, sn);
-    }
-    for (int q = 0; q < c.nq; ++q) {
-        c.carry[(size_t(q) * 2 + 0) * c.mu_pad + j] = Fp[q][0];
-        c.carry[(size_t(q) * 2 + 1) * c.mu_pad + j] = Fp[q][1];
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int e = e0 + i;
+            const long long k = kfirst + e;
+            if (e < nslots && k < c.nsteps) {
+                if (rp >= 0) c.rho[size_t(k) * c.ndirs + rp] = vp[i] + sp;
+                if (rn >= 0) c.rho[size_t(k) * c.ndirs + rn] = vn[i] + sn;
+                sp += dp[i];
+                sn += dn[i];
+            }
+        }
     }
     c.s_pos[j] = sp;
     c.s_neg[j] = sn;
