@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- LGG09 support evaluations/s on BASELINE.json config C5
+(synthetic stable LTI n=2000, box template = 4000 directions, 10^4 steps), sharded by direction
+over N GPUs of one node.  One "step" = one full pass of the hot path (all 10^4 time steps).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  See DESIGN.md §measurement for what each key means.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LGG09 support evals/s (dirs x steps)"
+UNIT = "evals/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=2000, help="state dimension of the synthetic workload")
+    ap.add_argument("--nsteps", type=int, default=10000, help="time steps per pass")
+    ap.add_argument("--time-block", type=int, default=0)
+    ap.add_argument("--cpu-sample-steps", type=int, default=0, help="time steps of the CPU sample (0: auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(wl, sample_steps):
+    """The reference's CPU algorithm (oracle port, GEMM-per-step shape of reach_inhomog.jl:174-218,
+    multi-threaded BLAS) on the first `sample_steps` time steps of the same workload."""
+    from oracle import lgg09_oracle as LO
+    t0 = time.perf_counter()
+    out = LO.reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, sample_steps, wl.V)
+    dt = time.perf_counter() - t0
+    return out, dt
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        n = 1
+    return min(n, len(os.sched_getaffinity(0))) if n else len(os.sched_getaffinity(0))
+
+
+def auto_sample_steps(wl):
+    # aim at ~10-20 s of CPU work: time two steps, scale
+    from oracle import lgg09_oracle as LO
+    t0 = time.perf_counter()
+    LO.reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, 3, wl.V)
+    per = (time.perf_counter() - t0) / 3
+    return int(max(5, min(400, 12.0 / max(per, 1e-4))))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from reach_b200 import workloads as W
+    wl = W.synthetic_c5(n=args.n, nsteps=args.nsteps)
+    sample = args.cpu_sample_steps or auto_sample_steps(wl)
+    ndirs = wl.dirs.shape[1]
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_sample(wl, max(2, sample // 10))
+    total = 0.0
+    for _ in range(args.steps):
+        _, dt = cpu_reference_sample(wl, sample)
+        total += dt
+    value = ndirs * sample * args.steps / total
+    cores = cpu_threads()
+    desc = "first %d of %d time steps, all %d directions, per bench step" % (sample, args.nsteps, ndirs)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": wl.name, "n": wl.n, "ndirs": ndirs, "nsteps": args.nsteps,
+                   "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                         "note": "NumPy/OpenBLAS restatement of the reference loops (Julia is not installed); "
+                                 "one multi-threaded GEMM per time step + vectorised support functions"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in self.rows:
+            for i, nm in enumerate(names):
+                if len(r) > 5 + i and r[5 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        # take the upper half (samples under load) for the median
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cublas_fp64_peak(torch, nn=8192, iters=6):
+    """FP64 roofline denominator: cuBLAS DGEMM nn^3 measured in this run (MEASURED_PEAKS.json
+    holds HBM and bf16 only)."""
+    a = torch.randn(nn, nn, dtype=torch.float64, device="cuda")
+    b = torch.randn(nn, nn, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, 2.0 * nn ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    del a, b
+    torch.cuda.empty_cache()
+    return best
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import reach_b200  # noqa: F401
+    from reach_b200 import _lib, workloads as W
+    from reach_b200.lgg09 import Lgg09Plan
+    from reach_b200.sharding import shard_directions, gather_support_values
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun with --nproc-per-node %d" % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = _lib.Context(local_rank)
+    wl = W.synthetic_c5(n=args.n, nsteps=args.nsteps)
+    n, ndirs, nsteps = wl.n, wl.dirs.shape[1], args.nsteps
+    local_dirs, rows_by_rank, mloc = shard_directions(wl.dirs, world, rank)
+
+    # device-resident inputs and output
+    out_T = torch.empty((nsteps, mloc), dtype=torch.float64, device="cuda")     # == mloc x nsteps col-major
+    plan = Lgg09Plan(ctx, n, mloc, nsteps, time_block=args.time_block)
+    plan.set_output(out_T.data_ptr())
+    plan.upload(wl.Phi, local_dirs, wl.Omega0, wl.V)
+    flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
+
+    def one_pass():
+        """Whole hot path, inputs resident in HBM: recurrence on this rank's chains + all-gather."""
+        flush.zero_()
+        barrier()
+        plan.run(sync=True)
+        st = plan.stats()
+        ms = st["ms"]
+        full = None
+        if world > 1:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            full = gather_support_values(out_T, rows_by_rank, ndirs)
+            e1.record()
+            torch.cuda.synchronize()
+            ms += e0.elapsed_time(e1)
+        return ms, st, full
+
+    peak_tf = cublas_fp64_peak(torch) if rank == 0 else 0.0
+    for _ in range(args.warmup):
+        one_pass()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    total_ms, launches, gemm_ms_acc, st = 0.0, 0, 0.0, None
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        ms, st, _ = one_pass()
+        total_ms += ms
+        launches += st["launches"]
+        gemm_ms_acc += st["gemm_ms"]
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = ndirs * nsteps * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: the one-shot C-ABI call with HOST buffers (pinned), H2D + compute + D2H (+ gather) ----
+    import ctypes as C
+    from reach_b200.support_program import flatten, to_c
+    Phi_h = torch.empty((n, n), dtype=torch.float64, pin_memory=True).numpy()          # column-major view below
+    Phi_h[...] = wl.Phi.T                                                              # buffer holds Phi col-major
+    dirs_h = torch.empty((mloc, n), dtype=torch.float64, pin_memory=True).numpy()
+    dirs_h[...] = local_dirs.T
+    rho_h = torch.empty((nsteps, mloc), dtype=torch.float64, pin_memory=True).numpy()
+    om, v = to_c(flatten(wl.Omega0, wl.Phi), n), to_c(flatten(wl.V, wl.Phi), n)
+    opts = _lib.reach_lgg09_opts()
+    ctx.lib.reach_lgg09_default_opts(C.byref(opts))
+    opts.time_block = args.time_block
+    h2d = Phi_h.nbytes + dirs_h.nbytes + 4 * n * 8
+    d2h = rho_h.nbytes
+
+    def e2e_pass():
+        barrier()
+        t0 = time.perf_counter()
+        ctx.check(ctx.lib.reach_lgg09(ctx.handle, n, mloc, nsteps, _lib.dptr(Phi_h), _lib.dptr(dirs_h), om.ptr(),
+                                      v.ptr(), None, C.byref(opts), _lib.dptr(rho_h), None))
+        if world > 1:
+            # the only exchange: every rank ends up with the full rho matrix on its host
+            loc = torch.from_numpy(rho_h).cuda(non_blocking=True)
+            full = gather_support_values(loc, rows_by_rank, ndirs)
+            full.cpu()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    e2e_pass()
+    e2e_t = [e2e_pass() for _ in range(max(1, args.steps))]
+    e2e_s = sum(e2e_t)
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = ndirs * nsteps * len(e2e_t) / e2e_s
+    # e2e result must be the same numbers as the device-resident run
+    same = bool(np.array_equal(rho_h, out_T.cpu().numpy()))
+
+    if rank == 0:
+        S = st["time_block"]
+        gemm_ms = gemm_ms_acc / args.steps                                  # mean duration of one launch
+        flops_per_launch = 2.0 * n * n * st["nchains"] * S                  # algorithmic: 2 n^2 per chain-step
+        achieved = flops_per_launch / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": wl.name, "n": n, "ndirs": ndirs, "nsteps": nsteps,
+                       "ndirs_per_gpu": mloc, "chains_per_gpu": st["nchains"], "time_block": S,
+                       "tile": "%dx%d" % (st["tile_m"], st["tile_n"]), "sharding": "template directions",
+                       "collective": "all-gather of per-rank rho blocks" if world > 1 else "none",
+                       "l2": "working set (row stack %d MB + rho %d MB) exceeds the 126 MB L2; 512 MB flush "
+                             "between passes" % ((S + 1) * 2048 * n * 8 >> 20, mloc * nsteps * 8 >> 20)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "timer": "host wall clock around reach_lgg09(host buffers), max over ranks",
+                    "bit_identical_to_device_resident_run": same},
+            "gpu_launches": launches,
+            "wall_s_timed_region": wall,
+            "roofline": {"bound": "tensor", "kernel": "nt_dgemm_kernel<...,Lgg09Epi> (FP64 DMMA + fused support epilogue)",
+                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": (achieved / peak_tf) if achieved and peak_tf else None,
+                         "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul f64) measured in this run, burst; "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "flops_per_launch": flops_per_launch, "launch_ms": gemm_ms,
+                         "launches_per_step": st["gemm_launches"],
+                         "gemm_share_of_step": st["gemm_launches"] * gemm_ms / (total_ms / args.steps),
+                         "traffic": None},
+        }
+        if not args.no_cpu_baseline:
+            sample = args.cpu_sample_steps or auto_sample_steps(wl)
+            ref, dt = cpu_reference_sample(wl, sample)
+            got = out_T[:sample].cpu().numpy().T if world == 1 else None
+            line["cpu_baseline"] = {
+                "value": ndirs * sample / dt, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                "sample": "first %d of %d time steps, all %d directions" % (sample, nsteps, ndirs)}
+            if got is not None:
+                scale = np.maximum(np.abs(ref), np.abs(ref).max(axis=1, keepdims=True))
+                line["cpu_baseline"]["max_scaled_diff_vs_gpu"] = float((np.abs(got - ref) / scale).max())
+        print(json.dumps(line), flush=True)
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -1,0 +1,67 @@
+"""Multi-GPU sharding of the LGG09 path: template directions are independent
+(`Threads.@threads for j in eachindex(ℓ)`, reach_inhomog.jl:35-40), so each rank owns a
+contiguous block of direction *chains* (a direction and its negation stay on the same rank so
+they keep sharing (Φᵀ)^k ℓ), and the only collective is one all-gather of the per-rank
+support-value blocks.  One process per GPU; `torch.distributed` (NCCL on the GPUs, gloo in the
+CPU tests) is plumbing only."""
+import numpy as np
+
+
+def chain_groups(dirs):
+    """Group directions into chains: ℓ and −ℓ (exact negation) share a chain.  Returns a list of
+    index lists in first-appearance order."""
+    n, m = dirs.shape
+    index = {}
+    groups = []
+    for j in range(m):
+        d = dirs[:, j]
+        nz = np.flatnonzero(d)
+        sign = -1.0 if len(nz) and d[nz[0]] < 0 else 1.0
+        key = (sign * d + 0.0).tobytes()
+        g = index.get(key)
+        if g is None or len(groups[g]) >= 2:
+            index[key] = len(groups)
+            groups.append([j])
+        else:
+            groups[g].append(j)
+    return groups
+
+
+def shard_directions(dirs, world, rank):
+    """Directions of `rank`: (local_dirs [n × mloc], global_rows [mloc_valid], mloc) with every
+    rank padded (zero directions, ρ ≡ 0) to the same mloc so the all-gather is uniform."""
+    if world == 1:
+        # single GPU: keep the caller's order, nothing to gather
+        return np.asfortranarray(dirs), [np.arange(dirs.shape[1], dtype=np.int64)], dirs.shape[1]
+    groups = chain_groups(dirs)
+    per = (len(groups) + world - 1) // world
+    rows_by_rank = []
+    for r in range(world):
+        rows = [j for g in groups[r * per:(r + 1) * per] for j in g]
+        rows_by_rank.append(np.array(rows, dtype=np.int64))
+    mloc = max(1, max(len(r) for r in rows_by_rank))
+    rows = rows_by_rank[rank]
+    local = np.zeros((dirs.shape[0], mloc), order="F")
+    local[:, :len(rows)] = dirs[:, rows]
+    return local, rows_by_rank, mloc
+
+
+def gather_support_values(local_T, rows_by_rank, ndirs, group=None):
+    """All-gather the per-rank blocks and place the rows.
+
+    local_T: torch tensor [nsteps, mloc] (i.e. the column-major mloc × nsteps block the device
+    path produced).  Returns a tensor [nsteps, ndirs] == column-major ndirs × nsteps, the
+    reference's ρℓ layout."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    nsteps, mloc = local_T.shape
+    flat = torch.empty((world * nsteps, mloc), dtype=local_T.dtype, device=local_T.device)
+    dist.all_gather_into_tensor(flat, local_T.contiguous(), group=group)
+    gathered = flat.view(world, nsteps, mloc)
+    out = torch.empty((nsteps, ndirs), dtype=local_T.dtype, device=local_T.device)
+    for r in range(world):
+        rows = torch.as_tensor(rows_by_rank[r], device=local_T.device)
+        if len(rows):
+            out.index_copy_(1, rows, gathered[r, :, :len(rows)])
+    return out

@@ -1,0 +1,148 @@
+"""Host-side logic: set flattening, templates, discretization, sharding maps (CPU only)."""
+import numpy as np
+import pytest
+
+import reach_b200 as rb
+from reach_b200 import discretization as D, support_program as sp, _lib, sharding
+from reach_b200.zonotope_ops import to_zonotope
+from oracle import lazysets_oracle as Z, lgg09_oracle as LO
+
+
+def eval_flat(alts, r0, r1):
+    """Evaluate a flattened program in plain NumPy (test helper)."""
+    best = None
+    for alt in alts:
+        v = 0.0
+        for t in alt:
+            d = r1 if t.which else r0
+            if t.M is not None:
+                d = t.M.T @ d
+            if t.c is not None:
+                v += float(t.c @ d)
+            if t.kind == _lib.REACH_TERM_BOX and t.r is not None:
+                v += float(t.r @ np.abs(d))
+            if t.kind == _lib.REACH_TERM_ZONO:
+                v += float(np.abs(t.G.T @ d).sum())
+        best = v if best is None else max(best, v)
+    return best
+
+
+def test_flatten_matches_lazy_support_function():
+    rng = np.random.default_rng(0)
+    n = 6
+    Phi = rng.standard_normal((n, n))
+    X0 = rb.Hyperrectangle(rng.standard_normal(n), rng.uniform(0, 1, n))
+    Zt = rb.Zonotope(rng.standard_normal(n), rng.standard_normal((n, 9)))
+    U = rb.LinearMap(rng.standard_normal((n, 2)), rb.Hyperrectangle(rng.standard_normal(2), rng.uniform(0, 1, 2)))
+    sets = [
+        X0, Zt, rb.BallInf(np.ones(n), 0.5), rb.Singleton(np.arange(n)), rb.ZeroSet(n),
+        rb.ConvexHull(X0, rb.MinkowskiSum(rb.MinkowskiSum(rb.LinearMap(Phi, X0), rb.MinkowskiSum(rb.Scale(0.1, U), X0)), Zt)),
+        rb.MinkowskiSum(rb.ConvexHull(X0, Zt), rb.ConvexHull(rb.LinearMap(Phi, Zt), U)),
+        rb.CartesianProduct(rb.Interval(-1, 3), rb.Zonotope(np.zeros(n - 1), rng.standard_normal((n - 1, 4)))),
+        rb.Scale(-2.0, rb.LinearMap(rng.standard_normal((n, n)), X0)),
+    ]
+    for X in sets:
+        alts = sp.flatten(X, Phi)
+        sp.to_c(alts, n)           # builds the ctypes structs without error
+        for _ in range(5):
+            r0 = rng.standard_normal(n)
+            want = Z.rho(r0, X)
+            got = eval_flat(alts, r0, Phi.T @ r0)
+            assert abs(got - want) <= 1e-12 * max(1.0, abs(want)), type(X).__name__
+
+
+def test_flatten_marks_phi_image_as_next_direction():
+    n = 3
+    Phi = np.arange(9.0).reshape(3, 3)
+    X0 = rb.BallInf(np.zeros(n), 1.0)
+    alts = sp.flatten(rb.ConvexHull(X0, rb.LinearMap(Phi, X0)), Phi)
+    assert [[t.which for t in a] for a in alts] == [[0], [1]]
+    assert all(t.M is None for a in alts for t in a)
+    alts = sp.flatten(rb.LinearMap(Phi + 1, X0), Phi)
+    assert alts[0][0].which == 0 and alts[0][0].M is not None
+
+
+def test_flatten_rejects_unbounded_and_unknown():
+    with pytest.raises(ValueError):
+        sp.flatten(rb.Universe(2))
+    with pytest.raises(NotImplementedError):
+        sp.flatten(rb.HalfSpace([1.0, 0.0], 1.0))
+
+
+def test_templates():
+    assert rb.BoxDirections(3).matrix().shape == (3, 6)
+    O = rb.OctDirections(3).matrix()
+    assert O.shape == (3, 18) and len({tuple(c) for c in O.T}) == 18
+    with pytest.raises(ValueError):
+        rb.LGG09(δ=0.1)
+    with pytest.raises(ValueError):
+        rb.LGG09(δ=0.1, vars=(1,))
+    assert len(rb.LGG09(δ=0.1, dirs=[np.array([1.0, 0.0]), np.array([0.0, -1.0])]).template) == 2
+    assert len(rb.LGG09(δ=0.1, template=np.array([1.0, 2.0])).template) == 1
+
+
+def test_forward_discretization_contains_exact_reach_set_samples():
+    """Ω₀ of the Forward model covers x(t), t ∈ [0, δ], for sampled x0, u (sanity of the host-side
+    restatement of ForwardModule.jl:137-164)."""
+    import scipy.linalg
+    rng = np.random.default_rng(2)
+    n, delta = 4, 0.05
+    A = -np.eye(n) + 0.3 * rng.standard_normal((n, n))
+    X0 = rb.Hyperrectangle(rng.standard_normal(n), 0.1 * np.ones(n))
+    Bm = rng.standard_normal((n, 2))
+    U0 = rb.Hyperrectangle(np.array([0.5, -0.2]), np.array([0.1, 0.2]))
+    ivp = D.forward(A, X0, delta, D.normalize_input(Bm, U0))
+    dirs = rng.standard_normal((n, 12))
+    sup = Z.rho(dirs, ivp.Omega0)
+    for _ in range(40):
+        x0 = X0.center + X0.radius * rng.uniform(-1, 1, n)
+        u = U0.center + U0.radius * rng.uniform(-1, 1, 2)
+        for t in np.linspace(0, delta, 5):
+            M = np.zeros((n + 1, n + 1))
+            M[:n, :n] = A * t
+            M[:n, n] = Bm @ u * t
+            x = (scipy.linalg.expm(M) @ np.r_[x0, 1.0])[:n]
+            assert np.all(dirs.T @ x <= sup + 1e-12)
+
+
+def test_split_order_first_dimension_fastest():
+    H = rb.Hyperrectangle(np.zeros(3), np.ones(3))
+    parts = rb.split(H, [2, 2, 1])
+    assert len(parts) == 4
+    np.testing.assert_allclose(parts[0].center, [-0.5, -0.5, 0])
+    np.testing.assert_allclose(parts[1].center, [0.5, -0.5, 0])
+    np.testing.assert_allclose(parts[2].center, [-0.5, 0.5, 0])
+    np.testing.assert_allclose(parts[0].radius, [0.5, 0.5, 1.0])
+
+
+def test_to_zonotope_skips_flat_dimensions():
+    c, G = to_zonotope(rb.Hyperrectangle(np.zeros(4), np.array([1.0, 0.0, 2.0, 0.0])))
+    assert G.shape == (4, 2) and G[0, 0] == 1.0 and G[2, 1] == 2.0
+
+
+def test_shard_directions_keeps_negations_together():
+    n = 5
+    dirs = np.hstack([np.eye(n), -np.eye(n), np.ones((n, 1))])
+    groups = sharding.chain_groups(dirs)
+    assert groups[:n] == [[i, n + i] for i in range(n)] and groups[n] == [2 * n]
+    seen = []
+    for r in range(3):
+        local, rows_by_rank, mloc = sharding.shard_directions(dirs, 3, r)
+        rows = rows_by_rank[r]
+        assert local.shape == (n, mloc)
+        np.testing.assert_array_equal(local[:, :len(rows)], dirs[:, rows])
+        assert not local[:, len(rows):].any()
+        seen += list(rows)
+    assert sorted(seen) == list(range(2 * n + 1))
+    local, rows_by_rank, mloc = sharding.shard_directions(dirs, 1, 0)
+    np.testing.assert_array_equal(local, dirs)
+
+
+def test_oracle_invariant_variant_stops_and_drops_the_triggering_step():
+    n = 2
+    Phi = np.diag([0.5, 0.9])
+    X0 = rb.Hyperrectangle(np.array([4.0, 4.0]), np.array([0.1, 0.1]))
+    dirs = LO.box_directions(n)
+    out, k = LO.reach_LGG09_invariant(dirs, X0, Phi, 50, rb.HalfSpace(np.array([-1.0, 0.0]), -1.0))
+    # x1 upper bound: 4.1 * 0.5^k ; disjoint from {x1 >= 1} once 4.1*0.5^k < 1  ->  k = 3
+    assert k == 3 and out.shape == (4, 3)
