@@ -8,5 +8,6 @@ from .directions import BoxDirections, OctDirections, CustomDirections  # noqa: 
 from .flowpipe import (Flowpipe, MixedFlowpipe, ReachSolution, TemplateReachSet, ReachSet,  # noqa: F401
                        TimeInterval, zeroT, rho)
 from .lgg09 import LGG09, Forward, NoBloating, FirstOrderZonotope, Lgg09Plan  # noqa: F401
+from .glgm06 import GLGM06, Glgm06Plan, reduce_order  # noqa: F401
 from .solve import solve, IVP, discretize  # noqa: F401
 from ._lib import Context, ReachError, default_context  # noqa: F401

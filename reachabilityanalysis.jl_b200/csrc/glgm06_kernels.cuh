@@ -1,1 +1,510 @@
+// glgm06_kernels.cuh -- device side of the GLGM06 zonotope flowpipe.
+//
+// Reference loop (src/Algorithms/GLGM06/reach_inhomog.jl:28-41), per initial set:
+//     R_k = reduce_order(P Omega0 (+) W, r, GIR05);  W = reduce_order(P U (+) W, r, GIR05);  P = P Phi
+// with linear_map_minkowski_sum (Continuous/setops.jl:7-25): c = P c1 + c2, G = [P G1 | G2].
+//
+// Device formulation.  P_k and W_k do not depend on the initial set, so the run is split in
+//   (1) the shared chain, sequential in k and small:  P_{k+1} = P_k Phi,  P_k [G_U | c_U],
+//       GIR05 of [P_k G_U | W_k]  -> W_{k+1}, plus, per step, the sort of W_k's generator weights
+//       and the prefix table of |W_k| in that order;
+//   (2) the batched part, parallel over (split, step): ONE nt_dgemm over the stack of all powers
+//       gives P_k [G0 | c0] for every split and step (generators are the rows of the X operand),
+//       its epilogue also emits each generator's sum|.| and max|.|; a per-(split,step) kernel
+//       ranks the split's own generators, merges them with the shared sorted list to find the
+//       GIR05 cut, and writes the selection, the box diagonal and the centre.
+// A reduced zonotope is stored as [own mapped generators | selection | diagonal] + a reference to
+// the step's shared generators, never as a dense n x (r n) matrix (device-resident Flowpipe).
 #pragma once
+
+#include "nt_dgemm.cuh"
+
+namespace reach {
+
+// ---- GEMM epilogue: store C with a per-N-block stride and emit per-row sum|c| / max|c| ----------
+struct GenEpi {
+    double* out;            // element (x, blk*nb + i) -> out[blk*blk_stride + x*ldc + i], i < n
+    long long blk_stride;
+    int ldc;
+    int n, nb;              // valid / padded columns per block
+    int m_valid;
+    double* psum;           // [nblk*tpb][m_pad] partial sum |c| over the tile's valid columns (may be NULL)
+    double* pmax;           // [nblk*tpb][m_pad] partial max |c|
+    int m_pad;
+
+    template <int MT, int NT, int WN, class TC>
+    __device__ __forceinline__ void run(double (&acc)[MT][NT][2], const TC& tc, double* smem) const {
+        constexpr int TM = TC::TM, TN = TC::TN;
+        const int col0 = tc.tn * TN;
+        const int blk = col0 / nb;
+        const int cib0 = col0 % nb;
+        double* o_blk = out + size_t(blk) * blk_stride;
+        double* red = smem;                              // [WN][2][TM]
+        const int wn = tc.wn0 / (NT * 8);
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const int ml = tc.wm0 + i * 8 + tc.g4;
+            const int m = tc.tm * TM + ml;
+            double s = 0.0, mx = 0.0;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const int c = cib0 + tc.wn0 + j * 8 + 2 * tc.t4;
+                const double v0 = acc[i][j][0], v1 = acc[i][j][1];
+                if (m < m_valid) {
+                    double* o = o_blk + size_t(m) * ldc + c;
+                    if (c + 1 < n && (ldc & 1) == 0) *reinterpret_cast<double2*>(o) = make_double2(v0, v1);
+                    else {
+                        if (c < n) o[0] = v0;
+                        if (c + 1 < n) o[1] = v1;
+                    }
+                }
+                if (c < n) { s += fabs(v0); mx = fmax(mx, fabs(v0)); }
+                if (c + 1 < n) { s += fabs(v1); mx = fmax(mx, fabs(v1)); }
+            }
+            if (psum) {
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                if (tc.t4 == 0) {
+                    red[(wn * 2 + 0) * TM + ml] = s;
+                    red[(wn * 2 + 1) * TM + ml] = mx;
+                }
+            }
+        }
+        if (!psum) return;
+        __syncthreads();
+        const int tpb = nb / TN;
+        const size_t prow = (size_t(blk) * tpb + cib0 / TN) * m_pad + size_t(tc.tm) * TM;
+        for (int ml = tc.tid; ml < TM; ml += tc.nthr) {
+            double s = 0.0, mx = 0.0;
+#pragma unroll
+            for (int w = 0; w < WN; ++w) {
+                s += red[(w * 2 + 0) * TM + ml];
+                mx = fmax(mx, red[(w * 2 + 1) * TM + ml]);
+            }
+            psum[prow + ml] = s;
+            pmax[prow + ml] = mx;
+        }
+    }
+};
+
+// ---- sorting: (weight, index) ascending, i.e. the stable order Julia's sortperm guarantees ------
+struct WKey {
+    double w;
+    int idx;
+};
+__device__ __forceinline__ bool wkey_less(const WKey& a, const WKey& b) {
+    return a.w < b.w || (a.w == b.w && a.idx < b.idx);
+}
+// bitonic sort of `np2` (power of two) keys in shared memory by all threads of the CTA
+__device__ inline void bitonic_sort(WKey* keys, int np2) {
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const bool up = (i & k) == 0;
+                    WKey a = keys[i], b = keys[ixj];
+                    if (wkey_less(b, a) == up) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+__device__ __forceinline__ int lower_bound_d(const double* a, int n, double v) {   // #{a_i < v}
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ int upper_bound_key(const WKey* a, int n, double v) {   // #{a_i.w <= v}
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid].w <= v) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// ---- shared chain, per step: weights + stable sort of the shared generators W_k, prefix of |W_k| --
+// GW: [pW][ldg] one generator per row.  Outputs: wB[pW] sorted weights, permB[pW] (sorted -> original),
+// bpref[(pW+1)][n]: bpref[t][i] = sum over the first t generators in sorted order of |g[i]|.
+// Single CTA; dynamic shared memory: np2 WKeys.
+static __global__ void glgm06_shared_prep_kernel(const double* __restrict__ GW, int ldg, int pW, int n, int np2,
+                                          double* __restrict__ wB, int* __restrict__ permB,
+                                          double* __restrict__ bpref) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    WKey* keys = reinterpret_cast<WKey*>(smraw);
+    for (int j = threadIdx.x; j < np2; j += blockDim.x) {
+        if (j < pW) {
+            double s = 0.0, mx = 0.0;
+            for (int i = 0; i < n; ++i) {
+                const double a = fabs(GW[size_t(j) * ldg + i]);
+                s += a;
+                mx = fmax(mx, a);
+            }
+            keys[j].w = s - mx;
+            keys[j].idx = j;
+        } else {
+            keys[j].w = INFINITY;
+            keys[j].idx = 0x7fffffff;
+        }
+    }
+    __syncthreads();
+    bitonic_sort(keys, np2);
+    for (int j = threadIdx.x; j < pW; j += blockDim.x) {
+        wB[j] = keys[j].w;
+        permB[j] = keys[j].idx;
+    }
+    // prefix table, one thread per coordinate i (sequential in sorted order)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double s = 0.0;
+        bpref[i] = 0.0;
+        for (int t = 0; t < pW; ++t) {
+            s += fabs(GW[size_t(keys[t].idx) * ldg + i]);
+            bpref[size_t(t + 1) * n + i] = s;
+        }
+    }
+}
+
+// ---- GIR05 of [own | shared] given the shared side's sorted weights ------------------------------
+// own: pa generators (rows of `A`, leading dimension lda) with weights computed here or supplied;
+// shared: pb generators already sorted (wB, permB, bpref).  kept = floor(n (r-1)) smallest-weight
+// generators are NOT boxed; m = pa + pb - kept are.  Results:
+//   pos_own[j]  output column of own generator j, or -1 if it went into the box
+//   *tb         number of boxed shared generators (the first tb in sorted order)
+//   diag[i]     sum over boxed generators of |g[i]|
+// Cooperative over one CTA; `keys` is shared memory for np2 >= pa keys; `sw` for pa doubles.
+__device__ inline void gir05_cut(const double* __restrict__ A, int lda, int pa, int n, WKey* keys, double* sw,
+                                 int np2, const double* __restrict__ wB, int pb, const double* __restrict__ bpref,
+                                 int kept, int* __restrict__ pos_own, int* tb_out, double* __restrict__ diag,
+                                 int* s_ta) {
+    const int m = pa + pb - kept;                      // > 0 by construction
+    bitonic_sort(keys, np2);
+    for (int i = threadIdx.x; i < pa; i += blockDim.x) sw[i] = keys[i].w;
+    if (threadIdx.x == 0) *s_ta = 0;
+    __syncthreads();
+    // own generator at sorted position i has union rank i + #{shared with weight < a_i} (ties: own first)
+    for (int i = threadIdx.x; i < pa; i += blockDim.x) {
+        const int lb = lower_bound_d(wB, pb, sw[i]);
+        if (i + lb < m) atomicMax(s_ta, i + 1);        // boxed; monotone in i, so ta = 1 + last boxed
+    }
+    __syncthreads();
+    const int ta = *s_ta;
+    const int tb = m - ta;
+    for (int i = threadIdx.x; i < pa; i += blockDim.x) {
+        int pos = -1;
+        if (i >= ta) {
+            const int lb = lower_bound_d(wB, pb, sw[i]);
+            pos = (i - ta) + max(0, lb - tb);
+        }
+        pos_own[keys[i].idx] = pos;
+    }
+    if (threadIdx.x == 0) *tb_out = tb;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double s = 0.0;
+        for (int t = 0; t < ta; ++t) s += fabs(A[size_t(keys[t].idx) * lda + i]);   // own, sorted order
+        diag[i] = s + (pb > 0 ? bpref[size_t(tb) * n + i] : 0.0);
+    }
+    __syncthreads();
+}
+
+// ---- batched per-(split, step) selection ----------------------------------------------------------
+struct SelectParams {
+    const double* A;        // [nblk][m_pad_rows][lda]: row = split*(p0+1) + g ; g == p0 is P c0
+    long long a_blk_stride;
+    int lda;
+    const double* psum;     // [nblk*tpb][m_pad]
+    const double* pmax;
+    int tpb, m_pad;
+    int n, p0, nsplits, nblk, r;
+    const int* pW;          // [nblk] shared generator count per step
+    const double* wB;       // [nblk][pWcap]
+    const double* bpref;    // [nblk][(pWcap+1)][n]
+    const double* cW;       // [nblk][n] centre of W at that step
+    int pWcap;
+    int* pos_own;           // [nblk][nsplits][p0]
+    int* tb;                // [nblk][nsplits]  (-1: no reduction at this step)
+    double* diag;           // [nblk][nsplits][n]
+    double* centre;         // [nblk][nsplits][n]
+};
+
+static __global__ void glgm06_select_kernel(const SelectParams s, int np2) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    WKey* keys = reinterpret_cast<WKey*>(smraw);
+    double* sw = reinterpret_cast<double*>(keys + np2);
+    __shared__ int s_ta;
+    const int split = blockIdx.x, b = blockIdx.y;
+    const int row0 = split * (s.p0 + 1);
+    const double* A = s.A + size_t(b) * s.a_blk_stride + size_t(row0) * s.lda;
+    const size_t o = size_t(b) * s.nsplits + split;
+    const int pb = s.pW[b];
+    // centre: P c0 + c_W
+    for (int i = threadIdx.x; i < s.n; i += blockDim.x)
+        s.centre[o * s.n + i] = A[size_t(s.p0) * s.lda + i] + s.cW[size_t(b) * s.n + i];
+    const int p = s.p0 + pb;
+    if (p <= s.r * s.n) {                               // r n >= p: returned unchanged
+        for (int j = threadIdx.x; j < s.p0; j += blockDim.x) s.pos_own[o * s.p0 + j] = j;
+        if (threadIdx.x == 0) s.tb[o] = -1;
+        return;
+    }
+    for (int j = threadIdx.x; j < np2; j += blockDim.x) {
+        if (j < s.p0) {
+            double sum = 0.0, mx = 0.0;
+            for (int t = 0; t < s.tpb; ++t) {
+                sum += s.psum[(size_t(b) * s.tpb + t) * s.m_pad + row0 + j];
+                mx = fmax(mx, s.pmax[(size_t(b) * s.tpb + t) * s.m_pad + row0 + j]);
+            }
+            keys[j].w = sum - mx;
+            keys[j].idx = j;
+        } else {
+            keys[j].w = INFINITY;
+            keys[j].idx = 0x7fffffff;
+        }
+    }
+    __syncthreads();
+    const int kept = s.n * (s.r - 1);
+    gir05_cut(A, s.lda, s.p0, s.n, keys, sw, np2, s.wB + size_t(b) * s.pWcap, pb,
+              s.bpref + size_t(b) * (s.pWcap + 1) * s.n, kept, s.pos_own + o * s.p0, s.tb + o,
+              s.diag + o * s.n, &s_ta);
+}
+
+// ---- shared chain: W_{k+1} = reduce_order([P G_U | W_k]) materialised -----------------------------
+// PU: [(pU+1)][ldp] rows = P g_U ..., last row = P c_U.  GW/cW in, GWn/cWn out.  pWn = new count.
+static __global__ void glgm06_w_reduce_kernel(const double* __restrict__ PU, int ldp, int pU,
+                                       const double* __restrict__ GW, int ldg, int pW,
+                                       const double* __restrict__ cW, const double* __restrict__ wB,
+                                       const int* __restrict__ permB, const double* __restrict__ bpref,
+                                       int n, int r, int np2, double* __restrict__ GWn, double* __restrict__ cWn,
+                                       int* __restrict__ scratch_pos) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    WKey* keys = reinterpret_cast<WKey*>(smraw);
+    double* sw = reinterpret_cast<double*>(keys + np2);
+    double* sdiag = sw + np2;
+    __shared__ int s_ta, s_tb;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) cWn[i] = PU[size_t(pU) * ldp + i] + cW[i];
+    const int p = pU + pW;
+    if (p <= r * n) {                                   // unchanged: [P G_U | W]
+        for (int idx = threadIdx.x; idx < p * n; idx += blockDim.x) {
+            const int g = idx / n, i = idx % n;
+            GWn[size_t(g) * ldg + i] = g < pU ? PU[size_t(g) * ldp + i] : GW[size_t(g - pU) * ldg + i];
+        }
+        return;
+    }
+    for (int j = threadIdx.x; j < np2; j += blockDim.x) {
+        if (j < pU) {
+            double sum = 0.0, mx = 0.0;
+            for (int i = 0; i < n; ++i) {
+                const double a = fabs(PU[size_t(j) * ldp + i]);
+                sum += a;
+                mx = fmax(mx, a);
+            }
+            keys[j].w = sum - mx;
+            keys[j].idx = j;
+        } else {
+            keys[j].w = INFINITY;
+            keys[j].idx = 0x7fffffff;
+        }
+    }
+    __syncthreads();
+    const int kept = n * (r - 1);
+    gir05_cut(PU, ldp, pU, n, keys, sw, np2, wB, pW, bpref, kept, scratch_pos, &s_tb, sdiag, &s_ta);
+    __syncthreads();
+    const int ta = s_ta, tb = s_tb;
+    // kept own generators
+    for (int j = threadIdx.x; j < pU; j += blockDim.x) {
+        const int pos = scratch_pos[j];
+        if (pos >= 0)
+            for (int i = 0; i < n; ++i) GWn[size_t(pos) * ldg + i] = PU[size_t(j) * ldp + i];
+    }
+    // kept shared generators: sorted position j >= tb lands after the kept own ones with weight <= w_j
+    for (int j = tb + threadIdx.x; j < pW; j += blockDim.x) {
+        const int ub = upper_bound_key(keys, pU, wB[j]);
+        const int pos = (j - tb) + max(0, ub - ta);
+        const double* src = GW + size_t(permB[j]) * ldg;
+        for (int i = 0; i < n; ++i) GWn[size_t(pos) * ldg + i] = src[i];
+    }
+    // the box: n axis-aligned generators
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        const int g = idx / n, i = idx % n;
+        GWn[size_t(kept + g) * ldg + i] = (g == i) ? sdiag[i] : 0.0;
+    }
+}
+
+// ---- stand-alone reduce_order(Z, r, GIR05) for a batch of zonotopes (post.jl:26) ------------------
+// G: [batch][p][ldg] rows = generators.  Out: Gr [batch][r n][ldg], sel [batch][r n] (source index or -1).
+static __global__ void glgm06_reduce_batch_kernel(const double* __restrict__ G, int ldg, int p, int n, int r, int np2,
+                                           double* __restrict__ Gr, int* __restrict__ sel, int* __restrict__ scratch_pos) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    WKey* keys = reinterpret_cast<WKey*>(smraw);
+    double* sw = reinterpret_cast<double*>(keys + np2);
+    double* sdiag = sw + np2;
+    __shared__ int s_ta, s_tb;
+    const int z = blockIdx.x;
+    const double* Gz = G + size_t(z) * p * ldg;
+    double* Go = Gr + size_t(z) * (r * n) * ldg;
+    int* pos = scratch_pos + size_t(z) * p;
+    for (int j = threadIdx.x; j < np2; j += blockDim.x) {
+        if (j < p) {
+            double sum = 0.0, mx = 0.0;
+            for (int i = 0; i < n; ++i) {
+                const double a = fabs(Gz[size_t(j) * ldg + i]);
+                sum += a;
+                mx = fmax(mx, a);
+            }
+            keys[j].w = sum - mx;
+            keys[j].idx = j;
+        } else {
+            keys[j].w = INFINITY;
+            keys[j].idx = 0x7fffffff;
+        }
+    }
+    __syncthreads();
+    const int kept = n * (r - 1);
+    gir05_cut(Gz, ldg, p, n, keys, sw, np2, nullptr, 0, nullptr, kept, pos, &s_tb, sdiag, &s_ta);
+    __syncthreads();
+    for (int j = threadIdx.x; j < p; j += blockDim.x) {
+        const int q = pos[j];
+        if (q >= 0) {
+            for (int i = 0; i < n; ++i) Go[size_t(q) * ldg + i] = Gz[size_t(j) * ldg + i];
+            if (sel) sel[size_t(z) * (r * n) + q] = j;
+        }
+    }
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        const int g = idx / n, i = idx % n;
+        Go[size_t(kept + g) * ldg + i] = (g == i) ? sdiag[i] : 0.0;
+        if (sel && i == 0) sel[size_t(z) * (r * n) + kept + g] = -1;
+    }
+}
+
+// ---- materialise one reduced zonotope (fetch) -----------------------------------------------------
+// Output: Gout [ngens][n] rows = generators (== n x ngens column-major), sel[ngens].
+static __global__ void glgm06_materialize_kernel(const double* __restrict__ A, int lda, int p0,
+                                          const int* __restrict__ pos_own, int tb,
+                                          const double* __restrict__ GW, int ldg, int pW,
+                                          const int* __restrict__ permB, const double* __restrict__ diag,
+                                          int n, int r, double* __restrict__ Gout, int* __restrict__ sel,
+                                          int* __restrict__ occupied /* [ngens] zeroed */) {
+    // single CTA
+    if (tb < 0) {                                       // not reduced: [own | shared] in original order
+        const int p = p0 + pW;
+        for (int idx = threadIdx.x; idx < p * n; idx += blockDim.x) {
+            const int g = idx / n, i = idx % n;
+            Gout[size_t(g) * n + i] = g < p0 ? A[size_t(g) * lda + i] : GW[size_t(g - p0) * ldg + i];
+            if (i == 0) sel[g] = g;
+        }
+        return;
+    }
+    const int kept = n * (r - 1);
+    for (int j = threadIdx.x; j < p0; j += blockDim.x) {
+        const int q = pos_own[j];
+        if (q >= 0) {
+            occupied[q] = 1;
+            sel[q] = j;
+            for (int i = 0; i < n; ++i) Gout[size_t(q) * n + i] = A[size_t(j) * lda + i];
+        }
+    }
+    __syncthreads();
+    // kept shared generators fill the free slots in sorted order (thread 0 walks; counts are small)
+    if (threadIdx.x == 0) {
+        int q = 0;
+        for (int j = tb; j < pW; ++j) {
+            while (q < kept && occupied[q]) ++q;
+            occupied[q] = 2 + j;                        // remember which sorted shared generator
+            ++q;
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < kept; q += blockDim.x) {
+        const int tag = occupied[q];
+        if (tag >= 2) {
+            const int j = tag - 2;
+            const int src = permB[j];
+            sel[q] = p0 + src;
+            for (int i = 0; i < n; ++i) Gout[size_t(q) * n + i] = GW[size_t(src) * ldg + i];
+        }
+    }
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+        const int g = idx / n, i = idx % n;
+        Gout[size_t(kept + g) * n + i] = (g == i) ? diag[i] : 0.0;
+        if (i == 0) sel[kept + g] = -1;
+    }
+}
+
+// ---- support function of every stored zonotope in one direction -----------------------------------
+// Shared part per step: sfx[b][t] = sum over sorted shared generators j >= t of |g_j . d| (t = 0..pW),
+// and for unreduced steps the plain total sits at t = 0.
+static __global__ void glgm06_shared_dots_kernel(const double* __restrict__ GW, long long gw_stride, int ldg,
+                                          const int* __restrict__ pW, const int* __restrict__ permB, int pWcap,
+                                          const double* __restrict__ d, int n, double* __restrict__ sfx) {
+    // one CTA per step; thread 0 does the suffix scan after a parallel dot phase
+    extern __shared__ __align__(16) unsigned char smraw[];
+    double* dots = reinterpret_cast<double*>(smraw);
+    const int b = blockIdx.x;
+    const int pb = pW[b];
+    const double* G = GW + size_t(b) * gw_stride;
+    for (int j = threadIdx.x; j < pb; j += blockDim.x) {
+        const double* g = G + size_t(permB[size_t(b) * pWcap + j]) * ldg;
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += g[i] * d[i];
+        dots[j] = fabs(s);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        sfx[size_t(b) * (pWcap + 1) + pb] = 0.0;
+        for (int j = pb - 1; j >= 0; --j) {
+            s += dots[j];
+            sfx[size_t(b) * (pWcap + 1) + j] = s;
+        }
+    }
+}
+
+struct SupportParams {
+    const double* A; long long a_blk_stride; int lda;
+    int n, p0, nsplits, nblk;
+    const int* pos_own; const int* tb; const double* diag; const double* centre;
+    const double* sfx; int pWcap;
+    const double* d;
+    double* out;            // [nblk+1][nsplits] ; row 0 is step 0 (filled separately)
+};
+static __global__ void glgm06_support_kernel(const SupportParams s) {
+    // one warp per (split, step)
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= s.nsplits * s.nblk) return;
+    const int split = warp % s.nsplits, b = warp / s.nsplits;
+    const size_t o = size_t(b) * s.nsplits + split;
+    const double* A = s.A + size_t(b) * s.a_blk_stride + size_t(split) * (s.p0 + 1) * s.lda;
+    const int tb = s.tb[o];
+    double acc = 0.0;
+    for (int i = lane; i < s.n; i += 32) {
+        acc += s.d[i] * s.centre[o * s.n + i];
+        if (tb >= 0) acc += fabs(s.d[i]) * s.diag[o * s.n + i];
+    }
+    for (int j = lane; j < s.p0; j += 32) {
+        if (tb < 0 || s.pos_own[o * s.p0 + j] >= 0) {
+            double dot = 0.0;
+            for (int i = 0; i < s.n; ++i) dot += A[size_t(j) * s.lda + i] * s.d[i];
+            acc += fabs(dot);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) s.out[size_t(b + 1) * s.nsplits + split] = acc + s.sfx[size_t(b) * (s.pWcap + 1) + (tb < 0 ? 0 : tb)];
+}
+
+// rho(d, Z) for dense zonotopes stored as rows [z][(p+1)][ld] (generators then centre): step 0 and
+// the homogeneous flowpipe.
+static __global__ void zono_support_dense_kernel(const double* __restrict__ Z, long long z_stride, int ld, int p, int n,
+                                          const double* __restrict__ d, int count, double* __restrict__ out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= count) return;
+    const double* z = Z + size_t(warp) * z_stride;
+    double acc = 0.0;
+    for (int j = lane; j <= p; j += 32) {
+        double dot = 0.0;
+        for (int i = 0; i < n; ++i) dot += z[size_t(j) * ld + i] * d[i];
+        acc += j < p ? fabs(dot) : dot;
+    }
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) out[warp] = acc;
+}
+
+}  // namespace reach

@@ -150,7 +150,7 @@ struct Lgg09Combine {
 // ---- combine, phase A: per-block feature totals -----------------------------------------------
 // Ftot[b][q][part][j] = sum over the row tiles of block b of the per-tile partials, in fixed tile
 // order (deterministic).  One thread per (chain j, block b).
-__global__ void lgg09_tilesum_kernel(const Lgg09Combine c, double* __restrict__ ftot) {
+static __global__ void lgg09_tilesum_kernel(const Lgg09Combine c, double* __restrict__ ftot) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = c.b_lo + blockIdx.y;
     if (j >= c.mu || b > c.b_hi) return;
@@ -249,7 +249,7 @@ __global__ void lgg09_eval_kernel(const Lgg09Combine c, const double* __restrict
 // ---- combine, phase C: running input sum, strictly in step order ---------------------------------
 // rho[j,k] = rho(r_k; Omega0) + s_k ;  s_{k+1} = s_k + rho(r_k; V)   (reach_inhomog.jl:56-57).
 // One thread per chain; loads are issued CH steps ahead of the dependent adds.
-__global__ void lgg09_prefix_kernel(const Lgg09Combine c, const double* __restrict__ dv, int nslots,
+static __global__ void lgg09_prefix_kernel(const Lgg09Combine c, const double* __restrict__ dv, int nslots,
                                     long long kfirst) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= c.mu) return;
@@ -284,23 +284,8 @@ __global__ void lgg09_prefix_kernel(const Lgg09Combine c, const double* __restri
     c.s_neg[j] = sn;
 }
 
-// out[r][c] = in[c][r] for an n x n block (in: ld_in, out: ld_out); used once per run to get
-// the row-major copy of Phi that seeds the power stack.
-__global__ void transpose_kernel(const double* __restrict__ in, int ld_in, double* __restrict__ out,
-                                 int ld_out, int n) {
-    __shared__ double tile[32][33];
-    int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 32 + threadIdx.y;
-    for (int dy = 0; dy < 32; dy += 8)
-        if (x < n && y + dy < n) tile[threadIdx.y + dy][threadIdx.x] = in[size_t(y + dy) * ld_in + x];
-    __syncthreads();
-    x = blockIdx.y * 32 + threadIdx.x;
-    y = blockIdx.x * 32 + threadIdx.y;
-    for (int dy = 0; dy < 32; dy += 8)
-        if (x < n && y + dy < n) out[size_t(y + dy) * ld_out + x] = tile[threadIdx.x][threadIdx.y + dy];
-}
-
 // rho(d_j, flowpipe) = max_k rho[j,k]  (Flowpipes/AbstractFlowpipe.jl:35-37); first maximiser.
-__global__ void max_over_steps_kernel(const double* __restrict__ rho, int ndirs, long long nsteps,
+static __global__ void max_over_steps_kernel(const double* __restrict__ rho, int ndirs, long long nsteps,
                                       double* __restrict__ vmax, long long* __restrict__ amax) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= ndirs) return;
@@ -322,7 +307,7 @@ struct InvCheck {
     double div;     // value = rho / div
     double bound;
 };
-__global__ void first_disjoint_kernel(const double* __restrict__ rho, int ndirs, long long nsteps,
+static __global__ void first_disjoint_kernel(const double* __restrict__ rho, int ndirs, long long nsteps,
                                       const InvCheck* __restrict__ checks, int nchecks,
                                       unsigned long long* __restrict__ first) {
     const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;

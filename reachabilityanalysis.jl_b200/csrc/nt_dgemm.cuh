@@ -197,4 +197,19 @@ inline cudaError_t launch_nt_dgemm(const GemmOperands& g, const Epi& epi, cudaSt
     return cudaGetLastError();
 }
 
+// out[r][c] = in[c][r] for an n x n block (in: ld_in, out: ld_out); used once per run to get
+// the row-major copy of Phi that seeds the power stack.
+static __global__ void transpose_kernel(const double* __restrict__ in, int ld_in, double* __restrict__ out,
+                                 int ld_out, int n) {
+    __shared__ double tile[32][33];
+    int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 32 + threadIdx.y;
+    for (int dy = 0; dy < 32; dy += 8)
+        if (x < n && y + dy < n) tile[threadIdx.y + dy][threadIdx.x] = in[size_t(y + dy) * ld_in + x];
+    __syncthreads();
+    x = blockIdx.y * 32 + threadIdx.x;
+    y = blockIdx.x * 32 + threadIdx.y;
+    for (int dy = 0; dy < 32; dy += 8)
+        if (x < n && y + dy < n) out[size_t(y + dy) * ld_out + x] = tile[threadIdx.x][threadIdx.y + dy];
+}
+
 }  // namespace reach
