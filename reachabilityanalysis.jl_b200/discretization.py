@@ -40,8 +40,23 @@ def _dense(A):
     return A.toarray() if sp.issparse(A) else np.asarray(A, dtype=np.float64)
 
 
+_memo = {}
+
+
+def _memoized(kind, A, delta, fn):
+    """Φ and Φ₂ depend only on (A, δ): the split caller (solve.jl:107-117 re-discretizes every
+    split) reuses them across the initial sets of a batch."""
+    key = (kind, A.shape, float(delta), hash(A.tobytes()))
+    if key not in _memo:
+        if len(_memo) > 8:
+            _memo.clear()
+        _memo[key] = fn()
+    return _memo[key]
+
+
 def _exp(A, delta):
-    return scipy.linalg.expm(_dense(A) * delta)
+    A = _dense(A)
+    return _memoized("exp", A, delta, lambda: scipy.linalg.expm(A * delta))
 
 
 def Phi1(A, delta):
@@ -58,11 +73,15 @@ def Phi2(A, delta):
     """Φ₂(A,δ) = Σ δ^{i+2}/(i+2)! A^i via the 3n×3n block exponential (Exponentiation.jl:407-426)."""
     A = _dense(A)
     n = A.shape[0]
-    P = np.zeros((3 * n, 3 * n))
-    P[:n, :n] = A * delta
-    P[:n, n:2 * n] = delta * np.eye(n)
-    P[n:2 * n, 2 * n:] = delta * np.eye(n)
-    return scipy.linalg.expm(P)[:n, 2 * n:]
+
+    def compute():
+        P = np.zeros((3 * n, 3 * n))
+        P[:n, :n] = A * delta
+        P[:n, n:2 * n] = delta * np.eye(n)
+        P[n:2 * n, 2 * n:] = delta * np.eye(n)
+        return scipy.linalg.expm(P)[:n, 2 * n:]
+
+    return _memoized("phi2", A, delta, compute)
 
 
 def normalize_input(B, U0):

@@ -106,3 +106,16 @@ def synthetic_c5(n=2000, delta=0.01, nsteps=10000, seed=0):
     V = S.MinkowskiSum(S.Scale(delta, U), S.Hyperrectangle(np.zeros(n), rpsi))
     Omega0 = S.ConvexHull(X0, S.MinkowskiSum(S.MinkowskiSum(S.LinearMap(Phi, X0), V), Eplus))
     return Workload("C5 synthetic stable LTI n=%d box" % n, Phi, Omega0, V, BoxDirections(n).matrix(), nsteps, delta)
+
+
+def building_c4(nsplits_per_dim=2, nsteps=1000, delta=0.002):
+    """C4: Building BLDF01, X0 split into 2^10 = 1024 boxes along its 10 non-flat leading dimensions
+    (`split(X0, [2×10, 1×38])`, first dimension fastest), GLGM06 with max_order = 10 and the
+    Forward(setops=:zono) model (the literal default FirstOrderZonotope is
+    arithmetically valid but useless at this ‖A‖δ).  Returns (Φ, [Ω₀ per split], V)."""
+    A, B, X0, U0 = building_sets()
+    parts = [nsplits_per_dim] * 10 + [1] * 38
+    splits = S.split(X0, parts)
+    U = D.normalize_input(B, U0)
+    ivps = [D.forward_zono(A, X, delta, U) for X in splits]
+    return ivps[0].Phi, [i.Omega0 for i in ivps], ivps[0].V
