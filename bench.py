@@ -16,10 +16,14 @@ import sys
 import threading
 import time
 
-import numpy as np
-
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# torchrun exports OMP_NUM_THREADS=1; rank 0 also runs the CPU baseline, which must use the host's cores
+if os.environ.get("RANK", "0") == "0":
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
+    os.environ.pop("OPENBLAS_NUM_THREADS", None)
+
+import numpy as np  # noqa: E402  (after the thread-count fix above)
 
 METRIC = "LGG09 support evals/s (dirs x steps)"
 UNIT = "evals/s"

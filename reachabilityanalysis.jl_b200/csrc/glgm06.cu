@@ -28,7 +28,7 @@ cudaError_t launch_tn64(const GemmOperands& g, const Epi& epi, cudaStream_t st) 
 }
 template <class Epi>
 cudaError_t launch_tn128(const GemmOperands& g, const Epi& epi, cudaStream_t st) {
-    return launch_nt_dgemm<2, 4, 8, 4, 4>(g, epi, st);     // 128 x 128 tiles
+    return launch_nt_dgemm_ws<2, 4, 8, 4, 5>(g, epi, st);  // 128 x 128 tiles, warp-specialised
 }
 
 constexpr int kMaxSort = 4096;     // generators ranked by one CTA (shared-memory bitonic sort)

@@ -73,7 +73,7 @@ struct GenEpi {
             }
         }
         if (!psum) return;
-        __syncthreads();
+        tc.sync();
         const int tpb = nb / TN;
         const size_t prow = (size_t(blk) * tpb + cib0 / TN) * m_pad + size_t(tc.tm) * TM;
         for (int ml = tc.tid; ml < TM; ml += tc.nthr) {

@@ -34,7 +34,8 @@ constexpr int kNumCfgs = 4;
 template <class Epi>
 cudaError_t launch_cfg(int cfg, const GemmOperands& g, const Epi& epi, cudaStream_t st) {
     switch (cfg) {
-        case 0: return launch_nt_dgemm<2, 4, 8, 4, 4>(g, epi, st);
+        case 0: return launch_nt_dgemm_ws<2, 4, 8, 4, 5>(g, epi, st);   // warp-specialised, 5-stage bulk-copy ring
+        case 100: return launch_nt_dgemm<2, 4, 8, 4, 4>(g, epi, st);    // v1 (cp.async ring), kept for A/B timing
         case 1: return launch_nt_dgemm<2, 2, 4, 4, 4>(g, epi, st);
         case 2: return launch_nt_dgemm<1, 4, 2, 4, 4>(g, epi, st);
         case 3: return launch_nt_dgemm<2, 4, 4, 4, 4>(g, epi, st);
@@ -254,7 +255,7 @@ namespace {
 // tiles lose a little to shared-memory traffic; every pass costs two launches; building the row
 // stack costs about S + 2 log2(S) passes of an n x n x n product, amortised over the run.
 double step_cost(const reach_lgg09_plan& p, const TileCfg& c, int S, int mu, int nrows, int sms) {
-    static const double eff[kNumCfgs] = {1.0, 0.85, 0.9, 0.92};
+    static const double eff[kNumCfgs] = {1.12, 0.85, 0.9, 0.92};   // cfg 0 is the warp-specialised kernel
     const int mu_pad = round_up(mu, c.TM);
     const int nbe = round_up(nrows, c.TN);
     const double slots = double(sms) * c.occ;
@@ -262,9 +263,9 @@ double step_cost(const reach_lgg09_plan& p, const TileCfg& c, int S, int mu, int
         const double waves = std::ceil(tiles / slots);
         const double mma = double(c.TM) * c.TN * p.Kp / (55.0 * eff[c.id]) * c.occ;
         const double mem = double(c.TM + c.TN) * p.Kp * 8.0 / 40.0 * c.occ;   // ~40 B/clk/SM from L2
-        return waves * (std::max(mma, mem) + 4000.0);
+        return waves * (std::max(mma, mem) + (c.id == 0 ? 12000.0 : 4000.0));   // prologue + epilogue
     };
-    const double launch = 12000.0;                                            // ~6 us per pass
+    const double launch = 60000.0;     // ~30 us per pass: GEMM + tile-sum + eval + prefix launches back to back
     double cost = (pass(double(mu_pad / c.TM) * (double(S) * nbe / c.TN)) + launch) / S;
     // stack build (64x64 tiles, occupancy 2), amortised
     int lg = 0;
@@ -278,16 +279,16 @@ double step_cost(const reach_lgg09_plan& p, const TileCfg& c, int S, int mu, int
 int choose_config(reach_lgg09_plan& p) {
     reach_ctx* ctx = p.ctx;
     const int nrows = p.n + p.ne;
-    int smax = 1;
-    while (smax * 2 <= 256 && int64_t(smax) * 2 <= std::max<int64_t>(1, p.nsteps)) smax *= 2;
+    const int smax = int(std::min<int64_t>(256, std::max<int64_t>(1, p.nsteps)));
     int best_cfg = -1, best_S = 1;
     double best = 1e300;
     for (int ci = 0; ci < kNumCfgs; ++ci) {
         const TileCfg& c = kCfgs[ci];
         if (p.opts.tile_m && p.opts.tile_m != c.TM) continue;
         if (p.opts.tile_n && p.opts.tile_n != c.TN) continue;
-        for (int S = 1; S <= smax; S *= 2) {
+        for (int S = 1; S <= std::max(smax, p.opts.time_block); ++S) {
             if (p.opts.time_block > 0 && S != p.opts.time_block) continue;
+            if (p.opts.time_block == 0 && S > 16 && (S & 3)) continue;        // coarse scan for large S
             const int nbe = round_up(nrows, c.TN);
             const int mu_pad = round_up(p.mu, c.TM);
             const double stack_bytes = double(S + 1) * nbe * p.Kp * 8.0;
@@ -295,13 +296,13 @@ int choose_config(reach_lgg09_plan& p) {
             if (S > 1 && (stack_bytes > 3e9 || feat_bytes > 1e9)) continue;
             const double cost = step_cost(p, c, S, p.mu, nrows, ctx->sm_count);
             // prefer the earlier (larger-tile, smaller-S) candidate unless clearly beaten
-            if (cost < best * 0.97) { best = cost; best_cfg = ci; best_S = S; }
+            if (cost < best * 0.985) { best = cost; best_cfg = ci; best_S = S; }
         }
     }
     if (best_cfg < 0)
         return set_error(ctx, REACH_EINVAL,
                          "no launch configuration matches time_block=%d tile_m=%d tile_n=%d "
-                         "(time_block must be a power of two <= min(256, nsteps); tiles 128x128, 64x64, 16x128, 64x128)",
+                         "(tiles are 128x128, 64x64, 16x128 or 64x128; the row stack must fit 3 GB)",
                          p.opts.time_block, p.opts.tile_m, p.opts.tile_n);
     p.cfg = best_cfg;
     p.S = best_S;
@@ -328,8 +329,8 @@ extern "C" int reach_lgg09_plan_create(reach_ctx* ctx, int n, int ndirs, int64_t
     if (ndirs < 1) return set_error(ctx, REACH_EINVAL, "need at least one template direction, got %d", ndirs);
     if (nsteps < 1) return set_error(ctx, REACH_EINVAL, "NSTEPS must be >= 1, got %lld", (long long)nsteps);
     if (opts && opts->time_block < 0) return set_error(ctx, REACH_EINVAL, "time_block < 0");
-    if (opts && opts->time_block > 0 && (opts->time_block & (opts->time_block - 1)))
-        return set_error(ctx, REACH_EINVAL, "time_block must be a power of two, got %d", opts->time_block);
+    if (opts && opts->time_block > 1024)
+        return set_error(ctx, REACH_EINVAL, "time_block must be <= 1024, got %d", opts->time_block);
     reach_lgg09_plan* p = new (std::nothrow) reach_lgg09_plan;
     if (!p) return set_error(ctx, REACH_ENOMEM, "out of host memory");
     p->ctx = ctx;
@@ -577,10 +578,12 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     REACH_TRY(plain_gemm(block(0), nbe, p->Qbuf[0].as<double>(), n, block(1), nbe));
     int qcur = 0;
     for (int s = 1; s < S; s *= 2) {
+        const int cnt = std::min(s, S - s);              // blocks s+1 .. s+cnt
         // Q_{2s} = Q_s Q_s : X = Q_s rows, Y[b][l] = Q_s[l][b] = P_s[b][l] = first n rows of block_s
-        REACH_TRY(plain_gemm(p->Qbuf[qcur].as<double>(), n, block(s), n, p->Qbuf[1 - qcur].as<double>(), n));
-        // blocks s+1..2s = blocks 1..s * P_s : Y = Q_s
-        REACH_TRY(plain_gemm(block(1), s * nbe, p->Qbuf[qcur].as<double>(), n, block(s + 1), s * nbe));
+        if (2 * s < S)
+            REACH_TRY(plain_gemm(p->Qbuf[qcur].as<double>(), n, block(s), n, p->Qbuf[1 - qcur].as<double>(), n));
+        // blocks s+1..s+cnt = blocks 1..cnt * P_s : Y = Q_s
+        REACH_TRY(plain_gemm(block(1), cnt * nbe, p->Qbuf[qcur].as<double>(), n, block(s + 1), cnt * nbe));
         qcur ^= 1;
     }
 

@@ -100,7 +100,7 @@ struct Lgg09Epi {
             }
             ++qa;
         }
-        __syncthreads();
+        tc.sync();
         // fixed-order sum over the WN warps that share a direction row -> deterministic
         const int nact = qa;
         for (int idx = tc.tid; idx < nact * 2 * TM; idx += tc.nthr) {

@@ -51,13 +51,19 @@ struct GemmOperands {
     int tiles_m, tiles_n;
 };
 
-template <int TM_, int TN_>
+// NAMED_BAR == 0: the whole CTA computes (sync = __syncthreads); otherwise only `nthr` consumer
+// threads reach the epilogue and synchronise on that named barrier (the producer warp is gone).
+template <int TM_, int TN_, int NAMED_BAR = 0>
 struct TileCoord {
     static constexpr int TM = TM_, TN = TN_;
     int tm, tn;        // tile indices
     int wm0, wn0;      // warp origin inside the tile
     int g4, t4;        // lane/4, lane%4
-    int tid, nthr;
+    int tid, nthr;     // thread id among / number of the threads that run the epilogue
+    __device__ __forceinline__ void sync() const {
+        if constexpr (NAMED_BAR == 0) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"n"(NAMED_BAR), "r"(nthr) : "memory");
+    }
 };
 
 template <int WM, int WN, int MT, int NT, int STAGES>
@@ -147,6 +153,164 @@ __global__ void __launch_bounds__(WM* WN * 32, 1) nt_dgemm_kernel(const GemmOper
     tc.wm0 = wm * MT * 8; tc.wn0 = wn * NT * 8;
     tc.g4 = g4; tc.t4 = t4; tc.tid = tid; tc.nthr = NTHR;
     epi.template run<MT, NT, WN>(acc, tc, smem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// v2 main loop: warp-specialised.  A producer warpgroup streams k-tiles into a STAGES-deep ring
+// with cp.async and signals each stage's "full" mbarrier when its copies have landed; WM*WN consumer
+// warps wait on "full", issue DMMAs and arrive on the stage's "empty" mbarrier; setmaxnreg moves
+// the producers' registers to the consumers.  The consumer warps never issue a copy and never meet at
+// a CTA-wide barrier, so the FP64 tensor pipe of a sub-partition only idles when its own data is late.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    const uint32_t a = smem_u32(bar);
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (!ok && ++spins > (1u << 27)) __trap();     // a protocol error must fail, not hang the GPU
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int WM, int WN, int MT, int NT, int STAGES>
+struct GemmShapeWS {
+    static constexpr int TM = WM * MT * 8, TN = WN * NT * 8;
+    // consumers + one producer warpgroup (register reallocation with setmaxnreg works per 4 warps)
+    static constexpr int NCONS = WM * WN * 32, NTHR = NCONS + 128;
+    static constexpr size_t TILE_BYTES = size_t(STAGES) * (TM + TN) * SK * sizeof(double);
+    static constexpr size_t SMEM = TILE_BYTES + 2 * STAGES * sizeof(uint64_t);
+};
+
+template <int WM, int WN, int MT, int NT, int STAGES, class Epi>
+__global__ void __launch_bounds__(WM* WN * 32 + 128, 1) nt_dgemm_ws_kernel(const GemmOperands g, const Epi epi) {
+    using Shape = GemmShapeWS<WM, WN, MT, NT, STAGES>;
+    constexpr int TM = Shape::TM, TN = Shape::TN, NCONS = Shape::NCONS;
+    extern __shared__ __align__(128) double smem[];
+    double* sX = smem;                                  // [STAGES][TM][SK]
+    double* sY = smem + size_t(STAGES) * TM * SK;       // [STAGES][TN][SK]
+    uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(smem) + Shape::TILE_BYTES);
+    uint64_t* empty = full + STAGES;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int tm = blockIdx.x % g.tiles_m;
+    const int tn = blockIdx.x / g.tiles_m;
+    const int KT = g.K / BK;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 128);                   // one deferred arrive per producer thread
+            mbar_init(&empty[s], WM * WN);              // one arrive per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp >= WM * WN) {
+        // ===== producer warpgroup: hands its registers to the DMMA warps and streams the k-tiles =====
+        // 16-byte cp.async (LDGSTS) into the padded rows; each producer thread then lets the stage's
+        // "full" mbarrier count the completion of its own copies (cp.async.mbarrier.arrive.noinc).
+        // (One cp.async.bulk per 128-byte row was measured 3x slower: the copy engine issues one
+        // small bulk copy per ~57 cycles.)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        const int ptid = tid - NCONS;                   // 0..127
+        const double* gX = g.X + size_t(tm) * TM * g.ldx;
+        const double* gY = g.Y + size_t(tn) * TN * g.ldy;
+        for (int kt = 0; kt < KT; ++kt) {
+            const int s = kt % STAGES;
+            const uint32_t ph = (kt / STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);               // slot free (passes immediately on the first lap)
+            double* dx = sX + size_t(s) * TM * SK;
+            double* dy = sY + size_t(s) * TN * SK;
+            const double* sx = gX + size_t(kt) * BK;
+            const double* sy = gY + size_t(kt) * BK;
+#pragma unroll
+            for (int c = ptid; c < TM * 8; c += 128) {
+                const int r = c >> 3, ch = c & 7;
+                cp_async16(dx + r * SK + ch * 2, sx + size_t(r) * g.ldx + ch * 2);
+            }
+#pragma unroll
+            for (int c = ptid; c < TN * 8; c += 128) {
+                const int r = c >> 3, ch = c & 7;
+                cp_async16(dy + r * SK + ch * 2, sy + size_t(r) * g.ldy + ch * 2);
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[s])) : "memory");
+        }
+        return;
+    }
+
+    // ===== consumer warps =====
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    const int wm = warp % WM, wn = warp / WM;
+    const int g4 = lane >> 2, t4 = lane & 3;
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int kt = 0; kt < KT; ++kt) {
+        const int s = kt % STAGES;
+        const uint32_t ph = (kt / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        const double* x = sX + (size_t(s) * TM + wm * MT * 8 + g4) * SK + t4;
+        const double* y = sY + (size_t(s) * TN + wn * NT * 8 + g4) * SK + t4;
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 4; ++k4) {
+            double a[MT], b[NT];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) a[i] = x[i * 8 * SK + k4 * 4];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) b[j] = y[j * 8 * SK + k4 * 4];
+#pragma unroll
+            for (int i = 0; i < MT; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);          // this warp is done reading stage s
+    }
+
+    TileCoord<TM, TN, 1> tc;
+    tc.tm = tm; tc.tn = tn;
+    tc.wm0 = wm * MT * 8; tc.wn0 = wn * NT * 8;
+    tc.g4 = g4; tc.t4 = t4; tc.tid = tid; tc.nthr = NCONS;
+    tc.sync();                                          // every consumer is past the main loop: smem is free
+    epi.template run<MT, NT, WN>(acc, tc, smem);
+}
+
+template <int WM, int WN, int MT, int NT, int STAGES, class Epi>
+inline cudaError_t launch_nt_dgemm_ws(const GemmOperands& g, const Epi& epi, cudaStream_t stream) {
+    using Shape = GemmShapeWS<WM, WN, MT, NT, STAGES>;
+    auto kern = nt_dgemm_ws_kernel<WM, WN, MT, NT, STAGES, Epi>;
+    static thread_local int configured_dev = -1;
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (configured_dev != dev) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Shape::SMEM));
+        if (e != cudaSuccess) return e;
+        configured_dev = dev;
+    }
+    if (g.tiles_m <= 0 || g.tiles_n <= 0) return cudaSuccess;
+    kern<<<g.tiles_m * g.tiles_n, Shape::NTHR, Shape::SMEM, stream>>>(g, epi);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------

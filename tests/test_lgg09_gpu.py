@@ -29,7 +29,7 @@ def random_sets(n, seed):
 
 
 @pytest.mark.parametrize("n,ndirs,nsteps", [(1, 2, 7), (5, 10, 40), (13, 7, 33), (48, 96, 64), (100, 37, 50)])
-@pytest.mark.parametrize("S", [1, 4])
+@pytest.mark.parametrize("S", [1, 4, 7])
 def test_random_forward_inhomog(ctx, n, ndirs, nsteps, S):
     A, _ = stable_system(n, n)
     X0, U, _ = random_sets(n, n)
@@ -200,7 +200,7 @@ def test_error_behaviour(ctx):
     with pytest.raises(ValueError):
         reach_homog_LGG09(np.eye(3), rb.Universe(3), Phi, 5, ctx=ctx)
     with pytest.raises(ValueError):
-        reach_homog_LGG09(np.eye(3), X0, Phi, 5, ctx=ctx, time_block=3)
+        reach_homog_LGG09(np.eye(3), X0, Phi, 5, ctx=ctx, time_block=4096)
     bad = Phi.copy()
     bad[0, 0] = np.nan
     with pytest.raises(ValueError):
