@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -49,6 +50,7 @@ struct reach_glgm06_plan {
     int pWcap = 0, lda = 0, tpb = 1;
     std::vector<int> pW;    // shared generator count used at block b (size nblk + 1)
     bool uploaded = false, ran = false;
+    bool force_stepwise = false;   // REACH_GLGM06_CHAIN=stepwise: use the per-step kernels even for small n (tests)
 
     DevBuf phi_cm, PhiT, PhiRows;       // column-major copy; rows = columns of Phi; rows = rows of Phi
     DevBuf Xown;                        // [m_pad][Kp]
@@ -110,6 +112,10 @@ extern "C" int reach_glgm06_plan_create(reach_ctx* ctx, int n, int64_t nsteps, i
     p->m_pad = round_up(p->M, 128);
     p->nblk = nsteps - 1;
     p->lda = round_up(n, 2);
+    {
+        const char* env = getenv("REACH_GLGM06_CHAIN");
+        p->force_stepwise = env && std::strcmp(env, "stepwise") == 0;
+    }
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e == cudaSuccess) e = cudaEventCreate(&p->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&p->ev1);
@@ -315,6 +321,35 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
     const size_t pblk = size_t(nb) * Kp;
     if (nblk > 0)   // P_0 = Phi (rows of Phi)
         REACH_CUDA(ctx, cudaMemcpyAsync(Pst, p->PhiRows.p, pblk * 8, cudaMemcpyDeviceToDevice, st));
+    // small n: the whole chain runs in one persistent CTA with P_k and Phi in shared memory
+    bool fused = n <= 64 && p->pU + 1 <= 256 && p->pWcap <= 2048 && nblk > 0 && !p->force_stepwise;
+    size_t chain_smem = 0;
+    if (fused) {
+        int np2 = 32;
+        while (np2 < p->pU) np2 <<= 1;
+        const size_t ldp = n + 1;
+        chain_smem = 8 * (3 * n * ldp + 2 * size_t(p->pU + 1) * ldp + 3 * size_t(p->pWcap) + np2 + n + 16 * size_t(n)) +
+                     16 * size_t(np2) + 4 * (2 * size_t(p->pWcap)) + 64;
+        if (chain_smem > ctx->smem_optin) fused = false;
+    }
+    if (fused) {
+        ChainParams c{};
+        c.n = n; c.ldk = Kp; c.nb = nb; c.pU = p->pU; c.r = r; c.pWcap = p->pWcap; c.nblk = nblk;
+        c.PhiT = p->PhiT.as<double>();
+        c.P0 = p->PhiRows.as<double>();
+        c.XU = p->XU.as<double>();
+        c.Pstack = Pst;
+        c.GWall = p->GWall.as<double>();
+        c.cWall = p->cWall.as<double>();
+        c.pW = p->pWdev.as<int>();
+        c.wB = p->wB.as<double>();
+        c.permB = p->permB.as<int>();
+        c.bpref = p->bpref.as<double>();
+        REACH_CUDA(ctx, cudaFuncSetAttribute(glgm06_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(chain_smem)));
+        glgm06_chain_kernel<<<1, 1024, chain_smem, st>>>(c);
+        REACH_CUDA(ctx, cudaGetLastError());
+        ++p->launches;
+    } else {
     const int urows = round_up(p->pU + 1, 64);
     const size_t gw_stride = size_t(p->pWcap) * n;
     for (int64_t b = 0; b < nblk; ++b) {
@@ -348,6 +383,8 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
         }
         if (b + 1 < nblk)   // P_{b+1} = P_b Phi : Y[m][l] = Phi(l, m) = rows of PhiT (mul!(cache, P, Phi), reach_inhomog.jl:38)
             REACH_TRY(gemm_store(Pst + b * pblk, n, p->PhiT.as<double>(), n, Pst + (b + 1) * pblk, Kp, n, n));
+    }
+
     }
 
     // ---- (2) batched part: all splits x all steps ----

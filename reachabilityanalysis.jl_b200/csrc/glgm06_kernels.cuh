@@ -329,6 +329,224 @@ static __global__ void glgm06_w_reduce_kernel(const double* __restrict__ PU, int
     }
 }
 
+// ---- shared chain, fused: ONE persistent CTA walks all steps (small n) -----------------------------
+// For n <= 64 (Building: n = 48) the whole per-step state of the shared chain -- P_k, Phi, [G_U|c_U],
+// the sorted weights of W_k -- fits in shared memory, and one step is ~10^5 FMAs: launching four
+// kernels per step costs far more than the arithmetic.  This kernel keeps P_k and Phi on chip for the
+// entire run and performs, per step: store P_k; P_k [G_U|c_U]; GIR05 cut of [P_k G_U | W_k]; W_{k+1}
+// materialised (global, L2-resident); the sorted order of W_{k+1} WITHOUT sorting (kept generators are
+// already ascending, the n box generators have weight exactly 0 and slot in after the zero-weight kept
+// ones -- the stable (weight, index) order); the prefix table of |W_{k+1}|; P_{k+1} = P_k Phi.
+struct ChainParams {
+    int n, ldk, nb;             // ldk = Kp (row pitch of Phi/P/XU buffers), nb = rows per P block
+    int pU, r, pWcap;
+    long long nblk;
+    const double* PhiT;         // [n][ldk] rows = columns of Phi
+    const double* P0;           // [n][ldk] rows of Phi (= P_0)
+    const double* XU;           // [(pU+1)][ldk]
+    double* Pstack;             // [nblk][nb][ldk]
+    double* GWall;              // [(nblk+1)][pWcap][n]
+    double* cWall;              // [(nblk+1)][n]
+    const int* pW;              // [nblk+1]
+    double* wB;                 // [nblk][pWcap]
+    int* permB;                 // [nblk][pWcap]
+    double* bpref;              // [nblk][(pWcap+1)][n]
+};
+
+static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const ChainParams c) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int n = c.n, pU = c.pU, ldp = n + 1;
+    const int np2 = [&] { int p = 32; while (p < pU) p <<= 1; return p; }();
+    // carve shared memory
+    double* sP[2];
+    sP[0] = reinterpret_cast<double*>(smraw);
+    sP[1] = sP[0] + n * ldp;
+    double* sPhiT = sP[1] + n * ldp;                  // [n][ldp]: sPhiT[m][l] = Phi(l, m)
+    double* sXU = sPhiT + n * ldp;                    // [(pU+1)][ldp]
+    double* sPU = sXU + (pU + 1) * ldp;               // [(pU+1)][ldp]
+    double* swB[2];
+    swB[0] = sPU + (pU + 1) * ldp;                    // sorted weights of the current / next W
+    swB[1] = swB[0] + c.pWcap;
+    double* swm = swB[1] + c.pWcap;                   // weights of the kept generators in merged order
+    double* sw = swm + c.pWcap;                       // sorted own weights [np2]
+    double* sdiag = sw + np2;                         // [n]
+    double* sseg = sdiag + n;                         // [n][NSEG] segment totals for the prefix table
+    constexpr int NSEG = 16;
+    WKey* keys = reinterpret_cast<WKey*>(sseg + n * NSEG);      // [np2]
+    int* sperm[2];
+    sperm[0] = reinterpret_cast<int*>(keys + np2);
+    sperm[1] = sperm[0] + c.pWcap;
+    __shared__ int s_ta, s_z;
+
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int idx = tid; idx < n * n; idx += nthr) {
+        const int a = idx / n, b = idx % n;
+        sP[0][a * ldp + b] = c.P0[size_t(a) * c.ldk + b];
+        sPhiT[a * ldp + b] = c.PhiT[size_t(a) * c.ldk + b];
+    }
+    for (int idx = tid; idx < (pU + 1) * n; idx += nthr) {
+        const int g = idx / n, l = idx % n;
+        sXU[g * ldp + l] = c.XU[size_t(g) * c.ldk + l];
+    }
+    __syncthreads();
+
+    // sorted order of W_0 = U: a real sort (once)
+    int cur = 0;
+    {
+        const int pW0 = c.pW[0];
+        const double* GW = c.GWall;
+        // reuse the bitonic sorter in chunks of np2w keys held in the `swm`/`sperm[1]` area is not possible
+        // (WKey storage), so sort through global scratch when pW0 > np2: W_0 has pU generators, pU <= np2.
+        for (int j = tid; j < np2; j += nthr) {
+            if (j < pW0) {
+                double s = 0.0, mx = 0.0;
+                for (int i = 0; i < n; ++i) { const double a = fabs(GW[size_t(j) * n + i]); s += a; mx = fmax(mx, a); }
+                keys[j].w = s - mx; keys[j].idx = j;
+            } else { keys[j].w = INFINITY; keys[j].idx = 0x7fffffff; }
+        }
+        __syncthreads();
+        bitonic_sort(keys, np2);
+        for (int j = tid; j < pW0; j += nthr) { swB[0][j] = keys[j].w; sperm[0][j] = keys[j].idx; }
+        __syncthreads();
+    }
+
+    for (long long b = 0; b < c.nblk; ++b) {
+        const int pWb = c.pW[b];
+        const double* P = sP[b & 1];
+        double* Pn = sP[(b + 1) & 1];
+        const double* GW = c.GWall + size_t(b) * c.pWcap * n;
+        double* GWn = c.GWall + size_t(b + 1) * c.pWcap * n;
+        const double* wBc = swB[cur];
+        const int* permc = sperm[cur];
+        double* bprefb = c.bpref + size_t(b) * (c.pWcap + 1) * n;
+
+        // (a) publish P_b, the sorted weights / permutation of W_b, and the prefix table of |W_b|
+        {
+            double* Pg = c.Pstack + size_t(b) * c.nb * c.ldk;
+            for (int idx = tid; idx < n * n; idx += nthr) Pg[size_t(idx / n) * c.ldk + idx % n] = P[(idx / n) * ldp + idx % n];
+            for (int j = tid; j < pWb; j += nthr) {
+                c.wB[size_t(b) * c.pWcap + j] = wBc[j];
+                c.permB[size_t(b) * c.pWcap + j] = permc[j];
+            }
+            // prefix over the sorted order, two-level: NSEG segments per coordinate
+            const int seglen = (pWb + NSEG - 1) / NSEG;
+            for (int idx = tid; idx < n * NSEG; idx += nthr) {
+                const int i = idx % n, sg = idx / n;
+                double s = 0.0;
+                const int t1 = min(pWb, (sg + 1) * seglen);
+                for (int t = sg * seglen; t < t1; ++t) s += fabs(GW[size_t(permc[t]) * n + i]);
+                sseg[i * NSEG + sg] = s;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < n * NSEG; idx += nthr) {
+                const int i = idx % n, sg = idx / n;
+                double s = 0.0;
+                for (int q = 0; q < sg; ++q) s += sseg[i * NSEG + q];
+                if (sg == 0) bprefb[i] = 0.0;
+                const int t1 = min(pWb, (sg + 1) * seglen);
+                for (int t = sg * seglen; t < t1; ++t) {
+                    s += fabs(GW[size_t(permc[t]) * n + i]);
+                    bprefb[size_t(t + 1) * n + i] = s;
+                }
+            }
+        }
+        if (b + 1 >= c.nblk) break;                      // W_{nblk} and P_{nblk} are never used
+
+        // (b) P_b [G_U | c_U]  and  P_{b+1} = P_b Phi
+        for (int idx = tid; idx < (pU + 1) * n; idx += nthr) {
+            const int g = idx / n, i = idx % n;
+            double s = 0.0;
+            for (int l = 0; l < n; ++l) s = fma(sXU[g * ldp + l], P[i * ldp + l], s);
+            sPU[g * ldp + i] = s;
+        }
+        for (int idx = tid; idx < n * n; idx += nthr) {
+            const int i = idx / n, m = idx % n;
+            double s = 0.0;
+            for (int l = 0; l < n; ++l) s = fma(P[i * ldp + l], sPhiT[m * ldp + l], s);
+            Pn[i * ldp + m] = s;
+        }
+        __syncthreads();
+        // centre of W_{b+1}
+        for (int i = tid; i < n; i += nthr) c.cWall[size_t(b + 1) * n + i] = sPU[pU * ldp + i] + c.cWall[size_t(b) * n + i];
+
+        // (c) own weights, sorted
+        for (int j = tid; j < np2; j += nthr) {
+            if (j < pU) {
+                double s = 0.0, mx = 0.0;
+                for (int i = 0; i < n; ++i) { const double a = fabs(sPU[j * ldp + i]); s += a; mx = fmax(mx, a); }
+                keys[j].w = s - mx; keys[j].idx = j;
+            } else { keys[j].w = INFINITY; keys[j].idx = 0x7fffffff; }
+        }
+        __syncthreads();
+        bitonic_sort(keys, np2);
+        for (int i = tid; i < pU; i += nthr) sw[i] = keys[i].w;
+        if (tid == 0) { s_ta = 0; s_z = 0; }
+        __syncthreads();
+
+        const int p = pU + pWb;
+        const bool reduce = p > c.r * n;
+        const int kept = reduce ? n * (c.r - 1) : p;
+        const int m = p - kept;
+        // (d) the cut: own generator at sorted position i has union rank i + #{shared with smaller weight}
+        if (reduce)
+            for (int i = tid; i < pU; i += nthr)
+                if (i + lower_bound_d(wBc, pWb, sw[i]) < m) atomicMax(&s_ta, i + 1);
+        __syncthreads();
+        const int ta = s_ta, tb = m - ta;
+        // (e) W_{b+1}: kept generators in merged (weight, index) order, then the box
+        for (int i = ta + (tid >> 5); i < pU; i += (nthr >> 5)) {           // one warp per generator row
+            const int pos = (i - ta) + max(0, lower_bound_d(wBc, pWb, sw[i]) - tb);
+            const int src = keys[i].idx;
+            for (int q = tid & 31; q < n; q += 32) GWn[size_t(pos) * n + q] = sPU[src * ldp + q];
+            if ((tid & 31) == 0) { swm[pos] = sw[i]; sperm[1 - cur][pos] = reduce ? pos : src; }
+        }
+        for (int j = tb + (tid >> 5); j < pWb; j += (nthr >> 5)) {
+            const int pos = (j - tb) + max(0, upper_bound_key(keys, pU, wBc[j]) - ta);
+            const double* src = GW + size_t(permc[j]) * n;
+            for (int q = tid & 31; q < n; q += 32) GWn[size_t(pos) * n + q] = src[q];
+            if ((tid & 31) == 0) { swm[pos] = wBc[j]; sperm[1 - cur][pos] = reduce ? pos : pU + permc[j]; }
+        }
+        if (reduce) {
+            for (int i = tid; i < n; i += nthr) {
+                double s = 0.0;
+                for (int t = 0; t < ta; ++t) s += fabs(sPU[keys[t].idx * ldp + i]);
+                sdiag[i] = s + bprefb[size_t(tb) * n + i];
+            }
+        }
+        __syncthreads();
+        if (!reduce) {
+            // unreduced W_{b+1} = [P G_U | W_b] keeps its ORIGINAL column order; only the sort order is merged.
+            // Rewrite the generators in original order (own first, then shared).
+            for (int idx = tid; idx < p * n; idx += nthr) {
+                const int g = idx / n, q = idx % n;
+                GWn[size_t(g) * n + q] = g < pU ? sPU[g * ldp + q] : GW[size_t(g - pU) * n + q];
+            }
+            for (int t = tid; t < p; t += nthr) swB[1 - cur][t] = swm[t];
+        } else {
+            for (int idx = tid; idx < n * n; idx += nthr) {
+                const int g = idx / n, i = idx % n;
+                GWn[size_t(kept + g) * n + i] = (g == i) ? sdiag[i] : 0.0;
+            }
+            // stable order of [kept ascending | n zero-weight box generators]:
+            //   zero-weight kept (z of them), then the box, then the rest
+            for (int t = tid; t < kept; t += nthr)
+                if (swm[t] == 0.0) atomicMax(&s_z, t + 1);
+            __syncthreads();
+            const int z = s_z;
+            for (int t = tid; t < kept + n; t += nthr) {
+                int src;                                  // column of W_{b+1} at sorted position t
+                if (t < z) src = t;
+                else if (t < z + n) src = kept + (t - z);
+                else src = t - n;
+                sperm[1 - cur][t] = src;
+                swB[1 - cur][t] = src < kept ? swm[src] : 0.0;
+            }
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+}
+
 // ---- stand-alone reduce_order(Z, r, GIR05) for a batch of zonotopes (post.jl:26) ------------------
 // G: [batch][p][ldg] rows = generators.  Out: Gr [batch][r n][ldg], sel [batch][r n] (source index or -1).
 static __global__ void glgm06_reduce_batch_kernel(const double* __restrict__ G, int ldg, int p, int n, int r, int np2,
