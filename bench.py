@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--time-block", type=int, default=0)
     ap.add_argument("--cpu-sample-steps", type=int, default=0, help="time steps of the CPU sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-glgm06", action="store_true", help="skip the GLGM06 C4 flowpipe wall-time leg")
+    ap.add_argument("--glgm06-steps", type=int, default=500)
     return ap.parse_args()
 
 
@@ -170,6 +172,44 @@ def cublas_fp64_peak(torch, nn=8192, iters=6):
     return best
 
 
+def glgm06_leg(args, ctx, torch, dist, world, rank):
+    """Second half of the metric: GLGM06 flowpipe wall-time on config C4 (Building, 1024 initial-set
+    splits, max_order 10, Forward(:zono) model), splits sharded over the ranks, no collective."""
+    from reach_b200 import workloads as W
+    from reach_b200.glgm06 import _run_batch, GLGM06
+    nsteps = args.glgm06_steps
+    Phi, Oms, V = W.building_c4(2, nsteps)
+    per = (len(Oms) + world - 1) // world
+    mine = Oms[rank * per:(rank + 1) * per]
+    plan = _run_batch(GLGM06(δ=0.002, max_order=10), Phi, mine, V, nsteps, ctx)       # warm-up run
+    ms = []
+    for _ in range(3):
+        if world > 1:
+            dist.barrier()
+        plan.run()
+        ms.append(plan.stats()["ms"])
+    t = min(ms)
+    if world > 1:
+        tt = torch.tensor([t], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt.item())
+    st = plan.stats()
+    out = {"workload": "C4 Building GLGM06 max_order=10, Forward(setops=:zono), %d splits x %d steps" % (len(Oms), nsteps),
+           "flowpipe_wall_ms": t, "zonotopes_per_s": len(Oms) * nsteps / (t * 1e-3), "splits_per_gpu": len(mine),
+           "generators_per_zonotope": 480, "launches": st["launches"], "bytes_stored_per_gpu": st["bytes_stored"],
+           "timer": "CUDA events around the run on the library stream, best of 3, max over ranks"}
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import glgm06_oracle as GO
+        k = min(100, nsteps)
+        t0 = time.perf_counter()
+        GO.post_GLGM06(Phi, Oms[0], k, 10, V)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"zonotopes_per_s": k / dt, "cores": 1, "kind": "port",
+                               "sample": "1 split x %d steps (NumPy restatement of reach_inhomog_GLGM06!)" % k}
+    plan.close()
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -285,6 +325,8 @@ def run_b200(args):
     # e2e result must be the same numbers as the device-resident run
     same = bool(np.array_equal(rho_h, out_T.cpu().numpy()))
 
+    glgm06 = None if args.no_glgm06 else glgm06_leg(args, ctx, torch, dist, world, rank)
+
     if rank == 0:
         S = st["time_block"]
         gemm_ms = gemm_ms_acc / args.steps                                  # mean duration of one launch
@@ -316,6 +358,8 @@ def run_b200(args):
                          "gemm_share_of_step": st["gemm_launches"] * gemm_ms / (total_ms / args.steps),
                          "traffic": None},
         }
+        if glgm06 is not None:
+            line["glgm06_c4"] = glgm06
         if not args.no_cpu_baseline:
             sample = args.cpu_sample_steps or auto_sample_steps(wl)
             ref, dt = cpu_reference_sample(wl, sample)
