@@ -119,7 +119,11 @@ typedef struct {
                              (noted at reach_homog.jl:108-110); results are bit-identical     */
     int32_t tile_m;       /* 0 = auto; else force the direction-tile size (testing)           */
     int32_t tile_n;       /* 0 = auto; else force the row-tile size (testing)                 */
-    int32_t reserved[4];
+    int32_t path;         /* 0 = auto; 1 = batched GEMM over the power stack; 2 = persistent
+                             warp-per-chain kernel (Phi' in shared memory, ELL form: small or
+                             sparse Phi, e.g. ISS -- the device analogue of `sparse=true`,
+                             LGG09/post.jl:25-27; strictly sequential association)            */
+    int32_t reserved[3];
 } reach_lgg09_opts;
 
 void reach_lgg09_default_opts(reach_lgg09_opts* o);

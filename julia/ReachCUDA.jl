@@ -25,8 +25,8 @@ struct ReachSetExpr
     terms::Ptr{ReachTerm}
 end
 struct ReachLGG09Opts
-    time_block::Int32; share_negated::Int32; tile_m::Int32; tile_n::Int32
-    reserved::NTuple{4,Int32}
+    time_block::Int32; share_negated::Int32; tile_m::Int32; tile_n::Int32; path::Int32
+    reserved::NTuple{3,Int32}
 end
 
 mutable struct Ctx

@@ -37,7 +37,7 @@ class reach_invariant(C.Structure):
 
 class reach_lgg09_opts(C.Structure):
     _fields_ = [("time_block", C.c_int32), ("share_negated", C.c_int32), ("tile_m", C.c_int32),
-                ("tile_n", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("tile_n", C.c_int32), ("path", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 # name -> (restype, argtypes); every symbol include/reach.h declares

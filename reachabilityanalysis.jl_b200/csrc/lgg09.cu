@@ -233,6 +233,11 @@ struct reach_lgg09_plan {
     DevBuf first_bad;      // unsigned long long
     int64_t nsteps_done = 0;
     DevBuf phi_cm;         // n x n column-major copy of Phi (source of the transpose)
+    // persistent warp-per-chain path (small / sparse Phi)
+    bool use_chain = false;
+    int ch_maxnnz = 0, ch_rpl = 0, ch_ne = 0;
+    size_t ch_smem = 0;
+    DevBuf ell_val, ell_col, Edev;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> gemm_ev;   // pairs around sampled main-loop GEMM launches
@@ -249,6 +254,32 @@ struct reach_lgg09_plan {
 };
 
 namespace {
+
+template <int RPL, int NE>
+int launch_chain_t(reach_ctx* ctx, const Lgg09Chain& c, size_t smem, cudaStream_t st) {
+    auto kern = lgg09_chain_kernel<RPL, 4, NE>;
+    REACH_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    kern<<<(c.mu + 3) / 4, 128, smem, st>>>(c);
+    REACH_CUDA(ctx, cudaGetLastError());
+    return REACH_OK;
+}
+template <int RPL>
+int launch_chain_r(reach_ctx* ctx, int ne, const Lgg09Chain& c, size_t smem, cudaStream_t st) {
+    if (ne == 0) return launch_chain_t<RPL, 0>(ctx, c, smem, st);
+    if (ne == 4) return launch_chain_t<RPL, 4>(ctx, c, smem, st);
+    return launch_chain_t<RPL, 8>(ctx, c, smem, st);
+}
+int launch_chain(reach_ctx* ctx, int rpl, int ne, const Lgg09Chain& c, size_t smem, cudaStream_t st) {
+    switch (rpl) {
+#define REACH_CHAIN_CASE(R) case R: return launch_chain_r<R>(ctx, ne, c, smem, st);
+        REACH_CHAIN_CASE(1) REACH_CHAIN_CASE(2) REACH_CHAIN_CASE(3) REACH_CHAIN_CASE(4)
+        REACH_CHAIN_CASE(5) REACH_CHAIN_CASE(6) REACH_CHAIN_CASE(7) REACH_CHAIN_CASE(8)
+        REACH_CHAIN_CASE(9) REACH_CHAIN_CASE(10) REACH_CHAIN_CASE(11) REACH_CHAIN_CASE(12)
+        REACH_CHAIN_CASE(13) REACH_CHAIN_CASE(14) REACH_CHAIN_CASE(15) REACH_CHAIN_CASE(16)
+#undef REACH_CHAIN_CASE
+    }
+    return set_error(ctx, REACH_EINVAL, "bad rows-per-lane %d", rpl);
+}
 
 // Cost model (SM cycles per time step) used to pick the tile shape and the time block S.
 // Calibrated on B200: a 128x128x2000 tile takes ~0.31 ms (~55 FP64 FMA/clk/SM sustained); smaller
@@ -418,6 +449,49 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
     p->mu = int(chains.size());
 
     REACH_TRY(choose_config(*p));
+    // ---- small / sparse Phi: ELL form of Phi' (row i of Phi' = column i of Phi) ----
+    std::vector<double> ell_val;
+    std::vector<int> ell_col;
+    p->use_chain = false;
+    const bool forced_gemm = p->opts.path == 1 || (p->opts.path == 0 && (p->opts.time_block > 0 || p->opts.tile_m || p->opts.tile_n));
+    if (!forced_gemm && n <= 512 && p->nq <= 4 && p->ne <= 8) {
+        int maxnnz = 0;
+        for (int i = 0; i < n; ++i) {
+            int cnt = 0;
+            for (int l = 0; l < n; ++l) cnt += Phi[size_t(i) * n + l] != 0.0;
+            maxnnz = std::max(maxnnz, cnt);
+        }
+        maxnnz = std::max(maxnnz, 1);
+        const int rpl = (n + 31) / 32;
+        const int npad = rpl * 32, nep = p->ne == 0 ? 0 : (p->ne <= 4 ? 4 : 8);
+        const size_t smem = size_t(maxnnz) * npad * 12 + size_t(8 + nep) * npad * 8 + size_t(4) * 2 * npad * 8;
+        // cycles per time step: sequential FMA chains (RPL interleaved) + feature reduction
+        const double chain_cycles = 400.0 + rpl * (22.0 * maxnnz + 170.0);      // measured on Building / ISS
+        const double waves = std::ceil(double(p->mu) / (ctx->sm_count * 16.0));
+        const double chain_cost = waves * chain_cycles;
+        const double gemm_cost = step_cost(*p, kCfgs[p->cfg], p->S, p->mu, n + p->ne, ctx->sm_count);
+        if (smem <= ctx->smem_optin && (p->opts.path == 2 || chain_cost < gemm_cost)) {
+            p->use_chain = true;
+            p->ch_maxnnz = maxnnz;
+            p->ch_rpl = rpl;
+            p->ch_ne = nep;
+            p->ch_smem = smem;
+            ell_val.assign(size_t(maxnnz) * npad, 0.0);
+            ell_col.assign(size_t(maxnnz) * npad, 0);
+            for (int i = 0; i < n; ++i) {
+                int z = 0;
+                for (int l = 0; l < n; ++l) {
+                    const double v = Phi[size_t(i) * n + l];       // Phi(l, i) = Phi'(i, l)
+                    if (v != 0.0) { ell_val[size_t(z) * npad + i] = v; ell_col[size_t(z) * npad + i] = l; ++z; }
+                }
+            }
+            p->S = 1;
+        }
+    }
+    if (p->opts.path == 2 && !p->use_chain)
+        return set_error(ctx, REACH_EUNSUPPORTED,
+                         "the persistent chain kernel needs n <= 512, <= 4 support features, <= 8 mapped rows and Phi' "
+                         "in ELL form within shared memory (n=%d, features=%d, mapped rows=%d)", n, p->nq, p->ne);
     const int TM = p->TM, TN = p->TN, S = p->S;
     p->mu_pad = round_up(p->mu, TM);
     p->nbe = round_up(n + p->ne, TN);
@@ -451,6 +525,17 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
         p->rho = p->rho_own.as<double>();
     }
 
+    if (p->use_chain) {
+        REACH_TRY(p->ell_val.alloc(ctx, ell_val.size() * 8, false));
+        REACH_TRY(p->ell_col.alloc(ctx, ell_col.size() * 4, false));
+        REACH_CUDA(ctx, cudaMemcpyAsync(p->ell_val.p, ell_val.data(), ell_val.size() * 8, cudaMemcpyHostToDevice, st));
+        REACH_CUDA(ctx, cudaMemcpyAsync(p->ell_col.p, ell_col.data(), ell_col.size() * 4, cudaMemcpyHostToDevice, st));
+        std::vector<double> E(size_t(std::max(1, p->ne)) * n, 0.0);
+        for (int e = 0; e < p->ne; ++e) std::memcpy(&E[size_t(e) * n], p->prog.erows[e].data(), sizeof(double) * n);
+        REACH_TRY(p->Edev.alloc(ctx, E.size() * 8, false));
+        REACH_CUDA(ctx, cudaMemcpyAsync(p->Edev.p, E.data(), E.size() * 8, cudaMemcpyHostToDevice, st));
+        REACH_CUDA(ctx, cudaStreamSynchronize(st));
+    }
     // ---- host staging + H2D ----
     // Phi: column-major n x n.  Row k of the row-major Phi (the seed Q_1) is produced on the
     // device by a transpose at run time; here we only ship the matrix.
@@ -555,6 +640,45 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
 
     REACH_CUDA(ctx, cudaEventRecord(p->ev0, st));
 
+    if (p->use_chain) {
+        Lgg09Chain c{};
+        c.prog = p->prog.dev;
+        c.n = n;
+        c.npad = p->ch_rpl * 32;
+        c.maxnnz = p->ch_maxnnz;
+        c.ell_val = p->ell_val.as<double>();
+        c.ell_col = p->ell_col.as<int>();
+        c.Wl = p->Wl.as<double>();
+        c.Wa = p->Wa.as<double>();
+        c.wstride = nbe;
+        c.nq = p->nq;
+        c.ne = p->ne;
+        c.E = p->Edev.as<double>();
+        c.L0 = p->L0.as<double>();
+        c.ldl = Kp;
+        c.mu = p->mu;
+        c.nsteps = p->nsteps;
+        c.need_next = p->prog.need_next ? 1 : 0;
+        c.row_pos = p->row_pos.as<int>();
+        c.row_neg = p->row_neg.as<int>();
+        c.rho = p->rho;
+        c.ndirs = p->ndirs;
+        REACH_TRY(launch_chain(ctx, p->ch_rpl, p->ch_ne, c, p->ch_smem, st));
+        ++p->launches;
+        if (p->nchecks > 0) {
+            REACH_CUDA(ctx, cudaMemsetAsync(p->first_bad.p, 0xFF, sizeof(unsigned long long), st));
+            const int th = 256;
+            const unsigned blocks = unsigned((p->nsteps + th - 1) / th);
+            first_disjoint_kernel<<<blocks, th, 0, st>>>(p->rho, p->ndirs, p->nsteps, p->checks.as<InvCheck>(),
+                                                          p->nchecks, p->first_bad.as<unsigned long long>());
+            REACH_CUDA(ctx, cudaGetLastError());
+            ++p->launches;
+        }
+        REACH_CUDA(ctx, cudaEventRecord(p->ev1, st));
+        p->ran = true;
+        return REACH_OK;
+    }
+
     // state reset so a plan can be re-run
     REACH_CUDA(ctx, cudaMemcpyAsync(p->Lbuf[0].p, p->L0.p, size_t(mu_pad) * Kp * sizeof(double), cudaMemcpyDeviceToDevice, st));
     REACH_CUDA(ctx, cudaMemsetAsync(p->s_pos.p, 0, p->s_pos.bytes, st));
@@ -567,10 +691,13 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         REACH_CUDA(ctx, cudaGetLastError());
         ++p->launches;
     }
+    // stack products use the warp-specialised 128x128 kernel when the blocks are tile-aligned and big
+    const bool big = (nbe % 128 == 0) && n >= 512;
     auto plain_gemm = [&](const double* X, int mrows, const double* Y, int yrows, double* out, int m_valid) -> int {
-        GemmOperands g{X, Y, Kp, Kp, Kp, round_up(mrows, 64) / 64, round_up(yrows, 64) / 64};
+        const int t = big ? 128 : 64;
+        GemmOperands g{X, Y, Kp, Kp, Kp, round_up(mrows, t) / t, round_up(yrows, t) / t};
         StoreEpi epi{out, Kp, m_valid, n};
-        REACH_CUDA(ctx, (launch_cfg(1, g, epi, st)));
+        REACH_CUDA(ctx, (launch_cfg(big ? 0 : 1, g, epi, st)));
         ++p->launches;
         return REACH_OK;
     };
@@ -792,8 +919,8 @@ extern "C" int reach_lgg09_plan_stats(reach_lgg09_plan* p, double* ms, int64_t* 
     if (ms) *ms = p->last_ms;
     if (launches) *launches = p->launches;
     if (time_block) *time_block = p->S;
-    if (tile_m) *tile_m = p->TM;
-    if (tile_n) *tile_n = p->TN;
+    if (tile_m) *tile_m = p->use_chain ? 0 : p->TM;
+    if (tile_n) *tile_n = p->use_chain ? 0 : p->TN;
     if (nchains) *nchains = p->mu;
     if (gemm_ms) *gemm_ms = p->gemm_ms;
     if (gemm_launches) *gemm_launches = p->gemm_total;

@@ -284,6 +284,178 @@ static __global__ void lgg09_prefix_kernel(const Lgg09Combine c, const double* _
     c.s_neg[j] = sn;
 }
 
+// ---- persistent warp-per-chain kernel for small / sparse Phi ---------------------------------------
+// When Phi' fits in shared memory in ELL form (dense n <~ 100, or a sparse Phi such as ISS: 540
+// non-zeros of 72 900 -- the reference runs that model with `sparse=true`, LGG09/post.jl:25-27),
+// one warp walks one direction chain through ALL time steps without ever leaving the SM:
+//     r_{k+1} = Phi' r_k  (row i on lane i%32; per row the non-zeros in ascending column order:
+//                          the strictly sequential association of the reference's mul!)
+//     features of r_{k+1} (lane-strided partial sums + butterfly), alternatives / max, running s,
+//     two 8-byte stores per step.
+// Cost per chain-step is O(nnz/32 + n*NQ/32) FMAs plus ~10 shuffle rounds -- for ISS ~10^2 cycles
+// where the dense GEMM path spends 135x the necessary flops.
+struct Lgg09Chain {
+    Lgg09Program prog;
+    int n, npad;                    // npad = RPL*32 >= n
+    int maxnnz;                     // ELL width
+    const double* ell_val;          // [maxnnz][npad]  (row i of Phi' = column i of Phi)
+    const int* ell_col;             // [maxnnz][npad]
+    const double* Wl;               // [nq][wstride] direct weights first (n), mapped weights at offset n
+    const double* Wa;
+    int wstride, nq, ne;
+    const double* E;                // [ne][n] mapped rows
+    const double* L0;               // [mu][ldl] chains
+    int ldl, mu;
+    long long nsteps;
+    int need_next;
+    const int* row_pos;
+    const int* row_neg;
+    double* rho;
+    int ndirs;
+};
+
+template <int RPL, int NQ, int NE>
+__global__ void __launch_bounds__(128) lgg09_chain_kernel(const Lgg09Chain c) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int npad = c.npad;
+    double* s_val = reinterpret_cast<double*>(smraw);                   // [maxnnz][npad]
+    double* s_a = s_val + size_t(c.maxnnz) * npad;                      // [NQ][npad]
+    double* s_b = s_a + NQ * npad;                                      // [NQ][npad]
+    double* s_E = s_b + NQ * npad;                                      // [NE][npad]
+    double* s_r = s_E + NE * npad;                                      // [warps][2][npad]
+    int* s_col = reinterpret_cast<int*>(s_r + size_t(blockDim.x >> 5) * 2 * npad);   // [maxnnz][npad]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int idx = tid; idx < c.maxnnz * npad; idx += blockDim.x) { s_val[idx] = c.ell_val[idx]; s_col[idx] = c.ell_col[idx]; }
+    for (int idx = tid; idx < NQ * npad; idx += blockDim.x) {
+        const int q = idx / npad, i = idx % npad;
+        const bool ok = q < c.nq && i < c.n;
+        s_a[idx] = ok ? c.Wl[size_t(q) * c.wstride + i] : 0.0;
+        s_b[idx] = ok ? c.Wa[size_t(q) * c.wstride + i] : 0.0;
+    }
+    for (int idx = tid; idx < NE * npad; idx += blockDim.x) {
+        const int e = idx / npad, i = idx % npad;
+        s_E[idx] = (e < c.ne && i < c.n) ? c.E[size_t(e) * c.n + i] : 0.0;
+    }
+    const int j = blockIdx.x * (blockDim.x >> 5) + warp;                // chain of this warp
+    double* r0 = s_r + size_t(warp) * 2 * npad;
+    double* r1 = r0 + npad;
+    if (j < c.mu)
+        for (int i = lane; i < npad; i += 32) r0[i] = i < c.n ? c.L0[size_t(j) * c.ldl + i] : 0.0;
+    __syncthreads();
+    if (j >= c.mu) return;
+
+    // mapped-row weights of every feature, replicated per lane (small)
+    double wlE[NQ][NE > 0 ? NE : 1], waE[NQ][NE > 0 ? NE : 1];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const bool ok = q < c.nq && e < c.ne;
+            wlE[q][e] = ok ? c.Wl[size_t(q) * c.wstride + c.n + e] : 0.0;
+            waE[q][e] = ok ? c.Wa[size_t(q) * c.wstride + c.n + e] : 0.0;
+        }
+
+    const int nq = c.nq;
+    auto features = [&](const double* r, double (&F)[NQ][2]) {
+        double lin[NQ], ab[NQ], y[NE > 0 ? NE : 1];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) lin[q] = ab[q] = 0.0;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) y[e] = 0.0;
+#pragma unroll
+        for (int t = 0; t < RPL; ++t) {
+            const int i = lane + 32 * t;
+            const double v = r[i];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                if (q < nq) {
+                    lin[q] = fma(s_a[q * npad + i], v, lin[q]);
+                    ab[q] = fma(s_b[q * npad + i], fabs(v), ab[q]);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < NE; ++e) y[e] = fma(s_E[e * npad + i], v, y[e]);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                if (q < nq) {
+                    lin[q] += __shfl_xor_sync(0xffffffffu, lin[q], off);
+                    ab[q] += __shfl_xor_sync(0xffffffffu, ab[q], off);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < NE; ++e) y[e] += __shfl_xor_sync(0xffffffffu, y[e], off);
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                lin[q] = fma(wlE[q][e], y[e], lin[q]);
+                ab[q] = fma(waE[q][e], fabs(y[e]), ab[q]);
+            }
+            F[q][0] = lin[q];
+            F[q][1] = ab[q];
+        }
+    };
+
+    const int rp = c.row_pos[j], rn = c.row_neg[j];
+    double sp = 0.0, sn = 0.0;
+    double Fp[NQ][2], Fc[NQ][2];
+    features(r0, Fp);
+    double* rc = r0;
+    double* rnx = r1;
+    for (long long k = 0; k < c.nsteps; ++k) {
+        const bool advance = c.need_next || k + 1 < c.nsteps;
+        if (advance) {
+            double acc[RPL];
+#pragma unroll
+            for (int t = 0; t < RPL; ++t) acc[t] = 0.0;
+            for (int z = 0; z < c.maxnnz; ++z) {
+#pragma unroll
+                for (int t = 0; t < RPL; ++t) {
+                    const int i = lane + 32 * t;
+                    acc[t] = fma(s_val[z * npad + i], rc[s_col[z * npad + i]], acc[t]);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < RPL; ++t) rnx[lane + 32 * t] = acc[t];
+            __syncwarp();
+            features(rnx, Fc);
+        } else {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) { Fc[q][0] = Fp[q][0]; Fc[q][1] = Fp[q][1]; }
+        }
+        // alternatives (max), terms (sum), +/- outputs, running input sum
+        double vp = 0.0, vn = 0.0;
+        for (int a = 0; a < c.prog.nalt; ++a) {
+            double ap = 0.0, an = 0.0;
+            const int q0 = c.prog.q0[a], q1 = c.prog.q1[a];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (q == q0) { ap += Fp[q][0] + Fp[q][1]; an += Fp[q][1] - Fp[q][0]; }
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (q == q1) { ap += Fc[q][0] + Fc[q][1]; an += Fc[q][1] - Fc[q][0]; }
+            if (a == 0) { vp = ap; vn = an; } else { vp = fmax(vp, ap); vn = fmax(vn, an); }
+        }
+        if (lane == 0) {
+            if (rp >= 0) c.rho[size_t(k) * c.ndirs + rp] = vp + sp;
+            if (rn >= 0) c.rho[size_t(k) * c.ndirs + rn] = vn + sn;
+        }
+        const int qv = c.prog.qV;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+            if (q == qv) { sp += Fp[q][0] + Fp[q][1]; sn += Fp[q][1] - Fp[q][0]; }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) { Fp[q][0] = Fc[q][0]; Fp[q][1] = Fc[q][1]; }
+        double* tmp = rc; rc = rnx; rnx = tmp;
+        __syncwarp();
+    }
+}
+
 // rho(d_j, flowpipe) = max_k rho[j,k]  (Flowpipes/AbstractFlowpipe.jl:35-37); first maximiser.
 static __global__ void max_over_steps_kernel(const double* __restrict__ rho, int ndirs, long long nsteps,
                                       double* __restrict__ vmax, long long* __restrict__ amax) {

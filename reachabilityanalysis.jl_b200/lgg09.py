@@ -94,13 +94,14 @@ def step_size(alg):
 class Lgg09Plan:
     """Device-resident LGG09 run: owns a `reach_lgg09_plan` (inputs, ρ matrix, statistics)."""
 
-    def __init__(self, ctx, n, ndirs, nsteps, time_block=0, share_negated=True, tile_m=0, tile_n=0):
+    def __init__(self, ctx, n, ndirs, nsteps, time_block=0, share_negated=True, tile_m=0, tile_n=0, path=0):
         self.ctx, self.lib = ctx, ctx.lib
         self.n, self.ndirs, self.nsteps = int(n), int(ndirs), int(nsteps)
         opts = L.reach_lgg09_opts()
         self.lib.reach_lgg09_default_opts(C.byref(opts))
         opts.time_block, opts.share_negated = int(time_block), int(bool(share_negated))
         opts.tile_m, opts.tile_n = int(tile_m), int(tile_n)
+        opts.path = {"auto": 0, "gemm": 1, "chain": 2}.get(path, path)
         self.handle = C.c_void_p()
         ctx.check(self.lib.reach_lgg09_plan_create(ctx.handle, self.n, self.ndirs, self.nsteps,
                                                    C.byref(opts), C.byref(self.handle)))

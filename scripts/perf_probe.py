@@ -41,11 +41,14 @@ which = sys.argv[1:] or ["c1", "c2", "c3", "c5"]
 if "c1" in which:
     wl = W.building_c1()
     for S in (0, 1, 16, 64, 256):
-        run("C1", wl, 10000, time_block=S)
+        run("C1", wl, 10000, time_block=S, path="gemm")
+    run("C1 chain", wl, 10000, path="chain")
 if "c2" in which:
     wl = W.iss_c2()
     for S in (0, 1, 8, 32):
-        run("C2", wl, 4096, time_block=S)
+        run("C2", wl, 4096, time_block=S, path="gemm")
+    run("C2 chain", wl, 4096, path="chain")
+    run("C2 auto full", wl, 33334)
 if "c3" in which:
     wl = W.heat_c3()
     for S in (0, 1, 2, 4):

@@ -205,3 +205,59 @@ def test_error_behaviour(ctx):
     bad[0, 0] = np.nan
     with pytest.raises(ValueError):
         reach_homog_LGG09(np.eye(3), X0, bad, 5, ctx=ctx)
+
+
+@pytest.mark.parametrize("n,ndirs,nsteps", [(1, 2, 7), (5, 10, 40), (33, 40, 64), (48, 96, 200), (100, 37, 50), (120, 12, 30)])
+def test_persistent_chain_kernel_matches_oracle(ctx, n, ndirs, nsteps):
+    """path=2: warp-per-chain kernel with Φᵀ in shared memory (ELL), strictly sequential association."""
+    A, _ = stable_system(n, n + 1)
+    X0, U, Z = random_sets(n, n + 1)
+    ivp = D.forward(A, X0, 0.05, U)
+    rng = np.random.default_rng(17)
+    dirs = np.hstack([np.eye(n), -np.eye(n)])[:, :ndirs] if ndirs <= 2 * n else rng.standard_normal((n, ndirs))
+    dirs[:, -1] = rng.standard_normal(n)
+    if n // 3 <= 8:            # the mapped input has n//3 rows; the chain kernel holds at most 8
+        ref = LO.reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, nsteps, ivp.V)
+        plan = reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, nsteps, None, ivp.V, ctx=ctx, path="chain")
+    else:                      # more mapped rows than the kernel holds: use the homogeneous problem
+        hom = D.forward(A, X0, 0.05)
+        ref = LO.reach_homog_LGG09(dirs, hom.Omega0, hom.Phi, nsteps)
+        plan = reach_homog_LGG09(dirs, hom.Omega0, hom.Phi, nsteps, ctx=ctx, path="chain")
+    assert plan.stats()["tile_m"] == 0           # the chain kernel ran, not the GEMM path
+    assert_support_parity(plan.sfmat(), ref)
+
+
+def test_chain_kernel_zonotope_sets_and_nsteps_one(ctx):
+    n = 12
+    A, Phi = stable_system(n, 4)
+    X0, U, Z = random_sets(n, 4)
+    Zs = rb.Zonotope(Z.center, Z.generators[:, :6])
+    dirs = np.hstack([np.eye(n), -np.eye(n)])
+    for Om, V, k in ((Zs, None, 25), (rb.ConvexHull(X0, rb.LinearMap(Phi, Zs)), rb.BallInf(np.zeros(n), 0.1), 25),
+                     (X0, None, 1), (rb.ZeroSet(n), rb.BallInf(np.zeros(n), 0.1), 9)):
+        ref = LO.reach_inhomog_LGG09(dirs, Om, Phi, k, V) if V is not None else LO.reach_homog_LGG09(dirs, Om, Phi, k)
+        got = reach_inhomog_LGG09(dirs, Om, Phi, k, None, V, ctx=ctx, path="chain").sfmat()
+        assert_support_parity(got, ref)
+
+
+def test_iss_sparse_phi_takes_the_chain_path(ctx):
+    """ISS: Φ has 540 non-zeros of 72 900; the auto-tuner must pick the persistent chain kernel
+    (the device analogue of the reference's `sparse=true`), and both paths agree with the oracle."""
+    prob, Cm = iss_problem()
+    ivp = D.forward(prob.A, prob.X0, 6e-4, D.normalize_input(prob.B, prob.U))
+    assert np.count_nonzero(ivp.Phi) == 540
+    dirs = rb.BoxDirections(270).matrix()
+    ref = LO.reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, 400, ivp.V)
+    auto = reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, 400, None, ivp.V, ctx=ctx)
+    assert auto.stats()["tile_m"] == 0
+    assert_support_parity(auto.sfmat(), ref)
+    gemm = reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, 400, None, ivp.V, ctx=ctx, path="gemm")
+    assert gemm.stats()["tile_m"] > 0
+    assert_support_parity(gemm.sfmat(), ref)
+
+
+def test_chain_path_rejects_what_it_cannot_hold(ctx):
+    n = 600
+    A, Phi = stable_system(n, 2)
+    with pytest.raises(NotImplementedError):
+        reach_homog_LGG09(np.eye(n)[:, :4], rb.BallInf(np.zeros(n), 1.0), Phi, 3, ctx=ctx, path="chain")
