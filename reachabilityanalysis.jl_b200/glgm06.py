@@ -215,24 +215,3 @@ def post_batch(alg, ivp, T=None, NSTEPS=None, Δt0=zeroT, ctx=None):
     divps = [discretize(IVP(ivp.A, X0, ivp.B, ivp.U, ivp.X), alg.δ, alg.approx_model) for X0 in ivp.X0]
     plan = _run_batch(alg, divps[0].Phi, [d.Omega0 for d in divps], divps[0].V, NSTEPS, ctx)
     return MixedFlowpipe([_flowpipe_of_split(plan, s, alg, Δt0) for s in range(len(divps))], {"plan": plan})
-
-
-def smoke(ctx):
-    """Tiny inhomogeneous run checked against the oracle (called from __graft_entry__.smoke)."""
-    from oracle import glgm06_oracle as GO
-    from . import discretization as D
-    rng = np.random.default_rng(0)
-    n = 6
-    A = -np.eye(n) + 0.3 * rng.standard_normal((n, n))
-    X0 = S.Hyperrectangle(rng.standard_normal(n), 0.1 * np.ones(n))
-    U = S.BallInf(np.zeros(n), 0.05)
-    ivp = D.first_order_zonotope(A, X0, 0.02, U)
-    alg = GLGM06(δ=0.02, max_order=3)
-    plan = _run_batch(alg, ivp.Phi, [ivp.Omega0], ivp.V, 40, ctx)
-    ref = GO.post_GLGM06(ivp.Phi, ivp.Omega0, 40, 3, ivp.V)
-    worst = 0.0
-    for k in (0, 1, 5, 39):
-        c, G = plan.fetch(0, k)
-        worst = max(worst, np.abs(c - ref[k][0]).max(), np.abs(G - ref[k][1]).max() if G.shape == ref[k][1].shape else np.inf)
-    assert worst <= 1e-10, "GLGM06 smoke parity failed: %.3e" % worst
-    print("smoke GLGM06 ok: n=%d steps=40 max abs err %.2e stats %s" % (n, worst, plan.stats()))
