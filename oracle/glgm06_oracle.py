@@ -59,3 +59,16 @@ def reach_inhomog_GLGM06(c0, G0, Phi, nsteps, max_order, cU, GU, return_diag=Fal
     if return_diag:
         return out, sels, gaps
     return out
+
+
+def first_disjoint_step(F, X):
+    """Early termination of the invariant variants (reach_homog.jl:76-147, reach_inhomog.jl:46-86):
+    `_isdisjoint(X, R_k) && break` is evaluated for k >= 2 (F[1] = Omega0 is stored unchecked) and
+    the disjoint set is not stored.  Returns the number of sets kept.  For a half-space
+    {a.x <= b} and a zonotope R the test is exact: disjoint iff  -rho(-a, R) > b."""
+    a, b = X.a, X.b
+    for k in range(1, len(F)):
+        c, G = F[k]
+        if -(float(-a @ c) + np.abs(G.T @ (-a)).sum()) > b:
+            return k
+    return len(F)

@@ -158,15 +158,47 @@ class _SplitView:
         key = d.tobytes()
         if key not in self.plan.__dict__.setdefault("_support_cache", {}):
             self.plan._support_cache[key] = self.plan.support(d)
-        return float(self.plan._support_cache[key][self.split].max())
+        return float(self.plan._support_cache[key][self.split][:self.nsets].max())
 
 
-def _flowpipe_of_split(plan, split, alg, dt0):
+def _flowpipe_of_split(plan, split, alg, dt0, nsets=None):
     def make(k, dt):
         c, G = plan.fetch(split, k)
         return ReachSet(S.Zonotope(c, G), dt)
 
-    return Flowpipe(plan.nsteps, make, alg.δ, dt0, {}, device=_SplitView(plan, split))
+    view = _SplitView(plan, split)
+    view.nsets = plan.nsteps if nsets is None else nsets
+    return Flowpipe(view.nsets, make, alg.δ, dt0, {}, device=view)
+
+
+def _sets_kept(plan, X):
+    """Invariant variants (reach_homog.jl:76-147, reach_inhomog.jl:46-86): per split, the number of
+    reach-sets before the first one that is disjoint from X (`_isdisjoint(X, R_k) && break`; the
+    first set is stored unchecked, the disjoint one is dropped).  Decided on the device from the
+    support function of every stored zonotope: for a half-space {a·x ≤ b} the test
+    −ρ(−a, R_k) > b is exact; for a box invariant each face is tested this way (the
+    `BoxEnclosure` disjointness method -- sufficient, not necessary)."""
+    n, nsteps = plan.n, plan.nsteps
+    if X is None or isinstance(X, S.Universe):
+        return np.full(plan.nsplits, nsteps, dtype=np.int64)
+    if isinstance(X, S.HalfSpace):
+        faces = [(X.a, X.b)]
+    elif isinstance(X, (S.Hyperrectangle, S.BallInf)):
+        r = X.radius if isinstance(X, S.Hyperrectangle) else np.full(n, X.radius)
+        faces = []
+        for i in range(n):
+            e = np.zeros(n)
+            e[i] = 1.0
+            faces.append((e, X.center[i] + r[i]))
+            faces.append((-e, -(X.center[i] - r[i])))
+    else:
+        raise NotImplementedError("invariant of type %s is not supported on the device" % type(X).__name__)
+    bad = np.zeros((plan.nsplits, nsteps), dtype=bool)
+    for a, b in faces:
+        bad |= -plan.support(-np.asarray(a, dtype=np.float64)) > b
+    bad[:, 0] = False
+    first = np.where(bad.any(axis=1), bad.argmax(axis=1), nsteps)
+    return first.astype(np.int64)
 
 
 def _run_batch(alg, Phi, Omega0_list, V, NSTEPS, ctx):
@@ -197,10 +229,8 @@ def post(alg, ivp, NSTEPS=None, Δt0=zeroT, ctx=None, **kwargs):
         NSTEPS = kwargs.get("NSTEPS")
         if NSTEPS is None:
             raise ValueError("`NSTEPS` not specified")
-    if ivp.X is not None and not isinstance(ivp.X, S.Universe):
-        raise NotImplementedError("GLGM06 with an invariant is not supported on the device yet")
     plan = _run_batch(alg, ivp.Phi, [ivp.Omega0], ivp.V, NSTEPS, ctx)
-    return _flowpipe_of_split(plan, 0, alg, Δt0)
+    return _flowpipe_of_split(plan, 0, alg, Δt0, int(_sets_kept(plan, ivp.X)[0]))
 
 
 def post_batch(alg, ivp, T=None, NSTEPS=None, Δt0=zeroT, ctx=None):
@@ -214,4 +244,6 @@ def post_batch(alg, ivp, T=None, NSTEPS=None, Δt0=zeroT, ctx=None):
         NSTEPS = _nsteps(T, alg.δ)
     divps = [discretize(IVP(ivp.A, X0, ivp.B, ivp.U, ivp.X), alg.δ, alg.approx_model) for X0 in ivp.X0]
     plan = _run_batch(alg, divps[0].Phi, [d.Omega0 for d in divps], divps[0].V, NSTEPS, ctx)
-    return MixedFlowpipe([_flowpipe_of_split(plan, s, alg, Δt0) for s in range(len(divps))], {"plan": plan})
+    kept = _sets_kept(plan, ivp.X)
+    return MixedFlowpipe([_flowpipe_of_split(plan, s, alg, Δt0, int(kept[s])) for s in range(len(divps))],
+                         {"plan": plan})

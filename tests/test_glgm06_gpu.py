@@ -174,3 +174,22 @@ def test_glgm06_errors(ctx):
     A = stable(3, 1, 0.1)
     with pytest.raises(ValueError):
         rb.solve(rb.IVP(A, rb.BallInf(np.zeros(3), 1.0)), alg=rb.GLGM06(δ=0.1), ctx=ctx)   # no T / NSTEPS
+
+
+def test_invariant_early_termination(ctx):
+    """reach_inhomog.jl:46-86 / reach_homog.jl:76-147: stop before the first set disjoint from X."""
+    n = 4
+    A = np.diag([-1.0, -2.0, -0.5, -1.5])
+    X0 = rb.Hyperrectangle(np.full(n, 5.0), np.full(n, 0.5))
+    inv = rb.HalfSpace(-np.eye(n)[0], -2.0)                       # x1 >= 2
+    for U in (None, rb.BallInf(np.zeros(n), 0.01)):
+        prob = rb.IVP(A, X0, None, U, inv)
+        sol = rb.solve(prob, NSTEPS=200, alg=rb.GLGM06(δ=0.05, max_order=3, approx_model=rb.Forward(setops="zono")), ctx=ctx)
+        ivp = D.forward_zono(A, X0, 0.05, U)
+        ref = GO.post_GLGM06(ivp.Phi, ivp.Omega0, 200, 3, ivp.V)
+        kept = GO.first_disjoint_step(ref, inv)
+        assert 1 < kept < 200 and len(sol) == kept
+        check_zonotope((sol[kept - 1].set.center, sol[kept - 1].set.generators), ref[kept - 1])
+        d = np.eye(n)[1]
+        want = max(Z.rho_zonotope(d, c, G) for c, G in ref[:kept])
+        assert abs(rb.rho(d, sol) - want) <= 1e-10 * abs(want)
