@@ -158,6 +158,26 @@ class Flowpipe:
         """Flowpipe.jl:304-306."""
         return self.ext["sfmat"]() if callable(self.ext.get("sfmat")) else self.ext["sfmat"]
 
+    def to_intervals(self, rows=(1, 2)):
+        """Flowpipe.jl:311-331: rows = (idx_pos_dir, idx_neg_dir), 1-based rows of the support
+        function matrix of a positive and the matching negative direction; returns the list of
+        (lo, hi, Δt) = (−ρ(−d), ρ(d), tspan) per reach-set.  Only the two rows are fetched from
+        the device."""
+        if len(rows) != 2:
+            raise ValueError("expected the number of rows of the support function matrix to be 2, got %d" % len(rows))
+        plan = self.device
+        if plan is not None and hasattr(plan, "fetch_rows"):
+            pos, neg = plan.fetch_rows([rows[0] - 1, rows[1] - 1])
+        else:
+            mat = self.support_function_matrix()
+            if mat.shape[0] < 2:
+                raise ValueError("the number of rows of the support function matrix should be at least 2, got %d"
+                                 % mat.shape[0])
+            pos, neg = mat[rows[0] - 1], mat[rows[1] - 1]
+        lo, hi = self._times()
+        from .sets import Interval
+        return [ReachSet(Interval(-neg[k], pos[k]), TimeInterval(lo[k], hi[k])) for k in range(self._n)]
+
     def rho(self, d):
         """ρ(d, fp) = max_k ρ(d, F[k]) (AbstractFlowpipe.jl:35-37)."""
         if self.device is not None and hasattr(self.device, "rho_flowpipe"):

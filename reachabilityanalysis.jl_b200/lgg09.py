@@ -91,6 +91,17 @@ def step_size(alg):
     return alg.δ
 
 
+def _as_torch(ptr, ndirs, nsteps, device):
+    """View the device-resident ρℓ (ndirs × nsteps, column-major) as a torch tensor [nsteps, ndirs]
+    without copying (plumbing for strided fetches and NCCL)."""
+    import torch
+
+    class _Holder:
+        __cuda_array_interface__ = {"shape": (nsteps, ndirs), "typestr": "<f8", "data": (int(ptr), False),
+                                    "version": 3, "strides": None}
+    return torch.as_tensor(_Holder(), device=torch.device("cuda", device))
+
+
 class Lgg09Plan:
     """Device-resident LGG09 run: owns a `reach_lgg09_plan` (inputs, ρ matrix, statistics)."""
 
@@ -164,6 +175,16 @@ class Lgg09Plan:
         if self._sfmat is None:
             self._sfmat = self.fetch(0, self.nsteps)[:, :self.nsteps_done]
         return self._sfmat
+
+    def fetch_rows(self, rows):
+        """Selected rows of ρℓ (all steps): strided device→host copies of 8·NSTEPS bytes each."""
+        m = self.sfmat() if self._sfmat is not None else None
+        if m is not None:
+            return [m[r] for r in rows]
+        import torch
+        t = _as_torch(self.device_rho, self.ndirs, self.nsteps, self.ctx.device)
+        self.sync()
+        return [t[:self.nsteps_done, r].cpu().numpy() for r in rows]
 
     def max_over_steps(self):
         vmax = np.empty(self.ndirs)

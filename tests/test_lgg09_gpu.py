@@ -261,3 +261,16 @@ def test_chain_path_rejects_what_it_cannot_hold(ctx):
     A, Phi = stable_system(n, 2)
     with pytest.raises(NotImplementedError):
         reach_homog_LGG09(np.eye(n)[:, :4], rb.BallInf(np.zeros(n), 1.0), Phi, 3, ctx=ctx, path="chain")
+
+
+def test_to_intervals_flowpipe_jl_311_331(ctx):
+    prob = building_problem()
+    sol = rb.solve(prob, NSTEPS=300, alg=rb.LGG09(δ=0.004, vars=(25,), n=48), ctx=ctx)
+    iv = sol.F.to_intervals()
+    mat = sol.F.support_function_matrix()
+    assert len(iv) == 300
+    for k in (0, 17, 299):
+        assert iv[k].set.hi == mat[0, k] and iv[k].set.lo == -mat[1, k]
+        assert iv[k].set.lo <= iv[k].set.hi
+    with pytest.raises(ValueError):
+        sol.F.to_intervals(rows=(1,))
