@@ -300,6 +300,7 @@ def run_b200(args):
     opts.time_block = args.time_block
     h2d = Phi_h.nbytes + dirs_h.nbytes + 4 * n * 8
     d2h = rho_h.nbytes
+    full_h = torch.empty((nsteps, ndirs), dtype=torch.float64, pin_memory=True) if (world > 1 and rank == 0) else None
 
     def e2e_pass():
         barrier()
@@ -307,10 +308,11 @@ def run_b200(args):
         ctx.check(ctx.lib.reach_lgg09(ctx.handle, n, mloc, nsteps, _lib.dptr(Phi_h), _lib.dptr(dirs_h), om.ptr(),
                                       v.ptr(), None, C.byref(opts), _lib.dptr(rho_h), None))
         if world > 1:
-            # the only exchange: every rank ends up with the full rho matrix on its host
+            # the only exchange: all-gather of the per-rank blocks; rank 0 lands the full matrix on its host
             loc = torch.from_numpy(rho_h).cuda(non_blocking=True)
             full = gather_support_values(loc, rows_by_rank, ndirs)
-            full.cpu()
+            if full_h is not None:
+                full_h.copy_(full, non_blocking=True)
         torch.cuda.synchronize()
         return time.perf_counter() - t0
 

@@ -204,6 +204,7 @@ extern "C" int reach_glgm06_plan_upload(reach_glgm06_plan* p, const double* Phi,
     }
     size_t free_b = 0, total_b = 0;
     REACH_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    free_b += ctx->cached_bytes;                      // blocks parked in the ctx cache are reusable
     if (need > size_t(0.9 * double(free_b)))
         return set_error(ctx, REACH_ENOMEM,
                          "the device-resident flowpipe needs %.1f GB but only %.1f GB of HBM are free; reduce NSTEPS "

@@ -10,7 +10,9 @@
 #include "lgg09_kernels.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -235,6 +237,7 @@ struct reach_lgg09_plan {
     DevBuf phi_cm;         // n x n column-major copy of Phi (source of the transpose)
     // persistent warp-per-chain path (small / sparse Phi)
     bool use_chain = false;
+    bool packed = false;   // stack blocks packed with stride round_up(n+ne, 8) (large n, 128x128 tiles)
     int ch_maxnnz = 0, ch_rpl = 0, ch_ne = 0;
     size_t ch_smem = 0;
     DevBuf ell_val, ell_col, Edev;
@@ -288,7 +291,8 @@ int launch_chain(reach_ctx* ctx, int rpl, int ne, const Lgg09Chain& c, size_t sm
 double step_cost(const reach_lgg09_plan& p, const TileCfg& c, int S, int mu, int nrows, int sms) {
     static const double eff[kNumCfgs] = {1.12, 0.85, 0.9, 0.92};   // cfg 0 is the warp-specialised kernel
     const int mu_pad = round_up(mu, c.TM);
-    const int nbe = round_up(nrows, c.TN);
+    const bool packed = c.id == 0 && nrows >= 128;
+    const int nbe = packed ? round_up(nrows, 8) : round_up(nrows, c.TN);
     const double slots = double(sms) * c.occ;
     auto pass = [&](double tiles) {
         const double waves = std::ceil(tiles / slots);
@@ -297,7 +301,7 @@ double step_cost(const reach_lgg09_plan& p, const TileCfg& c, int S, int mu, int
         return waves * (std::max(mma, mem) + (c.id == 0 ? 12000.0 : 4000.0));   // prologue + epilogue
     };
     const double launch = 60000.0;     // ~30 us per pass: GEMM + tile-sum + eval + prefix launches back to back
-    double cost = (pass(double(mu_pad / c.TM) * (double(S) * nbe / c.TN)) + launch) / S;
+    double cost = (pass(double(mu_pad / c.TM) * std::ceil(double(S) * nbe / c.TN)) + launch) / S;
     // stack build (64x64 tiles, occupancy 2), amortised
     int lg = 0;
     for (int s = 1; s < S; s *= 2) ++lg;
@@ -494,13 +498,15 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
                          "in ELL form within shared memory (n=%d, features=%d, mapped rows=%d)", n, p->nq, p->ne);
     const int TM = p->TM, TN = p->TN, S = p->S;
     p->mu_pad = round_up(p->mu, TM);
-    p->nbe = round_up(n + p->ne, TN);
-    p->tpb = p->nbe / TN;
+    p->packed = !p->use_chain && p->cfg == 0 && (n + p->ne) >= 128 && p->nq >= 1 && p->nq <= 8;
+    p->nbe = p->packed ? round_up(n + p->ne, 8) : round_up(n + p->ne, TN);
+    p->tpb = p->packed ? 1 : p->nbe / TN;
+    const size_t slice_tiles = (size_t(S + 1) * p->nbe + TN - 1) / TN;      // row tiles of the longest launch
     p->nq_pad = round_up(n, 128);
     const int nbe = p->nbe, mu_pad = p->mu_pad, nq = p->nq;
 
     // ---- device buffers ----
-    REACH_TRY(p->stack.alloc(ctx, size_t(S + 1) * nbe * Kp * sizeof(double)));
+    REACH_TRY(p->stack.alloc(ctx, (size_t(S + 1) * nbe + 256) * Kp * sizeof(double)));     // + slack rows (zero)
     REACH_TRY(p->Qbuf[0].alloc(ctx, size_t(p->nq_pad) * Kp * sizeof(double)));
     REACH_TRY(p->Qbuf[1].alloc(ctx, size_t(p->nq_pad) * Kp * sizeof(double)));
     REACH_TRY(p->L0.alloc(ctx, size_t(mu_pad) * Kp * sizeof(double)));
@@ -509,7 +515,7 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
     REACH_TRY(p->Wl.alloc(ctx, size_t(std::max(1, nq)) * nbe * sizeof(double)));
     REACH_TRY(p->Wa.alloc(ctx, size_t(std::max(1, nq)) * nbe * sizeof(double)));
     REACH_TRY(p->tile_mask.alloc(ctx, size_t(p->tpb) * sizeof(uint32_t)));
-    REACH_TRY(p->featpart.alloc(ctx, size_t(S + 1) * p->tpb * std::max(1, nq) * 2 * mu_pad * sizeof(double)));
+    REACH_TRY(p->featpart.alloc(ctx, (p->packed ? slice_tiles * 2 : size_t(S + 1) * p->tpb) * std::max(1, nq) * 2 * mu_pad * sizeof(double)));
     REACH_TRY(p->ftot.alloc(ctx, size_t(S + 1) * std::max(1, nq) * 2 * mu_pad * sizeof(double)));
     REACH_TRY(p->carry[0].alloc(ctx, size_t(std::max(1, nq)) * 2 * mu_pad * sizeof(double)));
     REACH_TRY(p->carry[1].alloc(ctx, size_t(std::max(1, nq)) * 2 * mu_pad * sizeof(double)));
@@ -566,7 +572,7 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
                 wl[size_t(q) * nbe + n + kv.first] = kv.second.first;
                 wa[size_t(q) * nbe + n + kv.first] = kv.second.second;
             }
-            for (int r = 0; r < nbe; ++r)
+            for (int r = 0; r < nbe && !p->packed; ++r)
                 if (wl[size_t(q) * nbe + r] != 0.0 || wa[size_t(q) * nbe + r] != 0.0) mask[r / TN] |= 1u << q;
         }
         REACH_CUDA(ctx, cudaMemcpyAsync(p->Wl.p, wl.data(), wl.size() * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -692,7 +698,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         ++p->launches;
     }
     // stack products use the warp-specialised 128x128 kernel when the blocks are tile-aligned and big
-    const bool big = (nbe % 128 == 0) && n >= 512;
+    const bool big = (p->packed || nbe % 128 == 0) && n >= 512;
     auto plain_gemm = [&](const double* X, int mrows, const double* Y, int yrows, double* out, int m_valid) -> int {
         const int t = big ? 128 : 64;
         GemmOperands g{X, Y, Kp, Kp, Kp, round_up(mrows, t) / t, round_up(yrows, t) / t};
@@ -728,6 +734,16 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     epi.featpart = p->featpart.as<double>();
     epi.mu_pad = mu_pad;
 
+    Lgg09PackedEpi pepi{};
+    pepi.ldl = Kp;
+    pepi.n = n;
+    pepi.nbe = nbe;
+    pepi.Wl = p->Wl.as<double>();
+    pepi.Wa = p->Wa.as<double>();
+    pepi.nq = p->nq;
+    pepi.featpart = p->featpart.as<double>();
+    pepi.mu_pad = mu_pad;
+
     Lgg09Combine cmb{};
     cmb.prog = p->prog.dev;
     cmb.featpart = p->featpart.as<double>();
@@ -750,7 +766,8 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         const int nblk = c.b_hi - c.b_lo + 1;
         if (nblk > 0) {
             dim3 grid(cblocks, nblk);
-            lgg09_tilesum_kernel<<<grid, cthreads, 0, st>>>(c, ftot);
+            if (p->packed) lgg09_tilesum_packed_kernel<<<grid, cthreads, 0, st>>>(c, p->featpart.as<double>(), ftot, nbe, TN);
+            else lgg09_tilesum_kernel<<<grid, cthreads, 0, st>>>(c, ftot);
             REACH_CUDA(ctx, cudaGetLastError());
             ++p->launches;
         }
@@ -792,24 +809,35 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     int cur = 0;
     if (T == 0) {
         // NSTEPS == 1 and nothing is evaluated at r_1: only the features of r_0 are needed
-        GemmOperands g{p->Lbuf[cur].as<double>(), block(0), Kp, Kp, Kp, mu_pad / TM, nbe / TN};
+        GemmOperands g{p->Lbuf[cur].as<double>(), block(0), Kp, Kp, Kp, mu_pad / TM, (nbe + TN - 1) / TN};
         epi.Lnext = p->Lbuf[1 - cur].as<double>();
         epi.block0 = 0;
         epi.store_block = -1;
-        REACH_CUDA(ctx, (launch_cfg(p->cfg, g, epi, st)));
+        if (p->packed) {
+            pepi.Lnext = epi.Lnext; pepi.slice_block0 = 0; pepi.store_block = -1;
+            REACH_CUDA(ctx, (launch_cfg(p->cfg, g, pepi, st)));
+        } else {
+            REACH_CUDA(ctx, (launch_cfg(p->cfg, g, epi, st)));
+        }
         ++p->launches;
         cmb.b_lo = 0; cmb.b_hi = 0; cmb.has_carry = 0; cmb.tail = 1; cmb.k0 = 0;
         REACH_TRY(combine(cmb));
     }
     for (int64_t t = 0; t < T; ++t) {
         const int b_lo = t == 0 ? 0 : 1;
-        GemmOperands g{p->Lbuf[cur].as<double>(), block(b_lo), Kp, Kp, Kp, mu_pad / TM, (S + 1 - b_lo) * nbe / TN};
+        GemmOperands g{p->Lbuf[cur].as<double>(), block(b_lo), Kp, Kp, Kp, mu_pad / TM,
+                       ((S + 1 - b_lo) * nbe + TN - 1) / TN};
         epi.Lnext = p->Lbuf[1 - cur].as<double>();
         epi.block0 = b_lo;
         epi.store_block = S;
         const bool sample = (t % sample_every) == 0;
         if (sample) REACH_CUDA(ctx, cudaEventRecord(p->gemm_ev[2 * p->gemm_sampled], st));
-        REACH_CUDA(ctx, (launch_cfg(p->cfg, g, epi, st)));
+        if (p->packed) {
+            pepi.Lnext = epi.Lnext; pepi.slice_block0 = b_lo; pepi.store_block = S;
+            REACH_CUDA(ctx, (launch_cfg(p->cfg, g, pepi, st)));
+        } else {
+            REACH_CUDA(ctx, (launch_cfg(p->cfg, g, epi, st)));
+        }
         if (sample) {
             REACH_CUDA(ctx, cudaEventRecord(p->gemm_ev[2 * p->gemm_sampled + 1], st));
             ++p->gemm_sampled;
@@ -930,14 +958,26 @@ extern "C" int reach_lgg09_plan_stats(reach_lgg09_plan* p, double* ms, int64_t* 
 extern "C" int reach_lgg09(reach_ctx* ctx, int n, int ndirs, int64_t nsteps, const double* Phi, const double* dirs,
                            const reach_setexpr* Omega0, const reach_setexpr* V, const reach_invariant* inv,
                            const reach_lgg09_opts* opts, double* rho_host, int64_t* nsteps_done) {
+    const bool timing = getenv("REACH_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t0 = now();
     reach_lgg09_plan* p = nullptr;
     REACH_TRY(reach_lgg09_plan_create(ctx, n, ndirs, nsteps, opts, &p));
     int rc = reach_lgg09_plan_upload(p, Phi, dirs, Omega0, V, inv);
+    auto t1 = now();
     if (rc == REACH_OK) rc = reach_lgg09_plan_run(p);
     if (rc == REACH_OK) rc = reach_lgg09_plan_sync(p);
+    auto t2 = now();
     if (rc == REACH_OK && rho_host) rc = reach_lgg09_plan_fetch(p, 0, nsteps, rho_host);
     if (rc == REACH_OK && nsteps_done) *nsteps_done = p->nsteps_done;
+    auto t3 = now();
     reach_lgg09_plan_destroy(p);
+    auto t4 = now();
+    if (timing) {
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[reach_lgg09] create+upload %.1f ms, run+sync %.1f ms, fetch %.1f ms, destroy %.1f ms\n",
+                ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4));
+    }
     return rc;
 }
 

@@ -122,6 +122,103 @@ struct Lgg09Epi {
     }
 };
 
+// Packed variant of the epilogue (large n): stack blocks follow each other with a stride of
+// nbe = round_up(n + ne, 8) rows instead of being padded to the tile height, so no DMMA work is spent
+// on padding rows (n = 2000: 2.3 %).  A 128-row tile can then straddle ONE block boundary (nbe >= TN);
+// the boundary is a multiple of 8, so every 8-row MMA sub-tile -- hence every (warp, j) -- belongs to
+// one block, and the tile emits two partial sums per feature: segment 0 (rows of the tile's first
+// block) and segment 1 (rows of the next block).
+struct Lgg09PackedEpi {
+    double* Lnext;
+    int ldl, n, nbe;
+    int slice_block0;           // absolute block index of the first row of this launch's stack slice
+    int store_block;            // absolute block whose rows are L_{k0+S}; -1: none
+    const double* Wl;           // [nq][nbe]
+    const double* Wa;
+    int nq;
+    double* featpart;           // [tiles_n][2 segments][nq][2][mu_pad]
+    int mu_pad;
+
+    template <int MT, int NT, int WN, class TC>
+    __device__ __forceinline__ void run(double (&acc)[MT][NT][2], const TC& tc, double* smem) const {
+        constexpr int TM = TC::TM, TN = TC::TN;
+        const int row0 = tc.tn * TN;
+        const int blk0 = row0 / nbe;
+        const int bnd = (blk0 + 1) * nbe - row0;     // tile-local row where the next block starts (>= TN: none)
+        int rib[NT];
+        bool seg1[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int cl = tc.wn0 + j * 8 + 2 * tc.t4;
+            seg1[j] = (tc.wn0 + j * 8) >= bnd;       // warp-uniform
+            rib[j] = row0 + cl - (blk0 + (seg1[j] ? 1 : 0)) * nbe;
+        }
+        // store the rows that belong to the store block
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            if (slice_block0 + blk0 + (seg1[j] ? 1 : 0) != store_block) continue;
+            const int c = rib[j];
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                const int m = tc.tm * TM + tc.wm0 + i * 8 + tc.g4;
+                double* o = Lnext + size_t(m) * ldl + c;
+                if (c + 1 < n) *reinterpret_cast<double2*>(o) = make_double2(acc[i][j][0], acc[i][j][1]);
+                else if (c < n) o[0] = acc[i][j][0];
+            }
+        }
+        double* red = smem;                          // [q][seg][wn][part][TM]
+        const int wn = tc.wn0 / (NT * 8);
+        for (int q = 0; q < nq; ++q) {
+            double wl[NT][2], wa[NT][2];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const double2 l2 = *reinterpret_cast<const double2*>(Wl + size_t(q) * nbe + rib[j]);
+                const double2 a2 = *reinterpret_cast<const double2*>(Wa + size_t(q) * nbe + rib[j]);
+                wl[j][0] = l2.x; wl[j][1] = l2.y;
+                wa[j][0] = a2.x; wa[j][1] = a2.y;
+            }
+#pragma unroll
+            for (int i = 0; i < MT; ++i) {
+                double lin[2] = {0.0, 0.0}, ab[2] = {0.0, 0.0};
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    double l = fma(wl[j][0], acc[i][j][0], 0.0);
+                    l = fma(wl[j][1], acc[i][j][1], l);
+                    double a = fma(wa[j][0], fabs(acc[i][j][0]), 0.0);
+                    a = fma(wa[j][1], fabs(acc[i][j][1]), a);
+                    if (seg1[j]) { lin[1] += l; ab[1] += a; } else { lin[0] += l; ab[0] += a; }
+                }
+#pragma unroll
+                for (int sg = 0; sg < 2; ++sg) {
+                    lin[sg] += __shfl_xor_sync(0xffffffffu, lin[sg], 1);
+                    ab[sg] += __shfl_xor_sync(0xffffffffu, ab[sg], 1);
+                    lin[sg] += __shfl_xor_sync(0xffffffffu, lin[sg], 2);
+                    ab[sg] += __shfl_xor_sync(0xffffffffu, ab[sg], 2);
+                }
+                if (tc.t4 == 0) {
+                    const int m = tc.wm0 + i * 8 + tc.g4;
+#pragma unroll
+                    for (int sg = 0; sg < 2; ++sg) {
+                        red[(((q * 2 + sg) * WN + wn) * 2 + 0) * TM + m] = lin[sg];
+                        red[(((q * 2 + sg) * WN + wn) * 2 + 1) * TM + m] = ab[sg];
+                    }
+                }
+            }
+        }
+        tc.sync();
+        for (int idx = tc.tid; idx < nq * 4 * TM; idx += tc.nthr) {
+            const int m = idx % TM;
+            const int part = (idx / TM) & 1;
+            const int sg = (idx / (2 * TM)) & 1;
+            const int q = idx / (4 * TM);
+            double v = 0.0;
+#pragma unroll
+            for (int w = 0; w < WN; ++w) v += red[(((q * 2 + sg) * WN + w) * 2 + part) * TM + m];
+            featpart[((((size_t(tc.tn) * 2 + sg) * nq + q) * 2) + part) * mu_pad + tc.tm * TM + m] = v;
+        }
+    }
+};
+
 struct Lgg09Program {
     int nalt;
     int qV;                         // feature of rho(., V), -1 when homogeneous
@@ -161,6 +258,28 @@ static __global__ void lgg09_tilesum_kernel(const Lgg09Combine c, double* __rest
             const size_t base = (((size_t(b) * c.tpb + t) * c.nq + q) * 2) * c.mu_pad + j;
             lin += c.featpart[base];
             ab += c.featpart[base + c.mu_pad];
+        }
+        ftot[((size_t(b) * c.nq + q) * 2 + 0) * c.mu_pad + j] = lin;
+        ftot[((size_t(b) * c.nq + q) * 2 + 1) * c.mu_pad + j] = ab;
+    }
+}
+
+// Packed layout: block b (relative to the launch slice) spans rows [rel*nbe, (rel+1)*nbe); it collects
+// segment 0 of the tiles that start inside it and segment 1 of the tile that starts in the previous block.
+static __global__ void lgg09_tilesum_packed_kernel(const Lgg09Combine c, const double* __restrict__ featpart,
+                                                   double* __restrict__ ftot, int nbe, int tn_rows) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = c.b_lo + blockIdx.y;
+    if (j >= c.mu || b > c.b_hi) return;
+    const int rel = b - c.b_lo;
+    const int t0 = (rel * nbe) / tn_rows, t1 = ((rel + 1) * nbe - 1) / tn_rows;
+    for (int q = 0; q < c.nq; ++q) {
+        double lin = 0.0, ab = 0.0;
+        for (int t = t0; t <= t1; ++t) {
+            const int sg = ((t * tn_rows) / nbe == rel) ? 0 : 1;
+            const size_t base = ((((size_t(t) * 2 + sg) * c.nq + q) * 2)) * c.mu_pad + j;
+            lin += featpart[base];
+            ab += featpart[base + c.mu_pad];
         }
         ftot[((size_t(b) * c.nq + q) * 2 + 0) * c.mu_pad + j] = lin;
         ftot[((size_t(b) * c.nq + q) * 2 + 1) * c.mu_pad + j] = ab;

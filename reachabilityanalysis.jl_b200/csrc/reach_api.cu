@@ -60,6 +60,7 @@ extern "C" void reach_destroy(reach_ctx* ctx) {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->stream);
     }
+    ctx_cache_flush(ctx);
     delete ctx;
 }
 

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <map>
 #include <string>
 #include <vector>
 #include <new>
@@ -19,6 +20,11 @@ struct reach_ctx {
     cudaStream_t stream = nullptr;
     char name[256] = {0};
     std::string err;
+    // Device-memory cache: cudaMalloc / cudaFree of the multi-GB plan buffers cost ~70 ms each per
+    // one-shot call; freed blocks are kept (size-keyed) and handed to the next plan of this ctx.
+    std::multimap<size_t, void*> free_blocks;
+    size_t cached_bytes = 0;
+    size_t cache_limit = size_t(48) << 30;
 };
 
 namespace reach {
@@ -51,31 +57,63 @@ inline int set_error(reach_ctx* ctx, int code, const char* fmt, ...) {
         if (rc__ != REACH_OK) return rc__; \
     } while (0)
 
-// RAII device buffer (freed with the plan that owns it)
+inline void ctx_cache_flush(reach_ctx* ctx) {
+    for (auto& kv : ctx->free_blocks) cudaFree(kv.second);
+    ctx->free_blocks.clear();
+    ctx->cached_bytes = 0;
+}
+
+// RAII device buffer (returned to the ctx cache with the plan that owns it).  All work on a ctx is
+// ordered on its single stream, so a cached block can be reused without further synchronisation.
 struct DevBuf {
     void* p = nullptr;
-    size_t bytes = 0;
+    size_t bytes = 0;       // requested
+    size_t cap = 0;         // allocated
+    reach_ctx* owner = nullptr;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            if (owner && owner->cached_bytes + cap <= owner->cache_limit) {
+                owner->free_blocks.emplace(cap, p);
+                owner->cached_bytes += cap;
+            } else {
+                cudaFree(p);
+            }
+        }
         p = nullptr;
-        bytes = 0;
+        bytes = cap = 0;
     }
     int alloc(reach_ctx* ctx, size_t n, bool zero = true) {
         release();
         if (n == 0) n = 16;
-        cudaError_t e = cudaMalloc(&p, n);
-        if (e != cudaSuccess) {
-            p = nullptr;
-            return set_error(ctx, REACH_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", n,
-                             cudaGetErrorString(e));
+        const size_t gran = size_t(1) << 20;
+        const size_t want = (n + gran - 1) / gran * gran;
+        owner = ctx;
+        auto it = ctx->free_blocks.lower_bound(want);
+        if (it != ctx->free_blocks.end() && it->first <= want + want / 4 + gran) {
+            p = it->second;
+            cap = it->first;
+            ctx->cached_bytes -= cap;
+            ctx->free_blocks.erase(it);
+        } else {
+            cudaError_t e = cudaMalloc(&p, want);
+            if (e != cudaSuccess) {             // make room: drop the cache and retry once
+                cudaGetLastError();
+                ctx_cache_flush(ctx);
+                e = cudaMalloc(&p, want);
+            }
+            if (e != cudaSuccess) {
+                p = nullptr;
+                return set_error(ctx, REACH_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+            }
+            cap = want;
         }
         bytes = n;
         if (zero) {
-            e = cudaMemsetAsync(p, 0, n, ctx->stream);
+            cudaError_t e = cudaMemsetAsync(p, 0, n, ctx->stream);
             if (e != cudaSuccess)
                 return set_error(ctx, REACH_ECUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e));
         }
