@@ -16,6 +16,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 using namespace reach;
@@ -411,46 +412,51 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
     p->nq = int(p->prog.feats.size());
 
     // ---- direction chains: l and -l share (Phi')^k l (reach_homog.jl:108-110) ----
-    std::vector<int> row_pos, row_neg;
-    std::vector<std::vector<double>> chains;
+    // chain c = sign_c * direction src_c (canonical orientation: first non-zero entry positive)
+    std::vector<int> row_pos, row_neg, chain_src;
+    std::vector<double> chain_sign;
     {
-        std::map<std::string, int> index;
-        std::vector<double> canon(n);
+        std::unordered_multimap<uint64_t, int> index;
+        index.reserve(size_t(ndirs) * 2);
         for (int j = 0; j < ndirs; ++j) {
             const double* d = dirs + size_t(j) * n;
             double sign = 1.0;
+            bool seen = false;
+            uint64_t h = 1469598103934665603ull;
             for (int i = 0; i < n; ++i) {
-                if (!std::isfinite(d[i])) return set_error(ctx, REACH_EINVAL, "direction %d is not finite", j);
+                const double v = d[i];
+                if (!std::isfinite(v)) return set_error(ctx, REACH_EINVAL, "direction %d is not finite", j);
+                if (!seen && v != 0.0 && p->opts.share_negated) { sign = v < 0 ? -1.0 : 1.0; seen = true; }
+                const double cv = sign * v + 0.0;                 // zeros before the first non-zero hash as +0
+                uint64_t bits;
+                std::memcpy(&bits, &cv, 8);
+                h = (h ^ bits) * 1099511628211ull;
             }
-            if (p->opts.share_negated)
-                for (int i = 0; i < n; ++i)
-                    if (d[i] != 0.0) { sign = d[i] < 0 ? -1.0 : 1.0; break; }
-            for (int i = 0; i < n; ++i) canon[i] = sign * d[i] + 0.0;
             int c = -1;
             if (p->opts.share_negated) {
-                std::string key(reinterpret_cast<const char*>(canon.data()), sizeof(double) * n);
-                auto it = index.find(key);
-                if (it != index.end()) {
-                    c = it->second;
-                    int& slot = sign > 0 ? row_pos[c] : row_neg[c];
-                    if (slot >= 0) c = -1;          // duplicate direction: give it its own chain
-                    else slot = j;
+                auto range = index.equal_range(h);
+                for (auto it = range.first; it != range.second && c < 0; ++it) {
+                    const int cand = it->second;
+                    const double* e = dirs + size_t(chain_src[cand]) * n;
+                    const double rel = sign * chain_sign[cand];   // d == rel * e ?
+                    bool same = true;
+                    for (int i = 0; i < n && same; ++i) same = (d[i] == rel * e[i]);
+                    if (!same) continue;
+                    int& slot = sign > 0 ? row_pos[cand] : row_neg[cand];
+                    if (slot < 0) { slot = j; c = cand; }        // else: duplicate direction, own chain
                 }
-                if (c < 0) {
-                    c = int(chains.size());
-                    chains.push_back(canon);
-                    row_pos.push_back(sign > 0 ? j : -1);
-                    row_neg.push_back(sign > 0 ? -1 : j);
-                    index[key] = c;
-                }
-            } else {
-                chains.push_back(canon);
-                row_pos.push_back(j);
-                row_neg.push_back(-1);
+            }
+            if (c < 0) {
+                c = int(chain_src.size());
+                chain_src.push_back(j);
+                chain_sign.push_back(sign);
+                row_pos.push_back(sign > 0 ? j : -1);
+                row_neg.push_back(sign > 0 ? -1 : j);
+                if (p->opts.share_negated) index.emplace(h, c);
             }
         }
     }
-    p->mu = int(chains.size());
+    p->mu = int(chain_src.size());
 
     REACH_TRY(choose_config(*p));
     // ---- small / sparse Phi: ELL form of Phi' (row i of Phi' = column i of Phi) ----
@@ -546,18 +552,28 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
     // Phi: column-major n x n.  Row k of the row-major Phi (the seed Q_1) is produced on the
     // device by a transpose at run time; here we only ship the matrix.
     REACH_CUDA(ctx, cudaMemcpyAsync(p->phi_cm.p, Phi, size_t(n) * n * sizeof(double), cudaMemcpyHostToDevice, st));
-    {   // block 0 of the stack = [I ; E] (rows of length Kp)
-        std::vector<double> b0(size_t(nbe) * Kp, 0.0);
-        for (int i = 0; i < n; ++i) b0[size_t(i) * Kp + i] = 1.0;
-        for (int e = 0; e < p->ne; ++e)
-            std::memcpy(&b0[size_t(n + e) * Kp], p->prog.erows[e].data(), sizeof(double) * n);
-        REACH_CUDA(ctx, cudaMemcpyAsync(p->stack.p, b0.data(), b0.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-        REACH_CUDA(ctx, cudaStreamSynchronize(st));
+    {   // block 0 of the stack = [I ; E]: ones on the diagonal (kernel), mapped rows copied row by row
+        set_identity_kernel<<<(n + 255) / 256, 256, 0, st>>>(p->stack.as<double>(), Kp, n);
+        REACH_CUDA(ctx, cudaGetLastError());
+        if (p->ne > 0) {
+            std::vector<double> E(size_t(p->ne) * n);
+            for (int e = 0; e < p->ne; ++e) std::memcpy(&E[size_t(e) * n], p->prog.erows[e].data(), sizeof(double) * n);
+            REACH_CUDA(ctx, cudaMemcpy2DAsync(p->stack.as<double>() + size_t(n) * Kp, size_t(Kp) * 8, E.data(),
+                                              size_t(n) * 8, size_t(n) * 8, p->ne, cudaMemcpyHostToDevice, st));
+            REACH_CUDA(ctx, cudaStreamSynchronize(st));
+        }
     }
-    {   // direction chains, one row each
-        std::vector<double> l0(size_t(mu_pad) * Kp, 0.0);
-        for (int c = 0; c < p->mu; ++c) std::memcpy(&l0[size_t(c) * Kp], chains[c].data(), sizeof(double) * n);
-        REACH_CUDA(ctx, cudaMemcpyAsync(p->L0.p, l0.data(), l0.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    {   // direction chains, one row each: ship the caller's direction matrix as is, orient on the device
+        DevBuf ddev, src, sgn;
+        REACH_TRY(ddev.alloc(ctx, size_t(n) * ndirs * 8, false));
+        REACH_TRY(src.alloc(ctx, size_t(p->mu) * 4, false));
+        REACH_TRY(sgn.alloc(ctx, size_t(p->mu) * 8, false));
+        REACH_CUDA(ctx, cudaMemcpyAsync(ddev.p, dirs, size_t(n) * ndirs * 8, cudaMemcpyHostToDevice, st));
+        REACH_CUDA(ctx, cudaMemcpyAsync(src.p, chain_src.data(), size_t(p->mu) * 4, cudaMemcpyHostToDevice, st));
+        REACH_CUDA(ctx, cudaMemcpyAsync(sgn.p, chain_sign.data(), size_t(p->mu) * 8, cudaMemcpyHostToDevice, st));
+        build_chains_kernel<<<p->mu, 128, 0, st>>>(ddev.as<double>(), n, src.as<int>(),
+                                                                          sgn.as<double>(), p->L0.as<double>(), Kp);
+        REACH_CUDA(ctx, cudaGetLastError());
         REACH_CUDA(ctx, cudaMemcpyAsync(p->row_pos.p, row_pos.data(), sizeof(int) * p->mu, cudaMemcpyHostToDevice, st));
         REACH_CUDA(ctx, cudaMemcpyAsync(p->row_neg.p, row_neg.data(), sizeof(int) * p->mu, cudaMemcpyHostToDevice, st));
         REACH_CUDA(ctx, cudaStreamSynchronize(st));

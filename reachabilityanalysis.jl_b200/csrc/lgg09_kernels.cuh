@@ -575,6 +575,18 @@ __global__ void __launch_bounds__(128) lgg09_chain_kernel(const Lgg09Chain c) {
     }
 }
 
+// stack block 0 starts with the identity: out[i][i] = 1 (the buffer is zero-filled)
+static __global__ void set_identity_kernel(double* __restrict__ out, int ld, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[size_t(i) * ld + i] = 1.0;
+}
+// L0[c][:] = sign_c * dirs[:, src_c] + 0.0  (canonical orientation; -0.0 normalised to +0.0)
+static __global__ void build_chains_kernel(const double* __restrict__ dirs, int n, const int* __restrict__ src,
+                                           const double* __restrict__ sign, double* __restrict__ L0, int ld) {
+    const int c = blockIdx.x;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) L0[size_t(c) * ld + i] = sign[c] * dirs[size_t(src[c]) * n + i] + 0.0;
+}
+
 // rho(d_j, flowpipe) = max_k rho[j,k]  (Flowpipes/AbstractFlowpipe.jl:35-37); first maximiser.
 static __global__ void max_over_steps_kernel(const double* __restrict__ rho, int ndirs, long long nsteps,
                                       double* __restrict__ vmax, long long* __restrict__ amax) {
