@@ -65,13 +65,17 @@ struct reach_glgm06_plan {
     DevBuf scratch_pos;
     int64_t bytes_stored = 0;
 
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_powers = nullptr, ev_gemm = nullptr;
+    cudaStream_t stream2 = nullptr;     // the batched GEMM runs here, beside the W chain on the ctx stream
     double last_ms = 0.0;
     int64_t launches = 0;
 
     ~reach_glgm06_plan() {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_powers) cudaEventDestroy(ev_powers);
+        if (ev_gemm) cudaEventDestroy(ev_gemm);
+        if (stream2) cudaStreamDestroy(stream2);
     }
 };
 
@@ -119,6 +123,9 @@ extern "C" int reach_glgm06_plan_create(reach_ctx* ctx, int n, int64_t nsteps, i
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e == cudaSuccess) e = cudaEventCreate(&p->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&p->ev1);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_powers, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_gemm, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->stream2, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete p;
         return set_error(ctx, REACH_ECUDA, "plan_create: %s", cudaGetErrorString(e));
@@ -130,6 +137,7 @@ extern "C" int reach_glgm06_plan_create(reach_ctx* ctx, int n, int64_t nsteps, i
 extern "C" void reach_glgm06_plan_destroy(reach_glgm06_plan* p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
+    if (p->stream2) cudaStreamSynchronize(p->stream2);
     cudaStreamSynchronize(p->ctx->stream);
     delete p;
 }
@@ -322,6 +330,7 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
     const size_t pblk = size_t(nb) * Kp;
     if (nblk > 0)   // P_0 = Phi (rows of Phi)
         REACH_CUDA(ctx, cudaMemcpyAsync(Pst, p->PhiRows.p, pblk * 8, cudaMemcpyDeviceToDevice, st));
+    bool overlap = false;
     // small n: the whole chain runs in one persistent CTA with P_k and Phi in shared memory
     bool fused = n <= 64 && p->pU + 1 <= 256 && p->pWcap <= 2048 && nblk > 0 && !p->force_stepwise;
     size_t chain_smem = 0;
@@ -336,8 +345,6 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
     if (fused) {
         ChainParams c{};
         c.n = n; c.ldk = Kp; c.nb = nb; c.pU = p->pU; c.r = r; c.pWcap = p->pWcap; c.nblk = nblk;
-        c.PhiT = p->PhiT.as<double>();
-        c.P0 = p->PhiRows.as<double>();
         c.XU = p->XU.as<double>();
         c.Pstack = Pst;
         c.GWall = p->GWall.as<double>();
@@ -346,6 +353,14 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
         c.wB = p->wB.as<double>();
         c.permB = p->permB.as<int>();
         c.bpref = p->bpref.as<double>();
+        // powers first (1 CTA, ~1 us per step) so that the batched GEMM can run beside the W chain
+        const size_t psmem = 8 * 3 * size_t(n) * (n + 1);
+        REACH_CUDA(ctx, cudaFuncSetAttribute(glgm06_powers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(psmem)));
+        glgm06_powers_kernel<<<1, 1024, psmem, st>>>(p->PhiRows.as<double>(), p->PhiT.as<double>(), n, Kp, nb, nblk, Pst);
+        REACH_CUDA(ctx, cudaGetLastError());
+        ++p->launches;
+        overlap = true;
+        REACH_CUDA(ctx, cudaEventRecord(p->ev_powers, st));
         REACH_CUDA(ctx, cudaFuncSetAttribute(glgm06_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(chain_smem)));
         glgm06_chain_kernel<<<1, 1024, chain_smem, st>>>(c);
         REACH_CUDA(ctx, cudaGetLastError());
@@ -389,6 +404,11 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
     }
 
     // ---- (2) batched part: all splits x all steps ----
+    cudaStream_t gst = st;                              // stream of the batched GEMM
+    if (overlap) {
+        gst = p->stream2;
+        REACH_CUDA(ctx, cudaStreamWaitEvent(gst, p->ev_powers, 0));
+    }
     if (nblk > 0) {
         GenEpi epi{};
         epi.out = p->A_store.as<double>();
@@ -411,9 +431,13 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
             e2.out = epi.out + b0 * epi.blk_stride;
             e2.psum = epi.psum + b0 * p->tpb * p->m_pad;
             e2.pmax = epi.pmax + b0 * p->tpb * p->m_pad;
-            if (p->TN == 64) REACH_CUDA(ctx, (launch_tn64(g, e2, st)));
-            else REACH_CUDA(ctx, (launch_tn128(g, e2, st)));
+            if (p->TN == 64) REACH_CUDA(ctx, (launch_tn64(g, e2, gst)));
+            else REACH_CUDA(ctx, (launch_tn128(g, e2, gst)));
             ++p->launches;
+        }
+        if (overlap) {                                  // the selection needs both the GEMM and the chain
+            REACH_CUDA(ctx, cudaEventRecord(p->ev_gemm, gst));
+            REACH_CUDA(ctx, cudaStreamWaitEvent(st, p->ev_gemm, 0));
         }
         SelectParams s{};
         s.A = p->A_store.as<double>();

@@ -337,14 +337,48 @@ static __global__ void glgm06_w_reduce_kernel(const double* __restrict__ PU, int
 // materialised (global, L2-resident); the sorted order of W_{k+1} WITHOUT sorting (kept generators are
 // already ascending, the n box generators have weight exactly 0 and slot in after the zero-weight kept
 // ones -- the stable (weight, index) order); the prefix table of |W_{k+1}|; P_{k+1} = P_k Phi.
+// All powers P_b = Phi^{b+1} (rows), sequentially P_{b+1} = P_b Phi as `mul!(cache, P, Phi)` does
+// (reach_inhomog.jl:38), by one CTA with P_b and Phi' in shared memory.  Running this first lets the
+// batched split GEMM (which only needs the powers) overlap with the W chain on a second stream.
+static __global__ void __launch_bounds__(1024, 1) glgm06_powers_kernel(const double* __restrict__ P0, const double* __restrict__ PhiT,
+                                                                       int n, int ldk, int nb, long long nblk,
+                                                                       double* __restrict__ Pstack) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    const int ldp = n + 1;
+    double* sP[2];
+    sP[0] = reinterpret_cast<double*>(smraw);
+    sP[1] = sP[0] + n * ldp;
+    double* sPhiT = sP[1] + n * ldp;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    for (int idx = tid; idx < n * n; idx += nthr) {
+        const int a = idx / n, b = idx % n;
+        sP[0][a * ldp + b] = P0[size_t(a) * ldk + b];
+        sPhiT[a * ldp + b] = PhiT[size_t(a) * ldk + b];
+    }
+    __syncthreads();
+    for (long long b = 0; b < nblk; ++b) {
+        const double* P = sP[b & 1];
+        double* Pn = sP[(b + 1) & 1];
+        double* Pg = Pstack + size_t(b) * nb * ldk;
+        for (int idx = tid; idx < n * n; idx += nthr) {
+            const int i = idx / n, m = idx % n;
+            Pg[size_t(i) * ldk + m] = P[i * ldp + m];
+            if (b + 1 < nblk) {
+                double s = 0.0;
+                for (int l = 0; l < n; ++l) s = fma(P[i * ldp + l], sPhiT[m * ldp + l], s);
+                Pn[i * ldp + m] = s;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 struct ChainParams {
     int n, ldk, nb;             // ldk = Kp (row pitch of Phi/P/XU buffers), nb = rows per P block
     int pU, r, pWcap;
     long long nblk;
-    const double* PhiT;         // [n][ldk] rows = columns of Phi
-    const double* P0;           // [n][ldk] rows of Phi (= P_0)
     const double* XU;           // [(pU+1)][ldk]
-    double* Pstack;             // [nblk][nb][ldk]
+    const double* Pstack;       // [nblk][nb][ldk], precomputed by glgm06_powers_kernel
     double* GWall;              // [(nblk+1)][pWcap][n]
     double* cWall;              // [(nblk+1)][n]
     const int* pW;              // [nblk+1]
@@ -381,8 +415,7 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
     const int tid = threadIdx.x, nthr = blockDim.x;
     for (int idx = tid; idx < n * n; idx += nthr) {
         const int a = idx / n, b = idx % n;
-        sP[0][a * ldp + b] = c.P0[size_t(a) * c.ldk + b];
-        sPhiT[a * ldp + b] = c.PhiT[size_t(a) * c.ldk + b];
+        sP[0][a * ldp + b] = c.Pstack[size_t(a) * c.ldk + b];          // P_0 (the powers are precomputed)
     }
     for (int idx = tid; idx < (pU + 1) * n; idx += nthr) {
         const int g = idx / n, l = idx % n;
@@ -422,8 +455,6 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
 
         // (a) publish P_b, the sorted weights / permutation of W_b, and the prefix table of |W_b|
         {
-            double* Pg = c.Pstack + size_t(b) * c.nb * c.ldk;
-            for (int idx = tid; idx < n * n; idx += nthr) Pg[size_t(idx / n) * c.ldk + idx % n] = P[(idx / n) * ldp + idx % n];
             for (int j = tid; j < pWb; j += nthr) {
                 c.wB[size_t(b) * c.pWcap + j] = wBc[j];
                 c.permB[size_t(b) * c.pWcap + j] = permc[j];
@@ -459,11 +490,9 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
             for (int l = 0; l < n; ++l) s = fma(sXU[g * ldp + l], P[i * ldp + l], s);
             sPU[g * ldp + i] = s;
         }
-        for (int idx = tid; idx < n * n; idx += nthr) {
-            const int i = idx / n, m = idx % n;
-            double s = 0.0;
-            for (int l = 0; l < n; ++l) s = fma(P[i * ldp + l], sPhiT[m * ldp + l], s);
-            Pn[i * ldp + m] = s;
+        {
+            const double* Pg = c.Pstack + size_t(b + 1) * c.nb * c.ldk;        // P_{b+1} for the next step
+            for (int idx = tid; idx < n * n; idx += nthr) Pn[(idx / n) * ldp + idx % n] = Pg[size_t(idx / n) * c.ldk + idx % n];
         }
         __syncthreads();
         // centre of W_{b+1}

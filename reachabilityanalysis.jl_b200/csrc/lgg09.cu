@@ -315,7 +315,7 @@ double step_cost(const reach_lgg09_plan& p, const TileCfg& c, int S, int mu, int
 int choose_config(reach_lgg09_plan& p) {
     reach_ctx* ctx = p.ctx;
     const int nrows = p.n + p.ne;
-    const int smax = int(std::min<int64_t>(256, std::max<int64_t>(1, p.nsteps)));
+    const int smax = int(std::min<int64_t>(1024, std::max<int64_t>(1, p.nsteps)));
     int best_cfg = -1, best_S = 1;
     double best = 1e300;
     for (int ci = 0; ci < kNumCfgs; ++ci) {
@@ -325,6 +325,7 @@ int choose_config(reach_lgg09_plan& p) {
         for (int S = 1; S <= std::max(smax, p.opts.time_block); ++S) {
             if (p.opts.time_block > 0 && S != p.opts.time_block) continue;
             if (p.opts.time_block == 0 && S > 16 && (S & 3)) continue;        // coarse scan for large S
+            if (p.opts.time_block == 0 && S > 128 && (S & 31)) continue;
             const int nbe = round_up(nrows, c.TN);
             const int mu_pad = round_up(p.mu, c.TM);
             const double stack_bytes = double(S + 1) * nbe * p.Kp * 8.0;
