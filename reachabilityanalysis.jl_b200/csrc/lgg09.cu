@@ -797,6 +797,13 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         const double* cin = p->carry[carry_cur].as<double>();
         double* cout = p->carry[1 - carry_cur].as<double>();
         double* dv = p->dv.as<double>();
+        if (c.prog.qV >= 0) {
+            // running input sums s_k of the steps this pass emits (first step: kfirst), before the evaluation
+            const long long kfirst = c.has_carry ? c.k0 + c.b_lo - 1 : (nblk > 0 ? c.k0 + c.b_lo : c.k0);
+            lgg09_prefix_kernel<<<(p->mu + PREFIX_CB - 1) / PREFIX_CB, PREFIX_THREADS, 0, st>>>(c, ftot, cin, dv, nslots, kfirst);
+            REACH_CUDA(ctx, cudaGetLastError());
+            ++p->launches;
+        }
         dim3 grid(cblocks, nslots);
         if (c.nq <= 4) lgg09_eval_kernel<4><<<grid, cthreads, 0, st>>>(c, ftot, cin, cout, dv);
         else if (c.nq <= 8) lgg09_eval_kernel<8><<<grid, cthreads, 0, st>>>(c, ftot, cin, cout, dv);
@@ -804,13 +811,6 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         REACH_CUDA(ctx, cudaGetLastError());
         ++p->launches;
         carry_cur ^= 1;
-        if (c.prog.qV >= 0) {
-            // first step emitted by this pass
-            const long long kfirst = c.has_carry ? c.k0 + c.b_lo - 1 : (nblk > 0 ? c.k0 + c.b_lo : c.k0);
-            lgg09_prefix_kernel<<<cblocks, cthreads, 0, st>>>(c, dv, nslots, kfirst);
-            REACH_CUDA(ctx, cudaGetLastError());
-            ++p->launches;
-        }
         return REACH_OK;
     };
 

@@ -291,12 +291,12 @@ static __global__ void lgg09_tilesum_packed_kernel(const Lgg09Combine c, const d
 //   has_carry: slot 0 = (carry, block b_lo), slot e = (block b_lo+e-1, block b_lo+e)
 //   otherwise: slot e = (block b_lo+e, block b_lo+e+1)
 //   tail     : one more slot (last, last) for a final step that needs nothing at r_{k+1}
-// rho(r_k; Omega0) goes straight into the output matrix; rho(r_k; V) into dv[e][2][mu_pad] for
-// the running-sum pass.  The thread of the last slot also writes the next pass's carry.
+// rho(r_k; Omega0) + s_k goes straight into the output matrix (s_k comes from the running-sum pass,
+// which runs first).  The thread of the last slot also writes the next pass's carry.
 template <int NQ>
 __global__ void lgg09_eval_kernel(const Lgg09Combine c, const double* __restrict__ ftot,
                                   const double* __restrict__ carry_in, double* __restrict__ carry_out,
-                                  double* __restrict__ dv) {
+                                  const double* __restrict__ sbuf) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int e = blockIdx.y;
     if (j >= c.mu) return;
@@ -340,18 +340,13 @@ __global__ void lgg09_eval_kernel(const Lgg09Combine c, const double* __restrict
                 if (q == q1) { ap += Fc[q][0] + Fc[q][1]; an += Fc[q][1] - Fc[q][0]; }
             if (a == 0) { vp = ap; vn = an; } else { vp = fmax(vp, ap); vn = fmax(vn, an); }
         }
+        if (c.prog.qV >= 0) {                                   // + s_k from the running-sum pass
+            vp += sbuf[(size_t(e) * 2 + 0) * c.mu_pad + j];
+            vn += sbuf[(size_t(e) * 2 + 1) * c.mu_pad + j];
+        }
         const int rp = c.row_pos[j], rn = c.row_neg[j];
         if (rp >= 0) c.rho[size_t(k) * c.ndirs + rp] = vp;
         if (rn >= 0) c.rho[size_t(k) * c.ndirs + rn] = vn;
-        const int qv = c.prog.qV;
-        if (qv >= 0) {
-            double dp = 0.0, dn = 0.0;
-#pragma unroll
-            for (int q = 0; q < NQ; ++q)
-                if (q == qv) { dp = Fp[q][0] + Fp[q][1]; dn = Fp[q][1] - Fp[q][0]; }
-            dv[(size_t(e) * 2 + 0) * c.mu_pad + j] = dp;
-            dv[(size_t(e) * 2 + 1) * c.mu_pad + j] = dn;
-        }
     }
     // the features of the last r of this pass seed the next one
     const int nslots = npair + (c.tail ? 1 : 0);
@@ -365,42 +360,90 @@ __global__ void lgg09_eval_kernel(const Lgg09Combine c, const double* __restrict
     }
 }
 
-// ---- combine, phase C: running input sum, strictly in step order ---------------------------------
-// rho[j,k] = rho(r_k; Omega0) + s_k ;  s_{k+1} = s_k + rho(r_k; V)   (reach_inhomog.jl:56-57).
-// One thread per chain; loads are issued CH steps ahead of the dependent adds.
-static __global__ void lgg09_prefix_kernel(const Lgg09Combine c, const double* __restrict__ dv, int nslots,
-                                    long long kfirst) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= c.mu) return;
-    constexpr int CH = 16;
-    const int rp = c.row_pos[j], rn = c.row_neg[j];
-    double sp = c.s_pos[j], sn = c.s_neg[j];
-    for (int e0 = 0; e0 < nslots; e0 += CH) {
-        double dp[CH], dn[CH], vp[CH], vn[CH];
+// ---- combine, running input sum, strictly in step order (runs between tile-sum and eval) ------------
+// s_{k+1} = s_k + rho(r_k; V)   (reach_inhomog.jl:56-57); sbuf[e][0/1][j] = s_k of the +chain / -chain for
+// emit slot e.  rho(+-r_k; V) = abs_qV(r_k) +- lin_qV(r_k) is read from the block totals (or the carry).
+// A CTA owns 16 chains.  Warps 1..7 stream the (lin, abs) totals of the slots into a 4-deep shared-memory
+// ring with cp.async, three chunks of 32 slots ahead; warp 0 runs the dependent adds (lane = chain and sign,
+// one add per step: the reference's order), so the chain of adds never waits for a global load.
+constexpr int PREFIX_CB = 16, PREFIX_CHK = 32, PREFIX_NBUF = 4, PREFIX_THREADS = 256;
+static __global__ void __launch_bounds__(PREFIX_THREADS) lgg09_prefix_kernel(const Lgg09Combine c, const double* __restrict__ ftot,
+                                                                             const double* __restrict__ carry_in,
+                                                                             double* __restrict__ sbuf, int nslots, long long kfirst) {
+    __shared__ __align__(16) double sv[PREFIX_NBUF][PREFIX_CHK][2][PREFIX_CB];
+    const int lane = threadIdx.x & 31;
+    const bool scanner = threadIdx.x < 32;
+    constexpr int NLOAD = PREFIX_THREADS - 32, ITEMS = PREFIX_CHK * 2 * PREFIX_CB;
+    const int nblk = c.b_hi - c.b_lo + 1;
+    const int npair = c.has_carry ? nblk : (nblk > 0 ? nblk - 1 : 0);
+    const int qv = c.prog.qV;
+    auto stage = [&](int buf, int e0) {                      // loader warps: totals of the "prev" block of each slot
+        if (e0 < nslots) {
 #pragma unroll
-        for (int i = 0; i < CH; ++i) {
-            const int e = e0 + i;
-            const long long k = kfirst + e;
-            const bool ok = e < nslots && k < c.nsteps;
-            dp[i] = ok ? dv[(size_t(e) * 2 + 0) * c.mu_pad + j] : 0.0;
-            dn[i] = ok ? dv[(size_t(e) * 2 + 1) * c.mu_pad + j] : 0.0;
-            vp[i] = (ok && rp >= 0) ? c.rho[size_t(k) * c.ndirs + rp] : 0.0;
-            vn[i] = (ok && rn >= 0) ? c.rho[size_t(k) * c.ndirs + rn] : 0.0;
-        }
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-            const int e = e0 + i;
-            const long long k = kfirst + e;
-            if (e < nslots && k < c.nsteps) {
-                if (rp >= 0) c.rho[size_t(k) * c.ndirs + rp] = vp[i] + sp;
-                if (rn >= 0) c.rho[size_t(k) * c.ndirs + rn] = vn[i] + sn;
-                sp += dp[i];
-                sn += dn[i];
+            for (int t = 0; t < (ITEMS + NLOAD - 1) / NLOAD; ++t) {
+                const int item = int(threadIdx.x) - 32 + NLOAD * t;
+                if (item >= ITEMS) break;
+                const int i = item / (2 * PREFIX_CB), part = (item / PREFIX_CB) & 1, ch = item % PREFIX_CB;
+                const int e = e0 + i, j = blockIdx.x * PREFIX_CB + ch;
+                double* dst = &sv[buf][i][part][ch];
+                if (j < c.mu && e < nslots && kfirst + e < c.nsteps) {
+                    int bp;
+                    if (e == npair) bp = nblk > 0 ? c.b_hi : -1;               // tail slot
+                    else if (c.has_carry) bp = e == 0 ? -1 : c.b_lo + e - 1;
+                    else bp = c.b_lo + e;
+                    const double* src = (bp < 0 ? carry_in + (size_t(qv) * 2) * c.mu_pad
+                                                : ftot + ((size_t(bp) * c.nq + qv) * 2) * c.mu_pad) + size_t(part) * c.mu_pad + j;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+                } else {
+                    *dst = 0.0;
+                }
             }
         }
+        cp_async_commit();                                   // one group per chunk, empty or not
+    };
+    const int ch = lane % PREFIX_CB, sign = lane / PREFIX_CB;
+    const int j = blockIdx.x * PREFIX_CB + ch;
+    const bool jok = j < c.mu;
+    double s = 0.0;
+    if (scanner) {
+        if (jok) s = sign ? c.s_neg[j] : c.s_pos[j];
+    } else {
+        for (int cidx = 0; cidx < PREFIX_NBUF - 1; ++cidx) stage(cidx, cidx * PREFIX_CHK);
+        cp_async_wait<PREFIX_NBUF - 2>();
     }
-    c.s_pos[j] = sp;
-    c.s_neg[j] = sn;
+    __syncthreads();
+    for (int cidx = 0; cidx * PREFIX_CHK < nslots; ++cidx) {
+        const int e0 = cidx * PREFIX_CHK, buf = cidx % PREFIX_NBUF;
+        if (!scanner) {
+            stage((cidx + PREFIX_NBUF - 1) % PREFIX_NBUF, (cidx + PREFIX_NBUF - 1) * PREFIX_CHK);
+            cp_async_wait<PREFIX_NBUF - 2>();                // chunk cidx + 1 has landed
+        } else if (jok) {
+            const long long left = min((long long)(nslots - e0), c.nsteps - kfirst - e0);
+            double* out = sbuf + (size_t(e0) * 2 + sign) * c.mu_pad + j;
+            const size_t ostride = size_t(2) * c.mu_pad;
+            if (left >= PREFIX_CHK) {                        // full chunk: branch-free, operands in registers first
+                double d[PREFIX_CHK];
+#pragma unroll
+                for (int i = 0; i < PREFIX_CHK; ++i) {
+                    const double lin = sv[buf][i][0][ch], ab = sv[buf][i][1][ch];
+                    d[i] = sign ? ab - lin : lin + ab;       // rho(-r_k; V) : rho(+r_k; V)
+                }
+#pragma unroll
+                for (int i = 0; i < PREFIX_CHK; ++i) {
+                    out[i * ostride] = s;
+                    s += d[i];
+                }
+            } else {
+                for (int i = 0; i < int(left); ++i) {
+                    const double lin = sv[buf][i][0][ch], ab = sv[buf][i][1][ch];
+                    out[i * ostride] = s;
+                    s += sign ? ab - lin : lin + ab;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (scanner && jok) { if (sign) c.s_neg[j] = s; else c.s_pos[j] = s; }
 }
 
 // ---- persistent warp-per-chain kernel for small / sparse Phi ---------------------------------------
