@@ -224,6 +224,13 @@ int reach_reduce_order_gir05(reach_ctx* ctx, int n, int p, int max_order, const 
  * (C[m x n] = X[m x k] * Y[n x k]'), returns achieved TFLOP/s; used by bench.py beside cuBLAS. */
 int reach_dgemm_probe(reach_ctx* ctx, int m, int n, int k, int iters, double* tflops);
 
+/* The same contraction on the INT8 tcgen05 tensor pipe through `slices` (4..8) error-free 7-bit digit planes
+ * per operand (csrc/oz_gemm.cuh): C[m x n] (row-major) = X[m x k] * Y[n x k]' for row-major host matrices.
+ * C_host may be NULL.  *tflops counts 2 m n k per launch (FP64-equivalent), *slice_ms the digit-plane
+ * conversion of both operands.  Used by the tests (accuracy against NumPy) and by bench.py. */
+int reach_ozgemm_probe(reach_ctx* ctx, int m, int n, int k, int slices, const double* X_host,
+                       const double* Y_host, double* C_host, int iters, double* tflops, double* slice_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,6 +87,8 @@ SIGNATURES = {
     "reach_reduce_order_gir05": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p,
                                            C.POINTER(C.c_int), c_int32_p]),
     "reach_dgemm_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p]),
+    "reach_ozgemm_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p,
+                                     c_double_p, C.c_int, c_double_p, c_double_p]),
 }
 
 _lib = None
@@ -164,6 +166,19 @@ class Context:
         out = C.c_double()
         self.check(self.lib.reach_dgemm_probe(self.handle, m, n, k, iters, C.byref(out)))
         return out.value
+
+    def ozgemm_probe(self, X, Y, slices=8, iters=1, want_result=True):
+        """C = X @ Y.T through the INT8-tcgen05 digit-plane GEMM; returns (C or None, TFLOP/s, slicing ms)."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        m, k = X.shape
+        n = Y.shape[0]
+        assert Y.shape[1] == k
+        Cm = np.empty((m, n)) if want_result else None
+        tf, sl = C.c_double(), C.c_double()
+        self.check(self.lib.reach_ozgemm_probe(self.handle, m, n, k, slices, dptr(X), dptr(Y), dptr(Cm), iters,
+                                               C.byref(tf), C.byref(sl)))
+        return Cm, tf.value, sl.value
 
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:

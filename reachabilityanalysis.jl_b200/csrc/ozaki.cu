@@ -1,0 +1,71 @@
+// ozaki.cu -- host side of the INT8-tcgen05 FP64-emulation GEMM (oz_gemm.cuh): the stand-alone probe used by
+// tests and bench.py.  The LGG09 main loop launches the same kernels from lgg09.cu.
+#include "reach_common.cuh"
+#include "oz_gemm.cuh"
+
+#include <vector>
+
+using namespace reach;
+
+// C[m x n] (row-major) = X[m x k] * Y[n x k]'  with X, Y row-major FP64 host matrices, through T digit planes.
+// C_host may be NULL (timing only).  *tflops = 2 m n k iters / time of the GEMM launches (slicing excluded),
+// *slice_ms = time of slicing both operands once.
+extern "C" int reach_ozgemm_probe(reach_ctx* ctx, int m, int n, int k, int slices, const double* X_host,
+                                  const double* Y_host, double* C_host, int iters, double* tflops, double* slice_ms) {
+    if (!ctx) return REACH_EINVAL;
+    if (m < 1 || n < 1 || k < 1 || iters < 1) return set_error(ctx, REACH_EINVAL, "probe sizes must be positive");
+    if (slices < 4 || slices > OZ_MAX_T) return set_error(ctx, REACH_EINVAL, "slices must be in 4..%d", OZ_MAX_T);
+    if (k > 32768) return set_error(ctx, REACH_EINVAL, "k must be <= 32768 (INT32 accumulator headroom)");
+    if (!X_host || !Y_host) return set_error(ctx, REACH_EINVAL, "X and Y must not be NULL");
+    REACH_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int T = slices;
+    const int tiles_m = (m + OZ_TM - 1) / OZ_TM, tiles_n = (n + OZ_TN - 1) / OZ_TN, nkb = (k + OZ_KB - 1) / OZ_KB;
+    DevBuf X, Y, C, Xq, Yq, eX, eY;
+    REACH_TRY(X.alloc(ctx, size_t(m) * k * 8, false));
+    REACH_TRY(Y.alloc(ctx, size_t(n) * k * 8, false));
+    REACH_TRY(C.alloc(ctx, size_t(m) * n * 8));
+    REACH_TRY(Xq.alloc(ctx, size_t(nkb) * tiles_m * T * OZ_TM * OZ_KB));
+    REACH_TRY(Yq.alloc(ctx, size_t(nkb) * tiles_n * T * OZ_TN * OZ_KB));
+    REACH_TRY(eX.alloc(ctx, size_t(tiles_m) * OZ_TM * 4));
+    REACH_TRY(eY.alloc(ctx, size_t(tiles_n) * OZ_TN * 4));
+    REACH_CUDA(ctx, cudaMemcpyAsync(X.p, X_host, size_t(m) * k * 8, cudaMemcpyHostToDevice, st));
+    REACH_CUDA(ctx, cudaMemcpyAsync(Y.p, Y_host, size_t(n) * k * 8, cudaMemcpyHostToDevice, st));
+    cudaEvent_t e0, e1, e2;
+    REACH_CUDA(ctx, cudaEventCreate(&e0));
+    REACH_CUDA(ctx, cudaEventCreate(&e1));
+    REACH_CUDA(ctx, cudaEventCreate(&e2));
+    REACH_CUDA(ctx, cudaEventRecord(e0, st));
+    oz_slice_kernel<OZ_TM><<<tiles_m * OZ_TM / 8, 256, 0, st>>>(X.as<double>(), k, m, k, T, nkb, tiles_m, Xq.as<int8_t>(), eX.as<int>());
+    REACH_CUDA(ctx, cudaGetLastError());
+    oz_slice_kernel<OZ_TN><<<tiles_n * OZ_TN / 8, 256, 0, st>>>(Y.as<double>(), k, n, k, T, nkb, tiles_n, Yq.as<int8_t>(), eY.as<int>());
+    REACH_CUDA(ctx, cudaGetLastError());
+    REACH_CUDA(ctx, cudaEventRecord(e1, st));
+    OzOperands g{Xq.as<int8_t>(), Yq.as<int8_t>(), eX.as<int>(), eY.as<int>(), nkb, tiles_m, tiles_m, 0, tiles_n, tiles_n};
+    OzStoreEpi epi{C.as<double>(), n, m, n};
+    REACH_CUDA(ctx, (launch_oz_gemm(T, g, epi, st)));          // warm-up (also the result)
+    REACH_CUDA(ctx, cudaStreamSynchronize(st));
+    REACH_CUDA(ctx, cudaEventRecord(e1, st));
+    for (int i = 0; i < iters; ++i) REACH_CUDA(ctx, (launch_oz_gemm(T, g, epi, st)));
+    REACH_CUDA(ctx, cudaEventRecord(e2, st));
+    REACH_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms_slice = 0.f, ms = 0.f;
+    REACH_CUDA(ctx, cudaEventElapsedTime(&ms, e1, e2));
+    (void)ms_slice;
+    if (slice_ms) {   // time the slicing separately
+        REACH_CUDA(ctx, cudaEventRecord(e0, st));
+        oz_slice_kernel<OZ_TM><<<tiles_m * OZ_TM / 8, 256, 0, st>>>(X.as<double>(), k, m, k, T, nkb, tiles_m, Xq.as<int8_t>(), eX.as<int>());
+        oz_slice_kernel<OZ_TN><<<tiles_n * OZ_TN / 8, 256, 0, st>>>(Y.as<double>(), k, n, k, T, nkb, tiles_n, Yq.as<int8_t>(), eY.as<int>());
+        REACH_CUDA(ctx, cudaEventRecord(e1, st));
+        REACH_CUDA(ctx, cudaStreamSynchronize(st));
+        float s = 0.f;
+        REACH_CUDA(ctx, cudaEventElapsedTime(&s, e0, e1));
+        *slice_ms = s;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    if (tflops) *tflops = 2.0 * m * double(n) * k * iters / (ms * 1e-3) / 1e12;
+    if (C_host) REACH_CUDA(ctx, cudaMemcpy(C_host, C.p, size_t(m) * n * 8, cudaMemcpyDeviceToHost));
+    return REACH_OK;
+}
