@@ -11,29 +11,35 @@
 // truncation error below (T+1) K 2^(-7T) relative to rowmax(X) * rowmax(Y) (T = 8: ~2^-42 worst case, ~2^-50 typical:
 // on par with DGEMM's own rounding).  The result is independent of the summation order, hence deterministic.
 //
-// Kernel shape (one CTA per 128 x 64 output tile, 6 warps):
-//   warp 4  producer: per 32-byte k-block two cp.async.bulk copies (all T digit planes of the X tile, of the Y
-//           tile) into a 4-stage shared-memory ring; the digit planes are stored in global memory already in the
+// Kernel shape (one CTA per 128 x 128 output tile, 18 warps):
+//   warp 16 producer: per 32-byte k-block two cp.async.bulk copies (the digit planes of the X tile, of the Y
+//           tile) into a 3-stage shared-memory ring; the digit planes are stored in global memory already in the
 //           canonical no-swizzle K-major UMMA layout (8-row x 16-byte core matrices), so a plain bulk copy lands
 //           the exact shared-memory image the MMA descriptors expect.
-//   warp 5  one thread issues tcgen05.mma.kind::i8 (M=128, N=64, K=32): T accumulators of 64 columns = the whole
-//           tensor memory (512 columns) for T = 8; tcgen05.commit frees the ring slot / signals the epilogue.
-//   warps 0-3 epilogue: tcgen05.ld 32x32b (thread = output row), Horner over the levels in FP64, scale, then the
-//           fused support-function epilogue (or a plain store).
+//   warp 17 one thread issues tcgen05.mma.kind::i8 (M=128, N=128, K=32): 4 level accumulators of 128 columns = the
+//           whole tensor memory (512 columns); T > 4 takes two passes over K (levels 0..3, then 4..T-1).
+//           tcgen05.commit frees the ring slot / signals the epilogue.  (A first version with N=64 and all 8 levels
+//           resident was bound by the shared-memory operand feed of the tensor pipe: 73 % of its peak at 49 % MMA
+//           utilisation, ncu profiles/; N=128 halves the operand bytes per MAC.)
+//   warps 0-15 epilogue: tcgen05.ld 32x32b (thread = output row x 32 columns), Horner over the levels in FP64 (exact),
+//           scale, then the fused support-function epilogue (or a plain store).
 #pragma once
 
 #include "nt_dgemm.cuh"
 
 namespace reach {
 
-constexpr int OZ_TM = 128, OZ_TN = 64, OZ_KB = 32, OZ_STAGES = 4, OZ_THREADS = 192;
-constexpr int OZ_MAX_T = 8;
+constexpr int OZ_TM = 128, OZ_TN = 128, OZ_KB = 32, OZ_STAGES = 3;
+constexpr int OZ_EPI_WARPS = 16, OZ_THREADS = (OZ_EPI_WARPS + 2) * 32;
+constexpr int OZ_CPT = OZ_TN / (OZ_EPI_WARPS / 4);    // output columns per epilogue thread (32)
+constexpr int OZ_MAX_T = 8, OZ_G = 4;                  // OZ_G levels live in tensor memory at a time (4 x 128 columns)
+constexpr int OZ_PLANE = OZ_TM * OZ_KB;                // bytes of one digit plane of a 128-row tile per k-block
 
 struct OzOperands {
     const int8_t* Xq;     // [nkb][tiles_m_total][T][16][2][8][16]
-    const int8_t* Yq;     // [nkb][tiles_n_total][T][ 8][2][8][16]
+    const int8_t* Yq;     // [nkb][tiles_n_total][T][16][2][8][16]
     const int* eX;        // [tiles_m_total*128] row exponents
-    const int* eY;        // [tiles_n_total*64]
+    const int* eY;        // [tiles_n_total*128]
     int nkb;              // k-blocks of 32
     int tiles_m, tiles_m_total;
     int tile_n0, tiles_n, tiles_n_total;   // this launch covers Y tiles [tile_n0, tile_n0 + tiles_n)
@@ -53,32 +59,43 @@ __device__ __forceinline__ double oz_scale(double v, int e) {   // v * 2^e, any 
     if (e >= -1000 && e <= 1000) return v * oz_pow2(e);
     return scalbn(v, e);
 }
+// exact int32 -> double without the conversion pipe: 2^52 + 2^31 + x has x in its low mantissa bits
+__device__ __forceinline__ double oz_i2d(uint32_t x) {
+    return __hiloint2double(0x43300000, int(x ^ 0x80000000u)) - 4503601774854144.0;
+}
 
 // ---- plain store epilogue (probe / tests): C -> out[m*ldc + n] -------------------------------------------
 struct OzStoreEpi {
     double* out;
     int ldc, m_valid, n_valid;
     struct State {};
+    static constexpr size_t SMEM = 0;
     __device__ __forceinline__ void prepare(unsigned char*, int, int) const {}
     __device__ __forceinline__ void begin(State&) const {}
+    // value of output (row m, column j of tile tn)
     __device__ __forceinline__ void accept(State&, const unsigned char*, int m, int tn, int j, double v) const {
         const int n = tn * OZ_TN + j;
         if (m < m_valid && n < n_valid) out[size_t(m) * ldc + n] = v;
     }
-    __device__ __forceinline__ void finish(State&, int, int, int) const {}
-    static constexpr size_t SMEM = 0;
+    __device__ __forceinline__ void finish(State&, unsigned char*, int, int, int, int) const {}
 };
 
+// Two passes over K ("sweeps") when T > 4: levels 0..3 first (digit planes 0..3 of both operands, 10 MMAs per k-block),
+// then levels 4..T-1 (all planes, up to 26 MMAs).  Each sweep's level sum  sum_d 2^(-7 (d - d0)) acc_d  is EXACT in
+// FP64 (<= 47 bits), so the epilogue threads keep sweep 1 as one double per output while sweep 2 runs.
 template <int T, class Epi>
 __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzOperands g, const Epi epi) {
-    constexpr uint32_t XBYTES = T * OZ_TM * OZ_KB, YBYTES = T * OZ_TN * OZ_KB, STAGE = XBYTES + YBYTES;
+    constexpr uint32_t SLOT = 2 * T * OZ_PLANE;                       // X planes then Y planes
+    constexpr int G1 = T < OZ_G ? T : OZ_G;
+    constexpr int NSWEEP = T > OZ_G ? 2 : 1;
     extern __shared__ __align__(1024) unsigned char oz_smem[];
     unsigned char* ring = oz_smem;
-    uint64_t* full = reinterpret_cast<uint64_t*>(oz_smem + size_t(OZ_STAGES) * STAGE);
+    uint64_t* full = reinterpret_cast<uint64_t*>(oz_smem + size_t(OZ_STAGES) * SLOT);
     uint64_t* empty = full + OZ_STAGES;
     uint64_t* tmem_full = empty + OZ_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    double* sYscale = reinterpret_cast<double*>(tmem_full + 2);       // [64] 2^eY of the tile's columns
+    uint64_t* tmem_empty = tmem_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+    double* sYscale = reinterpret_cast<double*>(tmem_empty + 2);      // [128] 2^eY of the tile's columns
     unsigned char* epi_smem = reinterpret_cast<unsigned char*>(sYscale + OZ_TN);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -88,10 +105,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzOperands
     if (tid == 0) {
         for (int s = 0; s < OZ_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, OZ_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 5) {   // the MMA warp owns the tensor-memory allocation (all 512 columns)
+    if (warp == OZ_EPI_WARPS + 1) {   // the MMA warp owns the tensor-memory allocation (all 512 columns)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -100,92 +118,126 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzOperands
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == OZ_EPI_WARPS) {
         // ===== producer =====
         if (lane == 0) {
-            const int8_t* gx = g.Xq + size_t(tm) * XBYTES;
-            const int8_t* gy = g.Yq + size_t(tn) * YBYTES;
-            const size_t xstep = size_t(g.tiles_m_total) * XBYTES, ystep = size_t(g.tiles_n_total) * YBYTES;
-            for (int kb = 0; kb < g.nkb; ++kb) {
-                const int s = kb % OZ_STAGES;
-                const uint32_t ph = (kb / OZ_STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], STAGE);
-                unsigned char* dst = ring + size_t(s) * STAGE;
-                bulk_copy_g2s(dst, gx + size_t(kb) * xstep, XBYTES, &full[s]);
-                bulk_copy_g2s(dst + XBYTES, gy + size_t(kb) * ystep, YBYTES, &full[s]);
+            const int8_t* gx = g.Xq + size_t(tm) * (T * OZ_PLANE);
+            const int8_t* gy = g.Yq + size_t(tn) * (T * OZ_PLANE);
+            const size_t xstep = size_t(g.tiles_m_total) * (T * OZ_PLANE), ystep = size_t(g.tiles_n_total) * (T * OZ_PLANE);
+            int jb = 0;
+            for (int sw = 0; sw < NSWEEP; ++sw) {
+                const uint32_t bytes = uint32_t(sw == 0 ? G1 : T) * OZ_PLANE;
+                for (int kb = 0; kb < g.nkb; ++kb, ++jb) {
+                    const int s = jb % OZ_STAGES;
+                    const uint32_t ph = (jb / OZ_STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], 2 * bytes);
+                    unsigned char* dst = ring + size_t(s) * SLOT;
+                    bulk_copy_g2s(dst, gx + size_t(kb) * xstep, bytes, &full[s]);
+                    bulk_copy_g2s(dst + T * OZ_PLANE, gy + size_t(kb) * ystep, bytes, &full[s]);
+                }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == OZ_EPI_WARPS + 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             // instruction descriptor: D = S32 (2<<4), A = B = signed 8-bit (1<<7, 1<<10), K-major both, N>>3 at 17, M>>4 at 24
             constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(OZ_TN >> 3) << 17) | (uint32_t(OZ_TM >> 4) << 24);
-            for (int kb = 0; kb < g.nkb; ++kb) {
-                const int s = kb % OZ_STAGES;
-                const uint32_t ph = (kb / OZ_STAGES) & 1;
-                mbar_wait(&full[s], ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t xs = smem_u32(ring + size_t(s) * STAGE), ys = xs + XBYTES;
-#pragma unroll
-                for (int d = 0; d < T; ++d) {
-#pragma unroll
-                    for (int sx = 0; sx <= d; ++sx) {
-                        const int sy = d - sx;
-                        // one digit plane of a tile: [rows/8][2 k-chunks][8 rows][16 B]: LBO = 128 B (next k-chunk), SBO = 256 B (next 8 rows)
-                        const uint64_t da = oz_smem_desc(xs + sx * (OZ_TM * OZ_KB), 128, 256);
-                        const uint64_t db = oz_smem_desc(ys + sy * (OZ_TN * OZ_KB), 128, 256);
-                        const uint32_t acc = (kb > 0 || sx > 0) ? 1u : 0u;
-                        asm volatile(
-                            "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
-                            " tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_base + uint32_t(d * OZ_TN)),
-                            "l"(da), "l"(db), "r"(idesc), "r"(acc)
-                            : "memory");
-                    }
+            int jb = 0;
+            for (int sw = 0; sw < NSWEEP; ++sw) {
+                if (sw == 1) {                                   // the epilogue has drained the sweep-1 accumulators
+                    mbar_wait(tmem_empty, 0);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                // frees the ring slot once the MMAs above have read it (implies fence::before_thread_sync)
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+                for (int kb = 0; kb < g.nkb; ++kb, ++jb) {
+                    const int s = jb % OZ_STAGES;
+                    const uint32_t ph = (jb / OZ_STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t xs = smem_u32(ring + size_t(s) * SLOT), ys = xs + T * OZ_PLANE;
+#pragma unroll
+                    for (int dd = 0; dd < OZ_G; ++dd) {
+                        const int d = sw * OZ_G + dd;
+                        if (d >= T) break;
+#pragma unroll
+                        for (int sx = 0; sx < T; ++sx) {
+                            if (sx > d) break;
+                            const int sy = d - sx;
+                            // one digit plane of a tile: [rows/8][2 k-chunks][8 rows][16 B]: LBO = 128 B (next k-chunk), SBO = 256 B (next 8 rows)
+                            const uint64_t da = oz_smem_desc(xs + sx * OZ_PLANE, 128, 256);
+                            const uint64_t db = oz_smem_desc(ys + sy * OZ_PLANE, 128, 256);
+                            const uint32_t acc = (kb > 0 || sx > 0) ? 1u : 0u;
+                            asm volatile(
+                                "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+                                " tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_base + uint32_t(dd * OZ_TN)),
+                                "l"(da), "l"(db), "r"(idesc), "r"(acc)
+                                : "memory");
+                        }
+                    }
+                    // frees the ring slot once the MMAs above have read it (implies fence::before_thread_sync)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(tmem_full)) : "memory");
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(tmem_full)) : "memory");
         }
     } else {
-        // ===== epilogue warps 0..3: thread = output row =====
-        const int ml = warp * 32 + lane;
+        // ===== epilogue warps 0..15: thread = (output row, 32-column group) =====
+        const int quarter = warp & 3, cgrp = warp >> 2;
+        const int ml = quarter * 32 + lane;
         const int m = tm * OZ_TM + ml;
+        const int col0 = cgrp * OZ_CPT;
         if (tid < OZ_TN) sYscale[tid] = oz_pow2(max(-1000, min(1000, g.eY[size_t(tn) * OZ_TN + tid])));
         epi.prepare(epi_smem, tn, tid);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int ex = g.eX[size_t(g.tiles_m_total > 0 ? tm : 0) * OZ_TM + ml] - 12;
+        asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory");
+        const int ex = g.eX[size_t(tm) * OZ_TM + ml] - 12;
         typename Epi::State st;
         epi.begin(st);
-        mbar_wait(tmem_full, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem_base + (uint32_t(warp * 32) << 16);
-#pragma unroll 1
-        for (int cc = 0; cc < OZ_TN / 8; ++cc) {
-            uint32_t a[T][8];
+        const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(col0);
+        double part[OZ_CPT];
 #pragma unroll
-            for (int d = 0; d < T; ++d)
-                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                             : "=r"(a[d][0]), "=r"(a[d][1]), "=r"(a[d][2]), "=r"(a[d][3]), "=r"(a[d][4]), "=r"(a[d][5]),
-                               "=r"(a[d][6]), "=r"(a[d][7])
-                             : "r"(taddr + uint32_t(d * OZ_TN + cc * 8)));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int sw = 0; sw < NSWEEP; ++sw) {
+            constexpr int dummy = 0; (void)dummy;
+            const int nlev = sw == 0 ? G1 : T - OZ_G;
+            mbar_wait(tmem_full, uint32_t(sw));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                double v = double(int(a[T - 1][jj]));
+            for (int cc = 0; cc < OZ_CPT / 8; ++cc) {
+                uint32_t a[OZ_G][8];
 #pragma unroll
-                for (int d = T - 2; d >= 0; --d) v = fma(v, 0.0078125, double(int(a[d][jj])));   // * 2^-7
-                const int j = cc * 8 + jj;
-                v = oz_scale(v * sYscale[j], ex);
-                epi.accept(st, epi_smem, m, tn, j, v);
+                for (int dd = 0; dd < OZ_G; ++dd) {
+                    if (dd < nlev)
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                     : "=r"(a[dd][0]), "=r"(a[dd][1]), "=r"(a[dd][2]), "=r"(a[dd][3]), "=r"(a[dd][4]),
+                                       "=r"(a[dd][5]), "=r"(a[dd][6]), "=r"(a[dd][7])
+                                     : "r"(taddr + uint32_t(dd * OZ_TN + cc * 8)));
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    double v = oz_i2d(a[nlev - 1][jj]);
+#pragma unroll
+                    for (int dd = OZ_G - 2; dd >= 0; --dd)
+                        if (dd < nlev - 1) v = fma(v, 0.0078125, oz_i2d(a[dd][jj]));   // * 2^-7, exact
+                    if (sw == 0) part[cc * 8 + jj] = v;
+                    else part[cc * 8 + jj] = fma(v, 3.7252902984619140625e-09, part[cc * 8 + jj]);   // 2^-28
+                }
+            }
+            if (sw + 1 < NSWEEP) {                               // accumulators may be overwritten
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty);
             }
         }
-        epi.finish(st, tm, tn, ml);
+#pragma unroll
+        for (int jl = 0; jl < OZ_CPT; ++jl) {
+            const int j = col0 + jl;
+            epi.accept(st, epi_smem, m, tn, j, oz_scale(part[jl] * sYscale[j], ex));
+        }
+        epi.finish(st, epi_smem, tm, tn, ml, cgrp);
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
-    if (warp == 5) {
+    if (warp == OZ_EPI_WARPS + 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -193,8 +245,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzOperands
 
 template <int T, class Epi>
 struct OzShape {
-    static constexpr size_t STAGE = size_t(T) * (OZ_TM + OZ_TN) * OZ_KB;
-    static constexpr size_t SMEM = OZ_STAGES * STAGE + (2 * OZ_STAGES + 2) * sizeof(uint64_t) + OZ_TN * sizeof(double) + Epi::SMEM;
+    static constexpr size_t SLOT = size_t(2) * T * OZ_PLANE;
+    static constexpr size_t SMEM = OZ_STAGES * SLOT + (2 * OZ_STAGES + 4) * sizeof(uint64_t) + OZ_TN * sizeof(double) + Epi::SMEM;
 };
 
 template <int T, class Epi>
