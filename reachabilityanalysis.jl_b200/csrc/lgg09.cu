@@ -8,6 +8,7 @@
 // first-disjoint-step reduction.
 #include "reach_common.cuh"
 #include "lgg09_kernels.cuh"
+#include "oz_gemm.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -31,8 +32,10 @@ struct TileCfg {
 const TileCfg kCfgs[] = {{0, 128, 128, 1},    // 2x4 warps, 64x32 warp tile  (large blocks)
                          {1, 64, 64, 2},      // 2x2 warps, 32x32 warp tile  (small n / stack build)
                          {2, 16, 128, 2},     // 1x4 warps, 16x32 warp tile  (a handful of directions)
-                         {3, 64, 128, 1}};    // 2x4 warps, 32x32 warp tile
-constexpr int kNumCfgs = 4;
+                         {3, 64, 128, 1},     // 2x4 warps, 32x32 warp tile
+                         {4, 128, 128, 1}};   // INT8 tcgen05 digit-plane GEMM (oz_gemm.cuh), packed blocks
+constexpr int kNumCfgs = 5;
+constexpr int kOzCfg = 4;
 
 template <class Epi>
 cudaError_t launch_cfg(int cfg, const GemmOperands& g, const Epi& epi, cudaStream_t st) {
@@ -239,6 +242,10 @@ struct reach_lgg09_plan {
     // persistent warp-per-chain path (small / sparse Phi)
     bool use_chain = false;
     bool packed = false;   // stack blocks packed with stride round_up(n+ne, 8) (large n, 128x128 tiles)
+    // INT8 tcgen05 digit-plane path (path == 3)
+    bool use_oz = false;
+    int oz_T = 8, oz_nkb = 0, oz_tiles_n = 0;
+    DevBuf Xq, Yq, eX, eY;
     int ch_maxnnz = 0, ch_rpl = 0, ch_ne = 0;
     size_t ch_smem = 0;
     DevBuf ell_val, ell_col, Edev;
@@ -290,16 +297,17 @@ int launch_chain(reach_ctx* ctx, int rpl, int ne, const Lgg09Chain& c, size_t sm
 // tiles lose a little to shared-memory traffic; every pass costs two launches; building the row
 // stack costs about S + 2 log2(S) passes of an n x n x n product, amortised over the run.
 double step_cost(const reach_lgg09_plan& p, const TileCfg& c, int S, int mu, int nrows, int sms) {
-    static const double eff[kNumCfgs] = {1.12, 0.85, 0.9, 0.92};   // cfg 0 is the warp-specialised kernel
+    // cfg 0 is the warp-specialised kernel; cfg 4 the digit-plane GEMM (T = 8: ~2.1x the DMMA rate, less for fewer planes)
+    static const double eff[kNumCfgs] = {1.12, 0.85, 0.9, 0.92, 2.3};
     const int mu_pad = round_up(mu, c.TM);
-    const bool packed = c.id == 0 && nrows >= 128;
+    const bool packed = (c.id == 0 || c.id == kOzCfg) && nrows >= 128;
     const int nbe = packed ? round_up(nrows, 8) : round_up(nrows, c.TN);
     const double slots = double(sms) * c.occ;
     auto pass = [&](double tiles) {
         const double waves = std::ceil(tiles / slots);
         const double mma = double(c.TM) * c.TN * p.Kp / (55.0 * eff[c.id]) * c.occ;
         const double mem = double(c.TM + c.TN) * p.Kp * 8.0 / 40.0 * c.occ;   // ~40 B/clk/SM from L2
-        return waves * (std::max(mma, mem) + (c.id == 0 ? 12000.0 : 4000.0));   // prologue + epilogue
+        return waves * (std::max(mma, mem) + (c.id == 0 || c.id == kOzCfg ? 12000.0 : 4000.0));   // prologue + epilogue
     };
     const double launch = 60000.0;     // ~30 us per pass: GEMM + tile-sum + eval + prefix launches back to back
     double cost = (pass(double(mu_pad / c.TM) * std::ceil(double(S) * nbe / c.TN)) + launch) / S;
@@ -320,6 +328,7 @@ int choose_config(reach_lgg09_plan& p) {
     double best = 1e300;
     for (int ci = 0; ci < kNumCfgs; ++ci) {
         const TileCfg& c = kCfgs[ci];
+        if ((ci == kOzCfg) != p.use_oz) continue;
         if (p.opts.tile_m && p.opts.tile_m != c.TM) continue;
         if (p.opts.tile_n && p.opts.tile_n != c.TN) continue;
         for (int S = 1; S <= std::max(smax, p.opts.time_block); ++S) {
@@ -459,12 +468,25 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
     }
     p->mu = int(chain_src.size());
 
+    // ---- INT8 tcgen05 digit-plane GEMM requested (path 3) ----
+    p->use_oz = false;
+    if (p->opts.path == 3) {
+        const int T = p->opts.reserved[0] ? p->opts.reserved[0] : 8;
+        if (T < 4 || T > OZ_MAX_T)
+            return set_error(ctx, REACH_EINVAL, "digit planes (opts.reserved[0]) must be in 4..%d, got %d", OZ_MAX_T, T);
+        if (n + p->ne < 128 || p->nq < 1 || p->nq > 4 || n > 32768)
+            return set_error(ctx, REACH_EUNSUPPORTED,
+                             "the digit-plane GEMM path needs 128 <= n + mapped rows, n <= 32768 and 1..4 support features "
+                             "(n=%d, mapped rows=%d, features=%d)", n, p->ne, p->nq);
+        p->use_oz = true;
+        p->oz_T = T;
+    }
     REACH_TRY(choose_config(*p));
     // ---- small / sparse Phi: ELL form of Phi' (row i of Phi' = column i of Phi) ----
     std::vector<double> ell_val;
     std::vector<int> ell_col;
     p->use_chain = false;
-    const bool forced_gemm = p->opts.path == 1 || (p->opts.path == 0 && (p->opts.time_block > 0 || p->opts.tile_m || p->opts.tile_n));
+    const bool forced_gemm = p->opts.path == 1 || p->opts.path == 3 || (p->opts.path == 0 && (p->opts.time_block > 0 || p->opts.tile_m || p->opts.tile_n));
     if (!forced_gemm && n <= 512 && p->nq <= 4 && p->ne <= 8) {
         int maxnnz = 0;
         for (int i = 0; i < n; ++i) {
@@ -505,7 +527,7 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
                          "in ELL form within shared memory (n=%d, features=%d, mapped rows=%d)", n, p->nq, p->ne);
     const int TM = p->TM, TN = p->TN, S = p->S;
     p->mu_pad = round_up(p->mu, TM);
-    p->packed = !p->use_chain && p->cfg == 0 && (n + p->ne) >= 128 && p->nq >= 1 && p->nq <= 8;
+    p->packed = !p->use_chain && (p->cfg == 0 || p->use_oz) && (n + p->ne) >= 128 && p->nq >= 1 && p->nq <= 8;
     p->nbe = p->packed ? round_up(n + p->ne, 8) : round_up(n + p->ne, TN);
     p->tpb = p->packed ? 1 : p->nbe / TN;
     const size_t slice_tiles = (size_t(S + 1) * p->nbe + TN - 1) / TN;      // row tiles of the longest launch
@@ -538,6 +560,15 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
         p->rho = p->rho_own.as<double>();
     }
 
+    if (p->use_oz) {
+        p->oz_nkb = (n + OZ_KB - 1) / OZ_KB;
+        p->oz_tiles_n = int((size_t(S + 1) * nbe + OZ_TN - 1) / OZ_TN);
+        const size_t plane_blk = size_t(p->oz_T) * OZ_PLANE;
+        REACH_TRY(p->Yq.alloc(ctx, size_t(p->oz_nkb) * p->oz_tiles_n * plane_blk, false));
+        REACH_TRY(p->eY.alloc(ctx, size_t(p->oz_tiles_n) * OZ_TN * sizeof(int)));
+        REACH_TRY(p->Xq.alloc(ctx, size_t(p->oz_nkb) * (mu_pad / OZ_TM) * plane_blk, false));
+        REACH_TRY(p->eX.alloc(ctx, size_t(mu_pad) * sizeof(int)));
+    }
     if (p->use_chain) {
         REACH_TRY(p->ell_val.alloc(ctx, ell_val.size() * 8, false));
         REACH_TRY(p->ell_col.alloc(ctx, ell_col.size() * 4, false));
@@ -737,6 +768,43 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         qcur ^= 1;
     }
 
+    if (p->use_oz) {   // digit planes of the whole row stack (once per run)
+        oz_slice_kernel<OZ_TN><<<p->oz_tiles_n * OZ_TN / 8, 256, 0, st>>>(stack, Kp, (S + 1) * nbe, n, p->oz_T, p->oz_nkb,
+                                                                      p->oz_tiles_n, p->Yq.as<int8_t>(), p->eY.as<int>());
+        REACH_CUDA(ctx, cudaGetLastError());
+        ++p->launches;
+    }
+    OzLgg09Epi<4> oepi{};
+    oepi.ldl = Kp;
+    oepi.n = n;
+    oepi.nbe = nbe;
+    oepi.Wl = p->Wl.as<double>();
+    oepi.Wa = p->Wa.as<double>();
+    oepi.nq = p->nq;
+    oepi.featpart = p->featpart.as<double>();
+    oepi.mu_pad = mu_pad;
+    // one pass of the digit-plane GEMM: L (fp64) -> digit planes, then blocks b_lo..S of the stack
+    auto oz_pass = [&](const double* Lcur, double* Lnext, int b_lo, int b_hi, int store_block, bool sample) -> int {
+        oz_slice_kernel<OZ_TM><<<mu_pad / 8, 256, 0, st>>>(Lcur, Kp, p->mu, n, p->oz_T, p->oz_nkb, mu_pad / OZ_TM,
+                                                          p->Xq.as<int8_t>(), p->eX.as<int>());
+        REACH_CUDA(ctx, cudaGetLastError());
+        ++p->launches;
+        const int tile_lo = int((size_t(b_lo) * nbe) / OZ_TN);
+        const int tile_hi = int((size_t(b_hi + 1) * nbe + OZ_TN - 1) / OZ_TN);
+        OzOperands g{p->Xq.as<int8_t>(), p->Yq.as<int8_t>(), p->eX.as<int>(), p->eY.as<int>(), p->oz_nkb,
+                     mu_pad / OZ_TM, mu_pad / OZ_TM, tile_lo, tile_hi - tile_lo, p->oz_tiles_n};
+        oepi.Lnext = Lnext;
+        oepi.store_block = store_block;
+        if (sample) REACH_CUDA(ctx, cudaEventRecord(p->gemm_ev[2 * p->gemm_sampled], st));
+        REACH_CUDA(ctx, (launch_oz_gemm(p->oz_T, g, oepi, st)));
+        if (sample) {
+            REACH_CUDA(ctx, cudaEventRecord(p->gemm_ev[2 * p->gemm_sampled + 1], st));
+            ++p->gemm_sampled;
+        }
+        ++p->launches;
+        return REACH_OK;
+    };
+
     // ---- main loop over super-steps ----
     const int64_t Kmax = p->nsteps - 1 + (p->prog.need_next ? 1 : 0);
     const int64_t T = (Kmax + S - 1) / S;
@@ -783,7 +851,8 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         const int nblk = c.b_hi - c.b_lo + 1;
         if (nblk > 0) {
             dim3 grid(cblocks, nblk);
-            if (p->packed) lgg09_tilesum_packed_kernel<<<grid, cthreads, 0, st>>>(c, p->featpart.as<double>(), ftot, nbe, TN);
+            if (p->packed) lgg09_tilesum_packed_kernel<<<grid, cthreads, 0, st>>>(c, p->featpart.as<double>(), ftot, nbe, TN,
+                                                                                  p->use_oz ? 0 : c.b_lo);
             else lgg09_tilesum_kernel<<<grid, cthreads, 0, st>>>(c, ftot);
             REACH_CUDA(ctx, cudaGetLastError());
             ++p->launches;
@@ -830,7 +899,10 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         epi.Lnext = p->Lbuf[1 - cur].as<double>();
         epi.block0 = 0;
         epi.store_block = -1;
-        if (p->packed) {
+        if (p->use_oz) {
+            REACH_TRY(oz_pass(p->Lbuf[cur].as<double>(), epi.Lnext, 0, 0, -1, false));
+            --p->launches;
+        } else if (p->packed) {
             pepi.Lnext = epi.Lnext; pepi.slice_block0 = 0; pepi.store_block = -1;
             REACH_CUDA(ctx, (launch_cfg(p->cfg, g, pepi, st)));
         } else {
@@ -848,6 +920,14 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         epi.block0 = b_lo;
         epi.store_block = S;
         const bool sample = (t % sample_every) == 0;
+        if (p->use_oz) {
+            REACH_TRY(oz_pass(p->Lbuf[cur].as<double>(), epi.Lnext, b_lo, S, S, sample));
+            ++p->gemm_total;
+            cmb.b_lo = b_lo; cmb.b_hi = S; cmb.has_carry = t > 0; cmb.tail = 0; cmb.k0 = t * S;
+            REACH_TRY(combine(cmb));
+            cur ^= 1;
+            continue;
+        }
         if (sample) REACH_CUDA(ctx, cudaEventRecord(p->gemm_ev[2 * p->gemm_sampled], st));
         if (p->packed) {
             pepi.Lnext = epi.Lnext; pepi.slice_block0 = b_lo; pepi.store_block = S;

@@ -267,11 +267,11 @@ static __global__ void lgg09_tilesum_kernel(const Lgg09Combine c, double* __rest
 // Packed layout: block b (relative to the launch slice) spans rows [rel*nbe, (rel+1)*nbe); it collects
 // segment 0 of the tiles that start inside it and segment 1 of the tile that starts in the previous block.
 static __global__ void lgg09_tilesum_packed_kernel(const Lgg09Combine c, const double* __restrict__ featpart,
-                                                   double* __restrict__ ftot, int nbe, int tn_rows) {
+                                                   double* __restrict__ ftot, int nbe, int tn_rows, int blk0) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int b = c.b_lo + blockIdx.y;
     if (j >= c.mu || b > c.b_hi) return;
-    const int rel = b - c.b_lo;
+    const int rel = b - blk0;                       // blk0: block that starts at row 0 of the tiled row range
     const int t0 = (rel * nbe) / tn_rows, t1 = ((rel + 1) * nbe - 1) / tn_rows;
     for (int q = 0; q < c.nq; ++q) {
         double lin = 0.0, ab = 0.0;

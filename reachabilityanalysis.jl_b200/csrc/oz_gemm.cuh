@@ -80,6 +80,86 @@ struct OzStoreEpi {
     __device__ __forceinline__ void finish(State&, unsigned char*, int, int, int, int) const {}
 };
 
+// ---- fused LGG09 epilogue on the digit-plane GEMM (packed stack layout, see Lgg09PackedEpi) ---------------
+// Stack rows are addressed absolutely (tile tn covers rows [128 tn, 128 tn + 128) of the stack; block b = row / nbe).
+// A tile straddles at most one block boundary (nbe >= 128): segment 0 = rows of the tile's first block, segment 1 =
+// rows of the next.  Thread (row m, 32 columns) accumulates lin_q / abs_q per segment; the four column groups of a
+// row are summed in fixed order through shared memory (the operand ring, idle by then).
+template <int NQ>
+struct OzLgg09Epi {
+    double* Lnext;              // [mu_pad][ldl]
+    int ldl, n, nbe;
+    int store_block;            // absolute block whose rows are L_{k0+S}; -1: none
+    const double* Wl;           // [nq][nbe]
+    const double* Wa;
+    int nq;
+    double* featpart;           // [tiles_n_total][2 segments][nq][2][mu_pad]
+    int mu_pad;
+    struct State { double lin[NQ][2], ab[NQ][2]; };
+    static constexpr size_t SMEM = size_t(OZ_TN) * (2 * NQ) * sizeof(double) + size_t(OZ_TN) * sizeof(int);
+
+    __device__ __forceinline__ void prepare(unsigned char* sm, int tn, int tid) const {
+        double* sw = reinterpret_cast<double*>(sm);                      // [2*NQ][128]: wl_q then wa_q
+        int* srib = reinterpret_cast<int*>(sw + size_t(2 * NQ) * OZ_TN); // row in block | store flag << 30
+        if (tid < OZ_TN) {
+            const int row = tn * OZ_TN + tid;
+            const int blk = row / nbe, rib = row - blk * nbe;
+            srib[tid] = rib | (blk == store_block ? (1 << 30) : 0);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                sw[(2 * q) * OZ_TN + tid] = q < nq ? Wl[size_t(q) * nbe + rib] : 0.0;
+                sw[(2 * q + 1) * OZ_TN + tid] = q < nq ? Wa[size_t(q) * nbe + rib] : 0.0;
+            }
+        }
+    }
+    __device__ __forceinline__ void begin(State& st) const {
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) st.lin[q][0] = st.lin[q][1] = st.ab[q][0] = st.ab[q][1] = 0.0;
+    }
+    __device__ __forceinline__ void accept(State& st, const unsigned char* sm, int m, int tn, int j, double v) const {
+        const double* sw = reinterpret_cast<const double*>(sm);
+        const int* srib = reinterpret_cast<const int*>(sw + size_t(2 * NQ) * OZ_TN);
+        const int info = srib[j], rib = info & 0x3FFFFFFF;
+        if ((info >> 30) && rib < n) Lnext[size_t(m) * ldl + rib] = v;
+        const int row0 = tn * OZ_TN;
+        const int bnd = (row0 / nbe + 1) * nbe - row0;                   // tile-local row where the next block starts
+        const double av = fabs(v);
+        if (j < bnd) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                st.lin[q][0] = fma(sw[(2 * q) * OZ_TN + j], v, st.lin[q][0]);
+                st.ab[q][0] = fma(sw[(2 * q + 1) * OZ_TN + j], av, st.ab[q][0]);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                st.lin[q][1] = fma(sw[(2 * q) * OZ_TN + j], v, st.lin[q][1]);
+                st.ab[q][1] = fma(sw[(2 * q + 1) * OZ_TN + j], av, st.ab[q][1]);
+            }
+        }
+    }
+    __device__ __forceinline__ void finish(State& st, unsigned char* ring, int tm, int tn, int ml, int cgrp) const {
+        double* red = reinterpret_cast<double*>(ring);                   // [cgrp 4][q][seg][part][128]
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+#pragma unroll
+            for (int sg = 0; sg < 2; ++sg) {
+                red[(((cgrp * NQ + q) * 2 + sg) * 2 + 0) * OZ_TM + ml] = st.lin[q][sg];
+                red[(((cgrp * NQ + q) * 2 + sg) * 2 + 1) * OZ_TM + ml] = st.ab[q][sg];
+            }
+        asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory");
+        // 512 threads, nq*4*128 outputs
+        const int t = cgrp * OZ_TM + ml;
+        for (int idx = t; idx < nq * 4 * OZ_TM; idx += OZ_EPI_WARPS * 32) {
+            const int r = idx % OZ_TM, part = (idx / OZ_TM) & 1, sg = (idx / (2 * OZ_TM)) & 1, q = idx / (4 * OZ_TM);
+            double v = 0.0;
+#pragma unroll
+            for (int c = 0; c < OZ_EPI_WARPS / 4; ++c) v += red[(((c * NQ + q) * 2 + sg) * 2 + part) * OZ_TM + r];
+            featpart[((((size_t(tn) * 2 + sg) * nq + q) * 2) + part) * mu_pad + tm * OZ_TM + r] = v;
+        }
+    }
+};
+
 // Two passes over K ("sweeps") when T > 4: levels 0..3 first (digit planes 0..3 of both operands, 10 MMAs per k-block),
 // then levels 4..T-1 (all planes, up to 26 MMAs).  Each sweep's level sum  sum_d 2^(-7 (d - d0)) acc_d  is EXACT in
 // FP64 (<= 47 bits), so the epilogue threads keep sweep 1 as one double per output while sweep 2 runs.
@@ -233,7 +313,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzOperands
             const int j = col0 + jl;
             epi.accept(st, epi_smem, m, tn, j, oz_scale(part[jl] * sYscale[j], ex));
         }
-        epi.finish(st, epi_smem, tm, tn, ml, cgrp);
+        epi.finish(st, ring, tm, tn, ml, cgrp);               // the ring is idle by now: every MMA has completed
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();

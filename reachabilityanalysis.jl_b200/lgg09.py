@@ -105,14 +105,16 @@ def _as_torch(ptr, ndirs, nsteps, device):
 class Lgg09Plan:
     """Device-resident LGG09 run: owns a `reach_lgg09_plan` (inputs, ρ matrix, statistics)."""
 
-    def __init__(self, ctx, n, ndirs, nsteps, time_block=0, share_negated=True, tile_m=0, tile_n=0, path=0):
+    def __init__(self, ctx, n, ndirs, nsteps, time_block=0, share_negated=True, tile_m=0, tile_n=0, path=0,
+                 digit_planes=0):
         self.ctx, self.lib = ctx, ctx.lib
         self.n, self.ndirs, self.nsteps = int(n), int(ndirs), int(nsteps)
         opts = L.reach_lgg09_opts()
         self.lib.reach_lgg09_default_opts(C.byref(opts))
         opts.time_block, opts.share_negated = int(time_block), int(bool(share_negated))
         opts.tile_m, opts.tile_n = int(tile_m), int(tile_n)
-        opts.path = {"auto": 0, "gemm": 1, "chain": 2}.get(path, path)
+        opts.path = {"auto": 0, "gemm": 1, "chain": 2, "int8": 3}.get(path, path)
+        opts.reserved[0] = int(digit_planes)      # 0 = 8 planes (FP64-level accuracy); 4..8
         self.handle = C.c_void_p()
         ctx.check(self.lib.reach_lgg09_plan_create(ctx.handle, self.n, self.ndirs, self.nsteps,
                                                    C.byref(opts), C.byref(self.handle)))
