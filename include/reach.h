@@ -119,11 +119,14 @@ typedef struct {
                              (noted at reach_homog.jl:108-110); results are bit-identical     */
     int32_t tile_m;       /* 0 = auto; else force the direction-tile size (testing)           */
     int32_t tile_n;       /* 0 = auto; else force the row-tile size (testing)                 */
-    int32_t path;         /* 0 = auto; 1 = batched GEMM over the power stack; 2 = persistent
+    int32_t path;         /* 0 = auto; 1 = batched FP64 (DMMA) GEMM over the power stack; 2 = persistent
                              warp-per-chain kernel (Phi' in shared memory, ELL form: small or
                              sparse Phi, e.g. ISS -- the device analogue of `sparse=true`,
-                             LGG09/post.jl:25-27; strictly sequential association)            */
-    int32_t reserved[3];
+                             LGG09/post.jl:25-27; strictly sequential association); 3 = the same
+                             batched GEMM on the INT8 tcgen05 pipe through error-free digit planes
+                             (unguarded when forced; auto picks it for large dense problems and
+                             guards it against the DMMA kernel, see reach_lgg09_plan_path)      */
+    int32_t reserved[3];  /* reserved[0]: digit planes of path 3 (0 = 8; 4..8)                  */
 } reach_lgg09_opts;
 
 void reach_lgg09_default_opts(reach_lgg09_opts* o);
@@ -164,6 +167,13 @@ void* reach_lgg09_plan_device_rho(reach_lgg09_plan* p);    /* device pointer, nd
 int  reach_lgg09_plan_stats(reach_lgg09_plan* p, double* ms, int64_t* launches,
                             int32_t* time_block, int32_t* tile_m, int32_t* tile_n,
                             int32_t* nchains, double* gemm_ms, int64_t* gemm_launches);
+/* Which main-loop kernel the plan uses / used: *path = 1 FP64 tensor-core (DMMA) GEMM, 2 persistent chain kernel,
+ * 3 INT8 tcgen05 digit-plane GEMM (FP64 emulation by error-free slicing, csrc/oz_gemm.cuh) with *digit_planes planes.
+ * When path 3 was chosen automatically it is guarded: *guard_checks sampled passes were recomputed on the DMMA kernel,
+ * *guard_max is the largest relative feature difference seen, and *fallback_pass >= 0 is the pass from which the run
+ * continued on the DMMA kernel because the difference exceeded 1e-12 (-1: never).  Any pointer may be NULL. */
+int  reach_lgg09_plan_path(reach_lgg09_plan* p, int32_t* path, int32_t* digit_planes, double* guard_max,
+                           int64_t* guard_checks, int64_t* fallback_pass);
 void reach_lgg09_plan_destroy(reach_lgg09_plan* p);
 
 /* ---------------------------------------------------------------------------------------------

@@ -244,8 +244,13 @@ struct reach_lgg09_plan {
     bool packed = false;   // stack blocks packed with stride round_up(n+ne, 8) (large n, 128x128 tiles)
     // INT8 tcgen05 digit-plane path (path == 3)
     bool use_oz = false;
+    bool oz_guard = false;        // auto-selected: sampled passes are re-run on the DMMA kernel and compared
     int oz_T = 8, oz_nkb = 0, oz_tiles_n = 0;
     DevBuf Xq, Yq, eX, eY;
+    DevBuf ftot_ref, guard_val, s_save;
+    double oz_guard_max = 0.0;    // largest sampled (int8 - DMMA) feature difference, relative to the feature scale
+    int64_t oz_fallback_pass = -1;   // pass at which the run fell back to the DMMA kernel (-1: never)
+    int64_t oz_checks = 0;
     int ch_maxnnz = 0, ch_rpl = 0, ch_ne = 0;
     size_t ch_smem = 0;
     DevBuf ell_val, ell_col, Edev;
@@ -470,6 +475,18 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
 
     // ---- INT8 tcgen05 digit-plane GEMM requested (path 3) ----
     p->use_oz = false;
+    p->oz_guard = false;
+    if (p->opts.path == 0 && !p->opts.tile_m && !p->opts.tile_n && n >= 512 && n <= 32768 && p->mu >= 96 &&
+        n + p->ne >= 128 && p->nq >= 1 && p->nq <= 4 && !getenv("REACH_NO_INT8")) {
+        // large dense problem: the INT8 tcgen05 digit-plane GEMM (~2x the FP64 tensor pipe), guarded: sampled passes
+        // are recomputed with the DMMA kernel and the run falls back to it if they differ by more than kOzGuardTol
+        const int T = p->opts.reserved[0] ? p->opts.reserved[0] : 8;
+        if (T < 4 || T > OZ_MAX_T)
+            return set_error(ctx, REACH_EINVAL, "digit planes (opts.reserved[0]) must be in 4..%d, got %d", OZ_MAX_T, T);
+        p->use_oz = true;
+        p->oz_guard = true;
+        p->oz_T = T;
+    }
     if (p->opts.path == 3) {
         const int T = p->opts.reserved[0] ? p->opts.reserved[0] : 8;
         if (T < 4 || T > OZ_MAX_T)
@@ -486,7 +503,7 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
     std::vector<double> ell_val;
     std::vector<int> ell_col;
     p->use_chain = false;
-    const bool forced_gemm = p->opts.path == 1 || p->opts.path == 3 || (p->opts.path == 0 && (p->opts.time_block > 0 || p->opts.tile_m || p->opts.tile_n));
+    const bool forced_gemm = p->opts.path == 1 || p->opts.path == 3 || p->use_oz || (p->opts.path == 0 && (p->opts.time_block > 0 || p->opts.tile_m || p->opts.tile_n));
     if (!forced_gemm && n <= 512 && p->nq <= 4 && p->ne <= 8) {
         int maxnnz = 0;
         for (int i = 0; i < n; ++i) {
@@ -568,6 +585,11 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
         REACH_TRY(p->eY.alloc(ctx, size_t(p->oz_tiles_n) * OZ_TN * sizeof(int)));
         REACH_TRY(p->Xq.alloc(ctx, size_t(p->oz_nkb) * (mu_pad / OZ_TM) * plane_blk, false));
         REACH_TRY(p->eX.alloc(ctx, size_t(mu_pad) * sizeof(int)));
+        if (p->oz_guard) {
+            REACH_TRY(p->ftot_ref.alloc(ctx, p->ftot.bytes));
+            REACH_TRY(p->guard_val.alloc(ctx, sizeof(unsigned long long)));
+            REACH_TRY(p->s_save.alloc(ctx, size_t(2) * mu_pad * sizeof(double)));
+        }
     }
     if (p->use_chain) {
         REACH_TRY(p->ell_val.alloc(ctx, ell_val.size() * 8, false));
@@ -847,12 +869,13 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     const int cthreads = 64, cblocks = (p->mu + cthreads - 1) / cthreads;
     double* ftot = p->ftot.as<double>();
     int carry_cur = 0;
+    bool oz_now = p->use_oz;      // false after the guard has sent the run back to the DMMA kernel
     auto combine = [&](const Lgg09Combine& c) -> int {
         const int nblk = c.b_hi - c.b_lo + 1;
         if (nblk > 0) {
             dim3 grid(cblocks, nblk);
             if (p->packed) lgg09_tilesum_packed_kernel<<<grid, cthreads, 0, st>>>(c, p->featpart.as<double>(), ftot, nbe, TN,
-                                                                                  p->use_oz ? 0 : c.b_lo);
+                                                                                  oz_now ? 0 : c.b_lo);
             else lgg09_tilesum_kernel<<<grid, cthreads, 0, st>>>(c, ftot);
             REACH_CUDA(ctx, cudaGetLastError());
             ++p->launches;
@@ -885,7 +908,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
 
     // sample at most 512 main-loop GEMM launches with event pairs
     const int64_t sample_every = std::max<int64_t>(1, (T + 511) / 512);
-    const size_t want_ev = size_t(2) * size_t((T + sample_every - 1) / sample_every + 1);
+    const size_t want_ev = size_t(2) * size_t((T + sample_every - 1) / sample_every + 3);
     while (p->gemm_ev.size() < want_ev) {
         cudaEvent_t e;
         REACH_CUDA(ctx, cudaEventCreate(&e));
@@ -912,6 +935,10 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         cmb.b_lo = 0; cmb.b_hi = 0; cmb.has_carry = 0; cmb.tail = 1; cmb.k0 = 0;
         REACH_TRY(combine(cmb));
     }
+    p->oz_guard_max = 0.0;
+    p->oz_fallback_pass = -1;
+    p->oz_checks = 0;
+    constexpr double kOzGuardTol = 1e-12;
     for (int64_t t = 0; t < T; ++t) {
         const int b_lo = t == 0 ? 0 : 1;
         GemmOperands g{p->Lbuf[cur].as<double>(), block(b_lo), Kp, Kp, Kp, mu_pad / TM,
@@ -920,20 +947,56 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         epi.block0 = b_lo;
         epi.store_block = S;
         const bool sample = (t % sample_every) == 0;
-        if (p->use_oz) {
+        cmb.b_lo = b_lo; cmb.b_hi = S; cmb.has_carry = t > 0; cmb.tail = 0; cmb.k0 = t * S;
+        // guarded digit-plane path: passes 0, 1, every 64th and the last are also run on the DMMA kernel
+        const bool check = oz_now && p->oz_guard && (t < 2 || (t & 63) == 0 || t == T - 1);
+        if (check) {
+            pepi.Lnext = epi.Lnext; pepi.slice_block0 = b_lo; pepi.store_block = S;
+            REACH_CUDA(ctx, (launch_cfg(0, g, pepi, st)));
+            dim3 grid(cblocks, S - b_lo + 1);
+            lgg09_tilesum_packed_kernel<<<grid, cthreads, 0, st>>>(cmb, p->featpart.as<double>(), p->ftot_ref.as<double>(), nbe, TN, b_lo);
+            REACH_CUDA(ctx, cudaGetLastError());
+            p->launches += 2;
+            REACH_CUDA(ctx, cudaMemcpyAsync(p->s_save.p, p->s_pos.p, size_t(mu_pad) * 8, cudaMemcpyDeviceToDevice, st));
+            REACH_CUDA(ctx, cudaMemcpyAsync(p->s_save.as<double>() + mu_pad, p->s_neg.p, size_t(mu_pad) * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        if (oz_now) {
             REACH_TRY(oz_pass(p->Lbuf[cur].as<double>(), epi.Lnext, b_lo, S, S, sample));
             ++p->gemm_total;
-            cmb.b_lo = b_lo; cmb.b_hi = S; cmb.has_carry = t > 0; cmb.tail = 0; cmb.k0 = t * S;
             REACH_TRY(combine(cmb));
-            cur ^= 1;
-            continue;
+            if (check) {
+                REACH_CUDA(ctx, cudaMemsetAsync(p->guard_val.p, 0, sizeof(unsigned long long), st));
+                lgg09_guard_kernel<<<(p->mu * p->nq + 127) / 128, 128, 0, st>>>(ftot, p->ftot_ref.as<double>(), p->nq, mu_pad, p->mu,
+                                                                               b_lo, S, p->guard_val.as<unsigned long long>());
+                REACH_CUDA(ctx, cudaGetLastError());
+                ++p->launches;
+                unsigned long long bits = 0;
+                REACH_CUDA(ctx, cudaMemcpyAsync(&bits, p->guard_val.p, sizeof(bits), cudaMemcpyDeviceToHost, st));
+                REACH_CUDA(ctx, cudaStreamSynchronize(st));
+                double worst;
+                std::memcpy(&worst, &bits, sizeof(worst));
+                ++p->oz_checks;
+                if (worst > p->oz_guard_max) p->oz_guard_max = worst;
+                if (!(worst <= kOzGuardTol)) {
+                    // not FP64-faithful on this problem (rows with a wide dynamic range): redo this pass and run the
+                    // rest on the FP64 tensor pipe
+                    oz_now = false;
+                    p->oz_fallback_pass = t;
+                    carry_cur ^= 1;
+                    REACH_CUDA(ctx, cudaMemcpyAsync(p->s_pos.p, p->s_save.p, size_t(mu_pad) * 8, cudaMemcpyDeviceToDevice, st));
+                    REACH_CUDA(ctx, cudaMemcpyAsync(p->s_neg.p, p->s_save.as<double>() + mu_pad, size_t(mu_pad) * 8, cudaMemcpyDeviceToDevice, st));
+                    --p->gemm_total;
+                }
+            }
+            if (oz_now) { cur ^= 1; continue; }
         }
+        const int dcfg = p->use_oz ? 0 : p->cfg;           // after a fallback: the warp-specialised DMMA kernel
         if (sample) REACH_CUDA(ctx, cudaEventRecord(p->gemm_ev[2 * p->gemm_sampled], st));
         if (p->packed) {
             pepi.Lnext = epi.Lnext; pepi.slice_block0 = b_lo; pepi.store_block = S;
-            REACH_CUDA(ctx, (launch_cfg(p->cfg, g, pepi, st)));
+            REACH_CUDA(ctx, (launch_cfg(dcfg, g, pepi, st)));
         } else {
-            REACH_CUDA(ctx, (launch_cfg(p->cfg, g, epi, st)));
+            REACH_CUDA(ctx, (launch_cfg(dcfg, g, epi, st)));
         }
         if (sample) {
             REACH_CUDA(ctx, cudaEventRecord(p->gemm_ev[2 * p->gemm_sampled + 1], st));
@@ -941,7 +1004,6 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         }
         ++p->launches;
         ++p->gemm_total;
-        cmb.b_lo = b_lo; cmb.b_hi = S; cmb.has_carry = t > 0; cmb.tail = 0; cmb.k0 = t * S;
         REACH_TRY(combine(cmb));
         cur ^= 1;
     }
@@ -1049,6 +1111,17 @@ extern "C" int reach_lgg09_plan_stats(reach_lgg09_plan* p, double* ms, int64_t* 
     if (nchains) *nchains = p->mu;
     if (gemm_ms) *gemm_ms = p->gemm_ms;
     if (gemm_launches) *gemm_launches = p->gemm_total;
+    return REACH_OK;
+}
+
+extern "C" int reach_lgg09_plan_path(reach_lgg09_plan* p, int32_t* path, int32_t* digit_planes, double* guard_max,
+                                     int64_t* guard_checks, int64_t* fallback_pass) {
+    if (!p) return REACH_EINVAL;
+    if (path) *path = p->use_chain ? 2 : (p->use_oz ? 3 : 1);
+    if (digit_planes) *digit_planes = p->use_oz ? p->oz_T : 0;
+    if (guard_max) *guard_max = p->oz_guard_max;
+    if (guard_checks) *guard_checks = p->oz_checks;
+    if (fallback_pass) *fallback_pass = p->oz_fallback_pass;
     return REACH_OK;
 }
 

@@ -286,6 +286,27 @@ static __global__ void lgg09_tilesum_packed_kernel(const Lgg09Combine c, const d
     }
 }
 
+// ---- guard of the INT8 digit-plane path: feature totals of a pass against the same pass on the DMMA kernel ----
+// Per (chain, feature): max over the pass's blocks of |d lin| + |d abs|, relative to the largest |lin| + |abs| of
+// that chain and feature in the pass; the worst ratio is kept with an integer atomicMax (non-negative doubles order
+// like their bit patterns).
+static __global__ void lgg09_guard_kernel(const double* __restrict__ ftot, const double* __restrict__ ftot_ref, int nq,
+                                          int mu_pad, int mu, int b_lo, int b_hi, unsigned long long* __restrict__ worst) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= mu * nq) return;
+    const int j = idx % mu, q = idx / mu;
+    double scale = 0.0, err = 0.0;
+    for (int b = b_lo; b <= b_hi; ++b) {
+        const size_t base = ((size_t(b) * nq + q) * 2) * mu_pad + j;
+        const double lr = ftot_ref[base], ar = ftot_ref[base + mu_pad];
+        scale = fmax(scale, fabs(lr) + fabs(ar));
+        err = fmax(err, fabs(ftot[base] - lr) + fabs(ftot[base + mu_pad] - ar));
+    }
+    double ratio = scale > 0.0 ? err / scale : (err > 0.0 ? 1.0e300 : 0.0);
+    if (!(ratio >= 0.0)) ratio = 1.0e300;                  // NaN
+    atomicMax(worst, (unsigned long long)__double_as_longlong(ratio));
+}
+
 // ---- combine, phase B: support values of Omega0 and V per (chain, step), fully parallel --------
 // Emit slot e of a pass pairs the features of r_k ("prev") with those of r_{k+1} ("cur"):
 //   has_carry: slot 0 = (carry, block b_lo), slot e = (block b_lo+e-1, block b_lo+e)

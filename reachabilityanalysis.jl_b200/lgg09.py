@@ -220,8 +220,14 @@ class Lgg09Plan:
         self.ctx.check(self.lib.reach_lgg09_plan_stats(
             self.handle, C.byref(ms), C.byref(launches), C.byref(S_), C.byref(tm), C.byref(tn),
             C.byref(mu), C.byref(gms), C.byref(gl)))
+        path, planes = C.c_int32(), C.c_int32()
+        gmax, gchecks, fb = C.c_double(), C.c_int64(), C.c_int64()
+        self.ctx.check(self.lib.reach_lgg09_plan_path(self.handle, C.byref(path), C.byref(planes), C.byref(gmax),
+                                                      C.byref(gchecks), C.byref(fb)))
         return dict(ms=ms.value, launches=launches.value, time_block=S_.value, tile_m=tm.value,
-                    tile_n=tn.value, nchains=mu.value, gemm_ms=gms.value, gemm_launches=gl.value)
+                    tile_n=tn.value, nchains=mu.value, gemm_ms=gms.value, gemm_launches=gl.value,
+                    path={1: "gemm", 2: "chain", 3: "int8"}[path.value], digit_planes=planes.value,
+                    guard_max=gmax.value, guard_checks=gchecks.value, fallback_pass=fb.value)
 
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:
