@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--n", type=int, default=2000, help="state dimension of the synthetic workload")
     ap.add_argument("--nsteps", type=int, default=10000, help="time steps per pass")
     ap.add_argument("--time-block", type=int, default=0)
+    ap.add_argument("--path", default="auto", choices=["auto", "gemm", "int8"],
+                    help="main-loop kernel: auto (INT8 digit-plane GEMM guarded by DMMA passes), gemm (FP64 DMMA), int8 (unguarded)")
     ap.add_argument("--cpu-sample-steps", type=int, default=0, help="time steps of the CPU sample (0: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-glgm06", action="store_true", help="skip the GLGM06 C4 flowpipe wall-time leg")
@@ -172,6 +174,37 @@ def cublas_fp64_peak(torch, nn=8192, iters=6):
     return best
 
 
+def cublaslt_int8_peak(torch, nn=8192, burst_iters=6, sustained_s=2.0):
+    """INT8 tensor roofline denominator: cuBLASLt INT8 GEMM nn^3 (torch._int_mm) measured in this run, as a burst
+    (best single launch) and sustained (back to back for ~sustained_s seconds, the regime of a kernel timed inside a
+    seconds-long pass).  MEASURED_PEAKS.json holds HBM and bf16 only."""
+    a = torch.randint(-64, 64, (nn, nn), dtype=torch.int8, device="cuda")
+    b = torch.randint(-64, 64, (nn, nn), dtype=torch.int8, device="cuda")
+    for _ in range(2):
+        torch._int_mm(a, b)
+    torch.cuda.synchronize()
+    ops = 2.0 * nn ** 3
+    best = 0.0
+    for _ in range(burst_iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch._int_mm(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, ops / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    iters = max(10, int(sustained_s / (ops / (best * 1e12))))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        torch._int_mm(a, b)
+    e1.record()
+    torch.cuda.synchronize()
+    sustained = ops * iters / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    del a, b
+    torch.cuda.empty_cache()
+    return best, sustained
+
+
 def glgm06_leg(args, ctx, torch, dist, world, rank):
     """Second half of the metric: GLGM06 flowpipe wall-time on config C4 (Building, 1024 initial-set
     splits, max_order 10, Forward(:zono) model), splits sharded over the ranks, no collective."""
@@ -241,7 +274,7 @@ def run_b200(args):
 
     # device-resident inputs and output
     out_T = torch.empty((nsteps, mloc), dtype=torch.float64, device="cuda")     # == mloc x nsteps col-major
-    plan = Lgg09Plan(ctx, n, mloc, nsteps, time_block=args.time_block)
+    plan = Lgg09Plan(ctx, n, mloc, nsteps, time_block=args.time_block, path=args.path)
     plan.set_output(out_T.data_ptr())
     plan.upload(wl.Phi, local_dirs, wl.Omega0, wl.V)
     flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
@@ -264,6 +297,7 @@ def run_b200(args):
         return ms, st, full
 
     peak_tf = cublas_fp64_peak(torch) if rank == 0 else 0.0
+    int8_burst, int8_sustained = cublaslt_int8_peak(torch) if rank == 0 else (0.0, 0.0)
     for _ in range(args.warmup):
         one_pass()
     sampler = ClockSampler(local_rank)
@@ -298,6 +332,7 @@ def run_b200(args):
     opts = _lib.reach_lgg09_opts()
     ctx.lib.reach_lgg09_default_opts(C.byref(opts))
     opts.time_block = args.time_block
+    opts.path = {"auto": 0, "gemm": 1, "int8": 3}[args.path]
     h2d = Phi_h.nbytes + dirs_h.nbytes + 4 * n * 8
     d2h = rho_h.nbytes
     full_h = torch.empty((nsteps, ndirs), dtype=torch.float64, pin_memory=True) if (world > 1 and rank == 0) else None
@@ -333,32 +368,70 @@ def run_b200(args):
         S = st["time_block"]
         gemm_ms = gemm_ms_acc / args.steps                                  # mean duration of one launch
         flops_per_launch = 2.0 * n * n * st["nchains"] * S                  # algorithmic: 2 n^2 per chain-step
-        achieved = flops_per_launch / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        achieved = flops_per_launch / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None   # FP64-equivalent TFLOP/s
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "lgg09_main_kernel_traffic.json")))
+            ent = tj.get(st["path"])
+            if ent and ent.get("n") == n and ent.get("chains") == st["nchains"]:
+                # DRAM bytes of one launch from the ncu --set full capture, scaled to this run's time block
+                traffic = ent["dram_bytes_per_launch"] * (S / float(ent["time_block"]))
+        except Exception:
+            pass
+        if st["path"] == "int8":
+            T = st["digit_planes"]
+            pairs = T * (T + 1) // 2
+            int8_ops = flops_per_launch * pairs                              # INT8 MMA work actually issued
+            ach_int8 = int8_ops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+            roofline = {
+                "bound": "tensor",
+                "kernel": "oz_gemm_kernel<%d, OzLgg09Epi> (INT8 tcgen05 digit-plane GEMM, FP64 by error-free slicing, "
+                          "fused support epilogue)" % T,
+                "achieved": ach_int8, "peak": int8_sustained, "unit": "TOP/s (INT8 tensor)",
+                "frac": (ach_int8 / int8_sustained) if ach_int8 and int8_sustained else None,
+                "peak_source": "cuBLASLt INT8 GEMM 8192^3 (torch._int_mm) measured in this run, sustained over ~2 s "
+                               "(the kernel is timed inside a seconds-long pass); burst %.0f TOP/s; "
+                               "MEASURED_PEAKS.json has no INT8 entry" % int8_burst,
+                "int8_ops_per_launch": int8_ops, "plane_pairs": pairs, "digit_planes": T,
+                "fp64_equivalent": {"achieved_tflops": achieved, "cublas_dgemm_tflops": peak_tf,
+                                    "ratio": (achieved / peak_tf) if achieved and peak_tf else None,
+                                    "note": "algorithmic 2 n^2 flop per chain-step; cuBLAS DGEMM 8192^3 measured in this run"},
+                "guard": {"checks": st["guard_checks"], "max_rel_diff_vs_dmma": st["guard_max"],
+                          "fallback_pass": st["fallback_pass"], "tolerance": 1e-12},
+                "flops_per_launch": flops_per_launch, "launch_ms": gemm_ms,
+                "launches_per_step": st["gemm_launches"],
+                "gemm_share_of_step": st["gemm_launches"] * gemm_ms / (total_ms / args.steps),
+                "traffic": traffic}
+        else:
+            roofline = {
+                "bound": "tensor", "kernel": "nt_dgemm_ws_kernel<...,Lgg09PackedEpi> (FP64 DMMA + fused support epilogue)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": (achieved / peak_tf) if achieved and peak_tf else None,
+                "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul f64) measured in this run, burst; "
+                               "MEASURED_PEAKS.json has no FP64 entry",
+                "flops_per_launch": flops_per_launch, "launch_ms": gemm_ms,
+                "launches_per_step": st["gemm_launches"],
+                "gemm_share_of_step": st["gemm_launches"] * gemm_ms / (total_ms / args.steps),
+                "traffic": traffic}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": wl.name, "n": n, "ndirs": ndirs, "nsteps": nsteps,
                        "ndirs_per_gpu": mloc, "chains_per_gpu": st["nchains"], "time_block": S,
-                       "tile": "%dx%d" % (st["tile_m"], st["tile_n"]), "sharding": "template directions",
+                       "tile": "%dx%d" % (st["tile_m"], st["tile_n"]), "main_kernel": st["path"],
+                       "sharding": "template directions",
                        "collective": "all-gather of per-rank rho blocks" if world > 1 else "none",
                        "l2": "working set (row stack %d MB + rho %d MB) exceeds the 126 MB L2; 512 MB flush "
-                             "between passes" % ((S + 1) * 2048 * n * 8 >> 20, mloc * nsteps * 8 >> 20)},
+                             "between passes" % ((S + 1) * 2048 * n * 8 * (2 if st["path"] == "int8" else 1) >> 20,
+                                                 mloc * nsteps * 8 >> 20)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "timer": "host wall clock around reach_lgg09(host buffers), max over ranks",
                     "bit_identical_to_device_resident_run": same},
             "gpu_launches": launches,
             "wall_s_timed_region": wall,
-            "roofline": {"bound": "tensor", "kernel": "nt_dgemm_kernel<...,Lgg09Epi> (FP64 DMMA + fused support epilogue)",
-                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": (achieved / peak_tf) if achieved and peak_tf else None,
-                         "peak_source": "cuBLAS DGEMM 8192^3 (torch.matmul f64) measured in this run, burst; "
-                                        "MEASURED_PEAKS.json has no FP64 entry",
-                         "flops_per_launch": flops_per_launch, "launch_ms": gemm_ms,
-                         "launches_per_step": st["gemm_launches"],
-                         "gemm_share_of_step": st["gemm_launches"] * gemm_ms / (total_ms / args.steps),
-                         "traffic": None},
+            "roofline": roofline,
         }
         if glgm06 is not None:
             line["glgm06_c4"] = glgm06
