@@ -951,12 +951,20 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         // guarded digit-plane path: passes 0, 1, every 64th and the last are also run on the DMMA kernel
         const bool check = oz_now && p->oz_guard && (t < 2 || (t & 63) == 0 || t == T - 1);
         if (check) {
-            pepi.Lnext = epi.Lnext; pepi.slice_block0 = b_lo; pepi.store_block = S;
-            REACH_CUDA(ctx, (launch_cfg(0, g, pepi, st)));
-            dim3 grid(cblocks, S - b_lo + 1);
-            lgg09_tilesum_packed_kernel<<<grid, cthreads, 0, st>>>(cmb, p->featpart.as<double>(), p->ftot_ref.as<double>(), nbe, TN, b_lo);
-            REACH_CUDA(ctx, cudaGetLastError());
-            p->launches += 2;
+            // reference features of blocks 1 and S (the first step of the pass and the block that becomes L_{k+S}) from
+            // the DMMA kernel; nothing of the run's state is touched (no store block, separate totals buffer)
+            for (int cb : {1, S}) {
+                GemmOperands gc{p->Lbuf[cur].as<double>(), block(cb), Kp, Kp, Kp, mu_pad / TM, (nbe + TN - 1) / TN};
+                pepi.Lnext = epi.Lnext; pepi.slice_block0 = cb; pepi.store_block = -1;
+                REACH_CUDA(ctx, (launch_cfg(0, gc, pepi, st)));
+                Lgg09Combine cc = cmb;
+                cc.b_lo = cb; cc.b_hi = cb;
+                dim3 grid(cblocks, 1);
+                lgg09_tilesum_packed_kernel<<<grid, cthreads, 0, st>>>(cc, p->featpart.as<double>(), p->ftot_ref.as<double>(), nbe, TN, cb);
+                REACH_CUDA(ctx, cudaGetLastError());
+                p->launches += 2;
+                if (S == 1) break;
+            }
             REACH_CUDA(ctx, cudaMemcpyAsync(p->s_save.p, p->s_pos.p, size_t(mu_pad) * 8, cudaMemcpyDeviceToDevice, st));
             REACH_CUDA(ctx, cudaMemcpyAsync(p->s_save.as<double>() + mu_pad, p->s_neg.p, size_t(mu_pad) * 8, cudaMemcpyDeviceToDevice, st));
         }
@@ -967,7 +975,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
             if (check) {
                 REACH_CUDA(ctx, cudaMemsetAsync(p->guard_val.p, 0, sizeof(unsigned long long), st));
                 lgg09_guard_kernel<<<(p->mu * p->nq + 127) / 128, 128, 0, st>>>(ftot, p->ftot_ref.as<double>(), p->nq, mu_pad, p->mu,
-                                                                               b_lo, S, p->guard_val.as<unsigned long long>());
+                                                                               1, S, p->guard_val.as<unsigned long long>());
                 REACH_CUDA(ctx, cudaGetLastError());
                 ++p->launches;
                 unsigned long long bits = 0;

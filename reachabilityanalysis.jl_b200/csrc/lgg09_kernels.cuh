@@ -286,17 +286,17 @@ static __global__ void lgg09_tilesum_packed_kernel(const Lgg09Combine c, const d
     }
 }
 
-// ---- guard of the INT8 digit-plane path: feature totals of a pass against the same pass on the DMMA kernel ----
-// Per (chain, feature): max over the pass's blocks of |d lin| + |d abs|, relative to the largest |lin| + |abs| of
-// that chain and feature in the pass; the worst ratio is kept with an integer atomicMax (non-negative doubles order
+// ---- guard of the INT8 digit-plane path: feature totals of a pass against the same blocks on the DMMA kernel ----
+// The first and the last block of the pass are sampled.  Per (chain, feature): max over the two blocks of
+// |d lin| + |d abs|, relative to the largest |lin| + |abs| of that chain and feature in them; the worst ratio is kept with an integer atomicMax (non-negative doubles order
 // like their bit patterns).
 static __global__ void lgg09_guard_kernel(const double* __restrict__ ftot, const double* __restrict__ ftot_ref, int nq,
-                                          int mu_pad, int mu, int b_lo, int b_hi, unsigned long long* __restrict__ worst) {
+                                          int mu_pad, int mu, int b_first, int b_last, unsigned long long* __restrict__ worst) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= mu * nq) return;
     const int j = idx % mu, q = idx / mu;
     double scale = 0.0, err = 0.0;
-    for (int b = b_lo; b <= b_hi; ++b) {
+    for (int b = b_first; b <= b_last; b += (b_last > b_first ? b_last - b_first : 1)) {   // the two sampled blocks
         const size_t base = ((size_t(b) * nq + q) * 2) * mu_pad + j;
         const double lr = ftot_ref[base], ar = ftot_ref[base + mu_pad];
         scale = fmax(scale, fabs(lr) + fabs(ar));
