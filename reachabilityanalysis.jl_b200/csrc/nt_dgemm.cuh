@@ -181,6 +181,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (!ok && ++spins > (1u << 27)) __trap();     // a protocol error must fail, not hang the GPU
     } while (!ok);
 }
+// The same wait for warps that idle through a whole main loop (epilogue warps waiting for the accumulators): sleep
+// between polls so that hundreds of spinning threads do not burn issue slots and power next to the tensor pipe.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns = 512) {
+    uint32_t ok = 0, spins = 0;
+    const uint32_t a = smem_u32(bar);
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (!ok) {
+            __nanosleep(ns);
+            if (++spins > (1u << 24)) __trap();
+        }
+    } while (!ok);
+}
 __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");

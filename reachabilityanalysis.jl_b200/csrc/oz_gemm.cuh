@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzOperands
         for (int sw = 0; sw < NSWEEP; ++sw) {
             constexpr int dummy = 0; (void)dummy;
             const int nlev = sw == 0 ? G1 : T - OZ_G;
-            mbar_wait(tmem_full, uint32_t(sw));
+            mbar_wait_sleep(tmem_full, uint32_t(sw));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int cc = 0; cc < OZ_CPT / 8; ++cc) {
