@@ -63,6 +63,7 @@ struct reach_glgm06_plan {
     DevBuf pos_own, tb, diag, centre;   // per (block, split)
     DevBuf H;                           // homogeneous: [nsteps][m_pad][Kp]
     DevBuf scratch_pos;
+    DevBuf progress;                    // powers published so far (chain kernel <- powers kernel)
     int64_t bytes_stored = 0;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_powers = nullptr, ev_gemm = nullptr;
@@ -353,18 +354,37 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
         c.wB = p->wB.as<double>();
         c.permB = p->permB.as<int>();
         c.bpref = p->bpref.as<double>();
-        // powers first (1 CTA, ~1 us per step) so that the batched GEMM can run beside the W chain
+        // The chain CTA goes first so that it owns an SM; the powers (1 CTA, ~8 us per step) and then the batched GEMM
+        // run beside it on the second stream.  The chain consumes the powers as they are published (progress counter);
+        // launched the other way round, the GEMM's CTAs fill every SM and the chain CTA (200 KB of shared memory) waits
+        // for the whole GEMM grid to drain.
+        // Every kernel that is launched while the chain CTA may be spinning on the progress counter must be loaded
+        // beforehand: with CUDA's lazy module loading the first launch of a kernel can wait for running kernels to
+        // finish, which would deadlock against the spinning chain.
+        {
+            cudaFuncAttributes fa;
+            REACH_CUDA(ctx, cudaFuncGetAttributes(&fa, glgm06_powers_kernel));
+            REACH_CUDA(ctx, cudaFuncGetAttributes(&fa, glgm06_select_kernel));
+            const GemmOperands none{nullptr, nullptr, Kp, Kp, Kp, 0, 0};
+            if (p->TN == 64) REACH_CUDA(ctx, (launch_tn64(none, GenEpi{}, p->stream2)));
+            else REACH_CUDA(ctx, (launch_tn128(none, GenEpi{}, p->stream2)));
+        }
+        if (!p->progress.p) REACH_TRY(p->progress.alloc(ctx, sizeof(int)));
+        REACH_CUDA(ctx, cudaMemsetAsync(p->progress.p, 0, sizeof(int), st));
+        c.progress = p->progress.as<int>();
+        REACH_CUDA(ctx, cudaEventRecord(p->ev_powers, st));          // "state reset, previous run finished"
         const size_t psmem = 8 * 3 * size_t(n) * (n + 1);
         REACH_CUDA(ctx, cudaFuncSetAttribute(glgm06_powers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(psmem)));
-        glgm06_powers_kernel<<<1, 1024, psmem, st>>>(p->PhiRows.as<double>(), p->PhiT.as<double>(), n, Kp, nb, nblk, Pst);
-        REACH_CUDA(ctx, cudaGetLastError());
-        ++p->launches;
-        overlap = true;
-        REACH_CUDA(ctx, cudaEventRecord(p->ev_powers, st));
         REACH_CUDA(ctx, cudaFuncSetAttribute(glgm06_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(chain_smem)));
         glgm06_chain_kernel<<<1, 1024, chain_smem, st>>>(c);
         REACH_CUDA(ctx, cudaGetLastError());
         ++p->launches;
+        REACH_CUDA(ctx, cudaStreamWaitEvent(p->stream2, p->ev_powers, 0));
+        glgm06_powers_kernel<<<1, 1024, psmem, p->stream2>>>(p->PhiRows.as<double>(), p->PhiT.as<double>(), n, Kp, nb, nblk, Pst,
+                                                             p->progress.as<int>());
+        REACH_CUDA(ctx, cudaGetLastError());
+        ++p->launches;
+        overlap = true;
     } else {
     const int urows = round_up(p->pU + 1, 64);
     const size_t gw_stride = size_t(p->pWcap) * n;
@@ -405,10 +425,7 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
 
     // ---- (2) batched part: all splits x all steps ----
     cudaStream_t gst = st;                              // stream of the batched GEMM
-    if (overlap) {
-        gst = p->stream2;
-        REACH_CUDA(ctx, cudaStreamWaitEvent(gst, p->ev_powers, 0));
-    }
+    if (overlap) gst = p->stream2;                      // after the powers kernel, in stream order
     if (nblk > 0) {
         GenEpi epi{};
         epi.out = p->A_store.as<double>();

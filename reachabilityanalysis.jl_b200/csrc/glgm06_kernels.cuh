@@ -342,7 +342,7 @@ static __global__ void glgm06_w_reduce_kernel(const double* __restrict__ PU, int
 // batched split GEMM (which only needs the powers) overlap with the W chain on a second stream.
 static __global__ void __launch_bounds__(1024, 1) glgm06_powers_kernel(const double* __restrict__ P0, const double* __restrict__ PhiT,
                                                                        int n, int ldk, int nb, long long nblk,
-                                                                       double* __restrict__ Pstack) {
+                                                                       double* __restrict__ Pstack, int* __restrict__ progress) {
     extern __shared__ __align__(16) unsigned char smraw[];
     const int ldp = n + 1;
     double* sP[2];
@@ -370,7 +370,28 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_powers_kernel(const dou
             }
         }
         __syncthreads();
+        if (tid == 0) {                                   // blocks 0..b are in global memory: publish (release)
+            __threadfence();
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(progress), "r"(int(b + 1)) : "memory");
+        }
     }
+}
+
+// The chain CTA is launched BEFORE the powers kernel (so that it owns an SM before the batched GEMM floods the
+// device) and consumes the powers as they are published.
+__device__ __forceinline__ void glgm06_wait_progress(const int* progress, int need) {
+    if (threadIdx.x == 0) {
+        int v = 0;
+        unsigned spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(progress) : "memory");
+            if (v < need) {
+                __nanosleep(200);
+                if (++spins > (1u << 26)) __trap();
+            }
+        } while (v < need);
+    }
+    __syncthreads();
 }
 
 struct ChainParams {
@@ -378,7 +399,8 @@ struct ChainParams {
     int pU, r, pWcap;
     long long nblk;
     const double* XU;           // [(pU+1)][ldk]
-    const double* Pstack;       // [nblk][nb][ldk], precomputed by glgm06_powers_kernel
+    const double* Pstack;       // [nblk][nb][ldk], produced concurrently by glgm06_powers_kernel
+    const int* progress;        // number of blocks of Pstack published so far
     double* GWall;              // [(nblk+1)][pWcap][n]
     double* cWall;              // [(nblk+1)][n]
     const int* pW;              // [nblk+1]
@@ -413,9 +435,10 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
     __shared__ int s_ta, s_z;
 
     const int tid = threadIdx.x, nthr = blockDim.x;
+    glgm06_wait_progress(c.progress, 1);
     for (int idx = tid; idx < n * n; idx += nthr) {
         const int a = idx / n, b = idx % n;
-        sP[0][a * ldp + b] = c.Pstack[size_t(a) * c.ldk + b];          // P_0 (the powers are precomputed)
+        sP[0][a * ldp + b] = __ldcg(c.Pstack + size_t(a) * c.ldk + b);  // P_0
     }
     for (int idx = tid; idx < (pU + 1) * n; idx += nthr) {
         const int g = idx / n, l = idx % n;
@@ -491,8 +514,9 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
             sPU[g * ldp + i] = s;
         }
         {
+            glgm06_wait_progress(c.progress, int(b) + 2);
             const double* Pg = c.Pstack + size_t(b + 1) * c.nb * c.ldk;        // P_{b+1} for the next step
-            for (int idx = tid; idx < n * n; idx += nthr) Pn[(idx / n) * ldp + idx % n] = Pg[size_t(idx / n) * c.ldk + idx % n];
+            for (int idx = tid; idx < n * n; idx += nthr) Pn[(idx / n) * ldp + idx % n] = __ldcg(Pg + size_t(idx / n) * c.ldk + idx % n);
         }
         __syncthreads();
         // centre of W_{b+1}
