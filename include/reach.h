@@ -126,7 +126,10 @@ typedef struct {
                              batched GEMM on the INT8 tcgen05 pipe through error-free digit planes
                              (unguarded when forced; auto picks it for large dense problems and
                              guards it against the DMMA kernel, see reach_lgg09_plan_path)      */
-    int32_t reserved[3];  /* reserved[0]: digit planes of path 3 (0 = 8; 4..8)                  */
+    int32_t reserved[3];  /* reserved[0]: digit planes of path 3 (0 = 8; 4..8)
+                             reserved[1]: 1 = box output: the two rows of a direction pair (l, -l) hold
+                             (lin, abs) = (centre, radius) of the box hull instead of abs +- lin
+                             (what reach_box uses; Omega0 must have one alternative)            */
 } reach_lgg09_opts;
 
 void reach_lgg09_default_opts(reach_lgg09_opts* o);
@@ -175,6 +178,17 @@ int  reach_lgg09_plan_stats(reach_lgg09_plan* p, double* ms, int64_t* launches,
 int  reach_lgg09_plan_path(reach_lgg09_plan* p, int32_t* path, int32_t* digit_planes, double* guard_max,
                            int64_t* guard_checks, int64_t* fallback_pass);
 void reach_lgg09_plan_destroy(reach_lgg09_plan* p);
+
+/* BOX (src/Algorithms/BOX/reach_homog.jl:8-47,50-69, reach_inhomog.jl:8-60): hyperrectangular flowpipe
+ *   non-recursive: c_k = Phi^(k-1) c_1 + W_k.c,  r_k = |Phi^(k-1)| r_1 + W_k.r,  W_2 = U, W_{k+1} = W_k (+) box(Phi^(k-1) U)
+ *   recursive    : H_k = box(Phi H_{k-1})          (homogeneous only, as in the reference)
+ * on the LGG09 device path (row i of Phi^k is the direction chain of e_i).  c0, r0: centre and radius of Omega0
+ * (already a hyperrectangle: BOX/post.jl:29); cU, rU: the input hyperrectangle or both NULL (homogeneous).
+ * c_host, r_host: n x nsteps column-major (column k = step k+1 of the reference), either may be NULL.  Invariants
+ * (`_isdisjoint(X, H_k) && break`) are checked by the caller on the returned boxes. */
+int reach_box(reach_ctx* ctx, int n, int64_t nsteps, const double* Phi, const double* c0, const double* r0,
+              const double* cU, const double* rU, int recursive, const reach_lgg09_opts* opts,
+              double* c_host, double* r_host);
 
 /* ---------------------------------------------------------------------------------------------
  * GLGM06: zonotope flowpipes for a batch of initial sets ("splits") that share Phi and U.

@@ -9,5 +9,6 @@ from .flowpipe import (Flowpipe, MixedFlowpipe, ReachSolution, TemplateReachSet,
                        TimeInterval, zeroT, rho)
 from .lgg09 import LGG09, Forward, NoBloating, FirstOrderZonotope, Lgg09Plan  # noqa: F401
 from .glgm06 import GLGM06, Glgm06Plan, reduce_order  # noqa: F401
+from .box import BOX  # noqa: F401
 from .solve import solve, IVP, discretize  # noqa: F401
 from ._lib import Context, ReachError, default_context  # noqa: F401

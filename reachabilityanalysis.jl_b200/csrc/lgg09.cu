@@ -425,6 +425,14 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
     REACH_TRY(build_program(ctx, n, Omega0, V, p->prog));
     p->ne = int(p->prog.erows.size());
     p->nq = int(p->prog.feats.size());
+    p->prog.dev.box = p->opts.reserved[1] ? 1 : 0;
+    if (p->prog.dev.box) {
+        if (p->prog.dev.nalt != 1)
+            return set_error(ctx, REACH_EINVAL, "box output (opts.reserved[1]) needs Omega0 to be a single sum of terms, got %d alternatives",
+                             p->prog.dev.nalt);
+        if (inv && inv->kind != REACH_INV_NONE)
+            return set_error(ctx, REACH_EUNSUPPORTED, "box output does not take an invariant (the caller checks disjointness on (c, r))");
+    }
 
     // ---- direction chains: l and -l share (Phi')^k l (reach_homog.jl:108-110) ----
     // chain c = sign_c * direction src_c (canonical orientation: first non-zero entry positive)
@@ -1157,6 +1165,57 @@ extern "C" int reach_lgg09(reach_ctx* ctx, int n, int ndirs, int64_t nsteps, con
                 ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4));
     }
     return rc;
+}
+
+// BOX algorithm (Algorithms/BOX/reach_homog.jl:8-47, reach_inhomog.jl:8-60): c_k = Phi^(k-1) c_1 + W_k.c,
+// r_k = |Phi^(k-1)| r_1 + W_k.r with W_{k+1} = W_k + (Phi^(k-1) U.c, |Phi^(k-1)| U.r).  Row i of Phi^k is the chain
+// (Phi')^k e_i, so this is the LGG09 recurrence over the box template with the (lin, abs) pair written out instead
+// of abs +- lin.  recursive != 0 (reach_homog.jl:50-69): H_k = box(Phi H_{k-1}), i.e. c_k = Phi c_{k-1} and
+// r_k = |Phi| r_{k-1} (homogeneous only, as in the reference): the same recurrence with singleton sets, once with
+// Phi and once with |Phi|.
+extern "C" int reach_box(reach_ctx* ctx, int n, int64_t nsteps, const double* Phi, const double* c0, const double* r0,
+                         const double* cU, const double* rU, int recursive, const reach_lgg09_opts* opts,
+                         double* c_host, double* r_host) {
+    if (!ctx) return REACH_EINVAL;
+    if (n < 1 || nsteps < 1) return set_error(ctx, REACH_EINVAL, "reach_box: n and NSTEPS must be >= 1");
+    if (!Phi || !c0 || !r0) return set_error(ctx, REACH_EINVAL, "reach_box: Phi, c0 and r0 must not be NULL");
+    if ((cU == nullptr) != (rU == nullptr)) return set_error(ctx, REACH_EINVAL, "reach_box: cU and rU must both be given or both be NULL");
+    for (int i = 0; i < n; ++i)
+        if (r0[i] < 0 || (rU && rU[i] < 0)) return set_error(ctx, REACH_EINVAL, "reach_box: negative radius");
+    if (recursive && cU)     // the reference has no such method either (reach_inhomog.jl only defines recursive::Val{false})
+        return set_error(ctx, REACH_EUNSUPPORTED, "reach_box: the recursive variant is defined for homogeneous systems only");
+    reach_lgg09_opts o;
+    if (opts) o = *opts; else reach_lgg09_default_opts(&o);
+    o.reserved[1] = 1;                                   // (lin, abs) outputs
+    o.share_negated = 1;
+    std::vector<double> dirs(size_t(n) * 2 * n, 0.0);    // [I, -I]: chain i = e_i, outputs i (centre) and n + i (radius)
+    for (int i = 0; i < n; ++i) { dirs[size_t(i) * n + i] = 1.0; dirs[size_t(n + i) * n + i] = -1.0; }
+    std::vector<double> out(size_t(2) * n * nsteps);
+    auto run = [&](const double* M, const double* oc, const double* orad, const double* vc, const double* vr) -> int {
+        reach_term t0{REACH_TERM_BOX, 0, 0, 0, nullptr, oc, orad, nullptr};
+        reach_term tv{REACH_TERM_BOX, 0, 0, 0, nullptr, vc, vr, nullptr};
+        const int32_t one = 1;
+        reach_setexpr O{1, &one, &t0}, V{1, &one, &tv};
+        return reach_lgg09(ctx, n, 2 * n, nsteps, M, dirs.data(), &O, (vc || vr) ? &V : nullptr, nullptr, &o, out.data(), nullptr);
+    };
+    auto scatter = [&](double* dst, int row0) {
+        if (!dst) return;
+        for (int64_t k = 0; k < nsteps; ++k)
+            std::memcpy(dst + size_t(k) * n, out.data() + size_t(k) * 2 * n + row0, sizeof(double) * n);
+    };
+    if (!recursive) {
+        REACH_TRY(run(Phi, c0, r0, cU, rU));
+        scatter(c_host, 0);
+        scatter(r_host, n);
+        return REACH_OK;
+    }
+    REACH_TRY(run(Phi, c0, nullptr, cU, nullptr));       // centres: singleton sets, Phi
+    scatter(c_host, 0);
+    std::vector<double> absPhi(size_t(n) * n);
+    for (size_t i = 0; i < absPhi.size(); ++i) absPhi[i] = std::fabs(Phi[i]);
+    REACH_TRY(run(absPhi.data(), r0, nullptr, rU, nullptr));   // radii: |Phi|^k r_0 + sum |Phi|^i r_U (all terms >= 0)
+    scatter(r_host, 0);
+    return REACH_OK;
 }
 
 // FP64 throughput probe of the DMMA kernel on an m x n x k problem (128x128 tiles).

@@ -221,10 +221,16 @@ struct Lgg09PackedEpi {
 
 struct Lgg09Program {
     int nalt;
+    int box;                        // 1: the two outputs of a chain are (lin, abs) = (centre, radius) of the box hull --
+                                    // the BOX algorithm (Algorithms/BOX/reach_homog.jl, reach_inhomog.jl) -- instead of
+                                    // (rho(+l), rho(-l)) = (abs + lin, abs - lin)
     int qV;                         // feature of rho(., V), -1 when homogeneous
     int8_t q0[LGG09_MAX_ALTS];      // per alternative: feature evaluated at r_k     (-1: none)
     int8_t q1[LGG09_MAX_ALTS];      // per alternative: feature evaluated at r_{k+1} (-1: none)
 };
+
+__device__ __forceinline__ double lgg09_out_pos(const Lgg09Program& p, double lin, double ab) { return p.box ? lin : lin + ab; }
+__device__ __forceinline__ double lgg09_out_neg(const Lgg09Program& p, double lin, double ab) { return p.box ? ab : ab - lin; }
 
 struct Lgg09Combine {
     Lgg09Program prog;
@@ -355,10 +361,10 @@ __global__ void lgg09_eval_kernel(const Lgg09Combine c, const double* __restrict
             const int q0 = c.prog.q0[a], q1 = c.prog.q1[a];
 #pragma unroll
             for (int q = 0; q < NQ; ++q)
-                if (q == q0) { ap += Fp[q][0] + Fp[q][1]; an += Fp[q][1] - Fp[q][0]; }
+                if (q == q0) { ap += lgg09_out_pos(c.prog, Fp[q][0], Fp[q][1]); an += lgg09_out_neg(c.prog, Fp[q][0], Fp[q][1]); }
 #pragma unroll
             for (int q = 0; q < NQ; ++q)
-                if (q == q1) { ap += Fc[q][0] + Fc[q][1]; an += Fc[q][1] - Fc[q][0]; }
+                if (q == q1) { ap += lgg09_out_pos(c.prog, Fc[q][0], Fc[q][1]); an += lgg09_out_neg(c.prog, Fc[q][0], Fc[q][1]); }
             if (a == 0) { vp = ap; vn = an; } else { vp = fmax(vp, ap); vn = fmax(vn, an); }
         }
         if (c.prog.qV >= 0) {                                   // + s_k from the running-sum pass
@@ -447,7 +453,7 @@ static __global__ void __launch_bounds__(PREFIX_THREADS) lgg09_prefix_kernel(con
 #pragma unroll
                 for (int i = 0; i < PREFIX_CHK; ++i) {
                     const double lin = sv[buf][i][0][ch], ab = sv[buf][i][1][ch];
-                    d[i] = sign ? ab - lin : lin + ab;       // rho(-r_k; V) : rho(+r_k; V)
+                    d[i] = sign ? lgg09_out_neg(c.prog, lin, ab) : lgg09_out_pos(c.prog, lin, ab);       // rho(-r_k; V) : rho(+r_k; V)
                 }
 #pragma unroll
                 for (int i = 0; i < PREFIX_CHK; ++i) {
@@ -458,7 +464,7 @@ static __global__ void __launch_bounds__(PREFIX_THREADS) lgg09_prefix_kernel(con
                 for (int i = 0; i < int(left); ++i) {
                     const double lin = sv[buf][i][0][ch], ab = sv[buf][i][1][ch];
                     out[i * ostride] = s;
-                    s += sign ? ab - lin : lin + ab;
+                    s += sign ? lgg09_out_neg(c.prog, lin, ab) : lgg09_out_pos(c.prog, lin, ab);
                 }
             }
         }
@@ -618,10 +624,10 @@ __global__ void __launch_bounds__(128) lgg09_chain_kernel(const Lgg09Chain c) {
             const int q0 = c.prog.q0[a], q1 = c.prog.q1[a];
 #pragma unroll
             for (int q = 0; q < NQ; ++q)
-                if (q == q0) { ap += Fp[q][0] + Fp[q][1]; an += Fp[q][1] - Fp[q][0]; }
+                if (q == q0) { ap += lgg09_out_pos(c.prog, Fp[q][0], Fp[q][1]); an += lgg09_out_neg(c.prog, Fp[q][0], Fp[q][1]); }
 #pragma unroll
             for (int q = 0; q < NQ; ++q)
-                if (q == q1) { ap += Fc[q][0] + Fc[q][1]; an += Fc[q][1] - Fc[q][0]; }
+                if (q == q1) { ap += lgg09_out_pos(c.prog, Fc[q][0], Fc[q][1]); an += lgg09_out_neg(c.prog, Fc[q][0], Fc[q][1]); }
             if (a == 0) { vp = ap; vn = an; } else { vp = fmax(vp, ap); vn = fmax(vn, an); }
         }
         if (lane == 0) {
@@ -631,7 +637,7 @@ __global__ void __launch_bounds__(128) lgg09_chain_kernel(const Lgg09Chain c) {
         const int qv = c.prog.qV;
 #pragma unroll
         for (int q = 0; q < NQ; ++q)
-            if (q == qv) { sp += Fp[q][0] + Fp[q][1]; sn += Fp[q][1] - Fp[q][0]; }
+            if (q == qv) { sp += lgg09_out_pos(c.prog, Fp[q][0], Fp[q][1]); sn += lgg09_out_neg(c.prog, Fp[q][0], Fp[q][1]); }
 #pragma unroll
         for (int q = 0; q < NQ; ++q) { Fp[q][0] = Fc[q][0]; Fp[q][1] = Fc[q][1]; }
         double* tmp = rc; rc = rnx; rnx = tmp;

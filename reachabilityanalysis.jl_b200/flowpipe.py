@@ -70,7 +70,7 @@ def samedir(u, v):
 
 
 class ReachSet:
-    """(set, Δt) with set = (centre, generators) of a zonotope."""
+    """(set, Δt) with set a Zonotope (GLGM06) or a Hyperrectangle (BOX)."""
 
     def __init__(self, Z, dt):
         self.set, self.dt = Z, dt
@@ -80,9 +80,11 @@ class ReachSet:
     tend = property(lambda s: s.dt.hi)
 
     def rho(self, d):
-        c, G = self.set.center, self.set.generators
         d = np.asarray(d, dtype=np.float64)
-        return float(d @ c + np.abs(G.T @ d).sum())
+        if hasattr(self.set, "generators"):
+            c, G = self.set.center, self.set.generators
+            return float(d @ c + np.abs(G.T @ d).sum())
+        return float(d @ self.set.center + np.abs(d) @ self.set.radius)      # Hyperrectangle (BOX)
 
 
 class Flowpipe:

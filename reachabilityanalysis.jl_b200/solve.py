@@ -53,6 +53,9 @@ def post_continuous(alg, ivp, T=None, NSTEPS=None, Δt0=zeroT, ctx=None):
     divp = discretize(ivp, delta, alg.approx_model)
     if isinstance(alg, _lgg09.LGG09):
         return _lgg09.post(alg, divp, NSTEPS, Δt0=Δt0, ctx=ctx)
+    from . import box as _box
+    if isinstance(alg, _box.BOX):
+        return _box.post(alg, divp, NSTEPS, Δt0=Δt0, ctx=ctx)
     from . import glgm06 as _glgm06
     return _glgm06.post(alg, divp, NSTEPS, Δt0=Δt0, ctx=ctx)
 
@@ -71,7 +74,8 @@ def solve(ivp, T=None, alg=None, NSTEPS=None, tspan=None, algorithm=None, opC=No
     else:
         dt0 = zeroT
     if isinstance(ivp.X0, (list, tuple)):
-        if not isinstance(alg, _lgg09.LGG09):
+        from . import box as _box
+        if not isinstance(alg, (_lgg09.LGG09, _box.BOX)):
             from . import glgm06 as _glgm06
             F = _glgm06.post_batch(alg, ivp, T=T, NSTEPS=NSTEPS, Δt0=dt0, ctx=ctx)
         else:
