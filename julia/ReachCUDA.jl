@@ -133,4 +133,36 @@ function reach_inhomog_GLGM06_cuda!(F::Vector{ReachSet{N,Zonotope{N,Vector{N},Ma
     return F
 end
 
+# --- reach_homog_BOX! / reach_inhomog_BOX! (BOX/reach_homog.jl:8-47,50-69, reach_inhomog.jl:8-60) -----------
+# Ω0 and U are already hyperrectangles here (BOX/post.jl:29,40).  `recursive` only exists without inputs.
+function reach_BOX_cuda!(F::Vector{ReachSet{N,Hyperrectangle{N,Vector{N},Vector{N}}}}, Ω0::Hyperrectangle{N},
+                         Φ::AbstractMatrix, NSTEPS::Integer, δ::N, X::LazySet, U::Union{Hyperrectangle,Nothing},
+                         recursive::Bool, Δt0::TimeInterval; ctx::Ctx=Ctx()) where {N}
+    n = dim(Ω0)
+    C = Matrix{N}(undef, n, NSTEPS)
+    R = Matrix{N}(undef, n, NSTEPS)
+    Φd, c0, r0 = Matrix{Float64}(Φ), Vector{Float64}(center(Ω0)), Vector{Float64}(radius_hyperrectangle(Ω0))
+    cU = U === nothing ? C_NULL : Vector{Float64}(center(U))
+    rU = U === nothing ? C_NULL : Vector{Float64}(radius_hyperrectangle(U))
+    GC.@preserve Φd c0 r0 cU rU C R begin
+        rc = ccall((:reach_box, lib), Cint,
+                   (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint,
+                    Ptr{ReachLGG09Opts}, Ptr{Float64}, Ptr{Float64}),
+                   ctx.h, n, NSTEPS, Φd, c0, r0, cU, rU, recursive, C_NULL, C, R)
+        check(ctx, rc)
+    end
+    Δt = (zero(N) .. δ) + Δt0
+    F[1] = ReachSet(Ω0, Δt)
+    k = 2
+    @inbounds while k <= NSTEPS
+        Hₖ = Hyperrectangle(C[:, k], R[:, k]; check_bounds=false)
+        !(X isa Universe) && _isdisjoint(X, Hₖ) && break      # the invariant check stays in Julia (reach_homog.jl:101)
+        Δt += δ
+        F[k] = ReachSet(Hₖ, Δt)
+        k += 1
+    end
+    k < NSTEPS + 1 && resize!(F, k - 1)
+    return F
+end
+
 end # module
