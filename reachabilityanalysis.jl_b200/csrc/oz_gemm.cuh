@@ -96,7 +96,8 @@ struct OzLgg09Epi {
     double* featpart;           // [tiles_n_total][2 segments][nq][2][mu_pad]
     int mu_pad;
     struct State { double lin[NQ][2], ab[NQ][2]; };
-    static constexpr size_t SMEM = size_t(OZ_TN) * (2 * NQ) * sizeof(double) + size_t(OZ_TN) * sizeof(int);
+    static constexpr size_t SMEM = size_t(OZ_TN) * (2 * NQ) * sizeof(double) + size_t(OZ_TN) * sizeof(int) +
+                                   size_t(NQ) * 4 * OZ_TM * sizeof(double);      // staged weights, row info, reduction buffer
 
     __device__ __forceinline__ void prepare(unsigned char* sm, int tn, int tid) const {
         double* sw = reinterpret_cast<double*>(sm);                      // [2*NQ][128]: wl_q then wa_q
@@ -138,24 +139,29 @@ struct OzLgg09Epi {
             }
         }
     }
-    __device__ __forceinline__ void finish(State& st, unsigned char* ring, int tm, int tn, int ml, int cgrp) const {
-        double* red = reinterpret_cast<double*>(ring);                   // [cgrp 4][q][seg][part][128]
+    __device__ __forceinline__ void finish(State& st, unsigned char* sm, int tm, int tn, int ml, int cgrp) const {
+        // red[q][seg][part][128 rows] after the staged weights: the four column groups of a row add their partials in
+        // fixed order (group 0 stores, 1..3 add), one named barrier between the phases -> deterministic
+        double* red = reinterpret_cast<double*>(sm + size_t(OZ_TN) * (2 * NQ) * sizeof(double) + size_t(OZ_TN) * sizeof(int));
 #pragma unroll
-        for (int q = 0; q < NQ; ++q)
+        for (int c = 0; c < OZ_EPI_WARPS / 4; ++c) {
+            if (cgrp == c) {
 #pragma unroll
-            for (int sg = 0; sg < 2; ++sg) {
-                red[(((cgrp * NQ + q) * 2 + sg) * 2 + 0) * OZ_TM + ml] = st.lin[q][sg];
-                red[(((cgrp * NQ + q) * 2 + sg) * 2 + 1) * OZ_TM + ml] = st.ab[q][sg];
+                for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                    for (int sg = 0; sg < 2; ++sg) {
+                        double* rl = &red[((q * 2 + sg) * 2 + 0) * OZ_TM + ml];
+                        double* ra = &red[((q * 2 + sg) * 2 + 1) * OZ_TM + ml];
+                        if (c == 0) { *rl = st.lin[q][sg]; *ra = st.ab[q][sg]; }
+                        else { *rl += st.lin[q][sg]; *ra += st.ab[q][sg]; }
+                    }
             }
-        asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory");
-        // 512 threads, nq*4*128 outputs
+            asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory");
+        }
         const int t = cgrp * OZ_TM + ml;
         for (int idx = t; idx < nq * 4 * OZ_TM; idx += OZ_EPI_WARPS * 32) {
             const int r = idx % OZ_TM, part = (idx / OZ_TM) & 1, sg = (idx / (2 * OZ_TM)) & 1, q = idx / (4 * OZ_TM);
-            double v = 0.0;
-#pragma unroll
-            for (int c = 0; c < OZ_EPI_WARPS / 4; ++c) v += red[(((c * NQ + q) * 2 + sg) * 2 + part) * OZ_TM + r];
-            featpart[((((size_t(tn) * 2 + sg) * nq + q) * 2) + part) * mu_pad + tm * OZ_TM + r] = v;
+            featpart[((((size_t(tn) * 2 + sg) * nq + q) * 2) + part) * mu_pad + tm * OZ_TM + r] = red[((q * 2 + sg) * 2 + part) * OZ_TM + r];
         }
     }
 };
@@ -163,6 +169,11 @@ struct OzLgg09Epi {
 // Two passes over K ("sweeps") when T > 4: levels 0..3 first (digit planes 0..3 of both operands, 10 MMAs per k-block),
 // then levels 4..T-1 (all planes, up to 26 MMAs).  Each sweep's level sum  sum_d 2^(-7 (d - d0)) acc_d  is EXACT in
 // FP64 (<= 47 bits), so the epilogue threads keep sweep 1 as one double per output while sweep 2 runs.
+//
+// Persistent: CTA c walks tiles c, c + gridDim.x, ...  The epilogue warps hand the accumulators back to the MMA
+// warp as soon as they have pulled a sweep into registers (tmem_empty), so the arithmetic part of a tile's epilogue
+// (scaling, support features, stores) runs while the tensor pipe is already in sweep 1 of the CTA's next tile, and
+// the producer keeps the ring full across tile boundaries.
 template <int T, class Epi>
 __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzOperands g, const Epi epi) {
     constexpr uint32_t SLOT = 2 * T * OZ_PLANE;                       // X planes then Y planes
@@ -179,8 +190,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzOperands
     unsigned char* epi_smem = reinterpret_cast<unsigned char*>(sYscale + OZ_TN);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tm = blockIdx.x % g.tiles_m;
-    const int tn = g.tile_n0 + blockIdx.x / g.tiles_m;
+    const int ntiles = g.tiles_m * g.tiles_n;
 
     if (tid == 0) {
         for (int s = 0; s < OZ_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -201,20 +211,22 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzOperands
     if (warp == OZ_EPI_WARPS) {
         // ===== producer =====
         if (lane == 0) {
-            const int8_t* gx = g.Xq + size_t(tm) * (T * OZ_PLANE);
-            const int8_t* gy = g.Yq + size_t(tn) * (T * OZ_PLANE);
             const size_t xstep = size_t(g.tiles_m_total) * (T * OZ_PLANE), ystep = size_t(g.tiles_n_total) * (T * OZ_PLANE);
             int jb = 0;
-            for (int sw = 0; sw < NSWEEP; ++sw) {
-                const uint32_t bytes = uint32_t(sw == 0 ? G1 : T) * OZ_PLANE;
-                for (int kb = 0; kb < g.nkb; ++kb, ++jb) {
-                    const int s = jb % OZ_STAGES;
-                    const uint32_t ph = (jb / OZ_STAGES) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], 2 * bytes);
-                    unsigned char* dst = ring + size_t(s) * SLOT;
-                    bulk_copy_g2s(dst, gx + size_t(kb) * xstep, bytes, &full[s]);
-                    bulk_copy_g2s(dst + T * OZ_PLANE, gy + size_t(kb) * ystep, bytes, &full[s]);
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int8_t* gx = g.Xq + size_t(t % g.tiles_m) * (T * OZ_PLANE);
+                const int8_t* gy = g.Yq + size_t(g.tile_n0 + t / g.tiles_m) * (T * OZ_PLANE);
+                for (int sw = 0; sw < NSWEEP; ++sw) {
+                    const uint32_t bytes = uint32_t(sw == 0 ? G1 : T) * OZ_PLANE;
+                    for (int kb = 0; kb < g.nkb; ++kb, ++jb) {
+                        const int s = jb % OZ_STAGES;
+                        const uint32_t ph = (jb / OZ_STAGES) & 1;
+                        mbar_wait(&empty[s], ph ^ 1);
+                        mbar_expect_tx(&full[s], 2 * bytes);
+                        unsigned char* dst = ring + size_t(s) * SLOT;
+                        bulk_copy_g2s(dst, gx + size_t(kb) * xstep, bytes, &full[s]);
+                        bulk_copy_g2s(dst + T * OZ_PLANE, gy + size_t(kb) * ystep, bytes, &full[s]);
+                    }
                 }
             }
         }
@@ -224,96 +236,103 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzOperands
             // instruction descriptor: D = S32 (2<<4), A = B = signed 8-bit (1<<7, 1<<10), K-major both, N>>3 at 17, M>>4 at 24
             constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(OZ_TN >> 3) << 17) | (uint32_t(OZ_TM >> 4) << 24);
             int jb = 0;
-            for (int sw = 0; sw < NSWEEP; ++sw) {
-                if (sw == 1) {                                   // the epilogue has drained the sweep-1 accumulators
-                    mbar_wait(tmem_empty, 0);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                }
-                for (int kb = 0; kb < g.nkb; ++kb, ++jb) {
-                    const int s = jb % OZ_STAGES;
-                    const uint32_t ph = (jb / OZ_STAGES) & 1;
-                    mbar_wait(&full[s], ph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t xs = smem_u32(ring + size_t(s) * SLOT), ys = xs + T * OZ_PLANE;
-#pragma unroll
-                    for (int dd = 0; dd < OZ_G; ++dd) {
-                        const int d = sw * OZ_G + dd;
-                        if (d >= T) break;
-#pragma unroll
-                        for (int sx = 0; sx < T; ++sx) {
-                            if (sx > d) break;
-                            const int sy = d - sx;
-                            // one digit plane of a tile: [rows/8][2 k-chunks][8 rows][16 B]: LBO = 128 B (next k-chunk), SBO = 256 B (next 8 rows)
-                            const uint64_t da = oz_smem_desc(xs + sx * OZ_PLANE, 128, 256);
-                            const uint64_t db = oz_smem_desc(ys + sy * OZ_PLANE, 128, 256);
-                            const uint32_t acc = (kb > 0 || sx > 0) ? 1u : 0u;
-                            asm volatile(
-                                "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
-                                " tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_base + uint32_t(dd * OZ_TN)),
-                                "l"(da), "l"(db), "r"(idesc), "r"(acc)
-                                : "memory");
-                        }
+            uint32_t nsweeps_done = 0;                            // sweeps issued so far (all tiles)
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                for (int sw = 0; sw < NSWEEP; ++sw, ++nsweeps_done) {
+                    if (nsweeps_done > 0) {                       // the epilogue has pulled the previous sweep out of TMEM
+                        mbar_wait(tmem_empty, (nsweeps_done - 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
-                    // frees the ring slot once the MMAs above have read it (implies fence::before_thread_sync)
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+                    for (int kb = 0; kb < g.nkb; ++kb, ++jb) {
+                        const int s = jb % OZ_STAGES;
+                        const uint32_t ph = (jb / OZ_STAGES) & 1;
+                        mbar_wait(&full[s], ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t xs = smem_u32(ring + size_t(s) * SLOT), ys = xs + T * OZ_PLANE;
+#pragma unroll
+                        for (int dd = 0; dd < OZ_G; ++dd) {
+                            const int d = sw * OZ_G + dd;
+                            if (d >= T) break;
+#pragma unroll
+                            for (int sx = 0; sx < T; ++sx) {
+                                if (sx > d) break;
+                                const int sy = d - sx;
+                                // one digit plane of a tile: [rows/8][2 k-chunks][8 rows][16 B]: LBO = 128 B (next k-chunk), SBO = 256 B (next 8 rows)
+                                const uint64_t da = oz_smem_desc(xs + sx * OZ_PLANE, 128, 256);
+                                const uint64_t db = oz_smem_desc(ys + sy * OZ_PLANE, 128, 256);
+                                const uint32_t acc = (kb > 0 || sx > 0) ? 1u : 0u;
+                                asm volatile(
+                                    "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+                                    " tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_base + uint32_t(dd * OZ_TN)),
+                                    "l"(da), "l"(db), "r"(idesc), "r"(acc)
+                                    : "memory");
+                            }
+                        }
+                        // frees the ring slot once the MMAs above have read it (implies fence::before_thread_sync)
+                        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(tmem_full)) : "memory");
                 }
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(tmem_full)) : "memory");
             }
         }
     } else {
         // ===== epilogue warps 0..15: thread = (output row, 32-column group) =====
         const int quarter = warp & 3, cgrp = warp >> 2;
         const int ml = quarter * 32 + lane;
-        const int m = tm * OZ_TM + ml;
         const int col0 = cgrp * OZ_CPT;
-        if (tid < OZ_TN) sYscale[tid] = oz_pow2(max(-1000, min(1000, g.eY[size_t(tn) * OZ_TN + tid])));
-        epi.prepare(epi_smem, tn, tid);
-        asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory");
-        const int ex = g.eX[size_t(tm) * OZ_TM + ml] - 12;
-        typename Epi::State st;
-        epi.begin(st);
         const uint32_t taddr = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(col0);
-        double part[OZ_CPT];
+        uint32_t nfull = 0;                                       // accumulator hand-overs consumed so far
+        for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            const int tm = t % g.tiles_m, tn = g.tile_n0 + t / g.tiles_m;
+            const int m = tm * OZ_TM + ml;
+            // every epilogue thread is past the previous tile's reads of the staged column data
+            asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory");
+            if (tid < OZ_TN) sYscale[tid] = oz_pow2(max(-1000, min(1000, g.eY[size_t(tn) * OZ_TN + tid])));
+            epi.prepare(epi_smem, tn, tid);
+            asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory");
+            const int ex = g.eX[size_t(tm) * OZ_TM + ml] - 12;
+            typename Epi::State st;
+            epi.begin(st);
+            double part[OZ_CPT];
 #pragma unroll
-        for (int sw = 0; sw < NSWEEP; ++sw) {
-            constexpr int dummy = 0; (void)dummy;
-            const int nlev = sw == 0 ? G1 : T - OZ_G;
-            mbar_wait_sleep(tmem_full, uint32_t(sw));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int sw = 0; sw < NSWEEP; ++sw, ++nfull) {
+                const int nlev = sw == 0 ? G1 : T - OZ_G;
+                mbar_wait_sleep(tmem_full, nfull & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int cc = 0; cc < OZ_CPT / 8; ++cc) {
-                uint32_t a[OZ_G][8];
+                for (int cc = 0; cc < OZ_CPT / 8; ++cc) {
+                    uint32_t a[OZ_G][8];
 #pragma unroll
-                for (int dd = 0; dd < OZ_G; ++dd) {
-                    if (dd < nlev)
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                                     : "=r"(a[dd][0]), "=r"(a[dd][1]), "=r"(a[dd][2]), "=r"(a[dd][3]), "=r"(a[dd][4]),
-                                       "=r"(a[dd][5]), "=r"(a[dd][6]), "=r"(a[dd][7])
-                                     : "r"(taddr + uint32_t(dd * OZ_TN + cc * 8)));
+                    for (int dd = 0; dd < OZ_G; ++dd) {
+                        if (dd < nlev)
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                         : "=r"(a[dd][0]), "=r"(a[dd][1]), "=r"(a[dd][2]), "=r"(a[dd][3]), "=r"(a[dd][4]),
+                                           "=r"(a[dd][5]), "=r"(a[dd][6]), "=r"(a[dd][7])
+                                         : "r"(taddr + uint32_t(dd * OZ_TN + cc * 8)));
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        double v = oz_i2d(a[nlev - 1][jj]);
+#pragma unroll
+                        for (int dd = OZ_G - 2; dd >= 0; --dd)
+                            if (dd < nlev - 1) v = fma(v, 0.0078125, oz_i2d(a[dd][jj]));   // * 2^-7, exact
+                        if (sw == 0) part[cc * 8 + jj] = v;
+                        else part[cc * 8 + jj] = fma(v, 3.7252902984619140625e-09, part[cc * 8 + jj]);   // 2^-28
+                    }
                 }
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    double v = oz_i2d(a[nlev - 1][jj]);
-#pragma unroll
-                    for (int dd = OZ_G - 2; dd >= 0; --dd)
-                        if (dd < nlev - 1) v = fma(v, 0.0078125, oz_i2d(a[dd][jj]));   // * 2^-7, exact
-                    if (sw == 0) part[cc * 8 + jj] = v;
-                    else part[cc * 8 + jj] = fma(v, 3.7252902984619140625e-09, part[cc * 8 + jj]);   // 2^-28
-                }
-            }
-            if (sw + 1 < NSWEEP) {                               // accumulators may be overwritten
+                // the accumulators may be overwritten: the next sweep (of this tile or of the CTA's next tile) can start
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_empty);
             }
-        }
 #pragma unroll
-        for (int jl = 0; jl < OZ_CPT; ++jl) {
-            const int j = col0 + jl;
-            epi.accept(st, epi_smem, m, tn, j, oz_scale(part[jl] * sYscale[j], ex));
+            for (int jl = 0; jl < OZ_CPT; ++jl) {
+                const int j = col0 + jl;
+                epi.accept(st, epi_smem, m, tn, j, oz_scale(part[jl] * sYscale[j], ex));
+            }
+            epi.finish(st, epi_smem, tm, tn, ml, cgrp);
         }
-        epi.finish(st, ring, tm, tn, ml, cgrp);               // the ring is idle by now: every MMA has completed
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
@@ -343,7 +362,13 @@ inline cudaError_t launch_oz_gemm_t(const OzOperands& g, const Epi& epi, cudaStr
         configured_dev = dev;
     }
     if (g.tiles_m <= 0 || g.tiles_n <= 0) return cudaSuccess;
-    kern<<<g.tiles_m * g.tiles_n, OZ_THREADS, smem, stream>>>(g, epi);
+    static thread_local int sms = 0;
+    if (sms == 0) {
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+    }
+    const int ntiles = g.tiles_m * g.tiles_n;
+    kern<<<ntiles < sms ? ntiles : sms, OZ_THREADS, smem, stream>>>(g, epi);      // persistent: one CTA per SM
     return cudaGetLastError();
 }
 
