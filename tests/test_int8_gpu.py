@@ -154,3 +154,26 @@ def test_auto_falls_back_to_dmma_on_wide_dynamic_range(ctx):
     denom = np.maximum(np.abs(ref), rowscale)
     denom[denom == 0] = 1.0
     assert (np.abs(forced.sfmat() - ref) / denom).max() > 1e-10
+
+
+@pytest.mark.parametrize("nsteps", [1, 2, 3])
+def test_lgg09_int8_path_tiny_step_counts(ctx, nsteps):
+    wl = _synthetic(140, nsteps, seed=2)
+    ref = LO.reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, wl.V)
+    for S in (0, 1, 4):
+        plan = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, path="int8", time_block=S)
+        assert_support_parity(plan.sfmat(), ref)
+
+
+def test_lgg09_int8_path_with_invariant_stops_early(ctx):
+    """Early termination (reach_inhomog.jl:174-218) is independent of the main-loop kernel."""
+    n, nsteps = 136, 60
+    wl = _synthetic(n, nsteps, seed=4)
+    ref = LO.reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, wl.V)
+    # x_1 <= b with b between the first and the last value of rho(-e_1): -rho(-e_1) is the lower bound of x_1
+    lower = -ref[n, :]
+    b = 0.5 * (lower[0] + lower.max()) if lower.max() > lower[0] else lower[0] - 1.0
+    X = rb.HalfSpace(np.eye(n)[0], float(b))
+    a = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, X, wl.V, ctx=ctx, path="int8")
+    g = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, X, wl.V, ctx=ctx, path="gemm")
+    assert a.nsteps_done == g.nsteps_done
