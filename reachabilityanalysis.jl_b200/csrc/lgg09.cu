@@ -275,7 +275,7 @@ template <int RPL, int NE>
 int launch_chain_t(reach_ctx* ctx, const Lgg09Chain& c, size_t smem, cudaStream_t st) {
     auto kern = lgg09_chain_kernel<RPL, 4, NE>;
     REACH_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    kern<<<(c.mu + 3) / 4, 128, smem, st>>>(c);
+    kern<<<c.mu, CHAIN_THREADS, smem, st>>>(c);                       // one CTA per chain
     REACH_CUDA(ctx, cudaGetLastError());
     return REACH_OK;
 }
@@ -287,14 +287,12 @@ int launch_chain_r(reach_ctx* ctx, int ne, const Lgg09Chain& c, size_t smem, cud
 }
 int launch_chain(reach_ctx* ctx, int rpl, int ne, const Lgg09Chain& c, size_t smem, cudaStream_t st) {
     switch (rpl) {
-#define REACH_CHAIN_CASE(R) case R: return launch_chain_r<R>(ctx, ne, c, smem, st);
-        REACH_CHAIN_CASE(1) REACH_CHAIN_CASE(2) REACH_CHAIN_CASE(3) REACH_CHAIN_CASE(4)
-        REACH_CHAIN_CASE(5) REACH_CHAIN_CASE(6) REACH_CHAIN_CASE(7) REACH_CHAIN_CASE(8)
-        REACH_CHAIN_CASE(9) REACH_CHAIN_CASE(10) REACH_CHAIN_CASE(11) REACH_CHAIN_CASE(12)
-        REACH_CHAIN_CASE(13) REACH_CHAIN_CASE(14) REACH_CHAIN_CASE(15) REACH_CHAIN_CASE(16)
-#undef REACH_CHAIN_CASE
+        case 1: return launch_chain_r<1>(ctx, ne, c, smem, st);
+        case 2: return launch_chain_r<2>(ctx, ne, c, smem, st);
+        case 3: return launch_chain_r<3>(ctx, ne, c, smem, st);
+        case 4: return launch_chain_r<4>(ctx, ne, c, smem, st);
     }
-    return set_error(ctx, REACH_EINVAL, "bad rows-per-lane %d", rpl);
+    return set_error(ctx, REACH_EINVAL, "bad rows-per-thread %d", rpl);
 }
 
 // Cost model (SM cycles per time step) used to pick the tile shape and the time block S.
@@ -520,12 +518,16 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
             maxnnz = std::max(maxnnz, cnt);
         }
         maxnnz = std::max(maxnnz, 1);
-        const int rpl = (n + 31) / 32;
-        const int npad = rpl * 32, nep = p->ne == 0 ? 0 : (p->ne <= 4 ? 4 : 8);
-        const size_t smem = size_t(maxnnz) * npad * 12 + size_t(8 + nep) * npad * 8 + size_t(4) * 2 * npad * 8;
-        // cycles per time step: sequential FMA chains (RPL interleaved) + feature reduction
-        const double chain_cycles = 400.0 + rpl * (22.0 * maxnnz + 170.0);      // measured on Building / ISS
-        const double waves = std::ceil(double(p->mu) / (ctx->sm_count * 16.0));
+        const int rpl = (n + CHAIN_THREADS - 1) / CHAIN_THREADS;
+        const int npad = rpl * CHAIN_THREADS, nep = p->ne == 0 ? 0 : (p->ne <= 4 ? 4 : 8);
+        const size_t smem = size_t(maxnnz) * npad * 12 + size_t(8 + nep) * npad * 8 + size_t(CHAIN_B + 1) * npad * 8 +
+                            size_t(CHAIN_B) * (8 + nep) * CHAIN_RED_LD * 8 + size_t(CHAIN_B + 1) * (8 + nep) * 8 +
+                            size_t(CHAIN_B) * 2 * 8 + 64;
+        // cycles per time step of one CTA (4 warps, one chain): SpMV + feature partials of RPL rows per thread, a
+        // butterfly, one CTA barrier; several CTAs share an SM
+        const double chain_cycles = 350.0 + rpl * (22.0 * maxnnz + 60.0);
+        const double per_sm = std::max(1.0, std::min(8.0, std::floor(200.0 * 1024 / double(smem))));
+        const double waves = std::ceil(double(p->mu) / (ctx->sm_count * per_sm));
         const double chain_cost = waves * chain_cycles;
         const double gemm_cost = step_cost(*p, kCfgs[p->cfg], p->S, p->mu, n + p->ne, ctx->sm_count);
         if (smem <= ctx->smem_optin && (p->opts.path == 2 || chain_cost < gemm_cost)) {
@@ -728,7 +730,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         Lgg09Chain c{};
         c.prog = p->prog.dev;
         c.n = n;
-        c.npad = p->ch_rpl * 32;
+        c.npad = p->ch_rpl * CHAIN_THREADS;
         c.maxnnz = p->ch_maxnnz;
         c.ell_val = p->ell_val.as<double>();
         c.ell_col = p->ell_col.as<int>();
@@ -747,7 +749,16 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         c.row_neg = p->row_neg.as<int>();
         c.rho = p->rho;
         c.ndirs = p->ndirs;
+        DevBuf dbgbuf;
+        if (getenv("REACH_CHAIN_DEBUG")) { REACH_TRY(dbgbuf.alloc(ctx, 64)); c.dbg = dbgbuf.as<long long>(); }
         REACH_TRY(launch_chain(ctx, p->ch_rpl, p->ch_ne, c, p->ch_smem, st));
+        if (c.dbg) {
+            long long h[4];
+            REACH_CUDA(ctx, cudaStreamSynchronize(st));
+            REACH_CUDA(ctx, cudaMemcpy(h, c.dbg, sizeof(h), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[chain dbg] cycles per step: spmv %.0f, reduce %.0f, eval %.0f, prefix/out %.0f\n",
+                    double(h[0]) / p->nsteps, double(h[1]) / p->nsteps, double(h[2]) / p->nsteps, double(h[3]) / p->nsteps);
+        }
         ++p->launches;
         if (p->nchecks > 0) {
             REACH_CUDA(ctx, cudaMemsetAsync(p->first_bad.p, 0xFF, sizeof(unsigned long long), st));

@@ -501,40 +501,55 @@ struct Lgg09Chain {
     const int* row_neg;
     double* rho;
     int ndirs;
+    long long* dbg;                 // optional [8] phase cycle counters of CTA 0 (NULL: off)
 };
 
+// One CTA (4 warps) per chain: thread t owns rows t, t+128, ... of r (RPL of them).  Only r_{k+1} = Phi' r_k is truly
+// sequential, everything else is instruction count -- the kernel is issue-bound (ncu: ~3400 SASS instructions of flat
+// stall profile, two warps per sub-partition), so it works in batches of CHAIN_B = 4 steps and splits the rest:
+//   (1) advance r through the batch, one CTA barrier per step (two shared loads, maxnnz FMAs, a store);
+//   (2) every thread: feature partials of its rows for all 4 vectors, parked in shared memory [value][thread];
+//       96..128 threads then add them up, 64 threads' worth each, in fixed order (deterministic; this replaces a
+//       5-round butterfly of 48 doubles per warp, which was a third of all instructions);
+//   (3) warp b evaluates step b of the batch (mapped rows, alternatives, rho(+-r; V)); the running input sum is
+//       propagated through the batch in step order from the four warps' increments.
+// (v1 ran a chain in one warp, v2/v3 one CTA per chain with butterflies and the evaluation replicated in every warp:
+//  all ~3000-3400 cycles per step on ISS.)
+constexpr int CHAIN_WARPS = 4, CHAIN_THREADS = CHAIN_WARPS * 32, CHAIN_B = 4;
+constexpr int CHAIN_RED_LD = CHAIN_THREADS + 2;      // row stride of the partials: == 2 (mod 16) doubles, see reduce_batch
+
 template <int RPL, int NQ, int NE>
-__global__ void __launch_bounds__(128) lgg09_chain_kernel(const Lgg09Chain c) {
+__global__ void __launch_bounds__(CHAIN_THREADS) lgg09_chain_kernel(const Lgg09Chain c) {
+    constexpr int NV = 2 * NQ + NE;                                      // raw sums per vector: lin_q, abs_q, y_e
+    static_assert(2 * CHAIN_B * NV <= CHAIN_THREADS, "two reducer threads per (vector, value)");
     extern __shared__ __align__(16) unsigned char smraw[];
-    const int npad = c.npad;
+    const int npad = c.npad;                                             // RPL * 128
     double* s_val = reinterpret_cast<double*>(smraw);                   // [maxnnz][npad]
     double* s_a = s_val + size_t(c.maxnnz) * npad;                      // [NQ][npad]
     double* s_b = s_a + NQ * npad;                                      // [NQ][npad]
     double* s_E = s_b + NQ * npad;                                      // [NE][npad]
-    double* s_r = s_E + NE * npad;                                      // [warps][2][npad]
-    int* s_col = reinterpret_cast<int*>(s_r + size_t(blockDim.x >> 5) * 2 * npad);   // [maxnnz][npad]
+    double* s_r = s_E + NE * npad;                                      // [CHAIN_B + 1][npad] ring of r vectors
+    double* s_red = s_r + (CHAIN_B + 1) * npad;                         // [CHAIN_B * NV][CHAIN_RED_LD]
+    double* s_tot = s_red + CHAIN_B * NV * CHAIN_RED_LD;                // [CHAIN_B + 1][NV] totals; [0] = carried r_k
+    double* s_dv = s_tot + (CHAIN_B + 1) * NV;                          // [CHAIN_B][2] increments of the running sums
+    int* s_col = reinterpret_cast<int*>(s_dv + CHAIN_B * 2);            // [maxnnz][npad]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j = blockIdx.x;                                            // chain of this CTA
 
-    for (int idx = tid; idx < c.maxnnz * npad; idx += blockDim.x) { s_val[idx] = c.ell_val[idx]; s_col[idx] = c.ell_col[idx]; }
-    for (int idx = tid; idx < NQ * npad; idx += blockDim.x) {
+    for (int idx = tid; idx < c.maxnnz * npad; idx += CHAIN_THREADS) { s_val[idx] = c.ell_val[idx]; s_col[idx] = c.ell_col[idx]; }
+    for (int idx = tid; idx < NQ * npad; idx += CHAIN_THREADS) {
         const int q = idx / npad, i = idx % npad;
         const bool ok = q < c.nq && i < c.n;
         s_a[idx] = ok ? c.Wl[size_t(q) * c.wstride + i] : 0.0;
         s_b[idx] = ok ? c.Wa[size_t(q) * c.wstride + i] : 0.0;
     }
-    for (int idx = tid; idx < NE * npad; idx += blockDim.x) {
+    for (int idx = tid; idx < NE * npad; idx += CHAIN_THREADS) {
         const int e = idx / npad, i = idx % npad;
         s_E[idx] = (e < c.ne && i < c.n) ? c.E[size_t(e) * c.n + i] : 0.0;
     }
-    const int j = blockIdx.x * (blockDim.x >> 5) + warp;                // chain of this warp
-    double* r0 = s_r + size_t(warp) * 2 * npad;
-    double* r1 = r0 + npad;
-    if (j < c.mu)
-        for (int i = lane; i < npad; i += 32) r0[i] = i < c.n ? c.L0[size_t(j) * c.ldl + i] : 0.0;
-    __syncthreads();
-    if (j >= c.mu) return;
+    for (int i = tid; i < npad; i += CHAIN_THREADS) s_r[i] = i < c.n ? c.L0[size_t(j) * c.ldl + i] : 0.0;
 
-    // mapped-row weights of every feature, replicated per lane (small)
+    // mapped-row weights of every feature, replicated per thread (small)
     double wlE[NQ][NE > 0 ? NE : 1], waE[NQ][NE > 0 ? NE : 1];
 #pragma unroll
     for (int q = 0; q < NQ; ++q)
@@ -544,105 +559,160 @@ __global__ void __launch_bounds__(128) lgg09_chain_kernel(const Lgg09Chain c) {
             wlE[q][e] = ok ? c.Wl[size_t(q) * c.wstride + c.n + e] : 0.0;
             waE[q][e] = ok ? c.Wa[size_t(q) * c.wstride + c.n + e] : 0.0;
         }
+    __syncthreads();
 
-    const int nq = c.nq;
-    auto features = [&](const double* r, double (&F)[NQ][2]) {
-        double lin[NQ], ab[NQ], y[NE > 0 ? NE : 1];
+    // raw sums of the vectors in ring slots slot0+1 .. slot0+nb -> s_tot[1..nb]   (two CTA barriers inside).
+    // The loop over the vectors is deliberately NOT unrolled: with everything unrolled the steady-state loop was ~1300
+    // SASS instructions (20 KB), beyond the instruction cache of a sub-partition that runs one or two warps -- ncu showed
+    // a flat profile of stall_no_inst and every phase ran ~6x slower than its instruction latencies add up to.
+    auto reduce_batch = [&](int slot0, int nb) {
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            int sl = slot0 + b + 1;
+            if (sl > CHAIN_B) sl -= CHAIN_B + 1;
+            const double* r = s_r + sl * npad;
+            double v[NV];
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) lin[q] = ab[q] = 0.0;
+            for (int x = 0; x < NV; ++x) v[x] = 0.0;
 #pragma unroll
-        for (int e = 0; e < NE; ++e) y[e] = 0.0;
+            for (int t = 0; t < RPL; ++t) {
+                const int i = tid + CHAIN_THREADS * t;
+                const double ri = r[i], ai = fabs(ri);
 #pragma unroll
-        for (int t = 0; t < RPL; ++t) {
-            const int i = lane + 32 * t;
-            const double v = r[i];
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                if (q < nq) {
-                    lin[q] = fma(s_a[q * npad + i], v, lin[q]);
-                    ab[q] = fma(s_b[q * npad + i], fabs(v), ab[q]);
+                for (int q = 0; q < NQ; ++q) {
+                    v[2 * q] = fma(s_a[q * npad + i], ri, v[2 * q]);
+                    v[2 * q + 1] = fma(s_b[q * npad + i], ai, v[2 * q + 1]);
                 }
+#pragma unroll
+                for (int e = 0; e < NE; ++e) v[2 * NQ + e] = fma(s_E[e * npad + i], ri, v[2 * NQ + e]);
             }
 #pragma unroll
-            for (int e = 0; e < NE; ++e) y[e] = fma(s_E[e * npad + i], v, y[e]);
+            for (int x = 0; x < NV; ++x) s_red[(b * NV + x) * CHAIN_RED_LD + tid] = v[x];
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                if (q < nq) {
-                    lin[q] += __shfl_xor_sync(0xffffffffu, lin[q], off);
-                    ab[q] += __shfl_xor_sync(0xffffffffu, ab[q], off);
+        __syncthreads();
+        {   // thread pair (2o, 2o+1) adds the 128 partials of value o: thread h takes the partials of threads == h (mod 2)
+            // in four interleaved fixed-order streams (16 dependent adds each), then a fixed tree.  Address
+            // o*130 + 2i + h: the 16 threads of a half-warp hit 16 different 8-byte banks.
+            const int o = tid >> 1, h = tid & 1;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            if (o < nb * NV) {
+                const double* src = s_red + o * CHAIN_RED_LD + h;
+#pragma unroll 4
+                for (int i = 0; i < 64; i += 4) {
+                    a0 += src[2 * i];
+                    a1 += src[2 * i + 2];
+                    a2 += src[2 * i + 4];
+                    a3 += src[2 * i + 6];
                 }
             }
-#pragma unroll
-            for (int e = 0; e < NE; ++e) y[e] += __shfl_xor_sync(0xffffffffu, y[e], off);
+            const double acc = (a0 + a1) + (a2 + a3);
+            const double other = __shfl_xor_sync(0xffffffffu, acc, 1);
+            if (h == 0 && o < nb * NV) s_tot[NV + o] = acc + other;
         }
+        __syncthreads();
+    };
+    // features F_q = (lin, abs) of the vector whose raw sums are s_tot[slot]
+    auto features = [&](int slot, double (&F)[NQ][2]) {
+        const double* v = s_tot + slot * NV;
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
+            double lin = v[2 * q], ab = v[2 * q + 1];
 #pragma unroll
             for (int e = 0; e < NE; ++e) {
-                lin[q] = fma(wlE[q][e], y[e], lin[q]);
-                ab[q] = fma(waE[q][e], fabs(y[e]), ab[q]);
+                lin = fma(wlE[q][e], v[2 * NQ + e], lin);
+                ab = fma(waE[q][e], fabs(v[2 * NQ + e]), ab);
             }
-            F[q][0] = lin[q];
-            F[q][1] = ab[q];
+            F[q][0] = lin;
+            F[q][1] = ab;
         }
     };
 
     const int rp = c.row_pos[j], rn = c.row_neg[j];
     double sp = 0.0, sn = 0.0;
-    double Fp[NQ][2], Fc[NQ][2];
-    features(r0, Fp);
-    double* rc = r0;
-    double* rnx = r1;
-    for (long long k = 0; k < c.nsteps; ++k) {
-        const bool advance = c.need_next || k + 1 < c.nsteps;
-        if (advance) {
+    int base = 0;                                                        // ring slot of r_k at the start of a batch
+    reduce_batch(CHAIN_B, 1);                                            // slot0 + 1 wraps to slot 0 = r_0
+    if (tid < NV) s_tot[tid] = s_tot[NV + tid];
+    __syncthreads();
+    long long tph[5] = {0, 0, 0, 0, 0};
+    for (long long k0 = 0; k0 < c.nsteps; k0 += CHAIN_B) {
+        const int nb = int(min((long long)CHAIN_B, c.nsteps - k0));
+        long long tq0 = clock64();
+        // (1) r_{k0+1} .. r_{k0+nb}: ring slots base+1 .. base+nb (mod CHAIN_B+1)
+#pragma unroll 1
+        for (int b = 0; b < nb; ++b) {
+            int sc = base + b, sx = base + b + 1;
+            if (sc > CHAIN_B) sc -= CHAIN_B + 1;
+            if (sx > CHAIN_B) sx -= CHAIN_B + 1;
+            const double* rc = s_r + sc * npad;
+            double* rnx = s_r + sx * npad;
             double acc[RPL];
 #pragma unroll
             for (int t = 0; t < RPL; ++t) acc[t] = 0.0;
+#pragma unroll 4
             for (int z = 0; z < c.maxnnz; ++z) {
 #pragma unroll
                 for (int t = 0; t < RPL; ++t) {
-                    const int i = lane + 32 * t;
+                    const int i = tid + CHAIN_THREADS * t;
                     acc[t] = fma(s_val[z * npad + i], rc[s_col[z * npad + i]], acc[t]);
                 }
             }
 #pragma unroll
-            for (int t = 0; t < RPL; ++t) rnx[lane + 32 * t] = acc[t];
-            __syncwarp();
-            features(rnx, Fc);
-        } else {
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) { Fc[q][0] = Fp[q][0]; Fc[q][1] = Fp[q][1]; }
+            for (int t = 0; t < RPL; ++t) rnx[tid + CHAIN_THREADS * t] = acc[t];
+            __syncthreads();
         }
-        // alternatives (max), terms (sum), +/- outputs, running input sum
+        long long tq1 = clock64();
+        // (2) raw sums of the nb new vectors -> s_tot[1..nb]
+        reduce_batch(base, nb);
+        long long tq2 = clock64();
+        // (3) warp b: step k0 + b from the features of r_{k0+b} (s_tot[b]) and r_{k0+b+1} (s_tot[b+1])
         double vp = 0.0, vn = 0.0;
-        for (int a = 0; a < c.prog.nalt; ++a) {
-            double ap = 0.0, an = 0.0;
-            const int q0 = c.prog.q0[a], q1 = c.prog.q1[a];
+        if (warp < nb) {
+            double Fp[NQ][2], Fc[NQ][2];
+            features(warp, Fp);
+            features(warp + 1, Fc);
+            for (int a = 0; a < c.prog.nalt; ++a) {
+                double ap = 0.0, an = 0.0;
+                const int q0 = c.prog.q0[a], q1 = c.prog.q1[a];
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+                    if (q == q0) { ap += lgg09_out_pos(c.prog, Fp[q][0], Fp[q][1]); an += lgg09_out_neg(c.prog, Fp[q][0], Fp[q][1]); }
+#pragma unroll
+                for (int q = 0; q < NQ; ++q)
+                    if (q == q1) { ap += lgg09_out_pos(c.prog, Fc[q][0], Fc[q][1]); an += lgg09_out_neg(c.prog, Fc[q][0], Fc[q][1]); }
+                if (a == 0) { vp = ap; vn = an; } else { vp = fmax(vp, ap); vn = fmax(vn, an); }
+            }
+            double dp = 0.0, dn = 0.0;
+            const int qv = c.prog.qV;
 #pragma unroll
             for (int q = 0; q < NQ; ++q)
-                if (q == q0) { ap += lgg09_out_pos(c.prog, Fp[q][0], Fp[q][1]); an += lgg09_out_neg(c.prog, Fp[q][0], Fp[q][1]); }
-#pragma unroll
-            for (int q = 0; q < NQ; ++q)
-                if (q == q1) { ap += lgg09_out_pos(c.prog, Fc[q][0], Fc[q][1]); an += lgg09_out_neg(c.prog, Fc[q][0], Fc[q][1]); }
-            if (a == 0) { vp = ap; vn = an; } else { vp = fmax(vp, ap); vn = fmax(vn, an); }
+                if (q == qv) { dp = lgg09_out_pos(c.prog, Fp[q][0], Fp[q][1]); dn = lgg09_out_neg(c.prog, Fp[q][0], Fp[q][1]); }
+            if (lane == 0) { s_dv[warp * 2] = dp; s_dv[warp * 2 + 1] = dn; }
         }
-        if (lane == 0) {
-            if (rp >= 0) c.rho[size_t(k) * c.ndirs + rp] = vp + sp;
-            if (rn >= 0) c.rho[size_t(k) * c.ndirs + rn] = vn + sn;
+        __syncthreads();
+        long long tq3 = clock64();
+        {   // running input sum, strictly in step order: s_{k+1} = s_k + rho(r_k; V)
+            double spw = sp, snw = sn;
+#pragma unroll 1
+            for (int b = 0; b < nb; ++b) {
+                if (b == warp && lane == 0) {
+                    const long long k = k0 + b;
+                    if (rp >= 0) c.rho[size_t(k) * c.ndirs + rp] = vp + spw;
+                    if (rn >= 0) c.rho[size_t(k) * c.ndirs + rn] = vn + snw;
+                }
+                spw += s_dv[b * 2];
+                snw += s_dv[b * 2 + 1];
+            }
+            sp = spw;
+            sn = snw;
         }
-        const int qv = c.prog.qV;
-#pragma unroll
-        for (int q = 0; q < NQ; ++q)
-            if (q == qv) { sp += lgg09_out_pos(c.prog, Fp[q][0], Fp[q][1]); sn += lgg09_out_neg(c.prog, Fp[q][0], Fp[q][1]); }
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) { Fp[q][0] = Fc[q][0]; Fp[q][1] = Fc[q][1]; }
-        double* tmp = rc; rc = rnx; rnx = tmp;
-        __syncwarp();
+        if (tid < NV) s_tot[tid] = s_tot[nb * NV + tid];                // features of r_{k0+nb} carry into the next batch
+        base += nb;
+        if (base > CHAIN_B) base -= CHAIN_B + 1;
+        __syncthreads();                                                 // s_tot, s_dv and the ring slots are reused
+        long long tq4 = clock64();
+        tph[0] += tq1 - tq0; tph[1] += tq2 - tq1; tph[2] += tq3 - tq2; tph[3] += tq4 - tq3;
     }
+    if (c.dbg && blockIdx.x == 0 && tid == 0) { c.dbg[0] = tph[0]; c.dbg[1] = tph[1]; c.dbg[2] = tph[2]; c.dbg[3] = tph[3]; }
 }
 
 // stack block 0 starts with the identity: out[i][i] = 1 (the buffer is zero-filled)
