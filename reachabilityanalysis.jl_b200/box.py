@@ -69,7 +69,7 @@ def _reach(c0, r0, Phi, NSTEPS, cU=None, rU=None, recursive=False, ctx=None, **o
     o = L.reach_lgg09_opts()
     ctx.lib.reach_lgg09_default_opts(C.byref(o))
     o.time_block = int(opts.get("time_block", 0))
-    o.path = {"auto": 0, "gemm": 1, "chain": 2, "int8": 3}.get(opts.get("path", 0), opts.get("path", 0))
+    o.path = {"auto": 0, "gemm": 1, "chain": 2, "int8": 3, "compact": 4}.get(opts.get("path", 0), opts.get("path", 0))
     cu = None if cU is None else np.ascontiguousarray(cU, dtype=np.float64)
     ru = None if rU is None else np.ascontiguousarray(rU, dtype=np.float64)
     Cm = np.empty((NSTEPS, n))        # == n x NSTEPS column-major

@@ -254,6 +254,11 @@ struct reach_lgg09_plan {
     int ch_maxnnz = 0, ch_rpl = 0, ch_ne = 0;
     size_t ch_smem = 0;
     DevBuf ell_val, ell_col, Edev;
+    // decoupled blocks: compact chains, parallel in time (path 4)
+    bool use_compact = false;
+    int cp_G = 0, cp_ne = 0, cp_nblk = 0, cp_log2 = 0, cp_mu_g = 0;
+    int64_t cp_sblk = 0;
+    DevBuf cpM, cpr0, cpwl, cpwa, cpE, cpWlE, cpWaE, cprstart, cpvoff;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaEvent_t> gemm_ev;   // pairs around sampled main-loop GEMM launches
@@ -293,6 +298,43 @@ int launch_chain(reach_ctx* ctx, int rpl, int ne, const Lgg09Chain& c, size_t sm
         case 4: return launch_chain_r<4>(ctx, ne, c, smem, st);
     }
     return set_error(ctx, REACH_EINVAL, "bad rows-per-thread %d", rpl);
+}
+
+template <int G, int NE>
+int launch_compact_t(reach_ctx* ctx, const Lgg09Compact& c, bool inhomog, cudaStream_t st, int64_t& launches) {
+    lgg09_compact_starts_kernel<G><<<(c.mu + 63) / 64, 64, 0, st>>>(c);
+    REACH_CUDA(ctx, cudaGetLastError());
+    ++launches;
+    const long long warps = (long long)(c.mu_g / (32 / G)) * c.nblk;
+    const unsigned grid = unsigned((warps + 3) / 4);
+    if (inhomog && c.nblk > 1) {
+        lgg09_compact_kernel<G, 4, NE, true><<<grid, 128, 0, st>>>(c);
+        REACH_CUDA(ctx, cudaGetLastError());
+        lgg09_compact_scan_kernel<<<(2 * c.mu + 127) / 128, 128, 0, st>>>(c.voff, c.mu, c.nblk);
+        REACH_CUDA(ctx, cudaGetLastError());
+        launches += 2;
+    } else {
+        REACH_CUDA(ctx, cudaMemsetAsync(c.voff, 0, size_t(c.nblk) * c.mu * 2 * sizeof(double), st));
+    }
+    lgg09_compact_kernel<G, 4, NE, false><<<grid, 128, 0, st>>>(c);
+    REACH_CUDA(ctx, cudaGetLastError());
+    ++launches;
+    return REACH_OK;
+}
+template <int G>
+int launch_compact_g(reach_ctx* ctx, int ne, const Lgg09Compact& c, bool inhomog, cudaStream_t st, int64_t& launches) {
+    if (ne == 0) return launch_compact_t<G, 0>(ctx, c, inhomog, st, launches);
+    if (ne == 4) return launch_compact_t<G, 4>(ctx, c, inhomog, st, launches);
+    return launch_compact_t<G, 8>(ctx, c, inhomog, st, launches);
+}
+int launch_compact(reach_ctx* ctx, int G, int ne, const Lgg09Compact& c, bool inhomog, cudaStream_t st, int64_t& launches) {
+    switch (G) {
+        case 2: return launch_compact_g<2>(ctx, ne, c, inhomog, st, launches);
+        case 4: return launch_compact_g<4>(ctx, ne, c, inhomog, st, launches);
+        case 8: return launch_compact_g<8>(ctx, ne, c, inhomog, st, launches);
+        case 16: return launch_compact_g<16>(ctx, ne, c, inhomog, st, launches);
+    }
+    return set_error(ctx, REACH_EINVAL, "bad compact group size %d", G);
 }
 
 // Cost model (SM cycles per time step) used to pick the tile shape and the time block S.
@@ -479,10 +521,65 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
     }
     p->mu = int(chain_src.size());
 
+    p->use_compact = false;
+    const bool forced_opts = p->opts.path == 1 || p->opts.path == 3 || (p->opts.path == 0 && (p->opts.time_block > 0 || p->opts.tile_m || p->opts.tile_n));
+    // ---- decoupled blocks: closure of every chain's support under the sparsity graph of Phi (path 4) ----
+    std::vector<int> cp_idx;                                  // [mu][G] closure rows, ascending, -1 padded
+    if (!forced_opts && p->opts.path != 2 && p->nq <= 4 && p->ne <= 8 && (p->opts.path == 4 || !getenv("REACH_NO_COMPACT"))) {
+        constexpr int GMAX = 16;
+        size_t nnz = 0;
+        for (size_t i = 0; i < size_t(n) * n; ++i) nnz += Phi[i] != 0.0;
+        if (nnz <= size_t(GMAX) * n) {                        // components of <= 16 rows hold <= 16 n non-zeros
+            std::vector<int> parent(n);
+            for (int i = 0; i < n; ++i) parent[i] = i;
+            auto find = [&](int x) { while (parent[x] != x) { parent[x] = parent[parent[x]]; x = parent[x]; } return x; };
+            for (int i = 0; i < n; ++i)
+                for (int l = 0; l < n; ++l)
+                    if (Phi[size_t(i) * n + l] != 0.0) { const int a = find(i), b = find(l); if (a != b) parent[std::max(a, b)] = std::min(a, b); }
+            std::vector<int> comp(n), csize(n, 0);
+            for (int i = 0; i < n; ++i) { comp[i] = find(i); ++csize[comp[i]]; }
+            std::vector<std::vector<int>> members(n);
+            for (int i = 0; i < n; ++i) members[comp[i]].push_back(i);
+            // mapped rows and direct weights only matter inside the closure, so they do not enlarge it
+            int gmax = 1;
+            bool ok = true;
+            std::vector<std::vector<int>> closure(p->mu);
+            for (int c = 0; c < p->mu && ok; ++c) {
+                const double* d = dirs + size_t(chain_src[c]) * n;
+                std::vector<int> comps;
+                int size = 0;
+                for (int i = 0; i < n && ok; ++i) {
+                    if (d[i] == 0.0) continue;
+                    if (std::find(comps.begin(), comps.end(), comp[i]) != comps.end()) continue;
+                    comps.push_back(comp[i]);
+                    size += csize[comp[i]];
+                    ok = size <= GMAX;
+                }
+                if (!ok) break;
+                for (int cid : comps) closure[c].insert(closure[c].end(), members[cid].begin(), members[cid].end());
+                std::sort(closure[c].begin(), closure[c].end());
+                gmax = std::max(gmax, size);
+            }
+            if (ok) {
+                int G = 2;
+                while (G < gmax) G *= 2;
+                p->use_compact = true;
+                p->cp_G = G;
+                cp_idx.assign(size_t(p->mu) * G, -1);
+                for (int c = 0; c < p->mu; ++c) std::copy(closure[c].begin(), closure[c].end(), cp_idx.begin() + size_t(c) * G);
+            }
+        }
+        if (p->opts.path == 4 && !p->use_compact)
+            return set_error(ctx, REACH_EUNSUPPORTED, "the compact-chain path needs every direction's closure under the sparsity "
+                             "graph of Phi to span at most %d rows", GMAX);
+    } else if (p->opts.path == 4) {
+        return set_error(ctx, REACH_EUNSUPPORTED, "the compact-chain path needs <= 4 support features and <= 8 mapped rows "
+                         "(features=%d, mapped rows=%d)", p->nq, p->ne);
+    }
     // ---- INT8 tcgen05 digit-plane GEMM requested (path 3) ----
     p->use_oz = false;
     p->oz_guard = false;
-    if (p->opts.path == 0 && !p->opts.tile_m && !p->opts.tile_n && n >= 512 && n <= 32768 && p->mu >= 96 &&
+    if (!p->use_compact && p->opts.path == 0 && !p->opts.tile_m && !p->opts.tile_n && n >= 512 && n <= 32768 && p->mu >= 96 &&
         n + p->ne >= 128 && p->nq >= 1 && p->nq <= 4 && !getenv("REACH_NO_INT8")) {
         // large dense problem: the INT8 tcgen05 digit-plane GEMM (~2x the FP64 tensor pipe), guarded: sampled passes
         // are recomputed with the DMMA kernel and the run falls back to it if they differ by more than kOzGuardTol
@@ -510,7 +607,8 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
     std::vector<int> ell_col;
     p->use_chain = false;
     const bool forced_gemm = p->opts.path == 1 || p->opts.path == 3 || p->use_oz || (p->opts.path == 0 && (p->opts.time_block > 0 || p->opts.tile_m || p->opts.tile_n));
-    if (!forced_gemm && n <= 512 && p->nq <= 4 && p->ne <= 8) {
+    if (p->use_compact) p->S = 1;
+    if (!p->use_compact && !forced_gemm && n <= 512 && p->nq <= 4 && p->ne <= 8) {
         int maxnnz = 0;
         for (int i = 0; i < n; ++i) {
             int cnt = 0;
@@ -610,6 +708,59 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
         for (int e = 0; e < p->ne; ++e) std::memcpy(&E[size_t(e) * n], p->prog.erows[e].data(), sizeof(double) * n);
         REACH_TRY(p->Edev.alloc(ctx, E.size() * 8, false));
         REACH_CUDA(ctx, cudaMemcpyAsync(p->Edev.p, E.data(), E.size() * 8, cudaMemcpyHostToDevice, st));
+        REACH_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    if (p->use_compact) {
+        const int G = p->cp_G, mu = p->mu, NQ = 4;
+        const int nep = p->ne == 0 ? 0 : (p->ne <= 4 ? 4 : 8);
+        p->cp_ne = nep;
+        p->cp_mu_g = round_up(mu, 32 / G);
+        // time blocks: enough (chain, block) groups for ~16 warps per SM, blocks of 2^s >= 64 steps
+        const int64_t wpb = p->cp_mu_g / (32 / G);
+        const int64_t want_blocks = std::max<int64_t>(1, (int64_t(ctx->sm_count) * 16 + wpb - 1) / wpb);
+        int64_t sblk = 64;
+        int lg = 6;
+        while (sblk * want_blocks < p->nsteps) { sblk *= 2; ++lg; }
+        p->cp_sblk = sblk;
+        p->cp_log2 = lg;
+        p->cp_nblk = int((p->nsteps + sblk - 1) / sblk);
+        std::vector<double> M(size_t(mu) * G * G, 0.0), r0(size_t(mu) * G, 0.0), wl(size_t(mu) * NQ * G, 0.0),
+            wa(size_t(mu) * NQ * G, 0.0), E(size_t(mu) * std::max(1, nep) * G, 0.0), WlE(size_t(NQ) * std::max(1, p->ne), 0.0),
+            WaE(size_t(NQ) * std::max(1, p->ne), 0.0);
+        for (int c = 0; c < mu; ++c) {
+            const int* idx = &cp_idx[size_t(c) * G];
+            const double* d = dirs + size_t(chain_src[c]) * n;
+            for (int i = 0; i < G; ++i) {
+                if (idx[i] < 0) continue;
+                r0[size_t(c) * G + i] = chain_sign[c] * d[idx[i]] + 0.0;
+                for (int l = 0; l < G; ++l)
+                    if (idx[l] >= 0) M[(size_t(c) * G + i) * G + l] = Phi[size_t(idx[i]) * n + idx[l]];   // Phi(idx_l, idx_i)
+                for (int q = 0; q < p->nq; ++q) {
+                    wl[(size_t(c) * NQ + q) * G + i] = p->prog.feats[q].a[idx[i]];
+                    wa[(size_t(c) * NQ + q) * G + i] = p->prog.feats[q].b[idx[i]];
+                }
+                for (int e = 0; e < p->ne; ++e) E[(size_t(c) * nep + e) * G + i] = p->prog.erows[e][idx[i]];
+            }
+        }
+        for (int q = 0; q < p->nq; ++q)
+            for (auto& kv : p->prog.feats[q].rows) {
+                WlE[size_t(q) * p->ne + kv.first] = kv.second.first;
+                WaE[size_t(q) * p->ne + kv.first] = kv.second.second;
+            }
+        auto ship = [&](DevBuf& b, const std::vector<double>& v) -> int {
+            REACH_TRY(b.alloc(ctx, v.size() * 8, false));
+            REACH_CUDA(ctx, cudaMemcpyAsync(b.p, v.data(), v.size() * 8, cudaMemcpyHostToDevice, st));
+            return REACH_OK;
+        };
+        REACH_TRY(ship(p->cpM, M));
+        REACH_TRY(ship(p->cpr0, r0));
+        REACH_TRY(ship(p->cpwl, wl));
+        REACH_TRY(ship(p->cpwa, wa));
+        REACH_TRY(ship(p->cpE, E));
+        REACH_TRY(ship(p->cpWlE, WlE));
+        REACH_TRY(ship(p->cpWaE, WaE));
+        REACH_TRY(p->cprstart.alloc(ctx, size_t(p->cp_nblk) * mu * G * 8, false));
+        REACH_TRY(p->cpvoff.alloc(ctx, size_t(p->cp_nblk) * mu * 2 * 8, false));
         REACH_CUDA(ctx, cudaStreamSynchronize(st));
     }
     // ---- host staging + H2D ----
@@ -726,6 +877,45 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
 
     REACH_CUDA(ctx, cudaEventRecord(p->ev0, st));
 
+    if (p->use_compact) {
+        Lgg09Compact c{};
+        c.prog = p->prog.dev;
+        c.mu = p->mu;
+        c.mu_g = p->cp_mu_g;
+        c.nq = p->nq;
+        c.ne = p->ne;
+        c.nblk = p->cp_nblk;
+        c.need_next = p->prog.need_next ? 1 : 0;
+        c.ndirs = p->ndirs;
+        c.nsteps = p->nsteps;
+        c.sblk = p->cp_sblk;
+        c.log2_sblk = p->cp_log2;
+        c.M = p->cpM.as<double>();
+        c.r0 = p->cpr0.as<double>();
+        c.wl = p->cpwl.as<double>();
+        c.wa = p->cpwa.as<double>();
+        c.E = p->cpE.as<double>();
+        c.WlE = p->cpWlE.as<double>();
+        c.WaE = p->cpWaE.as<double>();
+        c.rstart = p->cprstart.as<double>();
+        c.voff = p->cpvoff.as<double>();
+        c.row_pos = p->row_pos.as<int>();
+        c.row_neg = p->row_neg.as<int>();
+        c.rho = p->rho;
+        REACH_TRY(launch_compact(ctx, p->cp_G, p->cp_ne, c, p->prog.dev.qV >= 0, st, p->launches));
+        if (p->nchecks > 0) {
+            REACH_CUDA(ctx, cudaMemsetAsync(p->first_bad.p, 0xFF, sizeof(unsigned long long), st));
+            const int th = 256;
+            const unsigned blocks = unsigned((p->nsteps + th - 1) / th);
+            first_disjoint_kernel<<<blocks, th, 0, st>>>(p->rho, p->ndirs, p->nsteps, p->checks.as<InvCheck>(),
+                                                          p->nchecks, p->first_bad.as<unsigned long long>());
+            REACH_CUDA(ctx, cudaGetLastError());
+            ++p->launches;
+        }
+        REACH_CUDA(ctx, cudaEventRecord(p->ev1, st));
+        p->ran = true;
+        return REACH_OK;
+    }
     if (p->use_chain) {
         Lgg09Chain c{};
         c.prog = p->prog.dev;
@@ -1133,8 +1323,8 @@ extern "C" int reach_lgg09_plan_stats(reach_lgg09_plan* p, double* ms, int64_t* 
     if (ms) *ms = p->last_ms;
     if (launches) *launches = p->launches;
     if (time_block) *time_block = p->S;
-    if (tile_m) *tile_m = p->use_chain ? 0 : p->TM;
-    if (tile_n) *tile_n = p->use_chain ? 0 : p->TN;
+    if (tile_m) *tile_m = (p->use_chain || p->use_compact) ? 0 : p->TM;
+    if (tile_n) *tile_n = (p->use_chain || p->use_compact) ? 0 : p->TN;
     if (nchains) *nchains = p->mu;
     if (gemm_ms) *gemm_ms = p->gemm_ms;
     if (gemm_launches) *gemm_launches = p->gemm_total;
@@ -1144,7 +1334,7 @@ extern "C" int reach_lgg09_plan_stats(reach_lgg09_plan* p, double* ms, int64_t* 
 extern "C" int reach_lgg09_plan_path(reach_lgg09_plan* p, int32_t* path, int32_t* digit_planes, double* guard_max,
                                      int64_t* guard_checks, int64_t* fallback_pass) {
     if (!p) return REACH_EINVAL;
-    if (path) *path = p->use_chain ? 2 : (p->use_oz ? 3 : 1);
+    if (path) *path = p->use_compact ? 4 : (p->use_chain ? 2 : (p->use_oz ? 3 : 1));
     if (digit_planes) *digit_planes = p->use_oz ? p->oz_T : 0;
     if (guard_max) *guard_max = p->oz_guard_max;
     if (guard_checks) *guard_checks = p->oz_checks;

@@ -715,6 +715,213 @@ __global__ void __launch_bounds__(CHAIN_THREADS) lgg09_chain_kernel(const Lgg09C
     if (c.dbg && blockIdx.x == 0 && tid == 0) { c.dbg[0] = tph[0]; c.dbg[1] = tph[1]; c.dbg[2] = tph[2]; c.dbg[3] = tph[3]; }
 }
 
+// ---- decoupled blocks: compact chains, parallel in time ---------------------------------------------
+// r_k = (Phi')^k l only ever touches the rows reachable from supp(l) in the sparsity graph of Phi.  When that closure is
+// small for every chain (ISS: Phi = expm(A dt) is 135 decoupled 2x2 oscillators, so a box direction lives in 2 rows for
+// ever; any tiny system n <= 16), the chain is a G-dimensional recurrence with its own dense G x G matrix -- exact, the
+// rows outside the closure are exactly zero and add exact zeros to every sum of the reference.  A lane group of G lanes
+// owns one (chain, time block): local Phi' row, feature weights and mapped-row entries in registers, the mat-vec by
+// G shuffles + FMAs (ascending column order: the sequential association of the reference's mul!), feature sums by a
+// log2(G)-round butterfly.  Time is cut into blocks of sblk = 2^s steps: the block start vectors come from
+// (Phi_C')^sblk (s squarings, lgg09_compact_starts_kernel) -- the same reassociation through stored powers as the GEMM
+// path's time blocking -- so chains x blocks groups run at once instead of one 33 334-step dependent loop per chain.
+// The running input sum s_k needs the totals of the earlier blocks: pass ONLY_V sums rho(+-r_k; V) per block in step
+// order, lgg09_compact_scan_kernel turns the totals into block offsets (fixed order), the second pass writes rho once.
+struct Lgg09Compact {
+    Lgg09Program prog;
+    int mu, mu_g;                   // chains; chains padded to whole warps (32/G per warp)
+    int nq, ne, nblk, need_next, ndirs;
+    long long nsteps, sblk;         // steps per time block (power of two)
+    int log2_sblk;
+    const double* M;                // [mu][G][G]  M[c][i][l] = Phi'(idx_i, idx_l) = Phi(idx_l, idx_i)
+    const double* r0;               // [mu][G]
+    const double* wl;               // [mu][NQ][G] direct weights of the local rows
+    const double* wa;               // [mu][NQ][G]
+    const double* E;                // [mu][NE][G] mapped rows restricted to the closure
+    const double* WlE;              // [NQ][NE] mapped-row weights
+    const double* WaE;
+    double* rstart;                 // [nblk][mu][G]
+    double* voff;                   // [nblk][mu][2] block totals of rho(+-r; V), then exclusive offsets
+    const int* row_pos;
+    const int* row_neg;
+    double* rho;
+};
+
+template <int G>
+__global__ void lgg09_compact_starts_kernel(const Lgg09Compact c) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= c.mu) return;
+    double P[G * G], T[G * G];
+#pragma unroll
+    for (int x = 0; x < G * G; ++x) P[x] = c.M[size_t(ch) * G * G + x];
+    for (int s = 0; s < c.log2_sblk; ++s) {                              // P <- P * P
+#pragma unroll
+        for (int i = 0; i < G; ++i)
+#pragma unroll
+            for (int l = 0; l < G; ++l) {
+                double acc = 0.0;
+#pragma unroll
+                for (int m = 0; m < G; ++m) acc = fma(P[i * G + m], P[m * G + l], acc);
+                T[i * G + l] = acc;
+            }
+#pragma unroll
+        for (int x = 0; x < G * G; ++x) P[x] = T[x];
+    }
+    double r[G], rn[G];
+#pragma unroll
+    for (int i = 0; i < G; ++i) r[i] = c.r0[size_t(ch) * G + i];
+    for (int b = 0; b < c.nblk; ++b) {
+#pragma unroll
+        for (int i = 0; i < G; ++i) c.rstart[(size_t(b) * c.mu + ch) * G + i] = r[i];
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int l = 0; l < G; ++l) acc = fma(P[i * G + l], r[l], acc);
+            rn[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < G; ++i) r[i] = rn[i];
+    }
+}
+
+static __global__ void lgg09_compact_scan_kernel(double* __restrict__ voff, int mu, int nblk) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;                 // (chain, sign)
+    if (x >= 2 * mu) return;
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) {
+        const double t = voff[size_t(b) * 2 * mu + x];
+        voff[size_t(b) * 2 * mu + x] = s;
+        s += t;
+    }
+}
+
+template <int G, int NQ, int NE, bool ONLY_V>
+__global__ void __launch_bounds__(128) lgg09_compact_kernel(const Lgg09Compact c) {
+    constexpr int NEP = NE > 0 ? NE : 1;
+    constexpr int CPW = 32 / G;                                          // chains per warp
+    __shared__ double s_wlE[NQ][NEP], s_waE[NQ][NEP];
+    for (int x = threadIdx.x; x < NQ * NEP; x += blockDim.x) {
+        const int q = x / NEP, e = x % NEP;
+        const bool ok = q < c.nq && e < c.ne;
+        s_wlE[q][e] = ok ? c.WlE[q * c.ne + e] : 0.0;
+        s_waE[q][e] = ok ? c.WaE[q * c.ne + e] : 0.0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, i = lane % G, gbase = lane - i;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const int wpb = c.mu_g / CPW;                                        // warps per time block
+    const int b = int(warp / wpb);
+    if (b >= c.nblk) return;                                             // whole warps only
+    const int ch = int(warp % wpb) * CPW + lane / G;
+    const bool live = ch < c.mu;
+    const int cc = live ? ch : 0;                                        // padding groups replay chain 0, store nothing
+
+    double Mrow[G];
+#pragma unroll
+    for (int l = 0; l < G; ++l) Mrow[l] = c.M[(size_t(cc) * G + i) * G + l];
+    double wl[NQ], wa[NQ], Ei[NEP];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        wl[q] = q < c.nq ? c.wl[(size_t(cc) * NQ + q) * G + i] : 0.0;
+        wa[q] = q < c.nq ? c.wa[(size_t(cc) * NQ + q) * G + i] : 0.0;
+    }
+#pragma unroll
+    for (int e = 0; e < NEP; ++e) Ei[e] = (NE > 0 && e < c.ne) ? c.E[(size_t(cc) * NE + e) * G + i] : 0.0;
+    double r = c.rstart[(size_t(b) * c.mu + cc) * G + i];
+    const long long kb = b * c.sblk, ke = min(c.nsteps, kb + c.sblk);
+
+    auto next = [&](double v) {
+        double acc = 0.0;
+#pragma unroll
+        for (int l = 0; l < G; ++l) acc = fma(Mrow[l], __shfl_sync(0xffffffffu, v, gbase + l), acc);
+        return acc;
+    };
+    auto group_sum = [&](double v) {
+#pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        return v;
+    };
+
+    if (ONLY_V) {
+        // block totals of rho(+r_k; V), rho(-r_k; V), summed in step order
+        const int qv = c.prog.qV;
+        double wlv = 0.0, wav = 0.0, wlEv[NEP], waEv[NEP];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) if (q == qv) { wlv = wl[q]; wav = wa[q]; }
+#pragma unroll
+        for (int e = 0; e < NEP; ++e) { wlEv[e] = qv >= 0 ? s_wlE[qv][e] : 0.0; waEv[e] = qv >= 0 ? s_waE[qv][e] : 0.0; }
+        double tp = 0.0, tn = 0.0;
+        for (long long k = kb; k < ke; ++k) {
+            double lin = group_sum(wlv * r), ab = group_sum(wav * fabs(r));
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                const double y = group_sum(Ei[e] * r);
+                lin = fma(wlEv[e], y, lin);
+                ab = fma(waEv[e], fabs(y), ab);
+            }
+            tp += lgg09_out_pos(c.prog, lin, ab);
+            tn += lgg09_out_neg(c.prog, lin, ab);
+            r = next(r);
+        }
+        if (live && i == 0) {
+            c.voff[(size_t(b) * c.mu + ch) * 2] = tp;
+            c.voff[(size_t(b) * c.mu + ch) * 2 + 1] = tn;
+        }
+        return;
+    }
+
+    auto features = [&](double v, double (&F)[NQ][2]) {
+        double y[NEP];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) y[e] = group_sum(Ei[e] * v);
+        const double av = fabs(v);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            double lin = group_sum(wl[q] * v), ab = group_sum(wa[q] * av);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) {
+                lin = fma(s_wlE[q][e], y[e], lin);
+                ab = fma(s_waE[q][e], fabs(y[e]), ab);
+            }
+            F[q][0] = lin;
+            F[q][1] = ab;
+        }
+    };
+    const int rp = live ? c.row_pos[ch] : -1, rn = live ? c.row_neg[ch] : -1;
+    const int qv = c.prog.qV;
+    double sp = 0.0, sn = 0.0;
+    if (qv >= 0) { sp = c.voff[(size_t(b) * c.mu + cc) * 2]; sn = c.voff[(size_t(b) * c.mu + cc) * 2 + 1]; }
+    double Fp[NQ][2], Fc[NQ][2];
+    features(r, Fp);
+    for (long long k = kb; k < ke; ++k) {
+        r = next(r);
+        features(r, Fc);
+        double vp = 0.0, vn = 0.0;
+        for (int a = 0; a < c.prog.nalt; ++a) {
+            double ap = 0.0, an = 0.0;
+            const int q0 = c.prog.q0[a], q1 = c.prog.q1[a];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (q == q0) { ap += lgg09_out_pos(c.prog, Fp[q][0], Fp[q][1]); an += lgg09_out_neg(c.prog, Fp[q][0], Fp[q][1]); }
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (q == q1) { ap += lgg09_out_pos(c.prog, Fc[q][0], Fc[q][1]); an += lgg09_out_neg(c.prog, Fc[q][0], Fc[q][1]); }
+            if (a == 0) { vp = ap; vn = an; } else { vp = fmax(vp, ap); vn = fmax(vn, an); }
+        }
+        if (i == 0) {
+            if (rp >= 0) c.rho[size_t(k) * c.ndirs + rp] = vp + sp;
+            if (rn >= 0) c.rho[size_t(k) * c.ndirs + rn] = vn + sn;
+        }
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            if (q == qv) { sp += lgg09_out_pos(c.prog, Fp[q][0], Fp[q][1]); sn += lgg09_out_neg(c.prog, Fp[q][0], Fp[q][1]); }
+            Fp[q][0] = Fc[q][0];
+            Fp[q][1] = Fc[q][1];
+        }
+    }
+}
+
 // stack block 0 starts with the identity: out[i][i] = 1 (the buffer is zero-filled)
 static __global__ void set_identity_kernel(double* __restrict__ out, int ld, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

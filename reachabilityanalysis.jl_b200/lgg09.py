@@ -113,7 +113,7 @@ class Lgg09Plan:
         self.lib.reach_lgg09_default_opts(C.byref(opts))
         opts.time_block, opts.share_negated = int(time_block), int(bool(share_negated))
         opts.tile_m, opts.tile_n = int(tile_m), int(tile_n)
-        opts.path = {"auto": 0, "gemm": 1, "chain": 2, "int8": 3}.get(path, path)
+        opts.path = {"auto": 0, "gemm": 1, "chain": 2, "int8": 3, "compact": 4}.get(path, path)
         opts.reserved[0] = int(digit_planes)      # 0 = 8 planes (FP64-level accuracy); 4..8
         self.handle = C.c_void_p()
         ctx.check(self.lib.reach_lgg09_plan_create(ctx.handle, self.n, self.ndirs, self.nsteps,
@@ -226,7 +226,7 @@ class Lgg09Plan:
                                                       C.byref(gchecks), C.byref(fb)))
         return dict(ms=ms.value, launches=launches.value, time_block=S_.value, tile_m=tm.value,
                     tile_n=tn.value, nchains=mu.value, gemm_ms=gms.value, gemm_launches=gl.value,
-                    path={1: "gemm", 2: "chain", 3: "int8"}[path.value], digit_planes=planes.value,
+                    path={1: "gemm", 2: "chain", 3: "int8", 4: "compact"}[path.value], digit_planes=planes.value,
                     guard_max=gmax.value, guard_checks=gchecks.value, fallback_pass=fb.value)
 
     def close(self):

@@ -249,11 +249,98 @@ def test_iss_sparse_phi_takes_the_chain_path(ctx):
     dirs = rb.BoxDirections(270).matrix()
     ref = LO.reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, 400, ivp.V)
     auto = reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, 400, None, ivp.V, ctx=ctx)
-    assert auto.stats()["tile_m"] == 0
+    assert auto.stats()["path"] == "compact"      # 135 decoupled 2x2 oscillators: two rows per box direction
     assert_support_parity(auto.sfmat(), ref)
+    chain = reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, 400, None, ivp.V, ctx=ctx, path="chain")
+    assert chain.stats()["path"] == "chain"
+    assert_support_parity(chain.sfmat(), ref)
+    # the reference's own ISS run: the two directions +-C3 couple all 270 rows -> not compactable
+    d2 = np.column_stack([Cm[2], -Cm[2]])
+    ref2 = LO.reach_inhomog_LGG09(d2, ivp.Omega0, ivp.Phi, 400, ivp.V)
+    two = reach_inhomog_LGG09(d2, ivp.Omega0, ivp.Phi, 400, None, ivp.V, ctx=ctx)
+    assert two.stats()["path"] == "chain"
+    assert_support_parity(two.sfmat(), ref2)
     gemm = reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, 400, None, ivp.V, ctx=ctx, path="gemm")
     assert gemm.stats()["tile_m"] > 0
     assert_support_parity(gemm.sfmat(), ref)
+
+
+def block_diagonal_system(nblocks, g, seed, delta=0.05):
+    """Φ = expm(Aδ) of `nblocks` decoupled g×g systems, rows shuffled so the blocks are not contiguous."""
+    import scipy.linalg
+    rng = np.random.default_rng(seed)
+    n = nblocks * g
+    A = np.zeros((n, n))
+    for b in range(nblocks):
+        A[b * g:(b + 1) * g, b * g:(b + 1) * g] = -np.eye(g) + 0.7 * rng.standard_normal((g, g))
+    perm = rng.permutation(n)
+    A = A[np.ix_(perm, perm)]
+    Phi = np.zeros((n, n))
+    inv = np.argsort(perm)
+    for b in range(nblocks):
+        idx = inv[b * g:(b + 1) * g]
+        Phi[np.ix_(idx, idx)] = scipy.linalg.expm(A[np.ix_(idx, idx)] * delta)      # exact zeros off the blocks
+    return A, Phi, [inv[b * g:(b + 1) * g] for b in range(nblocks)]
+
+
+@pytest.mark.parametrize("nblocks,g,nsteps", [(40, 2, 700), (9, 3, 300), (7, 4, 150), (5, 8, 333), (3, 16, 200), (12, 1, 130)])
+def test_compact_chains_decoupled_blocks(ctx, nblocks, g, nsteps):
+    """path 4: every chain lives in the closure of its support under Φ's sparsity graph; lane groups × time blocks."""
+    A, Phi, blocks = block_diagonal_system(nblocks, g, 5 * nblocks + g)
+    n = nblocks * g
+    X0, U, Z = random_sets(n, n + 2)
+    rng = np.random.default_rng(3)
+    q = min(8, max(1, n // 3))
+    Bm = rng.standard_normal((n, q))
+    U0 = rb.Hyperrectangle(rng.uniform(-0.2, 0.2, q), 0.05 * rng.uniform(0, 1, q))
+    V = rb.MinkowskiSum(rb.LinearMap(0.05 * Bm, U0), rb.BallInf(np.zeros(n), 1e-3))
+    Om = rb.ConvexHull(X0, rb.MinkowskiSum(rb.LinearMap(Phi, X0), V))
+    dirs = np.hstack([np.eye(n), -np.eye(n)])
+    extra = np.zeros((n, 2))
+    extra[blocks[0], 0] = rng.standard_normal(g)                    # a direction inside one block
+    if 2 * g <= 16 and nblocks > 1:
+        extra[np.r_[blocks[0], blocks[1]], 1] = rng.standard_normal(2 * g)   # spanning two blocks
+    else:
+        extra[blocks[-1], 1] = rng.standard_normal(g)
+    dirs = np.hstack([dirs, extra])
+    ref = LO.reach_inhomog_LGG09(dirs, Om, Phi, nsteps, V)
+    plan = reach_inhomog_LGG09(dirs, Om, Phi, nsteps, None, V, ctx=ctx)
+    assert plan.stats()["path"] == "compact"
+    assert_support_parity(plan.sfmat(), ref)
+    forced = reach_inhomog_LGG09(dirs, Om, Phi, nsteps, None, V, ctx=ctx, path="compact")
+    assert np.array_equal(forced.sfmat(), plan.sfmat())
+    gemm = reach_inhomog_LGG09(dirs, Om, Phi, nsteps, None, V, ctx=ctx, path="gemm")
+    assert gemm.stats()["path"] == "gemm"
+    assert_support_parity(gemm.sfmat(), ref)
+    Zs = rb.Zonotope(Z.center, Z.generators[:, :6])              # six dense generators = six mapped rows
+    hom_ref = LO.reach_homog_LGG09(dirs, Zs, Phi, nsteps)
+    hom = reach_homog_LGG09(dirs, Zs, Phi, nsteps, ctx=ctx)
+    assert hom.stats()["path"] == "compact"
+    assert_support_parity(hom.sfmat(), hom_ref)
+
+
+@pytest.mark.parametrize("n,nsteps", [(1, 1), (2, 65), (5, 1000), (13, 64), (16, 129)])
+def test_compact_chains_tiny_dense_systems(ctx, n, nsteps):
+    A, _ = stable_system(n, n + 40)
+    X0, U, _ = random_sets(n, n + 40)
+    ivp = D.forward(A, X0, 0.05, U)
+    dirs = np.hstack([np.eye(n), -np.eye(n), np.random.default_rng(n).standard_normal((n, 3))])
+    ref = LO.reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, nsteps, ivp.V)
+    plan = reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, nsteps, None, ivp.V, ctx=ctx)
+    assert plan.stats()["path"] == "compact"
+    assert_support_parity(plan.sfmat(), ref)
+    seq = reach_inhomog_LGG09(dirs, ivp.Omega0, ivp.Phi, nsteps, None, ivp.V, ctx=ctx, path="chain")
+    assert seq.stats()["path"] == "chain"
+    assert_support_parity(plan.sfmat(), seq.sfmat())
+
+
+def test_compact_path_rejects_coupled_systems(ctx):
+    n = 48
+    A, Phi = stable_system(n, 2)
+    with pytest.raises(NotImplementedError):
+        reach_homog_LGG09(np.eye(n)[:, :4], rb.BallInf(np.zeros(n), 1.0), Phi, 3, ctx=ctx, path="compact")
+    auto = reach_homog_LGG09(np.eye(n)[:, :4], rb.BallInf(np.zeros(n), 1.0), Phi, 3, ctx=ctx)
+    assert auto.stats()["path"] != "compact"
 
 
 def test_chain_path_rejects_what_it_cannot_hold(ctx):
