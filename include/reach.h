@@ -179,6 +179,28 @@ int  reach_lgg09_plan_path(reach_lgg09_plan* p, int32_t* path, int32_t* digit_pl
                            int64_t* guard_checks, int64_t* fallback_pass);
 void reach_lgg09_plan_destroy(reach_lgg09_plan* p);
 
+/* LGG09 over a vector of initial sets -- the split caller `_solve_distributed` (src/Continuous/solve.jl:84-117),
+ * which in the reference re-runs `post` per initial set.  Phi, the template and V are shared; Omega0s[i] is the
+ * flattened Omega0 of split i.  The direction chains and the running input sum are computed once, the per-split
+ * part is one FP64 tensor-core contraction (csrc/lgg09_batch.inl).  Output: rho[split][step][dir], i.e. split i's
+ * ndirs x nsteps column-major matrix (the reference's rho_l, LGG09/post.jl:37-49) at offset i*ndirs*nsteps.
+ * No invariant (early termination is per split; use the plan API for that). */
+typedef struct reach_lgg09_batch reach_lgg09_batch;
+int  reach_lgg09_batch_create(reach_ctx* ctx, int n, int ndirs, int64_t nsteps, int nsplits,
+                              const double* Phi, const double* dirs,
+                              const reach_setexpr* Omega0s /* [nsplits] */, const reach_setexpr* V /* NULL: homogeneous */,
+                              reach_lgg09_batch** out);
+int  reach_lgg09_batch_run(reach_lgg09_batch* b);          /* asynchronous on the ctx stream */
+int  reach_lgg09_batch_sync(reach_lgg09_batch* b);
+int  reach_lgg09_batch_fetch(reach_lgg09_batch* b, int split, int64_t step0, int64_t nsteps, double* rho_host);
+/* split >= 0: rho(d_j, flowpipe of that split); split = -1: rho(d_j, MixedFlowpipe) = max over all splits and steps
+ * (Flowpipes/MixedFlowpipe.jl:66-68), reduced on the device */
+int  reach_lgg09_batch_max_over_steps(reach_lgg09_batch* b, int split, double* max_host /* ndirs */);
+int  reach_lgg09_batch_stats(reach_lgg09_batch* b, double* ms, int64_t* launches, int32_t* time_block,
+                             int32_t* alternatives, int32_t* feature_cols, int64_t* chunk_steps);
+void* reach_lgg09_batch_device_rho(reach_lgg09_batch* b);  /* device pointer, [nsplits][nsteps][ndirs] */
+void reach_lgg09_batch_destroy(reach_lgg09_batch* b);
+
 /* BOX (src/Algorithms/BOX/reach_homog.jl:8-47,50-69, reach_inhomog.jl:8-60): hyperrectangular flowpipe
  *   non-recursive: c_k = Phi^(k-1) c_1 + W_k.c,  r_k = |Phi^(k-1)| r_1 + W_k.r,  W_2 = U, W_{k+1} = W_k (+) box(Phi^(k-1) U)
  *   recursive    : H_k = box(Phi H_{k-1})          (homogeneous only, as in the reference)

@@ -71,6 +71,15 @@ SIGNATURES = {
                                          c_int32_p, c_int32_p, c_double_p, c_int64_p]),
     "reach_lgg09_plan_path": (C.c_int, [C.c_void_p, c_int32_p, c_int32_p, c_double_p, c_int64_p, c_int64_p]),
     "reach_lgg09_plan_destroy": (None, [C.c_void_p]),
+    "reach_lgg09_batch_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, c_double_p, c_double_p,
+                                           C.POINTER(reach_setexpr), C.POINTER(reach_setexpr), C.POINTER(C.c_void_p)]),
+    "reach_lgg09_batch_run": (C.c_int, [C.c_void_p]),
+    "reach_lgg09_batch_sync": (C.c_int, [C.c_void_p]),
+    "reach_lgg09_batch_fetch": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int64, c_double_p]),
+    "reach_lgg09_batch_max_over_steps": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
+    "reach_lgg09_batch_stats": (C.c_int, [C.c_void_p, c_double_p, c_int64_p, c_int32_p, c_int32_p, c_int32_p, c_int64_p]),
+    "reach_lgg09_batch_device_rho": (C.c_void_p, [C.c_void_p]),
+    "reach_lgg09_batch_destroy": (None, [C.c_void_p]),
     "reach_box": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, c_double_p, c_double_p, c_double_p, c_double_p, c_double_p,
                             C.c_int, C.POINTER(reach_lgg09_opts), c_double_p, c_double_p]),
     "reach_glgm06_plan_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int,

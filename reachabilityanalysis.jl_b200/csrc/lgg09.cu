@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -1450,3 +1451,5 @@ extern "C" int reach_dgemm_probe(reach_ctx* ctx, int m, int n, int k, int iters,
     *tflops = 2.0 * m * double(n) * k * iters / (ms * 1e-3) / 1e12;
     return REACH_OK;
 }
+
+#include "lgg09_batch.inl"

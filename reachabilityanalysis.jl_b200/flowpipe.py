@@ -204,6 +204,12 @@ class MixedFlowpipe:
         return iter(self.flowpipes)
 
     def rho(self, d):
+        dev = getattr(self, "device", None)
+        if dev is not None and hasattr(dev, "rho_flowpipe"):
+            try:
+                return dev.rho_flowpipe(d)       # one device reduction over every split and step
+            except NotImplementedError:
+                pass
         return max(fp.rho(d) for fp in self.flowpipes)
 
 

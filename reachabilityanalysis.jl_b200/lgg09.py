@@ -241,6 +241,145 @@ class Lgg09Plan:
             pass
 
 
+class Lgg09BatchPlan:
+    """LGG09 over a vector of initial sets sharing Φ, the template and V (`reach_lgg09_batch_*`): the split caller
+    `_solve_distributed` (src/Continuous/solve.jl:84-117) without re-running the chains per split.  The result
+    stays on the device as [split][step][dir]."""
+
+    def __init__(self, ctx, Phi, dirs, Omega0s, V, nsteps):
+        self.ctx, self.lib = ctx, ctx.lib
+        Phi, dirs = L.fmat(Phi), L.fmat(dirs)
+        n = Phi.shape[0]
+        if Phi.shape != (n, n):
+            raise ValueError("Φ must be square, got %s" % (Phi.shape,))
+        if dirs.shape[0] != n:
+            raise ValueError("the problem's dimension %d doesn't match the dimension of the template "
+                             "directions, %d" % (n, dirs.shape[0]))
+        if len(Omega0s) < 1:
+            raise ValueError("at least one initial set is required")
+        for Om in Omega0s:
+            if S.dim(Om) != n:
+                raise ValueError("Ω₀ has dimension %d, expected %d" % (S.dim(Om), n))
+        self.n, self.ndirs, self.nsteps, self.nsplits = n, dirs.shape[1], int(nsteps), len(Omega0s)
+        oms = [to_c(flatten(Om, Phi), n) for Om in Omega0s]
+        arr = (L.reach_setexpr * len(oms))(*[o.expr for o in oms])
+        v = to_c(flatten(V, Phi), n) if V is not None else None
+        if v is not None and v.expr.nalt != 1:
+            raise NotImplementedError("input sets containing a convex hull are not supported")
+        self._keep = (Phi, dirs, oms, arr, v)
+        self._dirs = dirs
+        self.handle = C.c_void_p()
+        ctx.check(self.lib.reach_lgg09_batch_create(
+            ctx.handle, n, self.ndirs, self.nsteps, self.nsplits, L.dptr(Phi), L.dptr(dirs),
+            C.cast(arr, C.POINTER(L.reach_setexpr)), v.ptr() if v is not None else None, C.byref(self.handle)))
+        self._cache = {}
+
+    def run(self, sync=True):
+        self.ctx.check(self.lib.reach_lgg09_batch_run(self.handle))
+        self._cache = {}
+        if sync:
+            self.ctx.check(self.lib.reach_lgg09_batch_sync(self.handle))
+        return self
+
+    def fetch(self, split, step0=0, nsteps=None):
+        """ρℓ of one split, (ndirs, nsteps), device→host."""
+        nsteps = self.nsteps - step0 if nsteps is None else nsteps
+        out = np.empty((self.ndirs, nsteps), order="F")
+        self.ctx.check(self.lib.reach_lgg09_batch_fetch(self.handle, int(split), step0, nsteps, L.dptr(out)))
+        return out
+
+    def sfmat(self, split):
+        if split not in self._cache:
+            self._cache[split] = self.fetch(split)
+        return self._cache[split]
+
+    def max_over_steps(self, split=-1):
+        """max over steps of every template row; split = -1: over all splits too (ρ(d, MixedFlowpipe))."""
+        out = np.empty(self.ndirs)
+        self.ctx.check(self.lib.reach_lgg09_batch_max_over_steps(self.handle, int(split), L.dptr(out)))
+        return out
+
+    def rho_flowpipe(self, d, split=-1):
+        d = np.asarray(d, dtype=np.float64)
+        D = self._dirs
+        for i in range(D.shape[1]):
+            ok, k = samedir(d, D[:, i])
+            if ok:
+                return float(self.max_over_steps(split)[i]) * k
+        raise NotImplementedError("ρ(d, flowpipe) for a non-template direction needs an LP")
+
+    def stats(self):
+        ms, launches, chunk = C.c_double(), C.c_int64(), C.c_int64()
+        S_, na, kc = C.c_int32(), C.c_int32(), C.c_int32()
+        self.ctx.check(self.lib.reach_lgg09_batch_stats(self.handle, C.byref(ms), C.byref(launches), C.byref(S_),
+                                                        C.byref(na), C.byref(kc), C.byref(chunk)))
+        return dict(ms=ms.value, launches=launches.value, time_block=S_.value, alternatives=na.value,
+                    feature_cols=kc.value, chunk_steps=chunk.value)
+
+    @property
+    def device_rho(self):
+        return self.lib.reach_lgg09_batch_device_rho(self.handle)
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.reach_lgg09_batch_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _SplitView:
+    """One split of a batch, with the interface Flowpipe expects from a device plan."""
+
+    def __init__(self, batch, split):
+        self.batch, self.split = batch, split
+
+    def sfmat(self):
+        return self.batch.sfmat(self.split)
+
+    def fetch_rows(self, rows):
+        m = self.sfmat()
+        return [m[r] for r in rows]
+
+    def rho_flowpipe(self, d):
+        return self.batch.rho_flowpipe(d, self.split)
+
+
+def post_batch(alg, ivps, NSTEPS, Δt0=zeroT, ctx=None):
+    """The vector-of-initial-sets form of `solve` (src/Continuous/solve.jl:84-117) for LGG09: `ivps` are the
+    discretised problems of the splits (same Φ and V, different Ω₀).  Returns a MixedFlowpipe whose flowpipes
+    share one device-resident batch; ρ(d, ·) over a template direction is one device reduction."""
+    from .flowpipe import MixedFlowpipe
+    ctx = ctx or L.default_context()
+    template = alg.template
+    first = ivps[0]
+    if first.n != template.n:
+        raise AssertionError("the problems' dimension %d doesn't match the dimension of the template "
+                             "directions, %d" % (first.n, template.n))
+    if any(iv.X is not None for iv in ivps):
+        raise NotImplementedError("the batched split caller does not take an invariant")
+    for iv in ivps[1:]:
+        if not np.array_equal(iv.Phi, first.Phi):
+            raise ValueError("the splits must share Φ")
+    batch = Lgg09BatchPlan(ctx, first.Phi, template.matrix(), [iv.Omega0 for iv in ivps], first.V, NSTEPS)
+    batch.run()
+    fps = []
+    for i in range(len(ivps)):
+        view = _SplitView(batch, i)
+
+        def make(k, dt, view=view):
+            return TemplateReachSet(template, view.sfmat()[:, k], dt)
+
+        fps.append(Flowpipe(NSTEPS, make, alg.δ, Δt0, {"sfmat": view.sfmat, "alg_vars": alg.vars}, device=view))
+    mixed = MixedFlowpipe(fps, {"batch": batch})
+    mixed.device = batch
+    return mixed
+
+
 def reach_homog_LGG09(dirs, Omega0, Phi, NSTEPS, X=None, ctx=None, **opts):
     """`reach_homog_LGG09!` (reach_homog.jl:6-33): returns the device-resident plan; `.sfmat()`
     is the ndirs × NSTEPS matrix ρℓ."""

@@ -78,6 +78,14 @@ def solve(ivp, T=None, alg=None, NSTEPS=None, tspan=None, algorithm=None, opC=No
         if not isinstance(alg, (_lgg09.LGG09, _box.BOX)):
             from . import glgm06 as _glgm06
             F = _glgm06.post_batch(alg, ivp, T=T, NSTEPS=NSTEPS, Δt0=dt0, ctx=ctx)
+        elif isinstance(alg, _lgg09.LGG09) and ivp.X is None:
+            # Φ, the template and V are shared: one batch on the device (lgg09.post_batch)
+            if NSTEPS is None:
+                if T is None:
+                    raise ValueError("the time horizon `T` (or `NSTEPS`) should be specified")
+                NSTEPS = _nsteps(T, alg.δ)
+            divps = [discretize(IVP(ivp.A, X0, ivp.B, ivp.U, None), alg.δ, alg.approx_model) for X0 in ivp.X0]
+            F = _lgg09.post_batch(alg, divps, NSTEPS, Δt0=dt0, ctx=ctx)
         else:
             F = MixedFlowpipe([post_continuous(alg, IVP(ivp.A, X0, ivp.B, ivp.U, ivp.X), T, NSTEPS, dt0, ctx)
                                for X0 in ivp.X0])
