@@ -624,7 +624,8 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
                             size_t(CHAIN_B) * 2 * 8 + 64;
         // cycles per time step of one CTA (4 warps, one chain): SpMV + feature partials of RPL rows per thread, a
         // butterfly, one CTA barrier; several CTAs share an SM
-        const double chain_cycles = 350.0 + rpl * (22.0 * maxnnz + 60.0);
+        // (measured: ISS rpl 3, 2 non-zeros per row: ~1370 cycles; Building rpl 1, 48 per row: ~2240)
+        const double chain_cycles = 700.0 + rpl * (30.0 * maxnnz + 200.0);
         const double per_sm = std::max(1.0, std::min(8.0, std::floor(200.0 * 1024 / double(smem))));
         const double waves = std::ceil(double(p->mu) / (ctx->sm_count * per_sm));
         const double chain_cost = waves * chain_cycles;

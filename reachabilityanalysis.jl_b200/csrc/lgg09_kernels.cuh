@@ -789,10 +789,15 @@ static __global__ void lgg09_compact_scan_kernel(double* __restrict__ voff, int 
     const int x = blockIdx.x * blockDim.x + threadIdx.x;                 // (chain, sign)
     if (x >= 2 * mu) return;
     double s = 0.0;
-    for (int b = 0; b < nblk; ++b) {
-        const double t = voff[size_t(b) * 2 * mu + x];
-        voff[size_t(b) * 2 * mu + x] = s;
-        s += t;
+    for (int b0 = 0; b0 < nblk; b0 += 16) {                              // 16 independent loads, then the ordered adds
+        double t[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) t[i] = b0 + i < nblk ? voff[size_t(b0 + i) * 2 * mu + x] : 0.0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (b0 + i < nblk) voff[size_t(b0 + i) * 2 * mu + x] = s;
+            s += t[i];
+        }
     }
 }
 
