@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-glgm06", action="store_true", help="skip the GLGM06 C4 flowpipe wall-time leg")
     ap.add_argument("--glgm06-steps", type=int, default=500)
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short C1 / C2 / split-caller legs (rank 0, N = 1 only)")
     return ap.parse_args()
 
 
@@ -212,8 +214,9 @@ def glgm06_leg(args, ctx, torch, dist, world, rank):
     from reach_b200.glgm06 import _run_batch, GLGM06
     nsteps = args.glgm06_steps
     Phi, Oms, V = W.building_c4(2, nsteps)
-    per = (len(Oms) + world - 1) // world
-    mine = Oms[rank * per:(rank + 1) * per]
+    from reach_b200.sharding import shard_splits
+    own = shard_splits(len(Oms), world, rank)
+    mine = Oms[own.start:own.stop]
     plan = _run_batch(GLGM06(δ=0.002, max_order=10), Phi, mine, V, nsteps, ctx)       # warm-up run
     ms = []
     for _ in range(3):
@@ -240,6 +243,45 @@ def glgm06_leg(args, ctx, torch, dist, world, rank):
         out["cpu_baseline"] = {"zonotopes_per_s": k / dt, "cores": 1, "kind": "port",
                                "sample": "1 split x %d steps (NumPy restatement of reach_inhomog_GLGM06!)" % k}
     plan.close()
+    return out
+
+
+def other_configs_leg(ctx):
+    """The small BASELINE configs and the split caller, device-resident, best of 3 (CUDA events on the library
+    stream): C1 Building (DMMA GEMM over the power stack), C2 ISS (compact chains: 135 decoupled 2x2 blocks),
+    LGG09 over 256 initial-set splits of Building (one batch)."""
+    import reach_b200 as rb
+    from reach_b200 import workloads as W, discretization as D, sets as S
+    from reach_b200.lgg09 import Lgg09Plan, Lgg09BatchPlan
+    out = {}
+    for key, wl in (("C1", W.building_c1()), ("C2", W.iss_c2())):
+        plan = Lgg09Plan(ctx, wl.n, wl.dirs.shape[1], wl.nsteps)
+        plan.upload(wl.Phi, wl.dirs, wl.Omega0, wl.V)
+        ms = []
+        for _ in range(4):
+            plan.run()
+            ms.append(plan.stats()["ms"])
+        st = plan.stats()
+        t = min(ms[1:])
+        out[key] = {"workload": wl.name, "ndirs": wl.dirs.shape[1], "nsteps": wl.nsteps, "ms": t,
+                    "evals_per_s": wl.dirs.shape[1] * wl.nsteps / (t * 1e-3), "path": st["path"],
+                    "launches": st["launches"], "time_block": st["time_block"]}
+        plan.close()
+    A, B, X0, U0 = W.building_sets()
+    U = D.normalize_input(B, U0)
+    ivps = [D.forward(A, X, 0.002, U) for X in S.split(X0, [2] * 8 + [1] * 40)]
+    nsteps = 10000
+    batch = Lgg09BatchPlan(ctx, ivps[0].Phi, rb.BoxDirections(48).matrix(), [iv.Omega0 for iv in ivps], ivps[0].V, nsteps)
+    ms = []
+    for _ in range(3):
+        batch.run()
+        ms.append(batch.stats()["ms"])
+    t = min(ms[1:])
+    out["C1_splits"] = {"workload": "Building BLDF01 LGG09 box template, X0 split into 256 boxes (solve.jl:84-117), one batch",
+                        "nsplits": len(ivps), "ndirs": 96, "nsteps": nsteps, "ms": t,
+                        "evals_per_s": len(ivps) * 96 * nsteps / (t * 1e-3), "launches": batch.stats()["launches"],
+                        "per_split_plan_ms": out["C1"]["ms"]}
+    batch.close()
     return out
 
 
@@ -435,6 +477,8 @@ def run_b200(args):
         }
         if glgm06 is not None:
             line["glgm06_c4"] = glgm06
+        if world == 1 and not args.no_other_configs:
+            line["other_configs"] = other_configs_leg(ctx)
         if not args.no_cpu_baseline:
             sample = args.cpu_sample_steps or auto_sample_steps(wl)
             ref, dt = cpu_reference_sample(wl, sample)

@@ -266,6 +266,16 @@ int reach_glgm06(reach_ctx* ctx, int n, int64_t nsteps, int nsplits, int max_ord
 int reach_reduce_order_gir05(reach_ctx* ctx, int n, int p, int max_order, const double* G,
                              double* Gred, int* pred, int32_t* sel);
 
+/* Device-side discretisation matrices (src/Discretization/Exponentiation.jl): Phi = exp(A*delta) (:168-171),
+ * Phi1(A, delta) = sum_i delta^(i+1)/(i+1)! A^i (:263-291) and Phi2(A, delta) = sum_i delta^(i+2)/(i+2)! A^i
+ * (:397-427), which the Forward and NoBloating models turn into (Phi, Omega0, V) (ForwardModule.jl:86-164,
+ * NoBloatingModule.jl:72-105).  The reference exponentiates a 2n x 2n / 3n x 3n block matrix; here the same
+ * scaling and squaring runs on the three n x n blocks with the FP64 tensor-core GEMM (csrc/expm.cu).
+ * A and the outputs are n x n column-major host matrices; any output may be NULL; *squarings (may be NULL)
+ * returns the scaling exponent s (delta/2^s is the Taylor step). */
+int reach_discretize_phi(reach_ctx* ctx, int n, const double* A, double delta,
+                         double* Phi, double* Phi1, double* Phi2, int32_t* squarings);
+
 /* FP64 GEMM throughput probe with this library's own DMMA kernel on an m x n x k problem
  * (C[m x n] = X[m x k] * Y[n x k]'), returns achieved TFLOP/s; used by bench.py beside cuBLAS. */
 int reach_dgemm_probe(reach_ctx* ctx, int m, int n, int k, int iters, double* tflops);

@@ -105,6 +105,48 @@ function reach_inhomog_LGG09_cuda!(F::Vector{RT}, dirs, Ω₀::LazySet{N}, Φ::A
     return ρℓ
 end
 
+# --- the split caller `_solve_distributed` (Continuous/solve.jl:84-117) for LGG09 -------------------------------
+# Ω₀s: the discretised initial sets of the splits (same Φ, U and template).  One device batch instead of one `post`
+# per split; returns the MixedFlowpipe the reference builds at solve.jl:116 plus the ρℓ matrices.
+function solve_distributed_LGG09_cuda(dirs, Ω₀s::Vector{<:LazySet{N}}, Φ::AbstractMatrix{N}, NSTEPS::Integer, δ::N,
+                                      U::Union{LazySet,Nothing}, Δt0::TimeInterval; ctx::Ctx=Ctx()) where {N}
+    ℓ = reduce(hcat, _collect(dirs))
+    n, ndirs = size(ℓ)
+    m = length(Ω₀s)
+    keep = Any[]
+    Φd = Matrix{Float64}(Φ)
+    oms = ReachSetExpr[setexpr(flatten(Ω₀, nothing, 1.0, 0, Φd), keep)[] for Ω₀ in Ω₀s]
+    v = U === nothing ? C_NULL : setexpr(flatten(U, nothing, 1.0, 0, Φd), keep)
+    ρ = Array{N}(undef, ndirs, NSTEPS, m)                      # split i: ρ[:, :, i], the reference's ρℓ layout
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep Φd ℓ oms ρ begin
+        check(ctx, ccall((:reach_lgg09_batch_create, lib), Cint,
+                         (Ptr{Cvoid}, Cint, Cint, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{ReachSetExpr},
+                          Ptr{ReachSetExpr}, Ref{Ptr{Cvoid}}), ctx.h, n, ndirs, NSTEPS, m, Φd, ℓ, oms, v, h))
+        try
+            check(ctx, ccall((:reach_lgg09_batch_run, lib), Cint, (Ptr{Cvoid},), h[]))
+            for i in 1:m
+                check(ctx, ccall((:reach_lgg09_batch_fetch, lib), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Float64}),
+                                 h[], i - 1, 0, NSTEPS, pointer(ρ, (i - 1) * ndirs * NSTEPS + 1)))
+            end
+        finally
+            ccall((:reach_lgg09_batch_destroy, lib), Cvoid, (Ptr{Cvoid},), h[])
+        end
+    end
+    RT = TemplateReachSet{N,eltype(dirs),typeof(dirs),typeof(view(ρ, :, 1, 1))}
+    fps = Vector{Flowpipe{N,RT,Vector{RT}}}(undef, m)
+    for i in 1:m
+        F = Vector{RT}(undef, NSTEPS)
+        Δt = (zero(N) .. δ) + Δt0
+        @inbounds for k in 1:NSTEPS
+            F[k] = TemplateReachSet(dirs, view(ρ, :, k, i), Δt)
+            Δt += δ
+        end
+        fps[i] = Flowpipe(F, Dict{Symbol,Any}(:sfmat => view(ρ, :, :, i)))
+    end
+    return MixedFlowpipe(fps)
+end
+
 # --- reach_inhomog_GLGM06! (GLGM06/reach_inhomog.jl:6-43) -----------------------------------------
 function reach_inhomog_GLGM06_cuda!(F::Vector{ReachSet{N,Zonotope{N,Vector{N},Matrix{N}}}}, Ω0::Zonotope{N},
                                     Φ::AbstractMatrix, NSTEPS::Integer, δ::Float64, max_order::Integer, ::Universe,

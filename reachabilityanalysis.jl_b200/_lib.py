@@ -98,6 +98,8 @@ SIGNATURES = {
                                c_double_p, C.c_int, c_int32_p]),
     "reach_reduce_order_gir05": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p,
                                            C.POINTER(C.c_int), c_int32_p]),
+    "reach_discretize_phi": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_double, c_double_p, c_double_p, c_double_p,
+                                       c_int32_p]),
     "reach_dgemm_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p]),
     "reach_ozgemm_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p,
                                      c_double_p, C.c_int, c_double_p, c_double_p]),

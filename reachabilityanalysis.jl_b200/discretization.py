@@ -2,6 +2,8 @@
 (Φ, Ω₀, V).  In the reference these stay in Julia and are out of scope for the device
 (north_star: "the discretization output … stays drop-in"); they live here only because Julia is
 not available to generate inputs for the ARCH-COMP configurations.  Not on the timed path.
+The matrix functions Φ, Φ₁, Φ₂ can be computed on the device instead (`set_device_context`,
+`device_phi` → `reach_discretize_phi`); SciPy's `expm` is then the checker.
 
   Forward            : src/Discretization/ForwardModule.jl:86-102 (homog), :137-164 (inhomog)
   NoBloating         : src/Discretization/NoBloatingModule.jl:72-105
@@ -54,8 +56,37 @@ def _memoized(kind, A, delta, fn):
     return _memo[key]
 
 
+_device_ctx = None
+
+
+def set_device_context(ctx):
+    """Route Φ, Φ₁, Φ₂ through the device (`reach_discretize_phi`, csrc/expm.cu) instead of SciPy's `expm`;
+    `None` switches back.  Returns the previous setting."""
+    global _device_ctx
+    prev, _device_ctx = _device_ctx, ctx
+    _memo.clear()
+    return prev
+
+
+def device_phi(ctx, A, delta, want=("Phi", "Phi1", "Phi2")):
+    """(Φ, Φ₁, Φ₂)(A, δ) on the device (Exponentiation.jl:168-171, 263-291, 397-427); entries not in `want` are None."""
+    import ctypes as C
+    from . import _lib as L
+    A = L.fmat(_dense(A))
+    n = A.shape[0]
+    if A.shape != (n, n):
+        raise ValueError("A must be square, got %s" % (A.shape,))
+    outs = {k: (np.empty((n, n), order="F") if k in want else None) for k in ("Phi", "Phi1", "Phi2")}
+    s = C.c_int32()
+    ctx.check(ctx.lib.reach_discretize_phi(ctx.handle, n, L.dptr(A), float(delta), L.dptr(outs["Phi"]),
+                                           L.dptr(outs["Phi1"]), L.dptr(outs["Phi2"]), C.byref(s)))
+    return outs["Phi"], outs["Phi1"], outs["Phi2"]
+
+
 def _exp(A, delta):
     A = _dense(A)
+    if _device_ctx is not None:
+        return _memoized("exp", A, delta, lambda: device_phi(_device_ctx, A, delta, ("Phi",))[0])
     return _memoized("exp", A, delta, lambda: scipy.linalg.expm(A * delta))
 
 
@@ -63,6 +94,8 @@ def Phi1(A, delta):
     """Φ₁(A,δ) = Σ δ^{i+1}/(i+1)! A^i via the 2n×2n block exponential (Exponentiation.jl:275-291)."""
     A = _dense(A)
     n = A.shape[0]
+    if _device_ctx is not None:
+        return device_phi(_device_ctx, A, delta, ("Phi1",))[1]
     P = np.zeros((2 * n, 2 * n))
     P[:n, :n] = A * delta
     P[:n, n:] = delta * np.eye(n)
@@ -75,6 +108,8 @@ def Phi2(A, delta):
     n = A.shape[0]
 
     def compute():
+        if _device_ctx is not None:
+            return device_phi(_device_ctx, A, delta, ("Phi2",))[2]
         P = np.zeros((3 * n, 3 * n))
         P[:n, :n] = A * delta
         P[:n, n:2 * n] = delta * np.eye(n)

@@ -65,3 +65,22 @@ def gather_support_values(local_T, rows_by_rank, ndirs, group=None):
         if len(rows):
             out.index_copy_(1, rows, gathered[r, :, :len(rows)])
     return out
+
+
+def shard_splits(nsplits, world, rank):
+    """Initial-set splits of `rank` (the GLGM06 / LGG09 split callers, solve.jl:84-117): contiguous, balanced
+    to within one split.  The splits are independent problems, so there is no data-path collective; each rank
+    keeps its flowpipes on its own device."""
+    base, extra = divmod(int(nsplits), int(world))
+    lo = rank * base + min(rank, extra)
+    return range(lo, lo + base + (1 if rank < extra else 0))
+
+
+def reduce_mixed_flowpipe_support(local_max, group=None):
+    """ρ(d_j, MixedFlowpipe) over ALL splits from the per-rank maxima over the rank's own splits and steps
+    (MixedFlowpipe.jl:66-68): one all-reduce(MAX) of an ndirs vector -- the only exchange a property check on a
+    sharded split run needs."""
+    import torch.distributed as dist
+    out = local_max.clone()
+    dist.all_reduce(out, op=dist.ReduceOp.MAX, group=group)
+    return out

@@ -61,10 +61,19 @@ def post_continuous(alg, ivp, T=None, NSTEPS=None, Δt0=zeroT, ctx=None):
 
 
 def solve(ivp, T=None, alg=None, NSTEPS=None, tspan=None, algorithm=None, opC=None, threading=False,
-          ctx=None):
+          ctx=None, device_discretize=False):
     """`solve(ivp; T, alg)` (solve.jl:49-76); a list of initial sets runs every split through the
     same Φ / input chain in one batch (`_solve_distributed`, solve.jl:103-117) and returns a
     MixedFlowpipe."""
+    if device_discretize:
+        # Φ, Φ₁, Φ₂ on the device too (reach_discretize_phi) instead of the host `exp`
+        from . import _lib as _L
+        ctx = ctx or _L.default_context()
+        prev = D.set_device_context(ctx)
+        try:
+            return solve(ivp, T, alg, NSTEPS, tspan, algorithm, opC, threading, ctx, False)
+        finally:
+            D.set_device_context(prev)
     alg = alg or algorithm or opC
     if alg is None:
         raise ValueError("an algorithm (`alg=LGG09(...)` or `alg=GLGM06(...)`) is required")

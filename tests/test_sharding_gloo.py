@@ -64,3 +64,58 @@ def test_two_rank_sharded_run_matches_unsharded():
     for rank, full, tmax in results:
         assert tmax == 2.0
         np.testing.assert_allclose(full, ref, rtol=0, atol=1e-13)
+
+
+def _split_problem():
+    rng = np.random.default_rng(11)
+    n = 5
+    A = -np.eye(n) + 0.2 * rng.standard_normal((n, n))
+    U = rb.BallInf(np.zeros(n), 0.05)
+    X0s = [rb.Hyperrectangle(rng.standard_normal(n), 0.1 * rng.uniform(0, 1, n)) for _ in range(5)]
+    ivps = [D.forward(A, X0, 0.05, U) for X0 in X0s]
+    dirs = np.hstack([np.eye(n), -np.eye(n)])
+    return ivps, dirs, 20
+
+
+def _split_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ivps, dirs, nsteps = _split_problem()
+    mine = sharding.shard_splits(len(ivps), world, rank)
+    local = np.full(dirs.shape[1], -np.inf)
+    for i in mine:           # the CPU oracle stands in for the device batch of this rank's splits
+        rho = LO.reach_inhomog_LGG09(dirs, ivps[i].Omega0, ivps[i].Phi, nsteps, ivps[i].V)
+        local = np.maximum(local, rho.max(axis=1))
+    full = sharding.reduce_mixed_flowpipe_support(torch.from_numpy(local))
+    q.put((rank, list(mine), full.numpy().copy()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_split_sharding_and_mixed_flowpipe_support():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_split_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ivps, dirs, nsteps = _split_problem()
+    ref = np.max([LO.reach_inhomog_LGG09(dirs, iv.Omega0, iv.Phi, nsteps, iv.V).max(axis=1) for iv in ivps], axis=0)
+    owned = sorted(i for _, mine, _ in results for i in mine)
+    assert owned == list(range(len(ivps)))                     # every split on exactly one rank
+    for rank, mine, full in results:
+        assert len(mine) in (2, 3)
+        np.testing.assert_array_equal(full, ref)
+
+
+def test_shard_splits_is_a_balanced_partition():
+    for nsplits in (1, 5, 8, 1024, 1025):
+        for world in (1, 2, 3, 8):
+            parts = [list(sharding.shard_splits(nsplits, world, r)) for r in range(world)]
+            assert sorted(i for p in parts for i in p) == list(range(nsplits))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
