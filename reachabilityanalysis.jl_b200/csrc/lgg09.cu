@@ -357,12 +357,18 @@ double step_cost(const reach_lgg09_plan& p, const TileCfg& c, int S, int mu, int
     };
     const double launch = 60000.0;     // ~30 us per pass: GEMM + tile-sum + eval + prefix launches back to back
     double cost = (pass(double(mu_pad / c.TM) * std::ceil(double(S) * nbe / c.TN)) + launch) / S;
-    // stack build (64x64 tiles, occupancy 2), amortised
-    int lg = 0;
-    for (int s = 1; s < S; s *= 2) ++lg;
-    const double nn_tiles = std::ceil(nbe / 64.0) * std::ceil(p.n / 64.0);
-    const double nn_pass = std::ceil(nn_tiles / (sms * 2.0)) * (64.0 * 64.0 * p.Kp / (55.0 * 0.85) * 2 + 4000.0) + 6000.0;
-    cost += (double(S) + 2.0 * lg) * nn_pass / double(std::max<int64_t>(1, p.nsteps));
+    // stack build by doubling (64x64 tiles, occupancy 2), amortised: one launch per product, each as many waves as its
+    // row count needs (for small n a whole doubling step is a single wave -- the build is ~2 log2(S) launches, not S)
+    auto product = [&](double rows) {
+        const double tiles = std::ceil(rows / 64.0) * std::ceil(p.n / 64.0);
+        return std::ceil(tiles / (sms * 2.0)) * (64.0 * 64.0 * p.Kp / (55.0 * 0.85) * 2 + 4000.0) + 6000.0;
+    };
+    double build = product(nbe);
+    for (int s = 1; s < S; s *= 2) {
+        if (2 * s < S) build += product(p.n);
+        build += product(double(std::min(s, S - s)) * nbe);
+    }
+    cost += build / double(std::max<int64_t>(1, p.nsteps));
     return cost;
 }
 
