@@ -262,6 +262,11 @@ struct reach_lgg09_plan {
     DevBuf cpM, cpr0, cpwl, cpwa, cpE, cpWlE, cpWaE, cprstart, cpvoff;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // side stream: the combine kernels (tile sums, running sum, evaluation) of pass t run beside the GEMM of pass t+1;
+    // the per-tile partials are double-buffered by pass parity
+    cudaStream_t st2 = nullptr;
+    cudaEvent_t ev_gemm[2] = {nullptr, nullptr}, ev_comb[2] = {nullptr, nullptr};
+    size_t fp_stride = 0;               // doubles per featpart buffer
     std::vector<cudaEvent_t> gemm_ev;   // pairs around sampled main-loop GEMM launches
     int gemm_sampled = 0;
     int64_t gemm_total = 0;
@@ -271,6 +276,9 @@ struct reach_lgg09_plan {
     ~reach_lgg09_plan() {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        for (auto e : ev_gemm) if (e) cudaEventDestroy(e);
+        for (auto e : ev_comb) if (e) cudaEventDestroy(e);
+        if (st2) cudaStreamDestroy(st2);
         for (auto e : gemm_ev) cudaEventDestroy(e);
     }
 };
@@ -440,6 +448,11 @@ extern "C" int reach_lgg09_plan_create(reach_ctx* ctx, int n, int ndirs, int64_t
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e == cudaSuccess) e = cudaEventCreate(&p->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&p->ev1);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->st2, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&p->ev_gemm[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_comb[i], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) {
         delete p;
         return set_error(ctx, REACH_ECUDA, "plan_create: %s", cudaGetErrorString(e));
@@ -677,7 +690,8 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
     REACH_TRY(p->Wl.alloc(ctx, size_t(std::max(1, nq)) * nbe * sizeof(double)));
     REACH_TRY(p->Wa.alloc(ctx, size_t(std::max(1, nq)) * nbe * sizeof(double)));
     REACH_TRY(p->tile_mask.alloc(ctx, size_t(p->tpb) * sizeof(uint32_t)));
-    REACH_TRY(p->featpart.alloc(ctx, (p->packed ? slice_tiles * 2 : size_t(S + 1) * p->tpb) * std::max(1, nq) * 2 * mu_pad * sizeof(double)));
+    p->fp_stride = (p->packed ? slice_tiles * 2 : size_t(S + 1) * p->tpb) * std::max(1, nq) * 2 * mu_pad;
+    REACH_TRY(p->featpart.alloc(ctx, 2 * p->fp_stride * sizeof(double)));
     REACH_TRY(p->ftot.alloc(ctx, size_t(S + 1) * std::max(1, nq) * 2 * mu_pad * sizeof(double)));
     REACH_TRY(p->carry[0].alloc(ctx, size_t(std::max(1, nq)) * 2 * mu_pad * sizeof(double)));
     REACH_TRY(p->carry[1].alloc(ctx, size_t(std::max(1, nq)) * 2 * mu_pad * sizeof(double)));
@@ -1024,7 +1038,9 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     oepi.mu_pad = mu_pad;
     // one pass of the digit-plane GEMM: L (fp64) -> digit planes, then blocks b_lo..S of the stack
     auto oz_pass = [&](const double* Lcur, double* Lnext, int b_lo, int b_hi, int store_block, bool sample) -> int {
-        oz_slice_kernel<OZ_TM><<<mu_pad / 8, 256, 0, st>>>(Lcur, Kp, p->mu, n, p->oz_T, p->oz_nkb, mu_pad / OZ_TM,
+        // a few hundred chains are only mu_pad/8 row groups: split the k range so that ~2 CTAs per SM are in flight
+        const int ksplit = std::max(1, std::min(8, (2 * ctx->sm_count) / std::max(1, mu_pad / 8)));
+        oz_slice_kernel<OZ_TM><<<dim3(mu_pad / 8, ksplit), 256, 0, st>>>(Lcur, Kp, p->mu, n, p->oz_T, p->oz_nkb, mu_pad / OZ_TM,
                                                           p->Xq.as<int8_t>(), p->eX.as<int>());
         REACH_CUDA(ctx, cudaGetLastError());
         ++p->launches;
@@ -1087,11 +1103,11 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     double* ftot = p->ftot.as<double>();
     int carry_cur = 0;
     bool oz_now = p->use_oz;      // false after the guard has sent the run back to the DMMA kernel
-    auto combine = [&](const Lgg09Combine& c) -> int {
+    auto combine = [&](const Lgg09Combine& c, cudaStream_t st) -> int {
         const int nblk = c.b_hi - c.b_lo + 1;
         if (nblk > 0) {
             dim3 grid(cblocks, nblk);
-            if (p->packed) lgg09_tilesum_packed_kernel<<<grid, cthreads, 0, st>>>(c, p->featpart.as<double>(), ftot, nbe, TN,
+            if (p->packed) lgg09_tilesum_packed_kernel<<<grid, cthreads, 0, st>>>(c, c.featpart, ftot, nbe, TN,
                                                                                   oz_now ? 0 : c.b_lo);
             else lgg09_tilesum_kernel<<<grid, cthreads, 0, st>>>(c, ftot);
             REACH_CUDA(ctx, cudaGetLastError());
@@ -1150,14 +1166,42 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         }
         ++p->launches;
         cmb.b_lo = 0; cmb.b_hi = 0; cmb.has_carry = 0; cmb.tail = 1; cmb.k0 = 0;
-        REACH_TRY(combine(cmb));
+        REACH_TRY(combine(cmb, st));
     }
     p->oz_guard_max = 0.0;
     p->oz_fallback_pass = -1;
     p->oz_checks = 0;
     constexpr double kOzGuardTol = 1e-12;
+    // Pass t's combine kernels only read what its GEMM wrote (per-tile partials, double-buffered by parity) and their
+    // own carried state, so they run on the side stream beside the GEMM of pass t+1; guard-checked passes stay serial.
+    const bool overlap = T > 2 && !getenv("REACH_NO_OVERLAP");
+    double* const fp_base = p->featpart.as<double>();
+    cudaStream_t st2 = p->st2;
+    bool side_busy[2] = {false, false};
+    auto join_side = [&]() -> int {
+        for (int i = 0; i < 2; ++i)
+            if (side_busy[i]) {
+                REACH_CUDA(ctx, cudaStreamWaitEvent(st, p->ev_comb[i], 0));
+                side_busy[i] = false;
+            }
+        return REACH_OK;
+    };
+    auto combine_pass = [&](const Lgg09Combine& c, bool side, int par) -> int {
+        if (!side) return combine(c, st);
+        REACH_CUDA(ctx, cudaEventRecord(p->ev_gemm[par], st));
+        REACH_CUDA(ctx, cudaStreamWaitEvent(st2, p->ev_gemm[par], 0));
+        REACH_TRY(combine(c, st2));
+        REACH_CUDA(ctx, cudaEventRecord(p->ev_comb[par], st2));
+        side_busy[par] = true;
+        return REACH_OK;
+    };
     for (int64_t t = 0; t < T; ++t) {
         const int b_lo = t == 0 ? 0 : 1;
+        const int par = int(t & 1);
+        {
+            double* fp = fp_base + (overlap ? size_t(par) * p->fp_stride : 0);
+            oepi.featpart = fp; epi.featpart = fp; pepi.featpart = fp; cmb.featpart = fp;
+        }
         GemmOperands g{p->Lbuf[cur].as<double>(), block(b_lo), Kp, Kp, Kp, mu_pad / TM,
                        ((S + 1 - b_lo) * nbe + TN - 1) / TN};
         epi.Lnext = p->Lbuf[1 - cur].as<double>();
@@ -1167,6 +1211,13 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         cmb.b_lo = b_lo; cmb.b_hi = S; cmb.has_carry = t > 0; cmb.tail = 0; cmb.k0 = t * S;
         // guarded digit-plane path: passes 0, 1, every 64th and the last are also run on the DMMA kernel
         const bool check = oz_now && p->oz_guard && (t < 2 || (t & 63) == 0 || t == T - 1);
+        const bool side = overlap && !check;
+        if (check) {
+            REACH_TRY(join_side());
+        } else if (side && side_busy[par]) {       // the combine of pass t-2 has read this parity's partials
+            REACH_CUDA(ctx, cudaStreamWaitEvent(st, p->ev_comb[par], 0));
+            side_busy[par] = false;
+        }
         if (check) {
             // reference features of blocks 1 and S (the first step of the pass and the block that becomes L_{k+S}) from
             // the DMMA kernel; nothing of the run's state is touched (no store block, separate totals buffer)
@@ -1177,7 +1228,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
                 Lgg09Combine cc = cmb;
                 cc.b_lo = cb; cc.b_hi = cb;
                 dim3 grid(cblocks, 1);
-                lgg09_tilesum_packed_kernel<<<grid, cthreads, 0, st>>>(cc, p->featpart.as<double>(), p->ftot_ref.as<double>(), nbe, TN, cb);
+                lgg09_tilesum_packed_kernel<<<grid, cthreads, 0, st>>>(cc, cc.featpart, p->ftot_ref.as<double>(), nbe, TN, cb);
                 REACH_CUDA(ctx, cudaGetLastError());
                 p->launches += 2;
                 if (S == 1) break;
@@ -1188,7 +1239,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         if (oz_now) {
             REACH_TRY(oz_pass(p->Lbuf[cur].as<double>(), epi.Lnext, b_lo, S, S, sample));
             ++p->gemm_total;
-            REACH_TRY(combine(cmb));
+            REACH_TRY(combine_pass(cmb, side, par));
             if (check) {
                 REACH_CUDA(ctx, cudaMemsetAsync(p->guard_val.p, 0, sizeof(unsigned long long), st));
                 lgg09_guard_kernel<<<(p->mu * p->nq + 127) / 128, 128, 0, st>>>(ftot, p->ftot_ref.as<double>(), p->nq, mu_pad, p->mu,
@@ -1229,13 +1280,14 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         }
         ++p->launches;
         ++p->gemm_total;
-        REACH_TRY(combine(cmb));
+        REACH_TRY(combine_pass(cmb, side, par));
         cur ^= 1;
     }
+    REACH_TRY(join_side());
     if (T > 0 && T * S < p->nsteps) {
         // one step left whose support values only need the carried features of r_{T S}
         cmb.b_lo = 1; cmb.b_hi = 0; cmb.has_carry = 1; cmb.tail = 1; cmb.k0 = T * S;
-        REACH_TRY(combine(cmb));
+        REACH_TRY(combine(cmb, st));
     }
 
     // ---- invariant: first step certified disjoint ----

@@ -385,7 +385,9 @@ inline cudaError_t launch_oz_gemm(int T, const OzOperands& g, const Epi& epi, cu
 }
 
 // ---- slicing: FP64 rows -> T digit planes in the UMMA core-matrix layout --------------------------------
-// One CTA per 8-row group.  Phase 1: row maxima -> exponents (2^e > max|x|).  Phase 2: thread = (row, 16-wide k chunk):
+// One CTA per 8-row group and k range (gridDim.y splits the 16-wide chunks of a row: a direction block of a few hundred
+// rows would otherwise occupy a fifth of the SMs; every CTA re-derives the row maxima, 8 rows from L2).
+// Phase 1: row maxima -> exponents (2^e > max|x|).  Phase 2: thread = (row, 16-wide k chunk):
 // 16 values -> T x 16 digits, written as T 16-byte stores (8 consecutive rows = one 128-byte core matrix).
 //   Q[((kb * tiles_total + tile) * T + s) * (TR*32) + ((g * 2 + c) * 8 + r) * 16 + b],   tile = row / TR, g = (row % TR) / 8
 template <int TR>
@@ -408,13 +410,15 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
             int e = 0;
             if (mx > 0.0 && mx < 1.0e308) e = ilogb(mx) + 1;           // 2^(e-1) <= mx < 2^e
             s_e[warp] = e;
-            eout[row] = e;
+            if (blockIdx.y == 0) eout[row] = e;
         }
     }
     __syncthreads();
     const int tile = row0 / TR, gidx = (row0 % TR) / 8;
     const int nchunks = nkb * 2;
-    for (int item = threadIdx.x; item < 8 * nchunks; item += blockDim.x) {
+    const int per = (nchunks + gridDim.y - 1) / gridDim.y;
+    const int item_lo = 8 * per * blockIdx.y, item_hi = min(8 * nchunks, item_lo + 8 * per);
+    for (int item = item_lo + threadIdx.x; item < item_hi; item += blockDim.x) {
         const int r = item & 7, chunk = item >> 3;
         const int row = row0 + r;
         const int kb = chunk >> 1, c = chunk & 1;
