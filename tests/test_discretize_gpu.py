@@ -34,6 +34,17 @@ def test_random_matrices(ctx, n, delta, scale):
     check(D.device_phi(ctx, A, delta), host_phis(A, delta))
 
 
+def test_exponentiation_jl_6_26_diagonal(ctx):
+    """test/discretization/exponentiation.jl:6-14: _exp([10 0; 0 20], 0.1) = diag(e, e^2); the reference compares
+    its dense `exp` with `==`, the device route (Taylor + 2 squarings) is held to a few ulp and exact zeros."""
+    Phi, P1, P2 = D.device_phi(ctx, np.array([[10.0, 0.0], [0.0, 20.0]]), 0.1)
+    want = np.array([[np.exp(1.0), 0.0], [0.0, np.exp(2.0)]])
+    assert Phi[0, 1] == 0.0 and Phi[1, 0] == 0.0
+    np.testing.assert_allclose(np.diag(Phi), np.diag(want), rtol=4e-16 * 8)
+    np.testing.assert_allclose(np.diag(P1), [(np.exp(1.0) - 1) / 10.0, (np.exp(2.0) - 1) / 20.0], rtol=1e-14)
+    np.testing.assert_allclose(np.diag(P2), [(np.exp(1.0) - 2) / 100.0, (np.exp(2.0) - 3) / 400.0], rtol=1e-14)
+
+
 def test_building_needs_scaling_and_matches(ctx):
     """‖A‖∞ δ = 23.7 at δ = 0.002: six squarings; also Φ₂(|A|, δ), the matrix the Forward model bloats with."""
     prob = building_problem()

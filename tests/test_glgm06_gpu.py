@@ -42,6 +42,24 @@ def test_flowpipes_jl_43_44_on_the_device(ctx):
     np.testing.assert_allclose(sigma, [0.7502062459270877, 0.6989729206916551], rtol=1e-12)
 
 
+def test_flowpipes_jl_56_70_projectile_inclusion_on_the_device(ctx):
+    """test/flowpipes/flowpipes.jl:56-70: GLGM06(δ=1e-2, Forward()), T = 20 ⇒ sol ⊆ {24 x1 + x3 <= 375};
+    support values of all 2000 zonotopes against the oracle's."""
+    from test_oracle_kat import projectile_problem
+    A, X0, U = projectile_problem()
+    alg = rb.GLGM06(δ=1e-2, approx_model=rb.Forward(setops="zono"))
+    sol = rb.solve(rb.IVP(A, X0, np.eye(4), U), T=20.0, alg=alg, ctx=ctx)
+    assert len(sol) == 2000
+    d = np.array([24.0, 0.0, 1.0, 0.0])
+    assert rb.rho(d, sol) <= 375.0
+    ivp = D.forward_zono(A, X0, 1e-2, U)
+    ref = GO.post_GLGM06(ivp.Phi, ivp.Omega0, 2000, 5, ivp.V)
+    want = max(Z.rho_zonotope(d, c, G) for c, G in ref)
+    assert abs(rb.rho(d, sol) - want) <= 1e-10 * abs(want)
+    for k in (0, 1, 500, 1999):
+        check_zonotope((sol[k].set.center, sol[k].set.generators), ref[k], "step %d" % k)
+
+
 @pytest.mark.parametrize("n,p_extra,nsteps", [(2, 0, 30), (5, 3, 60), (48, 0, 25), (70, 10, 12)])
 def test_homogeneous_matches_oracle(ctx, n, p_extra, nsteps):
     rng = np.random.default_rng(n)

@@ -125,3 +125,24 @@ def test_gir05_rules():
     for _ in range(20):
         d = rng.standard_normal(n)
         assert Z.rho_zonotope(d, c, G3) >= Z.rho_zonotope(d, c, G) - 1e-12
+
+
+def projectile_problem():
+    """test/flowpipes/flowpipes.jl:56-70: x' = Ax + u, x(0) = (0, 5, 100, 0), u = (0, 0, 0, -9.81)."""
+    import reach_b200 as rb
+    A = np.array([[0.0, 0.5, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.7], [0.0, 0.0, 0.0, 0.0]])
+    return A, rb.Singleton([0.0, 5.0, 100.0, 0.0]), rb.Singleton([0.0, 0.0, 0.0, -9.81])
+
+
+def test_flowpipes_jl_56_70_projectile_inclusion_glgm06_forward():
+    """`sol ⊆ {24 x1 + x3 <= 375}` for GLGM06(δ=1e-2, Forward()), T = 20: every reach-set's support value in
+    the constraint's direction stays below the offset (and the flowpipe really gets close to it)."""
+    from reach_b200 import discretization as D
+    from oracle import glgm06_oracle as GO, lazysets_oracle as Z
+    A, X0, U = projectile_problem()
+    ivp = D.forward_zono(A, X0, 1e-2, U)
+    F = GO.post_GLGM06(ivp.Phi, ivp.Omega0, 2000, 5, ivp.V)
+    d = np.array([24.0, 0.0, 1.0, 0.0])
+    rhos = np.array([Z.rho_zonotope(d, c, G) for c, G in F])
+    assert len(F) == 2000 and rhos.max() <= 375.0
+    assert rhos.max() > 300.0
