@@ -64,6 +64,7 @@ struct reach_glgm06_plan {
     DevBuf H;                           // homogeneous: [nsteps][m_pad][Kp]
     DevBuf scratch_pos;
     DevBuf progress;                    // powers published so far (chain kernel <- powers kernel)
+    DevBuf dbg;                         // phase cycle counters of the chain kernel (REACH_GLGM06_DEBUG)
     int64_t bytes_stored = 0;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_powers = nullptr, ev_gemm = nullptr;
@@ -339,8 +340,8 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
         int np2 = 32;
         while (np2 < p->pU) np2 <<= 1;
         const size_t ldp = n + 1;
-        chain_smem = 8 * (3 * n * ldp + 2 * size_t(p->pU + 1) * ldp + 3 * size_t(p->pWcap) + np2 + n + 16 * size_t(n)) +
-                     16 * size_t(np2) + 4 * (2 * size_t(p->pWcap)) + 64;
+        chain_smem = 8 * (3 * n * ldp + 2 * size_t(p->pU + 1) * ldp + 3 * size_t(p->pWcap) + np2 + n + GLGM06_NSEG * size_t(n)) +
+                     16 * size_t(np2) + 4 * (3 * size_t(p->pWcap) + size_t(p->pU)) + 64;
         if (chain_smem > ctx->smem_optin) fused = false;
     }
     if (fused) {
@@ -354,6 +355,10 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
         c.wB = p->wB.as<double>();
         c.permB = p->permB.as<int>();
         c.bpref = p->bpref.as<double>();
+        if (getenv("REACH_GLGM06_DEBUG")) {
+            if (!p->dbg.p) REACH_TRY(p->dbg.alloc(ctx, 64));
+            c.dbg = p->dbg.as<long long>();
+        }
         // The chain CTA goes first so that it owns an SM; the powers (1 CTA, ~8 us per step) and then the batched GEMM
         // run beside it on the second stream.  The chain consumes the powers as they are published (progress counter);
         // launched the other way round, the GEMM's CTAs fill every SM and the chain CTA (200 KB of shared memory) waits
@@ -515,6 +520,13 @@ extern "C" int reach_glgm06_plan_sync(reach_glgm06_plan* p) {
     float ms = 0.f;
     REACH_CUDA(ctx, cudaEventElapsedTime(&ms, p->ev0, p->ev1));
     p->last_ms = ms;
+    if (p->dbg.p && getenv("REACH_GLGM06_DEBUG")) {
+        long long h[6];
+        REACH_CUDA(ctx, cudaMemcpy(h, p->dbg.p, sizeof(h), cudaMemcpyDeviceToHost));
+        const double k = double(std::max<int64_t>(1, p->nsteps));
+        fprintf(stderr, "[glgm06 chain dbg] cycles per step: publish+prefix %.0f, P[G_U|c_U] %.0f, wait+load P %.0f, weights+sort %.0f, "
+                        "cut+copy W %.0f, diag+order %.0f\n", h[0] / k, h[1] / k, h[2] / k, h[3] / k, h[4] / k, h[5] / k);
+    }
     return REACH_OK;
 }
 

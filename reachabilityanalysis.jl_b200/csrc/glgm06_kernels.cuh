@@ -113,6 +113,45 @@ __device__ inline void bitonic_sort(WKey* keys, int np2) {
         }
     }
 }
+// The same sort for np2 <= 64 keys by ONE warp: two keys per lane in registers (element e lives in lane e & 31, slot
+// e >> 5), compare-exchange partners by shuffle (j < 32) or in-lane (j = 32): ~20 stages of a few shuffles instead of
+// ~20 CTA-wide barriers.  (weight, index) keys are distinct, so the result is the unique sorted order.
+__device__ inline void bitonic_sort_warp64(WKey* keys, int np2) {
+    const int lane = threadIdx.x & 31;
+    WKey v[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int e = lane + 32 * s;
+        if (e < np2) v[s] = keys[e]; else { v[s].w = INFINITY; v[s].idx = 0x7fffffff; }
+    }
+    for (int k = 2; k <= 64; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j == 32) {
+                // partner of element e is e ^ 32: the other slot of the same lane; (e & k) == 0 for k = 64: ascending
+                if (wkey_less(v[1], v[0])) { WKey t = v[0]; v[0] = v[1]; v[1] = t; }
+            } else {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int e = lane + 32 * s;
+                    WKey o;
+                    o.w = __shfl_xor_sync(0xffffffffu, v[s].w, j);
+                    o.idx = __shfl_xor_sync(0xffffffffu, v[s].idx, j);
+                    const bool up = (e & k) == 0;
+                    const bool lower = (e & j) == 0;               // this element is the lower index of the pair
+                    // ascending pair: lower keeps the smaller; descending pair: lower keeps the larger
+                    const bool take_min = (lower == up);
+                    const bool o_less = wkey_less(o, v[s]);
+                    if (take_min ? o_less : !o_less) v[s] = o;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int e = lane + 32 * s;
+        if (e < np2) keys[e] = v[s];
+    }
+}
 __device__ __forceinline__ int lower_bound_d(const double* a, int n, double v) {   // #{a_i < v}
     int lo = 0, hi = n;
     while (lo < hi) { int mid = (lo + hi) >> 1; if (a[mid] < v) lo = mid + 1; else hi = mid; }
@@ -394,6 +433,8 @@ __device__ __forceinline__ void glgm06_wait_progress(const int* progress, int ne
     __syncthreads();
 }
 
+constexpr int GLGM06_NSEG = 21;      // prefix-table segments per coordinate (48 x 21 = 1008 threads busy at n = 48)
+
 struct ChainParams {
     int n, ldk, nb;             // ldk = Kp (row pitch of Phi/P/XU buffers), nb = rows per P block
     int pU, r, pWcap;
@@ -407,6 +448,7 @@ struct ChainParams {
     double* wB;                 // [nblk][pWcap]
     int* permB;                 // [nblk][pWcap]
     double* bpref;              // [nblk][(pWcap+1)][n]
+    long long* dbg;             // optional [8] phase cycle counters (NULL: off)
 };
 
 static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const ChainParams c) {
@@ -427,11 +469,12 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
     double* sw = swm + c.pWcap;                       // sorted own weights [np2]
     double* sdiag = sw + np2;                         // [n]
     double* sseg = sdiag + n;                         // [n][NSEG] segment totals for the prefix table
-    constexpr int NSEG = 16;
+    constexpr int NSEG = GLGM06_NSEG;
     WKey* keys = reinterpret_cast<WKey*>(sseg + n * NSEG);      // [np2]
     int* sperm[2];
     sperm[0] = reinterpret_cast<int*>(keys + np2);
     sperm[1] = sperm[0] + c.pWcap;
+    int* spos = sperm[1] + c.pWcap;                   // [pWcap] destination row of every kept generator
     __shared__ int s_ta, s_z;
 
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -461,12 +504,15 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
             } else { keys[j].w = INFINITY; keys[j].idx = 0x7fffffff; }
         }
         __syncthreads();
-        bitonic_sort(keys, np2);
+        if (np2 <= 64) { if (tid < 32) bitonic_sort_warp64(keys, np2); __syncthreads(); }
+        else bitonic_sort(keys, np2);
         for (int j = tid; j < pW0; j += nthr) { swB[0][j] = keys[j].w; sperm[0][j] = keys[j].idx; }
         __syncthreads();
     }
 
+    long long tph[6] = {0, 0, 0, 0, 0, 0};
     for (long long b = 0; b < c.nblk; ++b) {
+        const long long tq0 = clock64();
         const int pWb = c.pW[b];
         const double* P = sP[b & 1];
         double* Pn = sP[(b + 1) & 1];
@@ -482,13 +528,21 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
                 c.wB[size_t(b) * c.pWcap + j] = wBc[j];
                 c.permB[size_t(b) * c.pWcap + j] = permc[j];
             }
-            // prefix over the sorted order, two-level: NSEG segments per coordinate
+            // prefix over the sorted order, two-level: NSEG segments per coordinate.  W_b lives in global memory (L2);
+            // the loads go out in batches of eight independent requests (one dependent L2 round trip per element was
+            // half of the step time at 480 generators), the additions keep their order.
             const int seglen = (pWb + NSEG - 1) / NSEG;
             for (int idx = tid; idx < n * NSEG; idx += nthr) {
                 const int i = idx % n, sg = idx / n;
                 double s = 0.0;
                 const int t1 = min(pWb, (sg + 1) * seglen);
-                for (int t = sg * seglen; t < t1; ++t) s += fabs(GW[size_t(permc[t]) * n + i]);
+                for (int t = sg * seglen; t < t1; t += 8) {
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = t + u < t1 ? fabs(__ldcg(GW + size_t(permc[t + u]) * n + i)) : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) if (t + u < t1) s += v[u];
+                }
                 sseg[i * NSEG + sg] = s;
             }
             __syncthreads();
@@ -498,13 +552,21 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
                 for (int q = 0; q < sg; ++q) s += sseg[i * NSEG + q];
                 if (sg == 0) bprefb[i] = 0.0;
                 const int t1 = min(pWb, (sg + 1) * seglen);
-                for (int t = sg * seglen; t < t1; ++t) {
-                    s += fabs(GW[size_t(permc[t]) * n + i]);
-                    bprefb[size_t(t + 1) * n + i] = s;
+                for (int t = sg * seglen; t < t1; t += 8) {
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = t + u < t1 ? fabs(__ldcg(GW + size_t(permc[t + u]) * n + i)) : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (t + u < t1) {
+                            s += v[u];
+                            bprefb[size_t(t + u + 1) * n + i] = s;
+                        }
                 }
             }
         }
         if (b + 1 >= c.nblk) break;                      // W_{nblk} and P_{nblk} are never used
+        const long long tq1 = clock64();
 
         // (b) P_b [G_U | c_U]  and  P_{b+1} = P_b Phi
         for (int idx = tid; idx < (pU + 1) * n; idx += nthr) {
@@ -513,12 +575,14 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
             for (int l = 0; l < n; ++l) s = fma(sXU[g * ldp + l], P[i * ldp + l], s);
             sPU[g * ldp + i] = s;
         }
+        const long long tq2 = clock64();
         {
             glgm06_wait_progress(c.progress, int(b) + 2);
             const double* Pg = c.Pstack + size_t(b + 1) * c.nb * c.ldk;        // P_{b+1} for the next step
             for (int idx = tid; idx < n * n; idx += nthr) Pn[(idx / n) * ldp + idx % n] = __ldcg(Pg + size_t(idx / n) * c.ldk + idx % n);
         }
         __syncthreads();
+        const long long tq3 = clock64();
         // centre of W_{b+1}
         for (int i = tid; i < n; i += nthr) c.cWall[size_t(b + 1) * n + i] = sPU[pU * ldp + i] + c.cWall[size_t(b) * n + i];
 
@@ -531,11 +595,13 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
             } else { keys[j].w = INFINITY; keys[j].idx = 0x7fffffff; }
         }
         __syncthreads();
-        bitonic_sort(keys, np2);
+        if (np2 <= 64) { if (tid < 32) bitonic_sort_warp64(keys, np2); __syncthreads(); }
+        else bitonic_sort(keys, np2);
         for (int i = tid; i < pU; i += nthr) sw[i] = keys[i].w;
         if (tid == 0) { s_ta = 0; s_z = 0; }
         __syncthreads();
 
+        const long long tq4 = clock64();
         const int p = pU + pWb;
         const bool reduce = p > c.r * n;
         const int kept = reduce ? n * (c.r - 1) : p;
@@ -547,18 +613,58 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
         __syncthreads();
         const int ta = s_ta, tb = m - ta;
         // (e) W_{b+1}: kept generators in merged (weight, index) order, then the box
-        for (int i = ta + (tid >> 5); i < pU; i += (nthr >> 5)) {           // one warp per generator row
+        // destination rows first (one binary search per kept generator, all at once), then two flat copies
+        for (int i = ta + tid; i < pU; i += nthr) {
             const int pos = (i - ta) + max(0, lower_bound_d(wBc, pWb, sw[i]) - tb);
-            const int src = keys[i].idx;
-            for (int q = tid & 31; q < n; q += 32) GWn[size_t(pos) * n + q] = sPU[src * ldp + q];
-            if ((tid & 31) == 0) { swm[pos] = sw[i]; sperm[1 - cur][pos] = reduce ? pos : src; }
+            swm[pos] = sw[i];
+            sperm[1 - cur][pos] = reduce ? pos : keys[i].idx;
+            spos[i] = pos;
         }
-        for (int j = tb + (tid >> 5); j < pWb; j += (nthr >> 5)) {
+        for (int j = tb + tid; j < pWb; j += nthr) {
             const int pos = (j - tb) + max(0, upper_bound_key(keys, pU, wBc[j]) - ta);
-            const double* src = GW + size_t(permc[j]) * n;
-            for (int q = tid & 31; q < n; q += 32) GWn[size_t(pos) * n + q] = src[q];
-            if ((tid & 31) == 0) { swm[pos] = wBc[j]; sperm[1 - cur][pos] = reduce ? pos : pU + permc[j]; }
+            swm[pos] = wBc[j];
+            sperm[1 - cur][pos] = reduce ? pos : pU + permc[j];
+            spos[pU + j] = pos;
         }
+        __syncthreads();
+        {
+            // row-wise copies, lanes over the coordinates (no index divisions: this phase was issue-bound on them);
+            // four shared rows per warp and trip so that eight L2 loads are in flight per lane
+            const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+            for (int i = ta + warp; i < pU; i += nwarps) {
+                const double* src = sPU + keys[i].idx * ldp;
+                double* dst = GWn + size_t(spos[i]) * n;
+                for (int q = lane; q < n; q += 32) dst[q] = src[q];
+            }
+            if (n <= 64) {
+                const bool hi = lane + 32 < n, lo = lane < n;
+                for (int j0 = tb + warp; j0 < pWb; j0 += 4 * nwarps) {
+                    double v[4][2];
+                    int jj[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        jj[u] = min(j0 + u * nwarps, pWb - 1);            // clamped: the loads need no branch
+                        const double* src = GW + size_t(permc[jj[u]]) * n;
+                        v[u][0] = __ldcg(src + (lo ? lane : 0));
+                        v[u][1] = __ldcg(src + (hi ? lane + 32 : 0));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (j0 + u * nwarps >= pWb) continue;
+                        double* dst = GWn + size_t(spos[pU + jj[u]]) * n;
+                        if (lo) dst[lane] = v[u][0];
+                        if (hi) dst[lane + 32] = v[u][1];
+                    }
+                }
+            } else {
+                for (int j = tb + warp; j < pWb; j += nwarps) {
+                    const double* src = GW + size_t(permc[j]) * n;
+                    double* dst = GWn + size_t(spos[pU + j]) * n;
+                    for (int q = lane; q < n; q += 32) dst[q] = __ldcg(src + q);
+                }
+            }
+        }
+        const long long tq5 = clock64();
         if (reduce) {
             for (int i = tid; i < n; i += nthr) {
                 double s = 0.0;
@@ -597,7 +703,11 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
         }
         __syncthreads();
         cur ^= 1;
+        const long long tq6 = clock64();
+        tph[0] += tq1 - tq0; tph[1] += tq2 - tq1; tph[2] += tq3 - tq2; tph[3] += tq4 - tq3; tph[4] += tq5 - tq4; tph[5] += tq6 - tq5;
     }
+    if (c.dbg && tid == 0)
+        for (int i = 0; i < 6; ++i) c.dbg[i] = tph[i];
 }
 
 // ---- stand-alone reduce_order(Z, r, GIR05) for a batch of zonotopes (post.jl:26) ------------------

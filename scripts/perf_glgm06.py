@@ -10,6 +10,8 @@ per_dim = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 ctx = _lib.default_context(0)
 t = time.time()
 Phi, Oms, V = W.building_c4(per_dim, nsteps)
+if len(sys.argv) > 3:
+    Oms = Oms[:int(sys.argv[3])]          # e.g. 128: one rank's share at 8 GPUs
 print("host discretization of %d splits: %.2f s" % (len(Oms), time.time() - t))
 alg = GLGM06(δ=0.002, max_order=10)
 t = time.time()
