@@ -25,6 +25,11 @@ int next_pow2(int x) {
 
 template <class Epi>
 cudaError_t launch_tn64(const GemmOperands& g, const Epi& epi, cudaStream_t st) {
+    // K <= 48 (Building): three k-tiles in all, so a 3-stage ring holds the whole operand panel and the smaller
+    // footprint (61 KB instead of 82) lets a third CTA share the SM: prologue, L2 round trip and store epilogue of one
+    // CTA overlap the MMA burst of the others (C4: 19.8 -> 17 ms; FP64-pipe floor incl. the 64-column block padding
+    // 10.8 ms).  A resident-X "panel" kernel walking several Y panels per CTA was measured slower (28.5 vs 26.9 ms).
+    if (g.K <= 3 * BK) return launch_nt_dgemm<2, 2, 4, 4, 3>(g, epi, st);
     return launch_nt_dgemm<2, 2, 4, 4, 4>(g, epi, st);     // 64 x 64 tiles
 }
 template <class Epi>
