@@ -346,7 +346,7 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
         while (np2 < p->pU) np2 <<= 1;
         const size_t ldp = n + 1;
         chain_smem = 8 * (3 * n * ldp + 2 * size_t(p->pU + 1) * ldp + 3 * size_t(p->pWcap) + np2 + n + GLGM06_NSEG * size_t(n)) +
-                     16 * size_t(np2) + 4 * (3 * size_t(p->pWcap) + size_t(p->pU)) + 64;
+                     16 * size_t(np2) + 4 * (3 * size_t(p->pWcap) + 2 * size_t(p->pU) + 2) + 64;
         if (chain_smem > ctx->smem_optin) fused = false;
     }
     if (fused) {

@@ -435,6 +435,32 @@ __device__ __forceinline__ void glgm06_wait_progress(const int* progress, int ne
 
 constexpr int GLGM06_NSEG = 21;      // prefix-table segments per coordinate (48 x 21 = 1008 threads busy at n = 48)
 
+// The powers kernel runs several times faster than the chain, so one poll usually covers many steps: `known` (the
+// same value in every thread) caches the last count read and the CTA only polls -- an L2 round trip plus a barrier --
+// when it is not enough.
+__device__ __forceinline__ void glgm06_wait_progress_cached(const int* progress, int need, int& known, int* s_known) {
+    if (known >= need) return;
+    if (threadIdx.x == 0) {
+        int v = 0;
+        unsigned spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(progress) : "memory");
+            if (v < need) {
+                __nanosleep(200);
+                if (++spins > (1u << 26)) __trap();
+            }
+        } while (v < need);
+        *s_known = v;
+    }
+    __syncthreads();
+    known = *s_known;
+    __syncthreads();                                  // s_known may be rewritten by the next poll
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+
 struct ChainParams {
     int n, ldk, nb;             // ldk = Kp (row pitch of Phi/P/XU buffers), nb = rows per P block
     int pU, r, pWcap;
@@ -475,10 +501,12 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
     sperm[0] = reinterpret_cast<int*>(keys + np2);
     sperm[1] = sperm[0] + c.pWcap;
     int* spos = sperm[1] + c.pWcap;                   // [pWcap] destination row of every kept generator
-    __shared__ int s_ta, s_z;
+    __shared__ int s_ta, s_z, s_known;
+    int* srow = spos + c.pWcap + pU;                  // [pU+1] column of a single-entry row of [G_U|c_U], -1: general
 
     const int tid = threadIdx.x, nthr = blockDim.x;
-    glgm06_wait_progress(c.progress, 1);
+    int known = 0;
+    glgm06_wait_progress_cached(c.progress, 1, known, &s_known);
     for (int idx = tid; idx < n * n; idx += nthr) {
         const int a = idx / n, b = idx % n;
         sP[0][a * ldp + b] = __ldcg(c.Pstack + size_t(a) * c.ldk + b);  // P_0
@@ -486,6 +514,15 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
     for (int idx = tid; idx < (pU + 1) * n; idx += nthr) {
         const int g = idx / n, l = idx % n;
         sXU[g * ldp + l] = c.XU[size_t(g) * c.ldk + l];
+    }
+    __syncthreads();
+    // axis-aligned input generators (a box or ball input: all but a few rows of [G_U|c_U]) have one non-zero entry: their
+    // image under P_b is a scaled column of P_b.  Skipping exact zeros leaves every fma chain's value unchanged.
+    for (int g = tid; g <= pU; g += nthr) {
+        int nz = 0, at = -1;
+        for (int l = 0; l < n; ++l)
+            if (sXU[g * ldp + l] != 0.0) { ++nz; at = l; }
+        srow[g] = nz == 1 ? at : -1;
     }
     __syncthreads();
 
@@ -521,6 +558,17 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
         const double* wBc = swB[cur];
         const int* permc = sperm[cur];
         double* bprefb = c.bpref + size_t(b) * (c.pWcap + 1) * n;
+        if (b + 1 < c.nblk) {
+            // P_{b+1} is only needed by the next step: start its copy into the idle buffer now (cp.async) and collect
+            // it after this step's own work
+            glgm06_wait_progress_cached(c.progress, int(b) + 2, known, &s_known);
+            const double* Pg = c.Pstack + size_t(b + 1) * c.nb * c.ldk;
+            for (int idx = tid; idx < n * n; idx += nthr) {
+                const int a = idx / n, l = idx - a * n;
+                cp_async8(Pn + a * ldp + l, Pg + size_t(a) * c.ldk + l);
+            }
+            cp_async_commit();
+        }
 
         // (a) publish P_b, the sorted weights / permutation of W_b, and the prefix table of |W_b|
         {
@@ -570,17 +618,16 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
 
         // (b) P_b [G_U | c_U]  and  P_{b+1} = P_b Phi
         for (int idx = tid; idx < (pU + 1) * n; idx += nthr) {
-            const int g = idx / n, i = idx % n;
+            const int g = idx / n, i = idx - g * n;
+            const int l1 = srow[g];
             double s = 0.0;
-            for (int l = 0; l < n; ++l) s = fma(sXU[g * ldp + l], P[i * ldp + l], s);
+            if (l1 >= 0) s = fma(sXU[g * ldp + l1], P[i * ldp + l1], s);
+            else
+                for (int l = 0; l < n; ++l) s = fma(sXU[g * ldp + l], P[i * ldp + l], s);
             sPU[g * ldp + i] = s;
         }
         const long long tq2 = clock64();
-        {
-            glgm06_wait_progress(c.progress, int(b) + 2);
-            const double* Pg = c.Pstack + size_t(b + 1) * c.nb * c.ldk;        // P_{b+1} for the next step
-            for (int idx = tid; idx < n * n; idx += nthr) Pn[(idx / n) * ldp + idx % n] = __ldcg(Pg + size_t(idx / n) * c.ldk + idx % n);
-        }
+        cp_async_wait<0>();                               // P_{b+1} (issued at the top of the step) has landed
         __syncthreads();
         const long long tq3 = clock64();
         // centre of W_{b+1}
