@@ -32,6 +32,19 @@ cudaError_t launch_tn64(const GemmOperands& g, const Epi& epi, cudaStream_t st) 
     if (g.K <= 3 * BK) return launch_nt_dgemm<2, 2, 4, 4, 3>(g, epi, st);
     return launch_nt_dgemm<2, 2, 4, 4, 4>(g, epi, st);     // 64 x 64 tiles
 }
+// 64 x TN tiles for the batched product at n <= 64: TN = n rounded up to 16, so that a power block has no padded
+// columns to multiply (n = 48: 48 instead of 64, a quarter of the DMMA work of that launch)
+template <class Epi>
+cudaError_t launch_small_tn(int TN, const GemmOperands& g, const Epi& epi, cudaStream_t st) {
+    const bool short_k = g.K <= 3 * BK;
+    switch (TN) {
+        case 16: return short_k ? launch_nt_dgemm<2, 2, 4, 1, 3>(g, epi, st) : launch_nt_dgemm<2, 2, 4, 1, 4>(g, epi, st);
+        case 32: return short_k ? launch_nt_dgemm<2, 2, 4, 2, 3>(g, epi, st) : launch_nt_dgemm<2, 2, 4, 2, 4>(g, epi, st);
+        case 48: return short_k ? launch_nt_dgemm<2, 2, 4, 3, 3>(g, epi, st) : launch_nt_dgemm<2, 2, 4, 3, 4>(g, epi, st);
+        case 64: return launch_tn64(g, epi, st);
+    }
+    return cudaErrorInvalidValue;
+}
 template <class Epi>
 cudaError_t launch_tn128(const GemmOperands& g, const Epi& epi, cudaStream_t st) {
     return launch_nt_dgemm_ws<2, 4, 8, 4, 5>(g, epi, st);  // 128 x 128 tiles, warp-specialised
@@ -112,8 +125,8 @@ extern "C" int reach_glgm06_plan_create(reach_ctx* ctx, int n, int64_t nsteps, i
     p->pU = pU;
     p->homog = pU < 0;
     p->Kp = round_up(n, BK);
-    p->TN = n <= 64 ? 64 : 128;
-    p->TM = p->TN;
+    p->TN = n <= 64 ? round_up(n, 16) : 128;
+    p->TM = n <= 64 ? 64 : 128;
     p->nb = round_up(n, p->TN);
     p->tpb = p->nb / p->TN;
     p->p0r = p0 > max_order * n ? max_order * n : p0;
@@ -228,8 +241,8 @@ extern "C" int reach_glgm06_plan_upload(reach_glgm06_plan* p, const double* Phi,
 
     // ---- Phi in the three layouts the contractions read ----
     REACH_TRY(p->phi_cm.alloc(ctx, size_t(n) * n * 8, false));
-    REACH_TRY(p->PhiT.alloc(ctx, size_t(nb) * Kp * 8));
-    REACH_TRY(p->PhiRows.alloc(ctx, size_t(nb) * Kp * 8));
+    REACH_TRY(p->PhiT.alloc(ctx, size_t(round_up(nb, 64)) * Kp * 8));          // 64-row tiles of gemm_store
+    REACH_TRY(p->PhiRows.alloc(ctx, size_t(round_up(nb, 64)) * Kp * 8));
     REACH_CUDA(ctx, cudaMemcpyAsync(p->phi_cm.p, Phi, size_t(n) * n * 8, cudaMemcpyHostToDevice, st));
     // rows of PhiT = columns of Phi (contiguous in column-major storage)
     REACH_CUDA(ctx, cudaMemcpy2DAsync(p->PhiT.p, size_t(Kp) * 8, p->phi_cm.p, size_t(n) * 8, size_t(n) * 8, n,
@@ -273,7 +286,7 @@ extern "C" int reach_glgm06_plan_upload(reach_glgm06_plan* p, const double* Phi,
         if (cU)
             REACH_CUDA(ctx, cudaMemcpyAsync(p->XU.as<double>() + size_t(p->pU) * Kp, cU, size_t(n) * 8,
                                             cudaMemcpyHostToDevice, st));
-        REACH_TRY(p->Pstack.alloc(ctx, size_t(std::max<int64_t>(1, nblk)) * nb * Kp * 8));
+        REACH_TRY(p->Pstack.alloc(ctx, (size_t(std::max<int64_t>(1, nblk)) * nb + 64) * Kp * 8));
         REACH_TRY(p->GWall.alloc(ctx, size_t(nblk + 1) * p->pWcap * n * 8));
         REACH_TRY(p->cWall.alloc(ctx, size_t(nblk + 1) * n * 8));
         REACH_TRY(p->wB.alloc(ctx, size_t(std::max<int64_t>(1, nblk)) * p->pWcap * 8));
@@ -376,7 +389,7 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
             REACH_CUDA(ctx, cudaFuncGetAttributes(&fa, glgm06_powers_kernel));
             REACH_CUDA(ctx, cudaFuncGetAttributes(&fa, glgm06_select_kernel));
             const GemmOperands none{nullptr, nullptr, Kp, Kp, Kp, 0, 0};
-            if (p->TN == 64) REACH_CUDA(ctx, (launch_tn64(none, GenEpi{}, p->stream2)));
+            if (p->TN <= 64) REACH_CUDA(ctx, (launch_small_tn(p->TN, none, GenEpi{}, p->stream2)));
             else REACH_CUDA(ctx, (launch_tn128(none, GenEpi{}, p->stream2)));
         }
         if (!p->progress.p) REACH_TRY(p->progress.alloc(ctx, sizeof(int)));
@@ -458,7 +471,7 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
             e2.out = epi.out + b0 * epi.blk_stride;
             e2.psum = epi.psum + b0 * p->tpb * p->m_pad;
             e2.pmax = epi.pmax + b0 * p->tpb * p->m_pad;
-            if (p->TN == 64) REACH_CUDA(ctx, (launch_tn64(g, e2, gst)));
+            if (p->TN <= 64) REACH_CUDA(ctx, (launch_small_tn(p->TN, g, e2, gst)));
             else REACH_CUDA(ctx, (launch_tn128(g, e2, gst)));
             ++p->launches;
         }
