@@ -258,6 +258,7 @@ struct reach_lgg09_plan {
     // decoupled blocks: compact chains, parallel in time (path 4)
     bool use_compact = false;
     int cp_G = 0, cp_ne = 0, cp_nblk = 0, cp_log2 = 0, cp_mu_g = 0;
+    unsigned cp_slot_used = 0;
     int64_t cp_sblk = 0;
     DevBuf cpM, cpr0, cpwl, cpwa, cpE, cpWlE, cpWaE, cprstart, cpvoff;
 
@@ -309,7 +310,7 @@ int launch_chain(reach_ctx* ctx, int rpl, int ne, const Lgg09Chain& c, size_t sm
     return set_error(ctx, REACH_EINVAL, "bad rows-per-thread %d", rpl);
 }
 
-template <int G, int NE>
+template <int G, int NALT, int NE>
 int launch_compact_t(reach_ctx* ctx, const Lgg09Compact& c, bool inhomog, cudaStream_t st, int64_t& launches) {
     lgg09_compact_starts_kernel<G><<<(c.mu + 63) / 64, 64, 0, st>>>(c);
     REACH_CUDA(ctx, cudaGetLastError());
@@ -317,7 +318,7 @@ int launch_compact_t(reach_ctx* ctx, const Lgg09Compact& c, bool inhomog, cudaSt
     const long long warps = (long long)(c.mu_g / (32 / G)) * c.nblk;
     const unsigned grid = unsigned((warps + 3) / 4);
     if (inhomog && c.nblk > 1) {
-        lgg09_compact_kernel<G, 4, NE, true><<<grid, 128, 0, st>>>(c);
+        lgg09_compact_kernel<G, NALT, NE, true><<<grid, 128, 0, st>>>(c);
         REACH_CUDA(ctx, cudaGetLastError());
         lgg09_compact_scan_kernel<<<(2 * c.mu + 127) / 128, 128, 0, st>>>(c.voff, c.mu, c.nblk);
         REACH_CUDA(ctx, cudaGetLastError());
@@ -325,25 +326,30 @@ int launch_compact_t(reach_ctx* ctx, const Lgg09Compact& c, bool inhomog, cudaSt
     } else {
         REACH_CUDA(ctx, cudaMemsetAsync(c.voff, 0, size_t(c.nblk) * c.mu * 2 * sizeof(double), st));
     }
-    lgg09_compact_kernel<G, 4, NE, false><<<grid, 128, 0, st>>>(c);
+    lgg09_compact_kernel<G, NALT, NE, false><<<grid, 128, 0, st>>>(c);
     REACH_CUDA(ctx, cudaGetLastError());
     ++launches;
     return REACH_OK;
 }
-template <int G>
+template <int G, int NALT>
 int launch_compact_g(reach_ctx* ctx, int ne, const Lgg09Compact& c, bool inhomog, cudaStream_t st, int64_t& launches) {
-    if (ne == 0) return launch_compact_t<G, 0>(ctx, c, inhomog, st, launches);
-    if (ne == 4) return launch_compact_t<G, 4>(ctx, c, inhomog, st, launches);
-    return launch_compact_t<G, 8>(ctx, c, inhomog, st, launches);
+    if (ne == 0) return launch_compact_t<G, NALT, 0>(ctx, c, inhomog, st, launches);
+    if (ne == 4) return launch_compact_t<G, NALT, 4>(ctx, c, inhomog, st, launches);
+    return launch_compact_t<G, NALT, 8>(ctx, c, inhomog, st, launches);
 }
-int launch_compact(reach_ctx* ctx, int G, int ne, const Lgg09Compact& c, bool inhomog, cudaStream_t st, int64_t& launches) {
+template <int NALT>
+int launch_compact_a(reach_ctx* ctx, int G, int ne, const Lgg09Compact& c, bool inhomog, cudaStream_t st, int64_t& launches) {
     switch (G) {
-        case 2: return launch_compact_g<2>(ctx, ne, c, inhomog, st, launches);
-        case 4: return launch_compact_g<4>(ctx, ne, c, inhomog, st, launches);
-        case 8: return launch_compact_g<8>(ctx, ne, c, inhomog, st, launches);
-        case 16: return launch_compact_g<16>(ctx, ne, c, inhomog, st, launches);
+        case 2: return launch_compact_g<2, NALT>(ctx, ne, c, inhomog, st, launches);
+        case 4: return launch_compact_g<4, NALT>(ctx, ne, c, inhomog, st, launches);
+        case 8: return launch_compact_g<8, NALT>(ctx, ne, c, inhomog, st, launches);
+        case 16: return launch_compact_g<16, NALT>(ctx, ne, c, inhomog, st, launches);
     }
     return set_error(ctx, REACH_EINVAL, "bad compact group size %d", G);
+}
+int launch_compact(reach_ctx* ctx, int G, int ne, const Lgg09Compact& c, bool inhomog, cudaStream_t st, int64_t& launches) {
+    if (c.prog.nalt == 1) return launch_compact_a<1>(ctx, G, ne, c, inhomog, st, launches);
+    return launch_compact_a<2>(ctx, G, ne, c, inhomog, st, launches);
 }
 
 // Cost model (SM cycles per time step) used to pick the tile shape and the time block S.
@@ -545,7 +551,7 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
     const bool forced_opts = p->opts.path == 1 || p->opts.path == 3 || (p->opts.path == 0 && (p->opts.time_block > 0 || p->opts.tile_m || p->opts.tile_n));
     // ---- decoupled blocks: closure of every chain's support under the sparsity graph of Phi (path 4) ----
     std::vector<int> cp_idx;                                  // [mu][G] closure rows, ascending, -1 padded
-    if (!forced_opts && p->opts.path != 2 && p->nq <= 4 && p->ne <= 8 && (p->opts.path == 4 || !getenv("REACH_NO_COMPACT"))) {
+    if (!forced_opts && p->opts.path != 2 && p->prog.dev.nalt <= 2 && p->ne <= 8 && (p->opts.path == 4 || !getenv("REACH_NO_COMPACT"))) {
         constexpr int GMAX = 16;
         size_t nnz = 0;
         for (size_t i = 0; i < size_t(n) * n; ++i) nnz += Phi[i] != 0.0;
@@ -593,8 +599,8 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
             return set_error(ctx, REACH_EUNSUPPORTED, "the compact-chain path needs every direction's closure under the sparsity "
                              "graph of Phi to span at most %d rows", GMAX);
     } else if (p->opts.path == 4) {
-        return set_error(ctx, REACH_EUNSUPPORTED, "the compact-chain path needs <= 4 support features and <= 8 mapped rows "
-                         "(features=%d, mapped rows=%d)", p->nq, p->ne);
+        return set_error(ctx, REACH_EUNSUPPORTED, "the compact-chain path needs <= 2 alternatives in Omega0 and <= 8 mapped rows "
+                         "(alternatives=%d, mapped rows=%d)", p->prog.dev.nalt, p->ne);
     }
     // ---- INT8 tcgen05 digit-plane GEMM requested (path 3) ----
     p->use_oz = false;
@@ -733,7 +739,7 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
         REACH_CUDA(ctx, cudaStreamSynchronize(st));
     }
     if (p->use_compact) {
-        const int G = p->cp_G, mu = p->mu, NQ = 4;
+        const int G = p->cp_G, mu = p->mu;
         const int nep = p->ne == 0 ? 0 : (p->ne <= 4 ? 4 : 8);
         p->cp_ne = nep;
         p->cp_mu_g = round_up(mu, 32 / G);
@@ -746,9 +752,17 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
         p->cp_sblk = sblk;
         p->cp_log2 = lg;
         p->cp_nblk = int((p->nsteps + sblk - 1) / sblk);
-        std::vector<double> M(size_t(mu) * G * G, 0.0), r0(size_t(mu) * G, 0.0), wl(size_t(mu) * NQ * G, 0.0),
-            wa(size_t(mu) * NQ * G, 0.0), E(size_t(mu) * std::max(1, nep) * G, 0.0), WlE(size_t(NQ) * std::max(1, p->ne), 0.0),
-            WaE(size_t(NQ) * std::max(1, p->ne), 0.0);
+        // evaluation slots: 2a = feature of alternative a at r_k, 2a+1 = at r_{k+1}, last = rho(.; V); -1 = absent
+        const int nalt = p->prog.dev.nalt, NS = 2 * nalt + 1;
+        std::vector<int> slot_q(NS, -1);
+        for (int a = 0; a < nalt; ++a) { slot_q[2 * a] = p->prog.dev.q0[a]; slot_q[2 * a + 1] = p->prog.dev.q1[a]; }
+        slot_q[2 * nalt] = p->prog.dev.qV;
+        p->cp_slot_used = 0;
+        for (int q = 0; q < NS; ++q)
+            if (slot_q[q] >= 0) p->cp_slot_used |= 1u << q;
+        std::vector<double> M(size_t(mu) * G * G, 0.0), r0(size_t(mu) * G, 0.0), wl(size_t(mu) * NS * G, 0.0),
+            wa(size_t(mu) * NS * G, 0.0), E(size_t(mu) * std::max(1, nep) * G, 0.0), WlE(size_t(NS) * std::max(1, p->ne), 0.0),
+            WaE(size_t(NS) * std::max(1, p->ne), 0.0);
         for (int c = 0; c < mu; ++c) {
             const int* idx = &cp_idx[size_t(c) * G];
             const double* d = dirs + size_t(chain_src[c]) * n;
@@ -757,18 +771,21 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
                 r0[size_t(c) * G + i] = chain_sign[c] * d[idx[i]] + 0.0;
                 for (int l = 0; l < G; ++l)
                     if (idx[l] >= 0) M[(size_t(c) * G + i) * G + l] = Phi[size_t(idx[i]) * n + idx[l]];   // Phi(idx_l, idx_i)
-                for (int q = 0; q < p->nq; ++q) {
-                    wl[(size_t(c) * NQ + q) * G + i] = p->prog.feats[q].a[idx[i]];
-                    wa[(size_t(c) * NQ + q) * G + i] = p->prog.feats[q].b[idx[i]];
+                for (int q = 0; q < NS; ++q) {
+                    if (slot_q[q] < 0) continue;
+                    wl[(size_t(c) * NS + q) * G + i] = p->prog.feats[slot_q[q]].a[idx[i]];
+                    wa[(size_t(c) * NS + q) * G + i] = p->prog.feats[slot_q[q]].b[idx[i]];
                 }
                 for (int e = 0; e < p->ne; ++e) E[(size_t(c) * nep + e) * G + i] = p->prog.erows[e][idx[i]];
             }
         }
-        for (int q = 0; q < p->nq; ++q)
-            for (auto& kv : p->prog.feats[q].rows) {
+        for (int q = 0; q < NS; ++q) {
+            if (slot_q[q] < 0) continue;
+            for (auto& kv : p->prog.feats[slot_q[q]].rows) {
                 WlE[size_t(q) * p->ne + kv.first] = kv.second.first;
                 WaE[size_t(q) * p->ne + kv.first] = kv.second.second;
             }
+        }
         auto ship = [&](DevBuf& b, const std::vector<double>& v) -> int {
             REACH_TRY(b.alloc(ctx, v.size() * 8, false));
             REACH_CUDA(ctx, cudaMemcpyAsync(b.p, v.data(), v.size() * 8, cudaMemcpyHostToDevice, st));
@@ -919,6 +936,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         c.E = p->cpE.as<double>();
         c.WlE = p->cpWlE.as<double>();
         c.WaE = p->cpWaE.as<double>();
+        c.slot_used = p->cp_slot_used;
         c.rstart = p->cprstart.as<double>();
         c.voff = p->cpvoff.as<double>();
         c.row_pos = p->row_pos.as<int>();

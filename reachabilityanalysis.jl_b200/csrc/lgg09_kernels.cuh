@@ -735,11 +735,12 @@ struct Lgg09Compact {
     int log2_sblk;
     const double* M;                // [mu][G][G]  M[c][i][l] = Phi'(idx_i, idx_l) = Phi(idx_l, idx_i)
     const double* r0;               // [mu][G]
-    const double* wl;               // [mu][NQ][G] direct weights of the local rows
-    const double* wa;               // [mu][NQ][G]
+    const double* wl;               // [mu][NS][G] direct weights of the local rows per evaluation slot (NS = 2 nalt + 1)
+    const double* wa;               // [mu][NS][G]
     const double* E;                // [mu][NE][G] mapped rows restricted to the closure
-    const double* WlE;              // [NQ][NE] mapped-row weights
+    const double* WlE;              // [NS][ne] mapped-row weights per slot
     const double* WaE;
+    unsigned slot_used;             // bit q: slot q has a feature
     double* rstart;                 // [nblk][mu][G]
     double* voff;                   // [nblk][mu][2] block totals of rho(+-r; V), then exclusive offsets
     const int* row_pos;
@@ -801,14 +802,19 @@ static __global__ void lgg09_compact_scan_kernel(double* __restrict__ voff, int 
     }
 }
 
-template <int G, int NQ, int NE, bool ONLY_V>
+// Evaluation slots instead of feature indices: slot 2a is the feature alternative a evaluates at r_k, slot 2a+1 the one
+// it evaluates at r_{k+1}, the last slot is rho(.; V).  The host gathers the weights per slot (zeros for an absent
+// feature), so the step loop has no runtime feature selection (the first version spent a third of its ~424 warp
+// instructions per step on selects) and skips unused slots / mapped rows with warp-uniform branches.
+template <int G, int NALT, int NE, bool ONLY_V>
 __global__ void __launch_bounds__(128) lgg09_compact_kernel(const Lgg09Compact c) {
     constexpr int NEP = NE > 0 ? NE : 1;
+    constexpr int NS = 2 * NALT + 1, SV = 2 * NALT;                      // slots; the V slot
     constexpr int CPW = 32 / G;                                          // chains per warp
-    __shared__ double s_wlE[NQ][NEP], s_waE[NQ][NEP];
-    for (int x = threadIdx.x; x < NQ * NEP; x += blockDim.x) {
+    __shared__ double s_wlE[NS][NEP], s_waE[NS][NEP];
+    for (int x = threadIdx.x; x < NS * NEP; x += blockDim.x) {
         const int q = x / NEP, e = x % NEP;
-        const bool ok = q < c.nq && e < c.ne;
+        const bool ok = e < c.ne;
         s_wlE[q][e] = ok ? c.WlE[q * c.ne + e] : 0.0;
         s_waE[q][e] = ok ? c.WaE[q * c.ne + e] : 0.0;
     }
@@ -821,20 +827,24 @@ __global__ void __launch_bounds__(128) lgg09_compact_kernel(const Lgg09Compact c
     const int ch = int(warp % wpb) * CPW + lane / G;
     const bool live = ch < c.mu;
     const int cc = live ? ch : 0;                                        // padding groups replay chain 0, store nothing
+    const unsigned used = c.slot_used;
 
     double Mrow[G];
 #pragma unroll
     for (int l = 0; l < G; ++l) Mrow[l] = c.M[(size_t(cc) * G + i) * G + l];
-    double wl[NQ], wa[NQ], Ei[NEP];
+    double wl[NS], wa[NS], Ei[NEP];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-        wl[q] = q < c.nq ? c.wl[(size_t(cc) * NQ + q) * G + i] : 0.0;
-        wa[q] = q < c.nq ? c.wa[(size_t(cc) * NQ + q) * G + i] : 0.0;
+    for (int q = 0; q < NS; ++q) {
+        wl[q] = c.wl[(size_t(cc) * NS + q) * G + i];
+        wa[q] = c.wa[(size_t(cc) * NS + q) * G + i];
     }
 #pragma unroll
     for (int e = 0; e < NEP; ++e) Ei[e] = (NE > 0 && e < c.ne) ? c.E[(size_t(cc) * NE + e) * G + i] : 0.0;
     double r = c.rstart[(size_t(b) * c.mu + cc) * G + i];
     const long long kb = b * c.sblk, ke = min(c.nsteps, kb + c.sblk);
+    // outputs of a (lin, abs) pair without selects: pos = lin + kpos*abs, neg = abs + kneg*lin
+    //   support values: (abs + lin, abs - lin)      box output: (lin, abs)      -- fma(x, 1, y) = x + y exactly
+    const double kpos = c.prog.box ? 0.0 : 1.0, kneg = c.prog.box ? 0.0 : -1.0;
 
     auto next = [&](double v) {
         double acc = 0.0;
@@ -847,26 +857,34 @@ __global__ void __launch_bounds__(128) lgg09_compact_kernel(const Lgg09Compact c
         for (int off = G / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
         return v;
     };
+    // padded mapped rows (e >= ne) have zero entries and zero weights: they add exact zeros, no guards needed
+    auto mapped = [&](double v, double (&y)[NEP]) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) y[e] = group_sum(Ei[e] * v);
+    };
+    // (lin, abs) of slot q at the vector v with mapped rows y
+    auto slot = [&](int q, double v, double av, const double (&y)[NEP], double& lin, double& ab) {
+        lin = group_sum(wl[q] * v);
+        ab = group_sum(wa[q] * av);
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            lin = fma(s_wlE[q][e], y[e], lin);
+            ab = fma(s_waE[q][e], fabs(y[e]), ab);
+        }
+    };
 
+    double y[NEP];
+#pragma unroll
+    for (int e = 0; e < NEP; ++e) y[e] = 0.0;
     if (ONLY_V) {
         // block totals of rho(+r_k; V), rho(-r_k; V), summed in step order
-        const int qv = c.prog.qV;
-        double wlv = 0.0, wav = 0.0, wlEv[NEP], waEv[NEP];
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) if (q == qv) { wlv = wl[q]; wav = wa[q]; }
-#pragma unroll
-        for (int e = 0; e < NEP; ++e) { wlEv[e] = qv >= 0 ? s_wlE[qv][e] : 0.0; waEv[e] = qv >= 0 ? s_waE[qv][e] : 0.0; }
         double tp = 0.0, tn = 0.0;
         for (long long k = kb; k < ke; ++k) {
-            double lin = group_sum(wlv * r), ab = group_sum(wav * fabs(r));
-#pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                const double y = group_sum(Ei[e] * r);
-                lin = fma(wlEv[e], y, lin);
-                ab = fma(waEv[e], fabs(y), ab);
-            }
-            tp += lgg09_out_pos(c.prog, lin, ab);
-            tn += lgg09_out_neg(c.prog, lin, ab);
+            double lin, ab;
+            mapped(r, y);
+            slot(SV, r, fabs(r), y, lin, ab);
+            tp += fma(ab, kpos, lin);
+            tn += fma(lin, kneg, ab);
             r = next(r);
         }
         if (live && i == 0) {
@@ -876,54 +894,60 @@ __global__ void __launch_bounds__(128) lgg09_compact_kernel(const Lgg09Compact c
         return;
     }
 
-    auto features = [&](double v, double (&F)[NQ][2]) {
-        double y[NEP];
-#pragma unroll
-        for (int e = 0; e < NE; ++e) y[e] = group_sum(Ei[e] * v);
-        const double av = fabs(v);
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            double lin = group_sum(wl[q] * v), ab = group_sum(wa[q] * av);
-#pragma unroll
-            for (int e = 0; e < NE; ++e) {
-                lin = fma(s_wlE[q][e], y[e], lin);
-                ab = fma(s_waE[q][e], fabs(y[e]), ab);
-            }
-            F[q][0] = lin;
-            F[q][1] = ab;
-        }
-    };
     const int rp = live ? c.row_pos[ch] : -1, rn = live ? c.row_neg[ch] : -1;
-    const int qv = c.prog.qV;
+    const bool has_v = (used >> SV) & 1u;
+    bool use0[NALT], use1[NALT];
+#pragma unroll
+    for (int a = 0; a < NALT; ++a) { use0[a] = (used >> (2 * a)) & 1u; use1[a] = (used >> (2 * a + 1)) & 1u; }
+    // output pointers advance by one column (ndirs doubles) per step; lanes that do not store keep a null pointer
+    double* out_p = (i == 0 && rp >= 0) ? c.rho + size_t(kb) * c.ndirs + rp : nullptr;
+    double* out_n = (i == 0 && rn >= 0) ? c.rho + size_t(kb) * c.ndirs + rn : nullptr;
+    const size_t ostride = size_t(c.ndirs);
     double sp = 0.0, sn = 0.0;
-    if (qv >= 0) { sp = c.voff[(size_t(b) * c.mu + cc) * 2]; sn = c.voff[(size_t(b) * c.mu + cc) * 2 + 1]; }
-    double Fp[NQ][2], Fc[NQ][2];
-    features(r, Fp);
+    if (has_v) { sp = c.voff[(size_t(b) * c.mu + cc) * 2]; sn = c.voff[(size_t(b) * c.mu + cc) * 2 + 1]; }
+    // features of the "current" vector: slot 2a of every alternative and the V slot, carried from step to step
+    double c_lin[NALT + 1], c_ab[NALT + 1];
+    mapped(r, y);
+    {
+        const double av = fabs(r);
+#pragma unroll
+        for (int a = 0; a <= NALT; ++a) {
+            const int q = a < NALT ? 2 * a : SV;
+            c_lin[a] = c_ab[a] = 0.0;
+            if ((used >> q) & 1u) slot(q, r, av, y, c_lin[a], c_ab[a]);
+        }
+    }
     for (long long k = kb; k < ke; ++k) {
-        r = next(r);
-        features(r, Fc);
+        r = next(r);                                                     // r_{k+1}
+        mapped(r, y);
+        const double av = fabs(r);
         double vp = 0.0, vn = 0.0;
-        for (int a = 0; a < c.prog.nalt; ++a) {
+#pragma unroll
+        for (int a = 0; a < NALT; ++a) {
             double ap = 0.0, an = 0.0;
-            const int q0 = c.prog.q0[a], q1 = c.prog.q1[a];
-#pragma unroll
-            for (int q = 0; q < NQ; ++q)
-                if (q == q0) { ap += lgg09_out_pos(c.prog, Fp[q][0], Fp[q][1]); an += lgg09_out_neg(c.prog, Fp[q][0], Fp[q][1]); }
-#pragma unroll
-            for (int q = 0; q < NQ; ++q)
-                if (q == q1) { ap += lgg09_out_pos(c.prog, Fc[q][0], Fc[q][1]); an += lgg09_out_neg(c.prog, Fc[q][0], Fc[q][1]); }
+            if (use0[a]) {
+                ap += fma(c_ab[a], kpos, c_lin[a]);
+                an += fma(c_lin[a], kneg, c_ab[a]);
+            }
+            if (use1[a]) {                                               // evaluated at r_{k+1}
+                double lin, ab;
+                slot(2 * a + 1, r, av, y, lin, ab);
+                ap += fma(ab, kpos, lin);
+                an += fma(lin, kneg, ab);
+            }
             if (a == 0) { vp = ap; vn = an; } else { vp = fmax(vp, ap); vn = fmax(vn, an); }
         }
-        if (i == 0) {
-            if (rp >= 0) c.rho[size_t(k) * c.ndirs + rp] = vp + sp;
-            if (rn >= 0) c.rho[size_t(k) * c.ndirs + rn] = vn + sn;
+        if (out_p) { *out_p = vp + sp; out_p += ostride; }
+        if (out_n) { *out_n = vn + sn; out_n += ostride; }
+        if (has_v) {                                                     // s_{k+1} = s_k + rho(r_k; V)
+            sp += fma(c_ab[NALT], kpos, c_lin[NALT]);
+            sn += fma(c_lin[NALT], kneg, c_ab[NALT]);
         }
+        // the current-vector slots of the next step
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) {
-            if (q == qv) { sp += lgg09_out_pos(c.prog, Fp[q][0], Fp[q][1]); sn += lgg09_out_neg(c.prog, Fp[q][0], Fp[q][1]); }
-            Fp[q][0] = Fc[q][0];
-            Fp[q][1] = Fc[q][1];
-        }
+        for (int a = 0; a < NALT; ++a)
+            if (use0[a]) slot(2 * a, r, av, y, c_lin[a], c_ab[a]);
+        if (has_v) slot(SV, r, av, y, c_lin[NALT], c_ab[NALT]);
     }
 }
 
