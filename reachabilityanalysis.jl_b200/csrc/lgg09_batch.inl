@@ -202,7 +202,9 @@ extern "C" int reach_lgg09_batch_create(reach_ctx* ctx, int n, int ndirs, int64_
     // time chunk of the column operand: <= ~2 GB, a multiple of S
     {
         const double per_step = double(ndirs) * Kc * 8.0;
-        int64_t c = int64_t(2.0e9 / per_step);
+        double budget = 2.0e9;
+        if (const char* env = getenv("REACH_BATCH_CHUNK_BYTES")) budget = std::max(1.0, atof(env));   // tests: force many chunks
+        int64_t c = int64_t(budget / per_step);
         c = std::max<int64_t>(S, c / S * S);
         b->chunk = std::min<int64_t>(c, round_up64(nsteps, S));
     }

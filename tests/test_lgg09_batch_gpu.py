@@ -109,6 +109,25 @@ def test_solve_with_a_vector_of_initial_sets_runs_one_batch(ctx):
     assert abs(sol.F.rho(e25) - max(one.F.rho(e25) for one in singles)) <= 1e-10 * abs(sol.F.rho(e25))
 
 
+def test_batch_time_chunks_of_the_column_operand(ctx, monkeypatch):
+    """The [y;|y|] column operand is produced in time chunks (2 GB by default); force chunks of one time block so that a
+    run crosses many chunk boundaries, including a ragged last one, and compare with the unchunked run."""
+    n, nsplits, nsteps = 13, 5, 333
+    A, _ = stable_system(n, 77)
+    _, U, _ = random_sets(n, 77)
+    ivps = [D.forward(A, X0, 0.05, U) for X0 in random_splits(n, nsplits, 77)]
+    dirs = np.hstack([np.eye(n), -np.eye(n)])
+    whole = Lgg09BatchPlan(ctx, ivps[0].Phi, dirs, [iv.Omega0 for iv in ivps], ivps[0].V, nsteps).run()
+    assert whole.stats()["chunk_steps"] >= nsteps
+    monkeypatch.setenv("REACH_BATCH_CHUNK_BYTES", "1")
+    parts = Lgg09BatchPlan(ctx, ivps[0].Phi, dirs, [iv.Omega0 for iv in ivps], ivps[0].V, nsteps).run()
+    st = parts.stats()
+    assert st["chunk_steps"] == st["time_block"] < nsteps
+    for i in range(nsplits):
+        assert np.array_equal(parts.sfmat(i), whole.sfmat(i))
+    assert_support_parity(parts.sfmat(2), LO.reach_inhomog_LGG09(dirs, ivps[2].Omega0, ivps[2].Phi, nsteps, ivps[2].V))
+
+
 def test_batch_argument_errors(ctx):
     n = 4
     A, Phi = stable_system(n, 1)
