@@ -247,14 +247,15 @@ def glgm06_leg(args, ctx, torch, dist, world, rank):
 
 
 def other_configs_leg(ctx):
-    """The small BASELINE configs and the split caller, device-resident, best of 3 (CUDA events on the library
+    """The other BASELINE configs and the split caller, device-resident, best of 3 (CUDA events on the library
     stream): C1 Building (DMMA GEMM over the power stack), C2 ISS (compact chains: 135 decoupled 2x2 blocks),
-    LGG09 over 256 initial-set splits of Building (one batch)."""
+    C3 HEAT02 (n = 1000, 2001 directions; first 2000 of the 10^4 steps, stack build included; the INT8 guard sends
+    it to the DMMA kernel at pass 0), LGG09 over 256 initial-set splits of Building (one batch)."""
     import reach_b200 as rb
     from reach_b200 import workloads as W, discretization as D, sets as S
     from reach_b200.lgg09 import Lgg09Plan, Lgg09BatchPlan
     out = {}
-    for key, wl in (("C1", W.building_c1()), ("C2", W.iss_c2())):
+    for key, wl in (("C1", W.building_c1()), ("C2", W.iss_c2()), ("C3", W.heat_c3(nsteps=2000))):
         plan = Lgg09Plan(ctx, wl.n, wl.dirs.shape[1], wl.nsteps)
         plan.upload(wl.Phi, wl.dirs, wl.Omega0, wl.V)
         ms = []
@@ -266,6 +267,8 @@ def other_configs_leg(ctx):
         out[key] = {"workload": wl.name, "ndirs": wl.dirs.shape[1], "nsteps": wl.nsteps, "ms": t,
                     "evals_per_s": wl.dirs.shape[1] * wl.nsteps / (t * 1e-3), "path": st["path"],
                     "launches": st["launches"], "time_block": st["time_block"]}
+        if st["path"] == "int8":      # guarded: fallback_pass >= 0 means the run continued on the FP64 (DMMA) kernel
+            out[key].update(guard_checks=st["guard_checks"], guard_max=st["guard_max"], fallback_pass=st["fallback_pass"])
         plan.close()
     A, B, X0, U0 = W.building_sets()
     U = D.normalize_input(B, U0)
