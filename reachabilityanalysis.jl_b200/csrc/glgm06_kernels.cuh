@@ -400,12 +400,34 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_powers_kernel(const dou
         double* Pn = sP[(b + 1) & 1];
         double* Pg = Pstack + size_t(b) * nb * ldk;
         for (int idx = tid; idx < n * n; idx += nthr) {
-            const int i = idx / n, m = idx % n;
+            const int i = idx / n, m = idx - i * n;
             Pg[size_t(i) * ldk + m] = P[i * ldp + m];
-            if (b + 1 < nblk) {
-                double s = 0.0;
-                for (int l = 0; l < n; ++l) s = fma(P[i * ldp + l], sPhiT[m * ldp + l], s);
-                Pn[i * ldp + m] = s;
+        }
+        if (b + 1 < nblk) {
+            // four rows of P_{b+1} per thread: one (conflict-free) load of Phi'(m, l) feeds four FMAs, the P_b entries
+            // are warp-wide broadcasts -- the plain one-output-per-thread loop was bound by shared-memory wavefronts
+            // (3 per FMA).  Every dot product keeps its sequential order over l.
+            const int nrb = (n + 3) / 4;
+            for (int idx = tid; idx < nrb * n; idx += nthr) {
+                const int ib = idx / n, m = idx - ib * n;
+                const int i0 = 4 * ib;
+                const double* p0 = P + min(i0, n - 1) * ldp;
+                const double* p1 = P + min(i0 + 1, n - 1) * ldp;
+                const double* p2 = P + min(i0 + 2, n - 1) * ldp;
+                const double* p3 = P + min(i0 + 3, n - 1) * ldp;
+                const double* ph = sPhiT + m * ldp;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                for (int l = 0; l < n; ++l) {
+                    const double f = ph[l];
+                    s0 = fma(p0[l], f, s0);
+                    s1 = fma(p1[l], f, s1);
+                    s2 = fma(p2[l], f, s2);
+                    s3 = fma(p3[l], f, s3);
+                }
+                Pn[i0 * ldp + m] = s0;
+                if (i0 + 1 < n) Pn[(i0 + 1) * ldp + m] = s1;
+                if (i0 + 2 < n) Pn[(i0 + 2) * ldp + m] = s2;
+                if (i0 + 3 < n) Pn[(i0 + 3) * ldp + m] = s3;
             }
         }
         __syncthreads();
