@@ -470,6 +470,7 @@ extern "C" int reach_lgg09_plan_create(reach_ctx* ctx, int n, int ndirs, int64_t
 extern "C" void reach_lgg09_plan_destroy(reach_lgg09_plan* p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
+    if (p->st2) cudaStreamSynchronize(p->st2);      // an error return can leave combine kernels in flight on the side stream
     cudaStreamSynchronize(p->ctx->stream);
     delete p;
 }
