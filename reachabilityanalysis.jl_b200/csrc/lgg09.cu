@@ -43,7 +43,10 @@ cudaError_t launch_cfg(int cfg, const GemmOperands& g, const Epi& epi, cudaStrea
     switch (cfg) {
         case 0: return launch_nt_dgemm_ws<2, 4, 8, 4, 5>(g, epi, st);   // warp-specialised, 5-stage bulk-copy ring
         case 100: return launch_nt_dgemm<2, 4, 8, 4, 4>(g, epi, st);    // v1 (cp.async ring), kept for A/B timing
-        case 1: return launch_nt_dgemm<2, 2, 4, 4, 4>(g, epi, st);
+        case 1:
+            // K <= 48: three k-tiles in all -- a 3-stage ring holds the whole panel and a third CTA fits beside (61 KB each)
+            if (g.K <= 3 * BK) return launch_nt_dgemm<2, 2, 4, 4, 3>(g, epi, st);
+            return launch_nt_dgemm<2, 2, 4, 4, 4>(g, epi, st);
         case 2: return launch_nt_dgemm<1, 4, 2, 4, 4>(g, epi, st);
         case 3: return launch_nt_dgemm<2, 4, 4, 4, 4>(g, epi, st);
     }
