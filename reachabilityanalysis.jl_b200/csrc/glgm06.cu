@@ -365,6 +365,7 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
     if (fused) {
         ChainParams c{};
         c.n = n; c.ldk = Kp; c.nb = nb; c.pU = p->pU; c.r = r; c.pWcap = p->pWcap; c.nblk = nblk;
+        c.pa_max = std::max(p->p0r, p->pU);
         c.XU = p->XU.as<double>();
         c.Pstack = Pst;
         c.GWall = p->GWall.as<double>();

@@ -486,6 +486,7 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 struct ChainParams {
     int n, ldk, nb;             // ldk = Kp (row pitch of Phi/P/XU buffers), nb = rows per P block
     int pU, r, pWcap;
+    int pa_max;                 // most generators any consumer of the prefix table brings along: max(p0, pU)
     long long nblk;
     const double* XU;           // [(pU+1)][ldk]
     const double* Pstack;       // [nblk][nb][ldk], produced concurrently by glgm06_powers_kernel
@@ -601,11 +602,15 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
             // prefix over the sorted order, two-level: NSEG segments per coordinate.  W_b lives in global memory (L2);
             // the loads go out in batches of eight independent requests (one dependent L2 round trip per element was
             // half of the step time at 480 generators), the additions keep their order.
-            const int seglen = (pWb + NSEG - 1) / NSEG;
+            // Only row tb of the table is ever read (the box diagonal of a reduction that boxes tb shared generators),
+            // and tb <= m = pa + pW_b - n (r - 1) for a consumer with pa own generators: the table stops at the largest
+            // m (C4: 167 of 480 rows), which is the L2 traffic of this phase cut by the same factor.
+            const int tmax = max(0, min(pWb, c.pa_max + pWb - n * (c.r - 1)));
+            const int seglen = (tmax + NSEG - 1) / NSEG;
             for (int idx = tid; idx < n * NSEG; idx += nthr) {
                 const int i = idx % n, sg = idx / n;
                 double s = 0.0;
-                const int t1 = min(pWb, (sg + 1) * seglen);
+                const int t1 = min(tmax, (sg + 1) * seglen);
                 for (int t = sg * seglen; t < t1; t += 8) {
                     double v[8];
 #pragma unroll
@@ -621,7 +626,7 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
                 double s = 0.0;
                 for (int q = 0; q < sg; ++q) s += sseg[i * NSEG + q];
                 if (sg == 0) bprefb[i] = 0.0;
-                const int t1 = min(pWb, (sg + 1) * seglen);
+                const int t1 = min(tmax, (sg + 1) * seglen);
                 for (int t = sg * seglen; t < t1; t += 8) {
                     double v[8];
 #pragma unroll
