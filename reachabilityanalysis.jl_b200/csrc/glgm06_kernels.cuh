@@ -669,8 +669,22 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
             } else { keys[j].w = INFINITY; keys[j].idx = 0x7fffffff; }
         }
         __syncthreads();
-        if (np2 <= 64) { if (tid < 32) bitonic_sort_warp64(keys, np2); __syncthreads(); }
-        else bitonic_sort(keys, np2);
+        if (pU <= nthr) {
+            // rank sort: thread j counts the keys below its own (pU broadcast reads, no barriers in between) and drops its
+            // key at that rank -- (weight, index) keys are distinct, so the ranks are a permutation.  One barrier pair
+            // instead of the ~20 dependent shuffle stages of a bitonic network.
+            WKey me{0.0, 0};
+            int rank = 0;
+            if (tid < pU) {
+                me = keys[tid];
+                for (int i = 0; i < pU; ++i) rank += wkey_less(keys[i], me) ? 1 : 0;
+            }
+            __syncthreads();
+            if (tid < pU) keys[rank] = me;
+            __syncthreads();
+        } else {
+            bitonic_sort(keys, np2);
+        }
         for (int i = tid; i < pU; i += nthr) sw[i] = keys[i].w;
         if (tid == 0) { s_ta = 0; s_z = 0; }
         __syncthreads();
