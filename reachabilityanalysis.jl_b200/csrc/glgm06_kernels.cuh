@@ -94,8 +94,10 @@ struct WKey {
     double w;
     int idx;
 };
+// bitwise, not short-circuit: the compiler turned `||` / `&&` into divergent branches with reconvergence barriers, which
+// cost ~150 cycles per comparison in the rank / sort loops of the chain kernel
 __device__ __forceinline__ bool wkey_less(const WKey& a, const WKey& b) {
-    return a.w < b.w || (a.w == b.w && a.idx < b.idx);
+    return bool(int(a.w < b.w) | (int(a.w == b.w) & int(a.idx < b.idx)));
 }
 // bitonic sort of `np2` (power of two) keys in shared memory by all threads of the CTA
 __device__ inline void bitonic_sort(WKey* keys, int np2) {
