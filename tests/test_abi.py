@@ -51,3 +51,66 @@ def test_product_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def _c_param_counts():
+    """name -> number of parameters, parsed from the prototypes in include/reach.h."""
+    src = open(os.path.join(ROOT, "include", "reach.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(reach_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    return out
+
+
+def test_ctypes_signatures_have_the_header_arity():
+    counts = _c_param_counts()
+    for name, (_, argtypes) in _lib.SIGNATURES.items():
+        assert counts[name] == len(argtypes), "%s: header has %d parameters, ctypes binding %d" % (
+            name, counts[name], len(argtypes))
+
+
+def test_julia_wrapper_ccalls_match_the_header():
+    """julia/ReachCUDA.jl cannot be executed here (no julia binary); at least every ccall must name a declared symbol
+    and pass as many arguments as the C prototype takes (type tuple and value list)."""
+    counts = _c_param_counts()
+    src = open(os.path.join(ROOT, "julia", "ReachCUDA.jl")).read()
+    src = re.sub(r"#[^\n]*", "", src)
+    calls = 0
+    for m in re.finditer(r"ccall\(\(:(reach_[a-z0-9_]+),\s*lib\),\s*\w+,\s*\(", src):
+        name = m.group(1)
+        assert name in counts, "ReachCUDA.jl calls %s, which include/reach.h does not declare" % name
+        i, depth = m.end(), 1                       # scan the type tuple
+        while depth:
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+        types = src[m.end():i - 1].strip().rstrip(",")
+        ntypes = 0 if not types else len(_split_top_level(types))
+        j, depth = i, 1                             # the value list runs to the closing paren of ccall
+        while depth:
+            depth += {"(": 1, ")": -1, "[": 1, "]": -1}.get(src[j], 0)
+            j += 1
+        values = src[i:j - 1].strip().lstrip(",").strip()
+        nvalues = 0 if not values else len(_split_top_level(values))
+        assert ntypes == counts[name], "%s: %d argument types, header has %d" % (name, ntypes, counts[name])
+        assert nvalues == counts[name], "%s: %d argument values, header has %d" % (name, nvalues, counts[name])
+        calls += 1
+    assert calls >= 8
+
+
+def _split_top_level(text):
+    parts, depth, cur = [], 0, ""
+    for ch in text:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        parts.append(cur)
+    return parts
