@@ -64,6 +64,32 @@ def test_batch_mixed_alternative_counts_and_single_step(ctx):
             assert_support_parity(batch.sfmat(i), LO.reach_inhomog_LGG09(dirs, Om, Phi, nsteps, V))
 
 
+@pytest.mark.parametrize("nalt", [3, 4, 8])
+def test_batch_nested_convex_hulls_use_the_wide_max(ctx, nalt):
+    """3..8 alternatives per split (nested convex hulls): the epilogue's max runs over 4 / 8 rows (lanes differing in
+    bits 2-4); splits with fewer alternatives repeat their first one."""
+    n, nsteps = 9, 50
+    A, Phi = stable_system(n, 31)
+    rng = np.random.default_rng(31)
+    V = rb.BallInf(np.zeros(n), 0.02)
+
+    def hull(k, seed):
+        r = np.random.default_rng(seed)
+        sets = [rb.Hyperrectangle(r.uniform(-1, 1, n), 0.1 * r.uniform(0, 1, n)) for _ in range(k)]
+        sets[1] = rb.MinkowskiSum(rb.LinearMap(Phi, sets[0]), V)          # one alternative evaluated at r_{k+1}
+        out = sets[0]
+        for X in sets[1:]:
+            out = rb.ConvexHull(out, X)
+        return out
+
+    oms = [hull(nalt, 1), hull(2, 2), hull(nalt, 3)]
+    dirs = np.hstack([np.eye(n), -np.eye(n), rng.standard_normal((n, 2))])
+    batch = Lgg09BatchPlan(ctx, Phi, dirs, oms, V, nsteps).run()
+    assert batch.stats()["alternatives"] == (4 if nalt <= 4 else 8)
+    for i, Om in enumerate(oms):
+        assert_support_parity(batch.sfmat(i), LO.reach_inhomog_LGG09(dirs, Om, Phi, nsteps, V))
+
+
 def test_batch_building_splits_equal_the_single_plan(ctx):
     """Building BLDF01 with X0 split into 16 boxes: the batch equals 16 separate device runs (and the oracle)."""
     prob = building_problem()
