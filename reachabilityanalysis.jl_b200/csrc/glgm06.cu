@@ -389,6 +389,10 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
             cudaFuncAttributes fa;
             REACH_CUDA(ctx, cudaFuncGetAttributes(&fa, glgm06_powers_kernel));
             REACH_CUDA(ctx, cudaFuncGetAttributes(&fa, glgm06_select_kernel));
+            REACH_CUDA(ctx, cudaFuncGetAttributes(&fa, glgm06_select_warp_kernel<1>));
+            REACH_CUDA(ctx, cudaFuncGetAttributes(&fa, glgm06_select_warp_kernel<2>));
+            REACH_CUDA(ctx, cudaFuncGetAttributes(&fa, glgm06_select_warp_kernel<4>));
+            REACH_CUDA(ctx, cudaFuncGetAttributes(&fa, glgm06_select_warp_kernel<8>));
             const GemmOperands none{nullptr, nullptr, Kp, Kp, Kp, 0, 0};
             if (p->TN <= 64) REACH_CUDA(ctx, (launch_small_tn(p->TN, none, GenEpi{}, p->stream2)));
             else REACH_CUDA(ctx, (launch_tn128(none, GenEpi{}, p->stream2)));
@@ -520,7 +524,13 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
             sb.tb += b0 * nsplits;
             sb.diag += b0 * size_t(nsplits) * n;
             sb.centre += b0 * size_t(nsplits) * n;
-            glgm06_select_kernel<<<dim3(nsplits, nbh), 128, smem, st>>>(sb, np2);
+            // up to 256 own generators: one warp per (split, step), keys in registers; beyond: one CTA, keys in shared memory
+            const unsigned wgrid = unsigned((size_t(nsplits) * nbh + 3) / 4);
+            if (np2 <= 32) glgm06_select_warp_kernel<1><<<wgrid, 128, 0, st>>>(sb, nbh);
+            else if (np2 == 64) glgm06_select_warp_kernel<2><<<wgrid, 128, 0, st>>>(sb, nbh);
+            else if (np2 == 128) glgm06_select_warp_kernel<4><<<wgrid, 128, 0, st>>>(sb, nbh);
+            else if (np2 == 256) glgm06_select_warp_kernel<8><<<wgrid, 128, 0, st>>>(sb, nbh);
+            else glgm06_select_kernel<<<dim3(nsplits, nbh), 128, smem, st>>>(sb, np2);
             REACH_CUDA(ctx, cudaGetLastError());
             ++p->launches;
         }
