@@ -74,7 +74,8 @@ struct reach_glgm06_plan {
     DevBuf Xown;                        // [m_pad][Kp]
     DevBuf XU, PU;                      // [(pU+1) padded to 64][Kp]
     DevBuf Pstack;                      // [nblk][nb][Kp]
-    DevBuf GWall, cWall;                // [(nblk+1)][pWcap][n], [(nblk+1)][n]
+    DevBuf GWall, cWall;                // [(nblk+1)][pWcap][n], [(nblk+1)][n]; GWall doubles as the generator pool
+    DevBuf slotB;                       // [(nblk+1)][pWcap] pool row of column r of W_b (identity in the stepwise path)
     DevBuf wB, permB, bpref, pWdev;     // per block
     DevBuf A_store;                     // [nblk][m_pad][lda]
     DevBuf psum, pmax;                  // [nblk*tpb][m_pad]
@@ -288,6 +289,12 @@ extern "C" int reach_glgm06_plan_upload(reach_glgm06_plan* p, const double* Phi,
                                             cudaMemcpyHostToDevice, st));
         REACH_TRY(p->Pstack.alloc(ctx, (size_t(std::max<int64_t>(1, nblk)) * nb + 64) * Kp * 8));
         REACH_TRY(p->GWall.alloc(ctx, size_t(nblk + 1) * p->pWcap * n * 8));
+        REACH_TRY(p->slotB.alloc(ctx, size_t(nblk + 1) * p->pWcap * 4, false));
+        {
+            const size_t cnt = size_t(nblk + 1) * p->pWcap;
+            glgm06_iota_kernel<<<unsigned((cnt + 255) / 256), 256, 0, st>>>(p->slotB.as<int>(), cnt);
+            REACH_CUDA(ctx, cudaGetLastError());
+        }
         REACH_TRY(p->cWall.alloc(ctx, size_t(nblk + 1) * n * 8));
         REACH_TRY(p->wB.alloc(ctx, size_t(std::max<int64_t>(1, nblk)) * p->pWcap * 8));
         REACH_TRY(p->permB.alloc(ctx, size_t(std::max<int64_t>(1, nblk)) * p->pWcap * 4));
@@ -359,7 +366,7 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
         while (np2 < p->pU) np2 <<= 1;
         const size_t ldp = n + 1;
         chain_smem = 8 * (3 * n * ldp + 2 * size_t(p->pU + 1) * ldp + 3 * size_t(p->pWcap) + np2 + n + GLGM06_NSEG * size_t(n)) +
-                     16 * size_t(np2) + 4 * (3 * size_t(p->pWcap) + 2 * size_t(p->pU) + 2) + 64;
+                     16 * size_t(np2) + 4 * (5 * size_t(p->pWcap) + 2 * size_t(p->pU) + 2) + 64;
         if (chain_smem > ctx->smem_optin) fused = false;
     }
     if (fused) {
@@ -374,6 +381,7 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
         c.wB = p->wB.as<double>();
         c.permB = p->permB.as<int>();
         c.bpref = p->bpref.as<double>();
+        c.slotB = p->slotB.as<int>();
         if (getenv("REACH_GLGM06_DEBUG")) {
             if (!p->dbg.p) REACH_TRY(p->dbg.alloc(ctx, 64));
             c.dbg = p->dbg.as<long long>();
@@ -617,7 +625,7 @@ extern "C" int reach_glgm06_plan_fetch(reach_glgm06_plan* p, int split, int64_t 
         REACH_TRY(occ.alloc(ctx, size_t(std::max(1, ng)) * 4));
         glgm06_materialize_kernel<<<1, 256, 0, st>>>(
             p->A_store.as<double>() + size_t(b) * p->m_pad * p->lda + size_t(split) * p->rows * p->lda, p->lda, p->p0r,
-            p->pos_own.as<int>() + o * p->p0r, tb, p->GWall.as<double>() + size_t(b) * p->pWcap * n, n, p->pW[b],
+            p->pos_own.as<int>() + o * p->p0r, tb, p->GWall.as<double>(), p->slotB.as<int>() + size_t(b) * p->pWcap, n, p->pW[b],
             p->permB.as<int>() + size_t(b) * p->pWcap, p->diag.as<double>() + o * n, n, p->r, Gd.as<double>(),
             seld.as<int>(), occ.as<int>());
         REACH_CUDA(ctx, cudaGetLastError());
@@ -660,7 +668,7 @@ extern "C" int reach_glgm06_plan_support(reach_glgm06_plan* p, const double* d, 
             if (smem > 48 * 1024)
                 REACH_CUDA(ctx, cudaFuncSetAttribute(glgm06_shared_dots_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
             glgm06_shared_dots_kernel<<<unsigned(p->nblk), 256, smem, st>>>(
-                p->GWall.as<double>(), (long long)p->pWcap * n, n, p->pWdev.as<int>(), p->permB.as<int>(), p->pWcap,
+                p->GWall.as<double>(), p->slotB.as<int>(), n, p->pWdev.as<int>(), p->permB.as<int>(), p->pWcap,
                 dd.as<double>(), n, sfx.as<double>());
             REACH_CUDA(ctx, cudaGetLastError());
             SupportParams s{};

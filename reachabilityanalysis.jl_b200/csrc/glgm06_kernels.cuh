@@ -567,6 +567,11 @@ __device__ __forceinline__ void glgm06_wait_progress(const int* progress, int ne
     __syncthreads();
 }
 
+static __global__ void glgm06_iota_kernel(int* __restrict__ out, size_t count) {
+    const size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (i < count) out[i] = int(i);
+}
+
 constexpr int GLGM06_NSEG = 21;      // prefix-table segments per coordinate (48 x 21 = 1008 threads busy at n = 48)
 
 // The powers kernel runs several times faster than the chain, so one poll usually covers many steps: `known` (the
@@ -609,6 +614,7 @@ struct ChainParams {
     double* wB;                 // [nblk][pWcap]
     int* permB;                 // [nblk][pWcap]
     double* bpref;              // [nblk][(pWcap+1)][n]
+    int* slotB;                 // [(nblk+1)][pWcap] row of the generator pool (= GWall) that holds column r of W_b
     long long* dbg;             // optional [8] phase cycle counters (NULL: off)
 };
 
@@ -638,6 +644,9 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
     int* spos = sperm[1] + c.pWcap;                   // [pWcap] destination row of every kept generator
     __shared__ int s_ta, s_z, s_known;
     int* srow = spos + c.pWcap + pU;                  // [pU+1] column of a single-entry row of [G_U|c_U], -1: general
+    int* sslot[2];                                    // pool row of every column of the current / next W
+    sslot[0] = srow + pU + 1;
+    sslot[1] = sslot[0] + c.pWcap;
 
     const int tid = threadIdx.x, nthr = blockDim.x;
     int known = 0;
@@ -682,13 +691,20 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
         __syncthreads();
     }
 
+    // W_0 = U sits in rows 0.. of the pool.  From here on a kept generator is never moved: W_{b+1} lists the pool rows of
+    // its columns (slotB), only the <= pU + n new generators of a step are written (into that step's own rows).
+    for (int r = tid; r < c.pW[0]; r += nthr) { sslot[0][r] = r; c.slotB[r] = r; }
+    __syncthreads();
     long long tph[6] = {0, 0, 0, 0, 0, 0};
     for (long long b = 0; b < c.nblk; ++b) {
         const long long tq0 = clock64();
         const int pWb = c.pW[b];
         const double* P = sP[b & 1];
         double* Pn = sP[(b + 1) & 1];
-        const double* GW = c.GWall + size_t(b) * c.pWcap * n;
+        const double* pool = c.GWall;
+        const int* slotc = sslot[cur];
+        int* slotn = sslot[1 - cur];
+        const int base_n = int(b + 1) * c.pWcap;          // pool row of column 0 of W_{b+1}'s own block
         double* GWn = c.GWall + size_t(b + 1) * c.pWcap * n;
         const double* wBc = swB[cur];
         const int* permc = sperm[cur];
@@ -726,7 +742,7 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
                 for (int t = sg * seglen; t < t1; t += 8) {
                     double v[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = t + u < t1 ? fabs(__ldcg(GW + size_t(permc[t + u]) * n + i)) : 0.0;
+                    for (int u = 0; u < 8; ++u) v[u] = t + u < t1 ? fabs(__ldcg(pool + size_t(slotc[permc[t + u]]) * n + i)) : 0.0;
 #pragma unroll
                     for (int u = 0; u < 8; ++u) if (t + u < t1) s += v[u];
                 }
@@ -742,7 +758,7 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
                 for (int t = sg * seglen; t < t1; t += 8) {
                     double v[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) v[u] = t + u < t1 ? fabs(__ldcg(GW + size_t(permc[t + u]) * n + i)) : 0.0;
+                    for (int u = 0; u < 8; ++u) v[u] = t + u < t1 ? fabs(__ldcg(pool + size_t(slotc[permc[t + u]]) * n + i)) : 0.0;
 #pragma unroll
                     for (int u = 0; u < 8; ++u)
                         if (t + u < t1) {
@@ -819,49 +835,23 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
             swm[pos] = sw[i];
             sperm[1 - cur][pos] = reduce ? pos : keys[i].idx;
             spos[i] = pos;
+            if (reduce) slotn[pos] = base_n + pos;                          // new generator, written below
         }
         for (int j = tb + tid; j < pWb; j += nthr) {
             const int pos = (j - tb) + max(0, upper_bound_key(keys, pU, wBc[j]) - ta);
             swm[pos] = wBc[j];
             sperm[1 - cur][pos] = reduce ? pos : pU + permc[j];
             spos[pU + j] = pos;
+            if (reduce) slotn[pos] = slotc[permc[j]];                       // kept generator: stays where it is
         }
         __syncthreads();
-        {
-            // row-wise copies, lanes over the coordinates (no index divisions: this phase was issue-bound on them);
-            // four shared rows per warp and trip so that eight L2 loads are in flight per lane
+        if (reduce) {
+            // only the kept own generators are written (row-wise, lanes over the coordinates)
             const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
             for (int i = ta + warp; i < pU; i += nwarps) {
                 const double* src = sPU + keys[i].idx * ldp;
                 double* dst = GWn + size_t(spos[i]) * n;
                 for (int q = lane; q < n; q += 32) dst[q] = src[q];
-            }
-            if (n <= 64) {
-                const bool hi = lane + 32 < n, lo = lane < n;
-                for (int j0 = tb + warp; j0 < pWb; j0 += 4 * nwarps) {
-                    double v[4][2];
-                    int jj[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        jj[u] = min(j0 + u * nwarps, pWb - 1);            // clamped: the loads need no branch
-                        const double* src = GW + size_t(permc[jj[u]]) * n;
-                        v[u][0] = __ldcg(src + (lo ? lane : 0));
-                        v[u][1] = __ldcg(src + (hi ? lane + 32 : 0));
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        if (j0 + u * nwarps >= pWb) continue;
-                        double* dst = GWn + size_t(spos[pU + jj[u]]) * n;
-                        if (lo) dst[lane] = v[u][0];
-                        if (hi) dst[lane + 32] = v[u][1];
-                    }
-                }
-            } else {
-                for (int j = tb + warp; j < pWb; j += nwarps) {
-                    const double* src = GW + size_t(permc[j]) * n;
-                    double* dst = GWn + size_t(spos[pU + j]) * n;
-                    for (int q = lane; q < n; q += 32) dst[q] = __ldcg(src + q);
-                }
             }
         }
         const long long tq5 = clock64();
@@ -876,16 +866,18 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
         if (!reduce) {
             // unreduced W_{b+1} = [P G_U | W_b] keeps its ORIGINAL column order; only the sort order is merged.
             // Rewrite the generators in original order (own first, then shared).
-            for (int idx = tid; idx < p * n; idx += nthr) {
-                const int g = idx / n, q = idx % n;
-                GWn[size_t(g) * n + q] = g < pU ? sPU[g * ldp + q] : GW[size_t(g - pU) * n + q];
+            for (int idx = tid; idx < pU * n; idx += nthr) {
+                const int g = idx / n, q = idx - g * n;
+                GWn[size_t(g) * n + q] = sPU[g * ldp + q];
             }
+            for (int g = tid; g < p; g += nthr) slotn[g] = g < pU ? base_n + g : slotc[g - pU];
             for (int t = tid; t < p; t += nthr) swB[1 - cur][t] = swm[t];
         } else {
             for (int idx = tid; idx < n * n; idx += nthr) {
                 const int g = idx / n, i = idx % n;
                 GWn[size_t(kept + g) * n + i] = (g == i) ? sdiag[i] : 0.0;
             }
+            for (int g = tid; g < n; g += nthr) slotn[kept + g] = base_n + kept + g;
             // stable order of [kept ascending | n zero-weight box generators]:
             //   zero-weight kept (z of them), then the box, then the rest
             for (int t = tid; t < kept; t += nthr)
@@ -902,6 +894,7 @@ static __global__ void __launch_bounds__(1024, 1) glgm06_chain_kernel(const Chai
             }
         }
         __syncthreads();
+        for (int r = tid; r < c.pW[b + 1]; r += nthr) c.slotB[size_t(b + 1) * c.pWcap + r] = slotn[r];
         cur ^= 1;
         const long long tq6 = clock64();
         tph[0] += tq1 - tq0; tph[1] += tq2 - tq1; tph[2] += tq3 - tq2; tph[3] += tq4 - tq3; tph[4] += tq5 - tq4; tph[5] += tq6 - tq5;
@@ -960,7 +953,7 @@ static __global__ void glgm06_reduce_batch_kernel(const double* __restrict__ G, 
 // Output: Gout [ngens][n] rows = generators (== n x ngens column-major), sel[ngens].
 static __global__ void glgm06_materialize_kernel(const double* __restrict__ A, int lda, int p0,
                                           const int* __restrict__ pos_own, int tb,
-                                          const double* __restrict__ GW, int ldg, int pW,
+                                          const double* __restrict__ pool, const int* __restrict__ rowslot, int ldg, int pW,
                                           const int* __restrict__ permB, const double* __restrict__ diag,
                                           int n, int r, double* __restrict__ Gout, int* __restrict__ sel,
                                           int* __restrict__ occupied /* [ngens] zeroed */) {
@@ -969,7 +962,7 @@ static __global__ void glgm06_materialize_kernel(const double* __restrict__ A, i
         const int p = p0 + pW;
         for (int idx = threadIdx.x; idx < p * n; idx += blockDim.x) {
             const int g = idx / n, i = idx % n;
-            Gout[size_t(g) * n + i] = g < p0 ? A[size_t(g) * lda + i] : GW[size_t(g - p0) * ldg + i];
+            Gout[size_t(g) * n + i] = g < p0 ? A[size_t(g) * lda + i] : pool[size_t(rowslot[g - p0]) * ldg + i];
             if (i == 0) sel[g] = g;
         }
         return;
@@ -1000,7 +993,7 @@ static __global__ void glgm06_materialize_kernel(const double* __restrict__ A, i
             const int j = tag - 2;
             const int src = permB[j];
             sel[q] = p0 + src;
-            for (int i = 0; i < n; ++i) Gout[size_t(q) * n + i] = GW[size_t(src) * ldg + i];
+            for (int i = 0; i < n; ++i) Gout[size_t(q) * n + i] = pool[size_t(rowslot[src]) * ldg + i];
         }
     }
     for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
@@ -1013,7 +1006,7 @@ static __global__ void glgm06_materialize_kernel(const double* __restrict__ A, i
 // ---- support function of every stored zonotope in one direction -----------------------------------
 // Shared part per step: sfx[b][t] = sum over sorted shared generators j >= t of |g_j . d| (t = 0..pW),
 // and for unreduced steps the plain total sits at t = 0.
-static __global__ void glgm06_shared_dots_kernel(const double* __restrict__ GW, long long gw_stride, int ldg,
+static __global__ void glgm06_shared_dots_kernel(const double* __restrict__ pool, const int* __restrict__ rowslot, int ldg,
                                           const int* __restrict__ pW, const int* __restrict__ permB, int pWcap,
                                           const double* __restrict__ d, int n, double* __restrict__ sfx) {
     // one CTA per step; thread 0 does the suffix scan after a parallel dot phase
@@ -1021,9 +1014,8 @@ static __global__ void glgm06_shared_dots_kernel(const double* __restrict__ GW, 
     double* dots = reinterpret_cast<double*>(smraw);
     const int b = blockIdx.x;
     const int pb = pW[b];
-    const double* G = GW + size_t(b) * gw_stride;
     for (int j = threadIdx.x; j < pb; j += blockDim.x) {
-        const double* g = G + size_t(permB[size_t(b) * pWcap + j]) * ldg;
+        const double* g = pool + size_t(rowslot[size_t(b) * pWcap + permB[size_t(b) * pWcap + j]]) * ldg;
         double s = 0.0;
         for (int i = 0; i < n; ++i) s += g[i] * d[i];
         dots[j] = fabs(s);
