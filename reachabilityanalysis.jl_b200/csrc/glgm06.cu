@@ -40,7 +40,7 @@ cudaError_t launch_small_tn(int TN, const GemmOperands& g, const Epi& epi, cudaS
     switch (TN) {
         case 16: return short_k ? launch_nt_dgemm<2, 2, 4, 1, 3>(g, epi, st) : launch_nt_dgemm<2, 2, 4, 1, 4>(g, epi, st);
         case 32: return short_k ? launch_nt_dgemm<2, 2, 4, 2, 3>(g, epi, st) : launch_nt_dgemm<2, 2, 4, 2, 4>(g, epi, st);
-        case 48: return short_k ? launch_nt_dgemm<2, 2, 4, 3, 3>(g, epi, st) : launch_nt_dgemm<2, 2, 4, 3, 4>(g, epi, st);
+        case 48: return short_k ? launch_nt_dgemm<2, 2, 4, 3, 3, 4>(g, epi, st) : launch_nt_dgemm<2, 2, 4, 3, 4>(g, epi, st);
         case 64: return launch_tn64(g, epi, st);
     }
     return cudaErrorInvalidValue;

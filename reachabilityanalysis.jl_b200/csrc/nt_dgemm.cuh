@@ -73,8 +73,9 @@ struct GemmShape {
 };
 
 // The accumulator of lane (g4,t4): acc[mt][nt][e] is C[wm0 + 8*mt + g4][wn0 + 8*nt + 2*t4 + e].
-template <int WM, int WN, int MT, int NT, int STAGES, class Epi>
-__global__ void __launch_bounds__(WM* WN * 32, 1) nt_dgemm_kernel(const GemmOperands g, const Epi epi) {
+// MINB: CTAs per SM the register allocation must allow (short-K launches are latency-bound per CTA and want 4).
+template <int WM, int WN, int MT, int NT, int STAGES, int MINB = 1, class Epi>
+__global__ void __launch_bounds__(WM* WN * 32, MINB) nt_dgemm_kernel(const GemmOperands g, const Epi epi) {
     using Shape = GemmShape<WM, WN, MT, NT, STAGES>;
     constexpr int TM = Shape::TM, TN = Shape::TN, NTHR = Shape::NTHR;
     extern __shared__ __align__(16) double smem[];
@@ -356,10 +357,10 @@ struct StoreEpi {
     }
 };
 
-template <int WM, int WN, int MT, int NT, int STAGES, class Epi>
+template <int WM, int WN, int MT, int NT, int STAGES, int MINB = 1, class Epi>
 inline cudaError_t launch_nt_dgemm(const GemmOperands& g, const Epi& epi, cudaStream_t stream) {
     using Shape = GemmShape<WM, WN, MT, NT, STAGES>;
-    auto kern = nt_dgemm_kernel<WM, WN, MT, NT, STAGES, Epi>;
+    auto kern = nt_dgemm_kernel<WM, WN, MT, NT, STAGES, MINB, Epi>;
     // the opt-in shared-memory size is a per-device function attribute
     static thread_local int configured_dev = -1;
     int dev = -1;
