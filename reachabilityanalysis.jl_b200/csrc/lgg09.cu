@@ -34,8 +34,9 @@ const TileCfg kCfgs[] = {{0, 128, 128, 1},    // 2x4 warps, 64x32 warp tile  (la
                          {1, 64, 64, 2},      // 2x2 warps, 32x32 warp tile  (small n / stack build)
                          {2, 16, 128, 2},     // 1x4 warps, 16x32 warp tile  (a handful of directions)
                          {3, 64, 128, 1},     // 2x4 warps, 32x32 warp tile
-                         {4, 128, 128, 1}};   // INT8 tcgen05 digit-plane GEMM (oz_gemm.cuh), packed blocks
-constexpr int kNumCfgs = 5;
+                         {4, 128, 128, 1},    // INT8 tcgen05 digit-plane GEMM (oz_gemm.cuh), packed blocks
+                         {5, 64, 48, 3}};     // 2x2 warps, 32x24 warp tile: stack blocks of <= 48 rows without padding (Building)
+constexpr int kNumCfgs = 6;
 constexpr int kOzCfg = 4;
 
 template <class Epi>
@@ -49,6 +50,9 @@ cudaError_t launch_cfg(int cfg, const GemmOperands& g, const Epi& epi, cudaStrea
             return launch_nt_dgemm<2, 2, 4, 4, 4>(g, epi, st);
         case 2: return launch_nt_dgemm<1, 4, 2, 4, 4>(g, epi, st);
         case 3: return launch_nt_dgemm<2, 4, 4, 4, 4>(g, epi, st);
+        case 5:
+            if (g.K <= 3 * BK) return launch_nt_dgemm<2, 2, 4, 3, 3>(g, epi, st);
+            return launch_nt_dgemm<2, 2, 4, 3, 4>(g, epi, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -361,7 +365,7 @@ int launch_compact(reach_ctx* ctx, int G, int ne, const Lgg09Compact& c, bool in
 // stack costs about S + 2 log2(S) passes of an n x n x n product, amortised over the run.
 double step_cost(const reach_lgg09_plan& p, const TileCfg& c, int S, int mu, int nrows, int sms) {
     // cfg 0 is the warp-specialised kernel; cfg 4 the digit-plane GEMM (T = 8: ~2.1x the DMMA rate, less for fewer planes)
-    static const double eff[kNumCfgs] = {1.12, 0.85, 0.9, 0.92, 2.3};
+    static const double eff[kNumCfgs] = {1.12, 0.85, 0.9, 0.92, 2.3, 0.85};
     const int mu_pad = round_up(mu, c.TM);
     const bool packed = (c.id == 0 || c.id == kOzCfg) && nrows >= 128;
     const int nbe = packed ? round_up(nrows, 8) : round_up(nrows, c.TN);
@@ -417,7 +421,7 @@ int choose_config(reach_lgg09_plan& p) {
     if (best_cfg < 0)
         return set_error(ctx, REACH_EINVAL,
                          "no launch configuration matches time_block=%d tile_m=%d tile_n=%d "
-                         "(tiles are 128x128, 64x64, 16x128 or 64x128; the row stack must fit 3 GB)",
+                         "(tiles are 128x128, 64x64, 64x48, 16x128 or 64x128; the row stack must fit 3 GB)",
                          p.opts.time_block, p.opts.tile_m, p.opts.tile_n);
     p.cfg = best_cfg;
     p.S = best_S;
