@@ -173,10 +173,19 @@ int  reach_lgg09_plan_stats(reach_lgg09_plan* p, double* ms, int64_t* launches,
 /* Which main-loop kernel the plan uses / used: *path = 1 FP64 tensor-core (DMMA) GEMM, 2 persistent chain kernel,
  * 3 INT8 tcgen05 digit-plane GEMM (FP64 emulation by error-free slicing, csrc/oz_gemm.cuh) with *digit_planes planes.
  * When path 3 was chosen automatically it is guarded: *guard_checks sampled passes were recomputed on the DMMA kernel,
- * *guard_max is the largest relative feature difference seen, and *fallback_pass >= 0 is the pass from which the run
- * continued on the DMMA kernel because the difference exceeded 1e-12 (-1: never).  Any pointer may be NULL. */
+ * *guard_max is the largest relative feature difference seen, and *fallback_pass >= 0 is the pass whose check failed
+ * (-1: never): the run was then redone on the DMMA kernel from the last verified pass on (reach_lgg09_plan_guard).
+ * Any pointer may be NULL. */
 int  reach_lgg09_plan_path(reach_lgg09_plan* p, int32_t* path, int32_t* digit_planes, double* guard_max,
                            int64_t* guard_checks, int64_t* fallback_pass);
+/* More on the guard of path 3.  Checks run at passes 0, 1, every 64th and the last.  A check compares (a) the pass's
+ * features on the INT8 kernel and on the DMMA kernel from the same direction rows (tolerance 1e-12) and (b) the INT8
+ * path's features with those of up to 128 sentinel chains that were propagated on the FP64 tensor pipe since pass 0
+ * (*drift_max, tolerance 1e-11: the drift accumulated over all passes so far).  After every passed check the state
+ * (direction rows, running input sums, carried features) is kept; a failed check restores the last kept state and
+ * recomputes every pass since then on the DMMA kernel: *replay_from is the first recomputed pass (-1: none),
+ * *replayed_passes the number of INT8 passes whose results were discarded.  Any pointer may be NULL. */
+int  reach_lgg09_plan_guard(reach_lgg09_plan* p, double* drift_max, int64_t* replay_from, int64_t* replayed_passes);
 void reach_lgg09_plan_destroy(reach_lgg09_plan* p);
 
 /* LGG09 over a vector of initial sets -- the split caller `_solve_distributed` (src/Continuous/solve.jl:84-117),

@@ -70,6 +70,7 @@ SIGNATURES = {
     "reach_lgg09_plan_stats": (C.c_int, [C.c_void_p, c_double_p, c_int64_p, c_int32_p, c_int32_p,
                                          c_int32_p, c_int32_p, c_double_p, c_int64_p]),
     "reach_lgg09_plan_path": (C.c_int, [C.c_void_p, c_int32_p, c_int32_p, c_double_p, c_int64_p, c_int64_p]),
+    "reach_lgg09_plan_guard": (C.c_int, [C.c_void_p, c_double_p, c_int64_p, c_int64_p]),
     "reach_lgg09_plan_destroy": (None, [C.c_void_p]),
     "reach_lgg09_batch_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, c_double_p, c_double_p,
                                            C.POINTER(reach_setexpr), C.POINTER(reach_setexpr), C.POINTER(C.c_void_p)]),

@@ -386,10 +386,12 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
             if (!p->dbg.p) REACH_TRY(p->dbg.alloc(ctx, 64));
             c.dbg = p->dbg.as<long long>();
         }
-        // The chain CTA goes first so that it owns an SM; the powers (1 CTA, ~8 us per step) and then the batched GEMM
-        // run beside it on the second stream.  The chain consumes the powers as they are published (progress counter);
-        // launched the other way round, the GEMM's CTAs fill every SM and the chain CTA (200 KB of shared memory) waits
-        // for the whole GEMM grid to drain.
+        // Launch order: the powers kernel (1 CTA, waits on nothing, ~8 us per step) FIRST on the second stream, then the
+        // chain CTA on the ctx stream, then the batched GEMM behind the powers in stream order.  The chain consumes the
+        // powers as they are published (progress counter).  Because its producer is already in flight (or, in a
+        // serialising environment -- ncu, compute-sanitizer, CUDA_LAUNCH_BLOCKING=1 -- already finished) when the chain
+        // starts, the spin can never wait on a kernel that has not been launched.  The GEMM's CTAs only arrive once
+        // the powers kernel is done, long after the chain CTA (200 KB of shared memory) has taken its SM.
         // Every kernel that is launched while the chain CTA may be spinning on the progress counter must be loaded
         // beforehand: with CUDA's lazy module loading the first launch of a kernel can wait for running kernels to
         // finish, which would deadlock against the spinning chain.
@@ -412,12 +414,12 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
         const size_t psmem = 8 * 3 * size_t(n) * (n + 1);
         REACH_CUDA(ctx, cudaFuncSetAttribute(glgm06_powers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(psmem)));
         REACH_CUDA(ctx, cudaFuncSetAttribute(glgm06_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(chain_smem)));
-        glgm06_chain_kernel<<<1, 1024, chain_smem, st>>>(c);
-        REACH_CUDA(ctx, cudaGetLastError());
-        ++p->launches;
         REACH_CUDA(ctx, cudaStreamWaitEvent(p->stream2, p->ev_powers, 0));
         glgm06_powers_kernel<<<1, 1024, psmem, p->stream2>>>(p->PhiRows.as<double>(), p->PhiT.as<double>(), n, Kp, nb, nblk, Pst,
                                                              p->progress.as<int>());
+        REACH_CUDA(ctx, cudaGetLastError());
+        ++p->launches;
+        glgm06_chain_kernel<<<1, 1024, chain_smem, st>>>(c);
         REACH_CUDA(ctx, cudaGetLastError());
         ++p->launches;
         overlap = true;

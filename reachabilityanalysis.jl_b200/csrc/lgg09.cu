@@ -255,7 +255,21 @@ struct reach_lgg09_plan {
     bool oz_guard = false;        // auto-selected: sampled passes are re-run on the DMMA kernel and compared
     int oz_T = 8, oz_nkb = 0, oz_tiles_n = 0;
     DevBuf Xq, Yq, eX, eY;
-    DevBuf ftot_ref, guard_val, s_save;
+    DevBuf ftot_ref, guard_val;
+    // State after the last verified pass (direction block, running input sums, carried features): a failed check
+    // restores it and replays every pass since then on the FP64 tensor pipe.
+    DevBuf L_snap, s_snap, carry_snap;
+    // Sentinel chains: up to 128 chains (evenly spaced over the template) are also propagated pass by pass on the FP64
+    // tensor pipe (block S only, on their own stream).  At a checked pass their features are computed from the FP64
+    // direction rows and compared with the INT8 path's features of the same chains, which started from the INT8 path's
+    // own rows: the difference is the drift accumulated since pass 0, not only the error of one pass.
+    DevBuf Lsh[2], ftot_sen, drift_val;
+    int nsen = 0, sen_stride = 1;
+    cudaStream_t st3 = nullptr;
+    cudaEvent_t ev_sen[2] = {nullptr, nullptr};
+    double oz_drift_max = 0.0;    // largest sentinel feature difference (INT8 chain vs FP64 chain), relative to the feature scale
+    int64_t oz_replay_from = -1;  // first pass recomputed on the DMMA kernel after a failed check (-1: none)
+    int64_t oz_replayed = 0;      // INT8 passes whose results were discarded and recomputed
     double oz_guard_max = 0.0;    // largest sampled (int8 - DMMA) feature difference, relative to the feature scale
     int64_t oz_fallback_pass = -1;   // pass at which the run fell back to the DMMA kernel (-1: never)
     int64_t oz_checks = 0;
@@ -286,7 +300,9 @@ struct reach_lgg09_plan {
         if (ev1) cudaEventDestroy(ev1);
         for (auto e : ev_gemm) if (e) cudaEventDestroy(e);
         for (auto e : ev_comb) if (e) cudaEventDestroy(e);
+        for (auto e : ev_sen) if (e) cudaEventDestroy(e);
         if (st2) cudaStreamDestroy(st2);
+        if (st3) cudaStreamDestroy(st3);
         for (auto e : gemm_ev) cudaEventDestroy(e);
     }
 };
@@ -462,9 +478,11 @@ extern "C" int reach_lgg09_plan_create(reach_ctx* ctx, int n, int ndirs, int64_t
     if (e == cudaSuccess) e = cudaEventCreate(&p->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&p->ev1);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->st2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->st3, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&p->ev_gemm[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_comb[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_sen[i], cudaEventDisableTiming);
     }
     if (e != cudaSuccess) {
         delete p;
@@ -478,6 +496,7 @@ extern "C" void reach_lgg09_plan_destroy(reach_lgg09_plan* p) {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
     if (p->st2) cudaStreamSynchronize(p->st2);      // an error return can leave combine kernels in flight on the side stream
+    if (p->st3) cudaStreamSynchronize(p->st3);
     cudaStreamSynchronize(p->ctx->stream);
     delete p;
 }
@@ -732,7 +751,15 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
         if (p->oz_guard) {
             REACH_TRY(p->ftot_ref.alloc(ctx, p->ftot.bytes));
             REACH_TRY(p->guard_val.alloc(ctx, sizeof(unsigned long long)));
-            REACH_TRY(p->s_save.alloc(ctx, size_t(2) * mu_pad * sizeof(double)));
+            REACH_TRY(p->L_snap.alloc(ctx, size_t(mu_pad) * Kp * sizeof(double)));
+            REACH_TRY(p->s_snap.alloc(ctx, size_t(2) * mu_pad * sizeof(double)));
+            REACH_TRY(p->carry_snap.alloc(ctx, p->carry[0].bytes));
+            p->nsen = std::min(p->mu, OZ_TM);
+            p->sen_stride = p->mu / p->nsen;
+            REACH_TRY(p->Lsh[0].alloc(ctx, size_t(OZ_TM) * Kp * sizeof(double)));
+            REACH_TRY(p->Lsh[1].alloc(ctx, size_t(OZ_TM) * Kp * sizeof(double)));
+            REACH_TRY(p->ftot_sen.alloc(ctx, p->ftot.bytes));
+            REACH_TRY(p->drift_val.alloc(ctx, sizeof(unsigned long long)));
         }
     }
     if (p->use_chain) {
@@ -1195,14 +1222,21 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         REACH_TRY(combine(cmb, st));
     }
     p->oz_guard_max = 0.0;
+    p->oz_drift_max = 0.0;
     p->oz_fallback_pass = -1;
+    p->oz_replay_from = -1;
+    p->oz_replayed = 0;
     p->oz_checks = 0;
-    constexpr double kOzGuardTol = 1e-12;
+    constexpr double kOzGuardTol = 1e-12;      // one pass, INT8 against DMMA from the same direction rows
+    constexpr double kOzDriftTol = 1e-11;      // accumulated since pass 0, INT8 chain against the FP64 sentinel chain
+    // test hook: the first check at a pass >= REACH_OZ_TRIP_AT is treated as failed (exercises the replay path)
+    const char* trip_env = getenv("REACH_OZ_TRIP_AT");
+    int64_t trip_at = trip_env ? atoll(trip_env) : -1;
     // Pass t's combine kernels only read what its GEMM wrote (per-tile partials, double-buffered by parity) and their
     // own carried state, so they run on the side stream beside the GEMM of pass t+1; guard-checked passes stay serial.
     const bool overlap = T > 2 && !getenv("REACH_NO_OVERLAP");
     double* const fp_base = p->featpart.as<double>();
-    cudaStream_t st2 = p->st2;
+    cudaStream_t st2 = p->st2, st3 = p->st3;
     bool side_busy[2] = {false, false};
     auto join_side = [&]() -> int {
         for (int i = 0; i < 2; ++i)
@@ -1221,6 +1255,37 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         side_busy[par] = true;
         return REACH_OK;
     };
+    // ---- guard state of the digit-plane path ----
+    const int nsen = p->nsen, sen_stride = p->sen_stride;
+    bool sen_on = oz_now && p->oz_guard && T > 0 && !getenv("REACH_OZ_NO_SENTINEL");
+    int sen_cur = 0;
+    int64_t t_snap = 0;                        // the state at the start of pass t_snap is the last verified one
+    if (sen_on) {
+        // sentinel rows = chains 0, stride, 2 stride, ... of L_0; the sentinel stream starts once the stack is built
+        REACH_CUDA(ctx, cudaMemsetAsync(p->Lsh[0].p, 0, p->Lsh[0].bytes, st));
+        REACH_CUDA(ctx, cudaMemcpy2DAsync(p->Lsh[0].p, size_t(Kp) * 8, p->L0.p, size_t(sen_stride) * Kp * 8, size_t(Kp) * 8, nsen,
+                                          cudaMemcpyDeviceToDevice, st));
+        REACH_CUDA(ctx, cudaEventRecord(p->ev_sen[0], st));
+        REACH_CUDA(ctx, cudaStreamWaitEvent(st3, p->ev_sen[0], 0));
+    }
+    // features of blocks 1 and S (the first step of the pass and the block that becomes L_{k+S}) on the DMMA kernel from
+    // the rows X; nothing of the run's state is touched (no store block, separate totals buffer)
+    auto dmma_features = [&](const double* X, int mtiles, int nchains, double* totals) -> int {
+        for (int cb : {1, S}) {
+            GemmOperands gc{X, block(cb), Kp, Kp, Kp, mtiles, (nbe + TN - 1) / TN};
+            pepi.Lnext = p->Lbuf[1 - cur].as<double>(); pepi.slice_block0 = cb; pepi.store_block = -1;
+            REACH_CUDA(ctx, (launch_cfg(0, gc, pepi, st)));
+            Lgg09Combine cc = cmb;
+            cc.b_lo = cb; cc.b_hi = cb; cc.mu = nchains;
+            dim3 grid((nchains + cthreads - 1) / cthreads, 1);
+            lgg09_tilesum_packed_kernel<<<grid, cthreads, 0, st>>>(cc, cc.featpart, totals, nbe, TN, cb);
+            REACH_CUDA(ctx, cudaGetLastError());
+            p->launches += 2;
+            if (S == 1) break;
+        }
+        return REACH_OK;
+    };
+    const int gemm_ev_pairs = int(p->gemm_ev.size() / 2);
     for (int64_t t = 0; t < T; ++t) {
         const int b_lo = t == 0 ? 0 : 1;
         const int par = int(t & 1);
@@ -1233,7 +1298,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         epi.Lnext = p->Lbuf[1 - cur].as<double>();
         epi.block0 = b_lo;
         epi.store_block = S;
-        const bool sample = (t % sample_every) == 0;
+        const bool sample = (t % sample_every) == 0 && p->gemm_sampled < gemm_ev_pairs;
         cmb.b_lo = b_lo; cmb.b_hi = S; cmb.has_carry = t > 0; cmb.tail = 0; cmb.k0 = t * S;
         // guarded digit-plane path: passes 0, 1, every 64th and the last are also run on the DMMA kernel
         const bool check = oz_now && p->oz_guard && (t < 2 || (t & 63) == 0 || t == T - 1);
@@ -1245,22 +1310,12 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
             side_busy[par] = false;
         }
         if (check) {
-            // reference features of blocks 1 and S (the first step of the pass and the block that becomes L_{k+S}) from
-            // the DMMA kernel; nothing of the run's state is touched (no store block, separate totals buffer)
-            for (int cb : {1, S}) {
-                GemmOperands gc{p->Lbuf[cur].as<double>(), block(cb), Kp, Kp, Kp, mu_pad / TM, (nbe + TN - 1) / TN};
-                pepi.Lnext = epi.Lnext; pepi.slice_block0 = cb; pepi.store_block = -1;
-                REACH_CUDA(ctx, (launch_cfg(0, gc, pepi, st)));
-                Lgg09Combine cc = cmb;
-                cc.b_lo = cb; cc.b_hi = cb;
-                dim3 grid(cblocks, 1);
-                lgg09_tilesum_packed_kernel<<<grid, cthreads, 0, st>>>(cc, cc.featpart, p->ftot_ref.as<double>(), nbe, TN, cb);
-                REACH_CUDA(ctx, cudaGetLastError());
-                p->launches += 2;
-                if (S == 1) break;
+            if (sen_on) {                          // the sentinel rows of pass t, propagated in FP64 since pass 0
+                REACH_CUDA(ctx, cudaEventRecord(p->ev_sen[1], st3));
+                REACH_CUDA(ctx, cudaStreamWaitEvent(st, p->ev_sen[1], 0));
+                REACH_TRY(dmma_features(p->Lsh[sen_cur].as<double>(), 1, nsen, p->ftot_sen.as<double>()));
             }
-            REACH_CUDA(ctx, cudaMemcpyAsync(p->s_save.p, p->s_pos.p, size_t(mu_pad) * 8, cudaMemcpyDeviceToDevice, st));
-            REACH_CUDA(ctx, cudaMemcpyAsync(p->s_save.as<double>() + mu_pad, p->s_neg.p, size_t(mu_pad) * 8, cudaMemcpyDeviceToDevice, st));
+            REACH_TRY(dmma_features(p->Lbuf[cur].as<double>(), mu_pad / TM, p->mu, p->ftot_ref.as<double>()));
         }
         if (oz_now) {
             REACH_TRY(oz_pass(p->Lbuf[cur].as<double>(), epi.Lnext, b_lo, S, S, sample));
@@ -1268,29 +1323,73 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
             REACH_TRY(combine_pass(cmb, side, par));
             if (check) {
                 REACH_CUDA(ctx, cudaMemsetAsync(p->guard_val.p, 0, sizeof(unsigned long long), st));
+                REACH_CUDA(ctx, cudaMemsetAsync(p->drift_val.p, 0, sizeof(unsigned long long), st));
                 lgg09_guard_kernel<<<(p->mu * p->nq + 127) / 128, 128, 0, st>>>(ftot, p->ftot_ref.as<double>(), p->nq, mu_pad, p->mu,
                                                                                1, S, p->guard_val.as<unsigned long long>());
                 REACH_CUDA(ctx, cudaGetLastError());
                 ++p->launches;
-                unsigned long long bits = 0;
-                REACH_CUDA(ctx, cudaMemcpyAsync(&bits, p->guard_val.p, sizeof(bits), cudaMemcpyDeviceToHost, st));
+                if (sen_on) {
+                    lgg09_guard_kernel<<<(nsen * p->nq + 127) / 128, 128, 0, st>>>(ftot, p->ftot_sen.as<double>(), p->nq, mu_pad, nsen,
+                                                                                  1, S, p->drift_val.as<unsigned long long>(), sen_stride);
+                    REACH_CUDA(ctx, cudaGetLastError());
+                    ++p->launches;
+                    // the sentinel stream may overwrite its older row buffer only after the features were taken from it
+                    REACH_CUDA(ctx, cudaEventRecord(p->ev_sen[0], st));
+                    REACH_CUDA(ctx, cudaStreamWaitEvent(st3, p->ev_sen[0], 0));
+                }
+                unsigned long long bits[2] = {0, 0};
+                REACH_CUDA(ctx, cudaMemcpyAsync(&bits[0], p->guard_val.p, sizeof(bits[0]), cudaMemcpyDeviceToHost, st));
+                REACH_CUDA(ctx, cudaMemcpyAsync(&bits[1], p->drift_val.p, sizeof(bits[1]), cudaMemcpyDeviceToHost, st));
                 REACH_CUDA(ctx, cudaStreamSynchronize(st));
-                double worst;
-                std::memcpy(&worst, &bits, sizeof(worst));
+                double worst, drift;
+                std::memcpy(&worst, &bits[0], sizeof(worst));
+                std::memcpy(&drift, &bits[1], sizeof(drift));
                 ++p->oz_checks;
                 if (worst > p->oz_guard_max) p->oz_guard_max = worst;
-                if (!(worst <= kOzGuardTol)) {
-                    // not FP64-faithful on this problem (rows with a wide dynamic range): redo this pass and run the
-                    // rest on the FP64 tensor pipe
+                if (drift > p->oz_drift_max) p->oz_drift_max = drift;
+                bool ok = worst <= kOzGuardTol && drift <= kOzDriftTol;          // NaN fails
+                if (trip_at >= 0 && t >= trip_at) { ok = false; trip_at = -1; }
+                if (ok) {
+                    // verified: keep the state at the start of pass t + 1 (L_{t+1}, running sums, carried features)
+                    REACH_CUDA(ctx, cudaMemcpyAsync(p->L_snap.p, p->Lbuf[1 - cur].p, size_t(mu_pad) * Kp * 8, cudaMemcpyDeviceToDevice, st));
+                    REACH_CUDA(ctx, cudaMemcpyAsync(p->s_snap.p, p->s_pos.p, size_t(mu_pad) * 8, cudaMemcpyDeviceToDevice, st));
+                    REACH_CUDA(ctx, cudaMemcpyAsync(p->s_snap.as<double>() + mu_pad, p->s_neg.p, size_t(mu_pad) * 8, cudaMemcpyDeviceToDevice, st));
+                    REACH_CUDA(ctx, cudaMemcpyAsync(p->carry_snap.p, p->carry[carry_cur].p, p->carry_snap.bytes, cudaMemcpyDeviceToDevice, st));
+                    t_snap = t + 1;
+                } else {
+                    // Not FP64-faithful on this problem (rows with a wide dynamic range), or drifting: everything since
+                    // the last verified pass is unverified INT8 output.  Restore that state and run passes t_snap .. T-1
+                    // on the FP64 tensor pipe (their support values overwrite the INT8 ones).
                     oz_now = false;
+                    sen_on = false;
                     p->oz_fallback_pass = t;
-                    carry_cur ^= 1;
-                    REACH_CUDA(ctx, cudaMemcpyAsync(p->s_pos.p, p->s_save.p, size_t(mu_pad) * 8, cudaMemcpyDeviceToDevice, st));
-                    REACH_CUDA(ctx, cudaMemcpyAsync(p->s_neg.p, p->s_save.as<double>() + mu_pad, size_t(mu_pad) * 8, cudaMemcpyDeviceToDevice, st));
-                    --p->gemm_total;
+                    p->oz_replay_from = t_snap;
+                    p->oz_replayed = t - t_snap + 1;
+                    if (t_snap == 0) {
+                        REACH_CUDA(ctx, cudaMemcpyAsync(p->Lbuf[0].p, p->L0.p, size_t(mu_pad) * Kp * 8, cudaMemcpyDeviceToDevice, st));
+                        REACH_CUDA(ctx, cudaMemsetAsync(p->s_pos.p, 0, p->s_pos.bytes, st));
+                        REACH_CUDA(ctx, cudaMemsetAsync(p->s_neg.p, 0, p->s_neg.bytes, st));
+                    } else {
+                        REACH_CUDA(ctx, cudaMemcpyAsync(p->Lbuf[0].p, p->L_snap.p, size_t(mu_pad) * Kp * 8, cudaMemcpyDeviceToDevice, st));
+                        REACH_CUDA(ctx, cudaMemcpyAsync(p->s_pos.p, p->s_snap.p, size_t(mu_pad) * 8, cudaMemcpyDeviceToDevice, st));
+                        REACH_CUDA(ctx, cudaMemcpyAsync(p->s_neg.p, p->s_snap.as<double>() + mu_pad, size_t(mu_pad) * 8, cudaMemcpyDeviceToDevice, st));
+                        REACH_CUDA(ctx, cudaMemcpyAsync(p->carry[0].p, p->carry_snap.p, p->carry_snap.bytes, cudaMemcpyDeviceToDevice, st));
+                    }
+                    cur = 0;
+                    carry_cur = 0;
+                    t = t_snap - 1;                // the loop increment makes it t_snap
+                    continue;
                 }
             }
-            if (oz_now) { cur ^= 1; continue; }
+            if (sen_on) {                          // sentinel rows of pass t + 1 = rows of pass t x block S, FP64, own stream
+                GemmOperands gs{p->Lsh[sen_cur].as<double>(), block(S), Kp, Kp, Kp, 1, round_up(n, 128) / 128};
+                StoreEpi sepi{p->Lsh[1 - sen_cur].as<double>(), Kp, nsen, n};
+                REACH_CUDA(ctx, (launch_cfg(0, gs, sepi, st3)));
+                ++p->launches;
+                sen_cur ^= 1;
+            }
+            cur ^= 1;
+            continue;
         }
         const int dcfg = p->use_oz ? 0 : p->cfg;           // after a fallback: the warp-specialised DMMA kernel
         if (sample) REACH_CUDA(ctx, cudaEventRecord(p->gemm_ev[2 * p->gemm_sampled], st));
@@ -1308,6 +1407,10 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         ++p->gemm_total;
         REACH_TRY(combine_pass(cmb, side, par));
         cur ^= 1;
+    }
+    if (p->use_oz && p->oz_guard && T > 0) {       // the sentinel stream reads the stack and the plan's buffers
+        REACH_CUDA(ctx, cudaEventRecord(p->ev_sen[1], st3));
+        REACH_CUDA(ctx, cudaStreamWaitEvent(st, p->ev_sen[1], 0));
     }
     REACH_TRY(join_side());
     if (T > 0 && T * S < p->nsteps) {
@@ -1425,6 +1528,14 @@ extern "C" int reach_lgg09_plan_path(reach_lgg09_plan* p, int32_t* path, int32_t
     if (guard_max) *guard_max = p->oz_guard_max;
     if (guard_checks) *guard_checks = p->oz_checks;
     if (fallback_pass) *fallback_pass = p->oz_fallback_pass;
+    return REACH_OK;
+}
+
+extern "C" int reach_lgg09_plan_guard(reach_lgg09_plan* p, double* drift_max, int64_t* replay_from, int64_t* replayed_passes) {
+    if (!p) return REACH_EINVAL;
+    if (drift_max) *drift_max = p->oz_drift_max;
+    if (replay_from) *replay_from = p->oz_replay_from;
+    if (replayed_passes) *replayed_passes = p->oz_replayed;
     return REACH_OK;
 }
 

@@ -297,16 +297,19 @@ static __global__ void lgg09_tilesum_packed_kernel(const Lgg09Combine c, const d
 // |d lin| + |d abs|, relative to the largest |lin| + |abs| of that chain and feature in them; the worst ratio is kept with an integer atomicMax (non-negative doubles order
 // like their bit patterns).
 static __global__ void lgg09_guard_kernel(const double* __restrict__ ftot, const double* __restrict__ ftot_ref, int nq,
-                                          int mu_pad, int mu, int b_first, int b_last, unsigned long long* __restrict__ worst) {
+                                          int mu_pad, int mu, int b_first, int b_last, unsigned long long* __restrict__ worst,
+                                          int stride = 1) {
+    // stride > 1: row j of ftot_ref (a sentinel chain) is compared with chain j * stride of ftot
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= mu * nq) return;
     const int j = idx % mu, q = idx / mu;
     double scale = 0.0, err = 0.0;
     for (int b = b_first; b <= b_last; b += (b_last > b_first ? b_last - b_first : 1)) {   // the two sampled blocks
-        const size_t base = ((size_t(b) * nq + q) * 2) * mu_pad + j;
+        const size_t row = ((size_t(b) * nq + q) * 2) * mu_pad;
+        const size_t base = row + j, mbase = row + size_t(j) * stride;
         const double lr = ftot_ref[base], ar = ftot_ref[base + mu_pad];
         scale = fmax(scale, fabs(lr) + fabs(ar));
-        err = fmax(err, fabs(ftot[base] - lr) + fabs(ftot[base + mu_pad] - ar));
+        err = fmax(err, fabs(ftot[mbase] - lr) + fabs(ftot[mbase + mu_pad] - ar));
     }
     double ratio = scale > 0.0 ? err / scale : (err > 0.0 ? 1.0e300 : 0.0);
     if (!(ratio >= 0.0)) ratio = 1.0e300;                  // NaN

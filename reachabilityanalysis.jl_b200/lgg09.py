@@ -224,10 +224,13 @@ class Lgg09Plan:
         gmax, gchecks, fb = C.c_double(), C.c_int64(), C.c_int64()
         self.ctx.check(self.lib.reach_lgg09_plan_path(self.handle, C.byref(path), C.byref(planes), C.byref(gmax),
                                                       C.byref(gchecks), C.byref(fb)))
+        drift, rfrom, rpl = C.c_double(), C.c_int64(), C.c_int64()
+        self.ctx.check(self.lib.reach_lgg09_plan_guard(self.handle, C.byref(drift), C.byref(rfrom), C.byref(rpl)))
         return dict(ms=ms.value, launches=launches.value, time_block=S_.value, tile_m=tm.value,
                     tile_n=tn.value, nchains=mu.value, gemm_ms=gms.value, gemm_launches=gl.value,
                     path={1: "gemm", 2: "chain", 3: "int8", 4: "compact"}[path.value], digit_planes=planes.value,
-                    guard_max=gmax.value, guard_checks=gchecks.value, fallback_pass=fb.value)
+                    guard_max=gmax.value, guard_checks=gchecks.value, fallback_pass=fb.value,
+                    drift_max=drift.value, replay_from=rfrom.value, replayed_passes=rpl.value)
 
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:

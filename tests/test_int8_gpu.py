@@ -177,3 +177,78 @@ def test_lgg09_int8_path_with_invariant_stops_early(ctx):
     a = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, X, wl.V, ctx=ctx, path="int8")
     g = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, X, wl.V, ctx=ctx, path="gemm")
     assert a.nsteps_done == g.nsteps_done
+
+
+def test_guard_failure_at_a_late_pass_replays_from_the_last_verified_pass(ctx, monkeypatch):
+    """A check that fails at pass t >= 64 must not keep the unverified INT8 passes since the last good check: the state
+    kept after that check is restored and every pass since then is recomputed on the FP64 tensor pipe
+    (REACH_OZ_TRIP_AT is the library's test hook: the first check at or after that pass is treated as failed)."""
+    n, nsteps = 520, 140
+    wl = _synthetic(n, nsteps, seed=7)
+    ref = LO.reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, wl.V)
+    monkeypatch.setenv("REACH_OZ_TRIP_AT", "3")          # checks run at passes 0, 1, 64, 128, last: trips at 64
+    plan = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=1)
+    monkeypatch.delenv("REACH_OZ_TRIP_AT")
+    st = plan.stats()
+    assert st["path"] == "int8" and st["fallback_pass"] == 64
+    assert st["replay_from"] == 2 and st["replayed_passes"] == 63        # passes 0 and 1 were verified, 2..64 are redone
+    assert_support_parity(plan.sfmat(), ref)
+    # from pass 2 on the numbers come from the DMMA kernel: they agree with the pure DMMA run far inside the tolerance
+    dmma = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=1, path="gemm")
+    assert_support_parity(plan.sfmat(), dmma.sfmat(), tol=1e-12)
+    # a failure at pass 0 restarts from the initial state: the whole run is FP64 tensor-pipe output
+    monkeypatch.setenv("REACH_OZ_TRIP_AT", "0")
+    again = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=1)
+    monkeypatch.delenv("REACH_OZ_TRIP_AT")
+    st = again.stats()
+    assert st["fallback_pass"] == 0 and st["replay_from"] == 0 and st["replayed_passes"] == 1
+    assert_support_parity(again.sfmat(), dmma.sfmat(), tol=1e-13)
+    # time-blocked run with the side stream active, failure at the last check
+    monkeypatch.setenv("REACH_OZ_TRIP_AT", "65")
+    tb = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, 700, None, wl.V, ctx=ctx, time_block=4)
+    monkeypatch.delenv("REACH_OZ_TRIP_AT")
+    st = tb.stats()
+    assert st["fallback_pass"] == 128 and st["replay_from"] == 65 and st["replayed_passes"] == 64
+    ref700 = LO.reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, 700, wl.V)
+    assert_support_parity(tb.sfmat(), ref700)
+
+
+def _decaying_mode_problem(n=512, slow=0.999, fast=0.7):
+    """Phi = Q diag(lambda) Q' (symmetric) with Q the normalised Hadamard matrix (all entries +-1/sqrt(n)): half the
+    modes decay like slow^k, the others like fast^k.  Omega0 is the segment [-q_f, q_f] along a fast mode, so
+    rho(r_k, Omega0) = |q_f . r_k| = fast^k / sqrt(n) for every box direction, while the rows r_k keep entries of size
+    slow^k: the support value is made of ever smaller parts of its operands."""
+    Q = scipy.linalg.hadamard(n) / np.sqrt(n)
+    lam = np.full(n, slow)
+    lam[n // 2:] = fast
+    Phi = (Q * lam) @ Q.T
+    Phi = 0.5 * (Phi + Phi.T)
+    g = Q[:, n - 1].copy()
+    return Phi, rb.Zonotope(np.zeros(n), g.reshape(n, 1))
+
+
+def test_guard_trips_by_itself_at_a_late_pass_when_the_dynamic_range_grows_with_time(ctx):
+    """Passes 0 and 1 are harmless (the support value is a large part of its operands), by pass 64 the support value is
+    fast^64 ~ 1e-10 of them: the INT8 and the FP64 kernels then differ far above 1e-12 of the feature, the check at
+    pass 64 fails, passes 2..64 are recomputed and the run finishes on the FP64 tensor pipe."""
+    n, nsteps = 512, 100
+    Phi, Om = _decaying_mode_problem(n)
+    dirs = np.hstack([np.eye(n), -np.eye(n)])
+    ref = LO.reach_homog_LGG09(dirs, Om, Phi, nsteps)
+    plan = reach_homog_LGG09(dirs, Om, Phi, nsteps, None, ctx=ctx, time_block=1)
+    st = plan.stats()
+    assert st["path"] == "int8" and st["fallback_pass"] == 64, st
+    assert st["replay_from"] == 2 and st["replayed_passes"] == 63
+    assert_support_parity(plan.sfmat(), ref)
+    dmma = reach_homog_LGG09(dirs, Om, Phi, nsteps, None, ctx=ctx, time_block=1, path="gemm")
+    assert_support_parity(plan.sfmat(), dmma.sfmat(), tol=1e-12)
+
+
+def test_sentinel_chains_report_the_accumulated_drift(ctx):
+    n, nsteps = 520, 300
+    wl = _synthetic(n, nsteps, seed=9)
+    plan = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=2)
+    st = plan.stats()
+    assert st["path"] == "int8" and st["fallback_pass"] == -1 and st["guard_checks"] >= 5
+    assert 0.0 < st["drift_max"] <= 1e-11 and st["replay_from"] == -1 and st["replayed_passes"] == 0
+    assert_support_parity(plan.sfmat(), LO.reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, wl.V))
