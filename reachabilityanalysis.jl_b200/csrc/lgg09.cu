@@ -242,10 +242,16 @@ struct reach_lgg09_plan {
     DevBuf row_pos, row_neg;   // [mu] int
     DevBuf rho_own;        // ndirs x nsteps
     double* rho = nullptr; // rho_own or caller-provided
-    DevBuf checks;         // InvCheck[]
+    // invariant: dual certificates per face (CSR, see first_disjoint_kernel)
+    DevBuf chk_ptr, chk_rows, chk_w, chk_bound;
     int nchecks = 0;
+    int inv_faces = 0, inv_covered = 0, inv_exact = 0;
     DevBuf first_bad;      // unsigned long long
+    unsigned long long* fb_host = nullptr;   // pinned: polled copies of first_bad (early exit of the pass loop)
+    cudaEvent_t ev_fb[2] = {nullptr, nullptr};
     int64_t nsteps_done = 0;
+    int64_t steps_computed = 0;              // steps whose support values the last run produced (== nsteps without early exit)
+    bool synced = false;
     DevBuf phi_cm;         // n x n column-major copy of Phi (source of the transpose)
     // persistent warp-per-chain path (small / sparse Phi)
     bool use_chain = false;
@@ -301,6 +307,8 @@ struct reach_lgg09_plan {
         for (auto e : ev_gemm) if (e) cudaEventDestroy(e);
         for (auto e : ev_comb) if (e) cudaEventDestroy(e);
         for (auto e : ev_sen) if (e) cudaEventDestroy(e);
+        for (auto e : ev_fb) if (e) cudaEventDestroy(e);
+        if (fb_host) cudaFreeHost(fb_host);
         if (st2) cudaStreamDestroy(st2);
         if (st3) cudaStreamDestroy(st3);
         for (auto e : gemm_ev) cudaEventDestroy(e);
@@ -886,41 +894,112 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
         REACH_CUDA(ctx, cudaStreamSynchronize(st));
     }
 
-    // ---- invariant -> support-value checks on template rows ----
+    // ---- invariant -> dual certificates over the template's support values (see first_disjoint_kernel) ----
     p->nchecks = 0;
+    p->inv_faces = p->inv_covered = p->inv_exact = 0;
     if (inv && inv->kind != REACH_INV_NONE) {
-        std::vector<InvCheck> checks;
+        struct Face { std::vector<double> a; double b; };
+        std::vector<Face> faces;
         if (inv->kind == REACH_INV_HALFSPACE) {
             if (!inv->a || !inv->b) return set_error(ctx, REACH_EINVAL, "half-space invariant needs a and b");
-            for (int j = 0; j < ndirs; ++j) {
-                const double* d = dirs + size_t(j) * n;
-                int at = -1;
-                for (int i = 0; i < n; ++i) if (inv->a[i] != 0.0) { at = i; break; }
-                if (at < 0) break;
-                const double lam = -d[at] / inv->a[at];
-                if (!(lam > 0)) continue;
-                bool same = true;
-                for (int i = 0; i < n && same; ++i) same = (d[i] == -lam * inv->a[i]);
-                if (same) checks.push_back({j, +1, -lam, inv->b[0]});     // -rho/lam > b
-            }
+            faces.push_back({std::vector<double>(inv->a, inv->a + n), inv->b[0]});
         } else if (inv->kind == REACH_INV_BOX) {
             if (!inv->a || !inv->b) return set_error(ctx, REACH_EINVAL, "box invariant needs lo and hi");
-            for (int j = 0; j < ndirs; ++j) {
-                const double* d = dirs + size_t(j) * n;
-                int nz = 0, at = -1;
-                for (int i = 0; i < n; ++i) if (d[i] != 0.0) { ++nz; at = i; }
-                if (nz != 1) continue;
-                if (d[at] > 0) checks.push_back({j, -1, d[at], inv->a[at]});   // rho/d_i < lo_i
-                else checks.push_back({j, +1, d[at], inv->b[at]});             // rho/d_i > hi_i
+            for (int i = 0; i < n; ++i) {
+                if (inv->a[i] > inv->b[i]) return set_error(ctx, REACH_EINVAL, "box invariant: lo[%d] > hi[%d]", i, i);
+                if (std::isfinite(inv->b[i])) { Face f{std::vector<double>(n, 0.0), inv->b[i]}; f.a[i] = 1.0; faces.push_back(std::move(f)); }
+                if (std::isfinite(inv->a[i])) { Face f{std::vector<double>(n, 0.0), -inv->a[i]}; f.a[i] = -1.0; faces.push_back(std::move(f)); }
             }
+        } else if (inv->kind == REACH_INV_POLYHEDRON) {
+            if (!inv->a || !inv->b || inv->m < 1) return set_error(ctx, REACH_EINVAL, "polyhedral invariant needs m >= 1 faces, A and b");
+            for (int f = 0; f < inv->m; ++f)
+                faces.push_back({std::vector<double>(inv->a + size_t(f) * n, inv->a + size_t(f + 1) * n), inv->b[f]});
         } else {
             return set_error(ctx, REACH_EUNSUPPORTED, "invariant kind %d is not supported on the device", inv->kind);
         }
-        p->nchecks = int(checks.size());
+        // axis rows of the template: d_j = c e_i
+        std::vector<int> pos_row(n, -1), neg_row(n, -1);
+        std::vector<double> pos_c(n, 0.0), neg_c(n, 0.0);
+        bool pure_box = true;
+        for (int j = 0; j < ndirs; ++j) {
+            const double* d = dirs + size_t(j) * n;
+            int nz = 0, at = -1;
+            for (int i = 0; i < n; ++i) if (d[i] != 0.0) { ++nz; at = i; }
+            if (nz != 1) { pure_box = false; continue; }
+            if (d[at] > 0 && pos_row[at] < 0) { pos_row[at] = j; pos_c[at] = d[at]; }
+            if (d[at] < 0 && neg_row[at] < 0) { neg_row[at] = j; neg_c[at] = -d[at]; }
+        }
+        for (int i = 0; i < n && pure_box; ++i) pure_box = pos_row[i] >= 0 && neg_row[i] >= 0;
+        std::vector<int> ptr{0}, rows;
+        std::vector<double> w, bound;
+        int covered = 0, exact_faces = 0;
+        for (const Face& f : faces) {
+            int at = -1, nnz = 0;
+            for (int i = 0; i < n; ++i) {
+                if (!std::isfinite(f.a[i])) return set_error(ctx, REACH_EINVAL, "invariant normal is not finite");
+                if (f.a[i] != 0.0) { if (at < 0) at = i; ++nnz; }
+            }
+            if (at < 0 || std::isnan(f.b)) return set_error(ctx, REACH_EINVAL, "invariant face with a zero normal or NaN offset");
+            if (f.b == INFINITY) { ++covered; ++exact_faces; continue; }          // never violated
+            bool done = false;
+            // (1) -a is a positive multiple of a template direction: d_j = -lam a
+            for (int j = 0; j < ndirs && !done; ++j) {
+                const double* d = dirs + size_t(j) * n;
+                const double lam = -d[at] / f.a[at];
+                if (!(lam > 0)) continue;
+                bool same = true;
+                for (int i = 0; i < n && same; ++i) same = (d[i] == -lam * f.a[i]);
+                if (!same) continue;
+                rows.push_back(j); w.push_back(1.0 / lam);
+                done = true;
+                ++exact_faces;
+            }
+            // (2) the +-e_i rows of the template: -a = sum_i max(-a_i,0) e_i + max(a_i,0) (-e_i)
+            if (!done) {
+                bool ok = true;
+                for (int i = 0; i < n && ok; ++i)
+                    if (f.a[i] > 0) ok = neg_row[i] >= 0; else if (f.a[i] < 0) ok = pos_row[i] >= 0;
+                if (ok) {
+                    for (int i = 0; i < n; ++i) {
+                        if (f.a[i] > 0) { rows.push_back(neg_row[i]); w.push_back(f.a[i] / neg_c[i]); }
+                        else if (f.a[i] < 0) { rows.push_back(pos_row[i]); w.push_back(-f.a[i] / pos_c[i]); }
+                    }
+                    done = true;
+                    if (pure_box || nnz == 1) ++exact_faces;
+                }
+            }
+            if (!done) continue;                                                  // no certificate for this face
+            ptr.push_back(int(rows.size()));
+            bound.push_back(-f.b);
+            ++covered;
+        }
+        p->inv_faces = int(faces.size());
+        p->inv_covered = covered;
+        // equivalent to the reference's _isdisjoint(X, set(F[k])) (an exact polyhedral test): one face with an exact
+        // certificate; several faces only when both sets are boxes (separable axis by axis)
+        p->inv_exact = (covered == p->inv_faces && exact_faces == p->inv_faces &&
+                        (p->inv_faces == 1 || (inv->kind == REACH_INV_BOX && pure_box))) ? 1 : 0;
+        p->nchecks = int(bound.size());
+        if (covered == 0)
+            return set_error(ctx, REACH_EUNSUPPORTED,
+                             "the invariant cannot be tested on the device with this template: no face normal is a template "
+                             "direction and the template lacks the +-e_i rows its normals need (the reference's exact test is an LP "
+                             "per step); add the invariant's normals to the template or check disjointness on the fetched values");
         if (p->nchecks) {
-            REACH_TRY(p->checks.alloc(ctx, checks.size() * sizeof(InvCheck), false));
-            REACH_CUDA(ctx, cudaMemcpyAsync(p->checks.p, checks.data(), checks.size() * sizeof(InvCheck), cudaMemcpyHostToDevice, st));
+            auto ship = [&](DevBuf& b, const void* src, size_t bytes) -> int {
+                REACH_TRY(b.alloc(ctx, bytes, false));
+                REACH_CUDA(ctx, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, st));
+                return REACH_OK;
+            };
+            REACH_TRY(ship(p->chk_ptr, ptr.data(), ptr.size() * sizeof(int)));
+            REACH_TRY(ship(p->chk_rows, rows.data(), rows.size() * sizeof(int)));
+            REACH_TRY(ship(p->chk_w, w.data(), w.size() * sizeof(double)));
+            REACH_TRY(ship(p->chk_bound, bound.data(), bound.size() * sizeof(double)));
             REACH_CUDA(ctx, cudaStreamSynchronize(st));
+            if (!p->fb_host) {
+                REACH_CUDA(ctx, cudaMallocHost(&p->fb_host, 2 * sizeof(unsigned long long)));
+                for (auto& e : p->ev_fb) REACH_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            }
         }
     }
     p->uploaded = true;

@@ -1007,23 +1007,30 @@ static __global__ void max_over_steps_kernel(const double* __restrict__ rho, int
     if (amax) amax[j] = at;
 }
 
-// Early termination (reach_homog.jl:418, reach_inhomog.jl:210): first step whose template
-// reach-set is certified disjoint from the invariant by one of its own support values.
-struct InvCheck {
-    int row;        // output row whose support value is tested
-    int sense;      // +1: violated if value > bound; -1: violated if value < bound
-    double div;     // value = rho / div
-    double bound;
+// Early termination (reach_homog.jl:418, reach_inhomog.jl:210): first step whose template reach-set
+// P_k = {x : d_j.x <= rho_j[k]} is certified disjoint from the invariant.  A face {a.x <= b} of the invariant is
+// disjoint from P_k iff min_{x in P_k} a.x > b; every lambda >= 0 with sum_j lambda_j d_j = -a gives the lower bound
+// min a.x >= -sum_j lambda_j rho_j[k] (weak duality), so "sum_j lambda_j rho_j[k] < -b" certifies it.  The host picks
+// lambda: one template row (-a is a positive multiple of it) or the +-e_i rows of a box template -- both exact there,
+// because the support values are attained (rho_j[k] = rho(d_j, Omega_k) and Omega_k is inside P_k).
+// Checks are stored in CSR form: check i = rows/weights [ptr[i], ptr[i+1]), bound[i] = -b.
+struct InvChecks {
+    const int* ptr;
+    const int* rows;
+    const double* w;
+    const double* bound;
+    int n;
 };
-static __global__ void first_disjoint_kernel(const double* __restrict__ rho, int ndirs, long long nsteps,
-                                      const InvCheck* __restrict__ checks, int nchecks,
-                                      unsigned long long* __restrict__ first) {
-    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (k >= nsteps) return;
+static __global__ void first_disjoint_kernel(const double* __restrict__ rho, int ndirs, long long k0, long long k1,
+                                             const InvChecks c, unsigned long long* __restrict__ first) {
+    const long long k = k0 + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (k >= k1) return;
+    const double* col = rho + size_t(k) * ndirs;
     bool bad = false;
-    for (int i = 0; i < nchecks && !bad; ++i) {
-        const double v = rho[size_t(k) * ndirs + checks[i].row] / checks[i].div;
-        bad = checks[i].sense > 0 ? (v > checks[i].bound) : (v < checks[i].bound);
+    for (int i = 0; i < c.n && !bad; ++i) {
+        double acc = 0.0;
+        for (int e = c.ptr[i]; e < c.ptr[i + 1]; ++e) acc = fma(c.w[e], col[c.rows[e]], acc);
+        bad = acc < c.bound[i];
     }
     if (bad) atomicMin(first, (unsigned long long)k);
 }

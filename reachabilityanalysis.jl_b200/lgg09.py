@@ -134,7 +134,7 @@ class Lgg09Plan:
         if S.dim(Omega0) != n:
             raise ValueError("Ω₀ has dimension %d, expected %d" % (S.dim(Omega0), n))
         om = to_c(flatten(Omega0, Phi), n)
-        v = to_c(flatten(V, Phi), n) if V is not None else None
+        v = to_c(flatten(V, None), n) if V is not None else None   # never the r_{k+1} shortcut: rho(r_k, V) is evaluated at r_k
         if v is not None and v.expr.nalt != 1:
             raise NotImplementedError("input sets containing a convex hull are not supported")
         inv, keep = invariant_to_c(X, n)
@@ -266,7 +266,7 @@ class Lgg09BatchPlan:
         self.n, self.ndirs, self.nsteps, self.nsplits = n, dirs.shape[1], int(nsteps), len(Omega0s)
         oms = [to_c(flatten(Om, Phi), n) for Om in Omega0s]
         arr = (L.reach_setexpr * len(oms))(*[o.expr for o in oms])
-        v = to_c(flatten(V, Phi), n) if V is not None else None
+        v = to_c(flatten(V, None), n) if V is not None else None   # never the r_{k+1} shortcut: rho(r_k, V) is evaluated at r_k
         if v is not None and v.expr.nalt != 1:
             raise NotImplementedError("input sets containing a convex hull are not supported")
         self._keep = (Phi, dirs, oms, arr, v)
