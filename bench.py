@@ -448,6 +448,45 @@ def other_configs_leg(ctx, torch, peak_tf, no_cpu):
             info["max_scaled_diff_vs_gpu"] = scaled_diff(got[:, :sample], ref)
             ent["cpu_baseline"] = info
         out[key] = ent
+    # early termination (reach_inhomog.jl:198-215): Building with an invariant x_i <= b that is first violated near the
+    # end of the transient (the latest step at which any lower bound of the box hull peaks); time saved = full run - this
+    try:
+        wl = W.building_c1()
+        n = wl.n
+        full = Lgg09Plan(ctx, n, 2 * n, wl.nsteps)
+        full.upload(wl.Phi, wl.dirs, wl.Omega0, wl.V)
+        full.run()
+        ref = full.sfmat()
+        lo = -ref[n:, :]
+        i = int(lo.argmax(axis=1).argmax())
+        kpk = int(lo[i].argmax())
+        b = float(0.5 * (lo[i, :max(1, kpk - 30)].max() + lo[i, kpk]))
+        e = np.zeros(n)
+        e[i] = 1.0
+        res = {}
+        for name, S_ in (("auto_time_block", 0), ("time_block_64", 64)):
+            f2 = Lgg09Plan(ctx, n, 2 * n, wl.nsteps, time_block=S_)
+            f2.upload(wl.Phi, wl.dirs, wl.Omega0, wl.V)
+            inv = Lgg09Plan(ctx, n, 2 * n, wl.nsteps, time_block=S_)
+            inv.upload(wl.Phi, wl.dirs, wl.Omega0, wl.V, S.HalfSpace(e, b))
+            tf, ti = [], []
+            for _ in range(4):
+                f2.run()
+                tf.append(f2.stats()["ms"])
+                inv.run()
+                ti.append(inv.stats()["ms"])
+            info = inv.invariant_info()
+            res[name] = {"time_block": inv.stats()["time_block"], "full_run_ms": min(tf[1:]), "with_invariant_ms": min(ti[1:]),
+                         "nsteps_done": inv.nsteps_done, "steps_computed": info["steps_computed"], "exact_test": info["exact"],
+                         "launches": inv.stats()["launches"], "full_run_launches": f2.stats()["launches"]}
+            f2.close()
+            inv.close()
+        out["C1_invariant_early_exit"] = {"workload": "Building BLDF01 LGG09 box template, invariant x_%d <= %.6g (first violated at step %d of %d)"
+                                          % (i + 1, b, res["time_block_64"]["nsteps_done"], wl.nsteps), **res,
+                                          "note": "the pass loop stops launching once a step is certified disjoint (host polls the flag two passes behind the device)"}
+        full.close()
+    except Exception as ex:                      # a diagnostic leg must not take the bench line down
+        out["C1_invariant_early_exit"] = {"error": repr(ex)}
     A, B, X0, U0 = W.building_sets()
     U = D.normalize_input(B, U0)
     ivps = [D.forward(A, X, 0.002, U) for X in S.split(X0, [2] * 8 + [1] * 40)]

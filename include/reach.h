@@ -94,20 +94,33 @@ typedef struct {
     const reach_term* terms;    /* sum(alt_len) entries                                        */
 } reach_setexpr;
 
-/* Invariant for the early-terminating variants (the `X` argument of reach_*_LGG09!):
- *   REACH_INV_NONE      Universe
- *   REACH_INV_HALFSPACE {x : a.x <= b}
- *   REACH_INV_BOX       [lo, hi]
- * Disjointness of the template reach-set from X is decided from the template's own support
- * values (exact when the needed +-a / +-e_i directions are in the template; otherwise no step
- * is ever reported disjoint). */
-#define REACH_INV_NONE      0
-#define REACH_INV_HALFSPACE 1
-#define REACH_INV_BOX       2
+/* Invariant for the early-terminating variants (the `X` argument of reach_*_LGG09!, reach_homog.jl:382-424,
+ * reach_inhomog.jl:174-218: `_isdisjoint(X, set(F[k])) && break`):
+ *   REACH_INV_NONE       Universe
+ *   REACH_INV_HALFSPACE  {x : a.x <= b}                       a: normal (n), b: offset (1)
+ *   REACH_INV_BOX        [lo, hi]                             a: lo (n), b: hi (n); +-inf allowed
+ *   REACH_INV_POLYHEDRON {x : A x <= b}, m faces              a: A row-major m x n (face i = a + i*n), b: offsets (m)
+ * The template reach-set is P_k = {x : d_j.x <= rho_j[k]}.  A face {a.x <= b} is disjoint from P_k iff
+ * min_{P_k} a.x > b.  The device certifies this from the template's own support values by weak duality
+ * (sum_j lambda_j rho_j[k] < -b for a fixed lambda >= 0 with sum_j lambda_j d_j = -a), with lambda chosen at upload:
+ *   (1) -a is a positive multiple of a template direction          -> exact for that face;
+ *   (2) the +-e_i rows of the template that a's non-zeros need    -> exact when the template is a box template
+ *       (only +-e_i directions, all of them) or a has one non-zero, otherwise sufficient (the box hull of P_k);
+ *   faces with neither are not tested.  If NO face can be tested, plan_upload fails with REACH_EUNSUPPORTED.
+ * The result equals the reference's exact polyhedral test when reach_lgg09_plan_invariant_info reports exact = 1:
+ * a single half-space with an exact certificate, or a box invariant with a box template.  In the other cases a step
+ * is only reported disjoint when it really is (never a false stop), but the run may stop later than the reference.
+ * The run stops launching device work once a step is certified disjoint (the triggering step is dropped, like
+ * `resize!(F, k - 1)`). */
+#define REACH_INV_NONE       0
+#define REACH_INV_HALFSPACE  1
+#define REACH_INV_BOX        2
+#define REACH_INV_POLYHEDRON 3
 typedef struct {
     int32_t kind;
-    const double* a;   /* HALFSPACE: normal (n)      BOX: lo (n) */
-    const double* b;   /* HALFSPACE: offset (1)      BOX: hi (n) */
+    int32_t m;         /* POLYHEDRON: number of faces (ignored otherwise; sits in what was padding) */
+    const double* a;   /* HALFSPACE: normal (n)      BOX: lo (n)      POLYHEDRON: A, row-major m x n */
+    const double* b;   /* HALFSPACE: offset (1)      BOX: hi (n)      POLYHEDRON: offsets (m)        */
 } reach_invariant;
 
 typedef struct {
@@ -178,6 +191,12 @@ int  reach_lgg09_plan_stats(reach_lgg09_plan* p, double* ms, int64_t* launches,
  * Any pointer may be NULL. */
 int  reach_lgg09_plan_path(reach_lgg09_plan* p, int32_t* path, int32_t* digit_planes, double* guard_max,
                            int64_t* guard_checks, int64_t* fallback_pass);
+/* Invariant coverage of the uploaded plan: *faces half-spaces make up the invariant, *covered of them have a device
+ * certificate, *exact = 1 when the device test is equivalent to the reference's `_isdisjoint(X, set(F[k]))`.
+ * *steps_computed (after a run): time steps whose support values were produced before the run stopped launching
+ * (== nsteps without an early exit; nsteps_done <= steps_computed).  Any pointer may be NULL. */
+int  reach_lgg09_plan_invariant_info(reach_lgg09_plan* p, int32_t* faces, int32_t* covered, int32_t* exact,
+                                     int64_t* steps_computed);
 /* More on the guard of path 3.  Checks run at passes 0, 1, every 64th and the last.  A check compares (a) the pass's
  * features on the INT8 kernel and on the DMMA kernel from the same direction rows (tolerance 1e-12) and (b) the INT8
  * path's features with those of up to 128 sentinel chains that were propagated on the FP64 tensor pipe since pass 0

@@ -58,7 +58,7 @@ def reach_inhomog_LGG09(dirs, Omega0, Phi, nsteps, U):
     return out
 
 
-def reach_LGG09_invariant(dirs, Omega0, Phi, nsteps, X, U=None):
+def reach_LGG09_invariant(dirs, Omega0, Phi, nsteps, X, U=None, exact=False):
     """Invariant variants (reach_homog.jl:382-424, reach_inhomog.jl:174-218) for the invariants
     this build supports on the device: a HalfSpace a·x ≤ b or a Hyperrectangle.  The template
     reach-set F[k] = {x : dirs_j·x ≤ ρℓ[j,k]} is declared disjoint from X when a template
@@ -67,7 +67,8 @@ def reach_LGG09_invariant(dirs, Omega0, Phi, nsteps, X, U=None):
        HalfSpace:      some direction j == −a/‖…‖ scaled:  −ρ(−a, F) > b
        Hyperrectangle: some i with  −ρ(−e_i, F) > hi_i  or  ρ(e_i, F) < lo_i.
     Returns (ρℓ[:, :k_stop], k_stop): the step that triggered the break is computed but dropped
-    (`resize!(F, k - 1)`, reach_homog.jl:421-423)."""
+    (`resize!(F, k - 1)`, reach_homog.jl:421-423).  exact=True uses the reference's own exact polyhedral test
+    (template_disjoint_lp, one LP per step) instead of the template-row certificates."""
     PhiT = np.ascontiguousarray(Phi.T)
     R = np.array(dirs, dtype=np.float64, copy=True)
     m = R.shape[1]
@@ -79,10 +80,44 @@ def reach_LGG09_invariant(dirs, Omega0, Phi, nsteps, X, U=None):
         if U is not None:
             s = s + rho(R, U)
         R = PhiT @ R
-        if template_disjoint(dirs, out[:, k], X):
+        if (template_disjoint_lp if exact else template_disjoint)(dirs, out[:, k], X):
             break
         k += 1
     return out[:, :k], k
+
+
+def _faces(X):
+    k = _name(X)
+    if k == "HalfSpace":
+        return [(np.asarray(X.a, dtype=float), float(X.b))]
+    if k == "HPolyhedron":
+        return [(np.asarray(h.a, dtype=float), float(h.b)) for h in X.constraints]
+    if k in ("Hyperrectangle", "BallInf"):
+        n = len(X.center)
+        r = X.radius if k == "Hyperrectangle" else np.full(n, X.radius)
+        out = []
+        for i in range(n):
+            e = np.zeros(n)
+            e[i] = 1.0
+            out.append((e, X.center[i] + r[i]))
+            out.append((-e, -(X.center[i] - r[i])))
+        return out
+    raise TypeError("invariant %s not supported" % k)
+
+
+def template_disjoint_lp(dirs, sf, X):
+    """The reference's test itself: `_isdisjoint(X, set(F[k]))` (reach_inhomog.jl:210) with the default method is the
+    exact emptiness of {x : dirs_j.x <= sf_j} ∩ X, which LazySets decides with a linear program (for a single half-space:
+    min a.x over the polytope > b).  Here: one LP feasibility problem (SciPy / HiGHS)."""
+    if _name(X) == "Universe":
+        return False
+    from scipy.optimize import linprog
+    faces = _faces(X)
+    A = np.vstack([np.asarray(dirs, dtype=float).T] + [a[None, :] for a, _ in faces])
+    b = np.concatenate([np.asarray(sf, dtype=float), [bb for _, bb in faces]])
+    keep = np.isfinite(b)
+    res = linprog(np.zeros(A.shape[1]), A_ub=A[keep], b_ub=b[keep], bounds=[(None, None)] * A.shape[1], method="highs")
+    return res.status == 2            # infeasible: the sets are disjoint
 
 
 def template_disjoint(dirs, sf, X):

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libreach_cuda.so")
 
 REACH_OK, REACH_EINVAL, REACH_ECUDA, REACH_ENOMEM, REACH_EUNSUPPORTED, REACH_ESTATE = 0, -1, -2, -3, -4, -5
 REACH_TERM_BOX, REACH_TERM_ZONO = 0, 1
-REACH_INV_NONE, REACH_INV_HALFSPACE, REACH_INV_BOX = 0, 1, 2
+REACH_INV_NONE, REACH_INV_HALFSPACE, REACH_INV_BOX, REACH_INV_POLYHEDRON = 0, 1, 2, 3
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -32,7 +32,7 @@ class reach_setexpr(C.Structure):
 
 
 class reach_invariant(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("a", c_double_p), ("b", c_double_p)]
+    _fields_ = [("kind", C.c_int32), ("m", C.c_int32), ("a", c_double_p), ("b", c_double_p)]
 
 
 class reach_lgg09_opts(C.Structure):
@@ -70,6 +70,7 @@ SIGNATURES = {
     "reach_lgg09_plan_stats": (C.c_int, [C.c_void_p, c_double_p, c_int64_p, c_int32_p, c_int32_p,
                                          c_int32_p, c_int32_p, c_double_p, c_int64_p]),
     "reach_lgg09_plan_path": (C.c_int, [C.c_void_p, c_int32_p, c_int32_p, c_double_p, c_int64_p, c_int64_p]),
+    "reach_lgg09_plan_invariant_info": (C.c_int, [C.c_void_p, c_int32_p, c_int32_p, c_int32_p, c_int64_p]),
     "reach_lgg09_plan_guard": (C.c_int, [C.c_void_p, c_double_p, c_int64_p, c_int64_p]),
     "reach_lgg09_plan_destroy": (None, [C.c_void_p]),
     "reach_lgg09_batch_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, c_double_p, c_double_p,

@@ -1029,6 +1029,20 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     p->gemm_sampled = 0;
 
     REACH_CUDA(ctx, cudaEventRecord(p->ev0, st));
+    p->synced = false;
+    p->steps_computed = p->nsteps;
+    const InvChecks ichk{p->chk_ptr.as<int>(), p->chk_rows.as<int>(), p->chk_w.as<double>(), p->chk_bound.as<double>(), p->nchecks};
+    // first step in [k0, k1) whose reach-set is certified disjoint from the invariant (atomicMin into first_bad)
+    auto disjoint_scan = [&](long long k0, long long k1, cudaStream_t s) -> int {
+        if (p->nchecks <= 0 || k1 <= k0) return REACH_OK;
+        const int th = 128;
+        first_disjoint_kernel<<<unsigned((k1 - k0 + th - 1) / th), th, 0, s>>>(p->rho, p->ndirs, k0, k1, ichk,
+                                                                                p->first_bad.as<unsigned long long>());
+        REACH_CUDA(ctx, cudaGetLastError());
+        ++p->launches;
+        return REACH_OK;
+    };
+    if (p->nchecks > 0) REACH_CUDA(ctx, cudaMemsetAsync(p->first_bad.p, 0xFF, sizeof(unsigned long long), st));
 
     if (p->use_compact) {
         Lgg09Compact c{};
@@ -1057,15 +1071,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         c.row_neg = p->row_neg.as<int>();
         c.rho = p->rho;
         REACH_TRY(launch_compact(ctx, p->cp_G, p->cp_ne, c, p->prog.dev.qV >= 0, st, p->launches));
-        if (p->nchecks > 0) {
-            REACH_CUDA(ctx, cudaMemsetAsync(p->first_bad.p, 0xFF, sizeof(unsigned long long), st));
-            const int th = 256;
-            const unsigned blocks = unsigned((p->nsteps + th - 1) / th);
-            first_disjoint_kernel<<<blocks, th, 0, st>>>(p->rho, p->ndirs, p->nsteps, p->checks.as<InvCheck>(),
-                                                          p->nchecks, p->first_bad.as<unsigned long long>());
-            REACH_CUDA(ctx, cudaGetLastError());
-            ++p->launches;
-        }
+        REACH_TRY(disjoint_scan(0, p->nsteps, st));
         REACH_CUDA(ctx, cudaEventRecord(p->ev1, st));
         p->ran = true;
         return REACH_OK;
@@ -1104,15 +1110,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
                     double(h[0]) / p->nsteps, double(h[1]) / p->nsteps, double(h[2]) / p->nsteps, double(h[3]) / p->nsteps);
         }
         ++p->launches;
-        if (p->nchecks > 0) {
-            REACH_CUDA(ctx, cudaMemsetAsync(p->first_bad.p, 0xFF, sizeof(unsigned long long), st));
-            const int th = 256;
-            const unsigned blocks = unsigned((p->nsteps + th - 1) / th);
-            first_disjoint_kernel<<<blocks, th, 0, st>>>(p->rho, p->ndirs, p->nsteps, p->checks.as<InvCheck>(),
-                                                          p->nchecks, p->first_bad.as<unsigned long long>());
-            REACH_CUDA(ctx, cudaGetLastError());
-            ++p->launches;
-        }
+        REACH_TRY(disjoint_scan(0, p->nsteps, st));
         REACH_CUDA(ctx, cudaEventRecord(p->ev1, st));
         p->ran = true;
         return REACH_OK;
@@ -1325,13 +1323,33 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
             }
         return REACH_OK;
     };
+    // Early exit (reach_inhomog.jl:198-215: `_isdisjoint(X, set(F[k])) && break`): every pass scans the steps it emitted
+    // and copies the "first disjoint step" word to pinned host memory; the host reads the copy of pass t-2 before it
+    // launches pass t, so it stays two passes ahead of the device (no pipeline stall) and stops launching as soon as a
+    // step has been certified disjoint.
+    bool fb_pending[2] = {false, false};
+    bool stopped = false;
+    if (p->nchecks > 0) p->fb_host[0] = p->fb_host[1] = ~0ull;
+    auto scan_and_poll = [&](long long k0, long long k1, cudaStream_t s, int slot) -> int {
+        if (p->nchecks <= 0) return REACH_OK;
+        REACH_TRY(disjoint_scan(k0, std::min<long long>(k1, p->nsteps), s));
+        REACH_CUDA(ctx, cudaMemcpyAsync(&p->fb_host[slot], p->first_bad.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        REACH_CUDA(ctx, cudaEventRecord(p->ev_fb[slot], s));
+        fb_pending[slot] = true;
+        return REACH_OK;
+    };
     auto combine_pass = [&](const Lgg09Combine& c, bool side, int par) -> int {
-        if (!side) return combine(c, st);
-        REACH_CUDA(ctx, cudaEventRecord(p->ev_gemm[par], st));
-        REACH_CUDA(ctx, cudaStreamWaitEvent(st2, p->ev_gemm[par], 0));
-        REACH_TRY(combine(c, st2));
-        REACH_CUDA(ctx, cudaEventRecord(p->ev_comb[par], st2));
-        side_busy[par] = true;
+        cudaStream_t cs = side ? st2 : st;
+        if (side) {
+            REACH_CUDA(ctx, cudaEventRecord(p->ev_gemm[par], st));
+            REACH_CUDA(ctx, cudaStreamWaitEvent(st2, p->ev_gemm[par], 0));
+        }
+        REACH_TRY(combine(c, cs));
+        REACH_TRY(scan_and_poll(c.k0, c.k0 + S, cs, par));
+        if (side) {
+            REACH_CUDA(ctx, cudaEventRecord(p->ev_comb[par], st2));
+            side_busy[par] = true;
+        }
         return REACH_OK;
     };
     // ---- guard state of the digit-plane path ----
@@ -1368,6 +1386,15 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     for (int64_t t = 0; t < T; ++t) {
         const int b_lo = t == 0 ? 0 : 1;
         const int par = int(t & 1);
+        if (fb_pending[par]) {                     // the invariant scan of pass t-2
+            REACH_CUDA(ctx, cudaEventSynchronize(p->ev_fb[par]));
+            fb_pending[par] = false;
+            if (p->fb_host[par] != ~0ull) {
+                stopped = true;
+                p->steps_computed = std::min<int64_t>(p->nsteps, t * int64_t(S));
+                break;
+            }
+        }
         {
             double* fp = fp_base + (overlap ? size_t(par) * p->fp_stride : 0);
             oepi.featpart = fp; epi.featpart = fp; pepi.featpart = fp; cmb.featpart = fp;
@@ -1456,6 +1483,12 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
                     }
                     cur = 0;
                     carry_cur = 0;
+                    if (p->nchecks > 0) {          // the invariant scans of the discarded passes are void
+                        REACH_CUDA(ctx, cudaMemsetAsync(p->first_bad.p, 0xFF, sizeof(unsigned long long), st));
+                        REACH_TRY(disjoint_scan(0, t_snap * int64_t(S), st));
+                        fb_pending[0] = fb_pending[1] = false;
+                        p->fb_host[0] = p->fb_host[1] = ~0ull;
+                    }
                     t = t_snap - 1;                // the loop increment makes it t_snap
                     continue;
                 }
@@ -1492,22 +1525,14 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         REACH_CUDA(ctx, cudaStreamWaitEvent(st, p->ev_sen[1], 0));
     }
     REACH_TRY(join_side());
-    if (T > 0 && T * S < p->nsteps) {
+    if (!stopped && T > 0 && T * S < p->nsteps) {
         // one step left whose support values only need the carried features of r_{T S}
         cmb.b_lo = 1; cmb.b_hi = 0; cmb.has_carry = 1; cmb.tail = 1; cmb.k0 = T * S;
         REACH_TRY(combine(cmb, st));
+        REACH_TRY(disjoint_scan(T * int64_t(S), p->nsteps, st));
     }
 
-    // ---- invariant: first step certified disjoint ----
-    if (p->nchecks > 0) {
-        REACH_CUDA(ctx, cudaMemsetAsync(p->first_bad.p, 0xFF, sizeof(unsigned long long), st));
-        const int th = 256;
-        const unsigned blocks = unsigned((p->nsteps + th - 1) / th);
-        first_disjoint_kernel<<<blocks, th, 0, st>>>(p->rho, p->ndirs, p->nsteps, p->checks.as<InvCheck>(),
-                                                      p->nchecks, p->first_bad.as<unsigned long long>());
-        REACH_CUDA(ctx, cudaGetLastError());
-        ++p->launches;
-    }
+    if (p->nchecks > 0 && T == 0) REACH_TRY(disjoint_scan(0, p->nsteps, st));
     REACH_CUDA(ctx, cudaEventRecord(p->ev1, st));
     p->ran = true;
     return REACH_OK;
@@ -1529,12 +1554,13 @@ extern "C" int reach_lgg09_plan_sync(reach_lgg09_plan* p) {
         acc += t;
     }
     p->gemm_ms = p->gemm_sampled ? acc / p->gemm_sampled : 0.0;   // mean per launch
-    p->nsteps_done = p->nsteps;
+    p->nsteps_done = p->steps_computed;
     if (p->nchecks > 0) {
         unsigned long long fb = 0;
         REACH_CUDA(ctx, cudaMemcpy(&fb, p->first_bad.p, sizeof(fb), cudaMemcpyDeviceToHost));
-        if (fb != ~0ull && int64_t(fb) < p->nsteps) p->nsteps_done = int64_t(fb);
+        if (fb != ~0ull && int64_t(fb) < p->nsteps_done) p->nsteps_done = int64_t(fb);
     }
+    p->synced = true;
     return REACH_OK;
 }
 
@@ -1556,6 +1582,7 @@ extern "C" int reach_lgg09_plan_fetch(reach_lgg09_plan* p, int64_t step0, int64_
 extern "C" int reach_lgg09_plan_nsteps_done(reach_lgg09_plan* p, int64_t* out) {
     if (!p || !out) return REACH_EINVAL;
     if (!p->ran) return set_error(p->ctx, REACH_ESTATE, "nsteps_done before plan_run");
+    if (!p->synced) REACH_TRY(reach_lgg09_plan_sync(p));
     *out = p->nsteps_done;
     return REACH_OK;
 }
@@ -1566,12 +1593,13 @@ extern "C" int reach_lgg09_plan_max_over_steps(reach_lgg09_plan* p, double* max_
     if (!p->ran) return set_error(ctx, REACH_ESTATE, "max_over_steps before plan_run");
     if (!max_host) return set_error(ctx, REACH_EINVAL, "max_host is NULL");
     REACH_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!p->synced) REACH_TRY(reach_lgg09_plan_sync(p));          // nsteps_done is only known after the run has finished
     DevBuf vmax, amax;
     REACH_TRY(vmax.alloc(ctx, sizeof(double) * p->ndirs, false));
     REACH_TRY(amax.alloc(ctx, sizeof(long long) * p->ndirs, false));
     const int th = 128;
     max_over_steps_kernel<<<(p->ndirs + th - 1) / th, th, 0, ctx->stream>>>(
-        p->rho, p->ndirs, p->nsteps_done > 0 ? p->nsteps_done : p->nsteps, vmax.as<double>(), amax.as<long long>());
+        p->rho, p->ndirs, p->nsteps_done, vmax.as<double>(), amax.as<long long>());   // empty flowpipe: -inf, argmax -1
     REACH_CUDA(ctx, cudaGetLastError());
     REACH_CUDA(ctx, cudaMemcpyAsync(max_host, vmax.p, sizeof(double) * p->ndirs, cudaMemcpyDeviceToHost, ctx->stream));
     if (argmax_host) {
@@ -1610,6 +1638,16 @@ extern "C" int reach_lgg09_plan_path(reach_lgg09_plan* p, int32_t* path, int32_t
     return REACH_OK;
 }
 
+extern "C" int reach_lgg09_plan_invariant_info(reach_lgg09_plan* p, int32_t* faces, int32_t* covered, int32_t* exact,
+                                               int64_t* steps_computed) {
+    if (!p) return REACH_EINVAL;
+    if (faces) *faces = p->inv_faces;
+    if (covered) *covered = p->inv_covered;
+    if (exact) *exact = p->inv_exact;
+    if (steps_computed) *steps_computed = p->ran ? p->steps_computed : 0;
+    return REACH_OK;
+}
+
 extern "C" int reach_lgg09_plan_guard(reach_lgg09_plan* p, double* drift_max, int64_t* replay_from, int64_t* replayed_passes) {
     if (!p) return REACH_EINVAL;
     if (drift_max) *drift_max = p->oz_drift_max;
@@ -1631,7 +1669,7 @@ extern "C" int reach_lgg09(reach_ctx* ctx, int n, int ndirs, int64_t nsteps, con
     if (rc == REACH_OK) rc = reach_lgg09_plan_run(p);
     if (rc == REACH_OK) rc = reach_lgg09_plan_sync(p);
     auto t2 = now();
-    if (rc == REACH_OK && rho_host) rc = reach_lgg09_plan_fetch(p, 0, nsteps, rho_host);
+    if (rc == REACH_OK && rho_host && p->nsteps_done > 0) rc = reach_lgg09_plan_fetch(p, 0, p->nsteps_done, rho_host);
     if (rc == REACH_OK && nsteps_done) *nsteps_done = p->nsteps_done;
     auto t3 = now();
     reach_lgg09_plan_destroy(p);

@@ -175,8 +175,16 @@ class Lgg09Plan:
 
     def sfmat(self):
         if self._sfmat is None:
-            self._sfmat = self.fetch(0, self.nsteps)[:, :self.nsteps_done]
+            self._sfmat = self.fetch(0, self.nsteps_done)
         return self._sfmat
+
+    def invariant_info(self):
+        """Coverage of the invariant by the device test: faces, faces with a certificate, whether the test equals
+        the reference's exact `_isdisjoint(X, set(F[k]))`, and how many steps the last run computed before it
+        stopped launching (include/reach.h, reach_lgg09_plan_invariant_info)."""
+        f, c, e, k = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+        self.ctx.check(self.lib.reach_lgg09_plan_invariant_info(self.handle, C.byref(f), C.byref(c), C.byref(e), C.byref(k)))
+        return dict(faces=f.value, covered=c.value, exact=bool(e.value), steps_computed=k.value)
 
     def fetch_rows(self, rows):
         """Selected rows of ρℓ (all steps): strided device→host copies of 8·NSTEPS bytes each."""
@@ -416,6 +424,13 @@ def post(alg, ivp, NSTEPS=None, Δt0=zeroT, ctx=None, **kwargs):
     plan = reach_inhomog_LGG09(template, ivp.Omega0, ivp.Phi, NSTEPS, ivp.X, ivp.V, ctx=ctx,
                                time_block=alg.time_block, share_negated=alg.share_negated)
     nsets = plan.nsteps_done
+    info = plan.invariant_info()
+    if info["faces"] and not info["exact"]:
+        # the reference decides `_isdisjoint(X, set(F[k]))` with an LP per step; the device test is sufficient only here
+        import warnings
+        warnings.warn("LGG09 invariant: %d of %d faces are tested on the device and the test is sufficient, not exact, for "
+                      "this template -- the flowpipe may be longer than the reference's (never shorter)"
+                      % (info["covered"], info["faces"]), RuntimeWarning, stacklevel=2)
 
     def make(k, dt):
         return TemplateReachSet(template, plan.sfmat()[:, k], dt)

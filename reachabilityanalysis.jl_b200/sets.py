@@ -15,7 +15,7 @@ import numpy as np
 
 __all__ = [
     "Hyperrectangle", "BallInf", "Interval", "Singleton", "ZeroSet", "Universe", "Zonotope",
-    "LinearMap", "Scale", "MinkowskiSum", "ConvexHull", "CartesianProduct", "HalfSpace",
+    "LinearMap", "Scale", "MinkowskiSum", "ConvexHull", "CartesianProduct", "HalfSpace", "HPolyhedron",
     "dim", "split",
 ]
 
@@ -171,6 +171,18 @@ class HalfSpace:
         object.__setattr__(self, "b", float(b))
 
 
+@dataclass(frozen=True, eq=False)
+class HPolyhedron:
+    """{x : a_i·x ≤ b_i for all i} -- an invariant made of several half-spaces."""
+    constraints: tuple
+
+    def __init__(self, constraints):
+        cs = tuple(constraints)
+        if not cs or not all(isinstance(c, HalfSpace) for c in cs):
+            raise ValueError("HPolyhedron needs a non-empty list of HalfSpace constraints")
+        object.__setattr__(self, "constraints", cs)
+
+
 def dim(X) -> int:
     if isinstance(X, (Hyperrectangle, BallInf, Zonotope)):
         return len(X.center)
@@ -190,6 +202,8 @@ def dim(X) -> int:
         return dim(X.X) + dim(X.Y)
     if isinstance(X, HalfSpace):
         return len(X.a)
+    if isinstance(X, HPolyhedron):
+        return len(X.constraints[0].a)
     raise TypeError("not a set: %r" % (type(X),))
 
 

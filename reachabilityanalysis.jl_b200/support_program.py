@@ -139,10 +139,16 @@ def invariant_to_c(X, n):
     if isinstance(X, S.HalfSpace):
         a = np.ascontiguousarray(X.a)
         b = np.array([X.b])
-        return L.reach_invariant(L.REACH_INV_HALFSPACE, L.dptr(a), L.dptr(b)), [a, b]
+        return L.reach_invariant(L.REACH_INV_HALFSPACE, 1, L.dptr(a), L.dptr(b)), [a, b]
+    if isinstance(X, S.HPolyhedron):
+        A = np.ascontiguousarray(np.stack([h.a for h in X.constraints]))     # row-major m x n
+        if A.shape[1] != n:
+            raise ValueError("invariant of dimension %d in a %d-dimensional problem" % (A.shape[1], n))
+        b = np.array([h.b for h in X.constraints])
+        return L.reach_invariant(L.REACH_INV_POLYHEDRON, len(b), L.dptr(A), L.dptr(b)), [A, b]
     if isinstance(X, (S.Hyperrectangle, S.BallInf)):
         r = X.radius if isinstance(X, S.Hyperrectangle) else np.full(n, X.radius)
         lo = np.ascontiguousarray(X.center - r)
         hi = np.ascontiguousarray(X.center + r)
-        return L.reach_invariant(L.REACH_INV_BOX, L.dptr(lo), L.dptr(hi)), [lo, hi]
+        return L.reach_invariant(L.REACH_INV_BOX, 0, L.dptr(lo), L.dptr(hi)), [lo, hi]
     raise NotImplementedError("invariant of type %s is not supported on the device" % type(X).__name__)

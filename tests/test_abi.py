@@ -32,7 +32,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.reach_term) == 4 * 4 + 4 * 8
     assert ctypes.sizeof(_lib.reach_setexpr) == 8 + 8 + 8
     assert ctypes.sizeof(_lib.reach_lgg09_opts) == 8 * 4
-    assert ctypes.sizeof(_lib.reach_invariant) == 8 + 8 + 8
+    assert ctypes.sizeof(_lib.reach_invariant) == 8 + 8 + 8          # kind + m share the first 8 bytes
 
 
 def test_no_cpu_fallback():

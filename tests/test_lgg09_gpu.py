@@ -3,8 +3,8 @@ import numpy as np
 import pytest
 
 import reach_b200 as rb
-from reach_b200 import discretization as D
-from reach_b200.lgg09 import reach_inhomog_LGG09, reach_homog_LGG09, post
+from reach_b200 import discretization as D, workloads as W
+from reach_b200.lgg09 import reach_inhomog_LGG09, reach_homog_LGG09, post, Lgg09Plan
 from oracle import lgg09_oracle as LO
 from conftest import building_problem, iss_problem, assert_support_parity
 
@@ -361,3 +361,109 @@ def test_to_intervals_flowpipe_jl_311_331(ctx):
         assert iv[k].set.lo <= iv[k].set.hi
     with pytest.raises(ValueError):
         sol.F.to_intervals(rows=(1,))
+
+
+def _decay_problem(n=6, seed=2):
+    import scipy.linalg
+    rng = np.random.default_rng(seed)
+    A = -np.diag(rng.uniform(0.5, 2.0, n)) + 0.2 * rng.standard_normal((n, n))
+    Phi = scipy.linalg.expm(A * 0.05)
+    X0 = rb.Hyperrectangle(np.full(n, 5.0) + rng.uniform(-1, 1, n), np.full(n, 0.3))
+    return Phi, X0, rng
+
+
+def test_invariant_general_halfspace_with_box_template_matches_the_exact_lp_test(ctx):
+    """reach_homog.jl:418 `_isdisjoint(X, set(F[k]))` is an exact polyhedral test (an LP in LazySets).  With a box
+    template the device decides any half-space exactly from the +-e_i rows (min a.x over a box is separable)."""
+    Phi, X0, rng = _decay_problem()
+    n = Phi.shape[0]
+    dirs = rb.BoxDirections(n).matrix()
+    a = -rng.uniform(0.2, 1.0, n)                        # a.x <= b with a dense normal that is no template direction
+    ref_all = LO.reach_homog_LGG09(dirs, X0, Phi, 150)
+    lo = -ref_all[n:, :]                                 # lower bounds of the box hull per step
+    mins = (a[:, None] * np.where(a[:, None] > 0, lo, ref_all[:n, :])).sum(axis=0)        # min a.x per step
+    b = float(0.5 * (mins[5] + mins[60]))                # crossed somewhere between steps 5 and 60
+    inv = rb.HalfSpace(a, b)
+    ref, k = LO.reach_LGG09_invariant(dirs, X0, Phi, 150, inv, exact=True)
+    assert 5 <= k <= 60
+    for opts in ({}, {"path": "gemm", "time_block": 4}, {"path": "chain"}):
+        plan = reach_homog_LGG09(dirs, X0, Phi, 150, X=inv, ctx=ctx, **opts)
+        info = plan.invariant_info()
+        assert info["faces"] == 1 and info["covered"] == 1 and info["exact"]
+        assert plan.nsteps_done == k, (opts, plan.nsteps_done, k)
+        assert_support_parity(plan.sfmat(), ref)
+    # several faces (HPolyhedron): each face is tested; exactness is only claimed for one face or box-vs-box
+    inv2 = rb.HPolyhedron([rb.HalfSpace(a, b), rb.HalfSpace(-np.eye(n)[1], -1e-3)])
+    plan = reach_homog_LGG09(dirs, X0, Phi, 150, X=inv2, ctx=ctx)
+    info = plan.invariant_info()
+    assert info["faces"] == 2 and info["covered"] == 2 and not info["exact"]
+    ref2, k2 = LO.reach_LGG09_invariant(dirs, X0, Phi, 150, inv2, exact=True)
+    assert plan.nsteps_done >= k2 and plan.nsteps_done <= k        # never a false stop; no later than the single face
+    # box invariant with a box template: exact (axis by axis)
+    box = rb.Hyperrectangle(np.full(n, 4.0), np.full(n, 3.0))
+    plan = reach_homog_LGG09(dirs, X0, Phi, 150, X=box, ctx=ctx)
+    assert plan.invariant_info()["exact"]
+    assert plan.nsteps_done == LO.reach_LGG09_invariant(dirs, X0, Phi, 150, box, exact=True)[1]
+
+
+def test_invariant_sufficient_only_and_unsupported_templates(ctx):
+    Phi, X0, rng = _decay_problem(seed=3)
+    n = Phi.shape[0]
+    a = -rng.uniform(0.2, 1.0, n)
+    oct_dirs = rb.OctDirections(n).matrix()
+    ref_all = LO.reach_homog_LGG09(oct_dirs, X0, Phi, 150)
+    inv = rb.HalfSpace(a, float(a @ (X0.center * 0.35)))
+    ref, k = LO.reach_LGG09_invariant(oct_dirs, X0, Phi, 150, inv, exact=True)
+    assert 0 < k < 150
+    plan = reach_homog_LGG09(oct_dirs, X0, Phi, 150, X=inv, ctx=ctx)
+    info = plan.invariant_info()
+    assert info["covered"] == 1 and not info["exact"]    # the box rows of the oct template: sufficient, not exact
+    assert k <= plan.nsteps_done <= 150                  # may stop later than the reference, never earlier
+    assert_support_parity(plan.sfmat()[:, :k], ref)
+    # a template without the rows the normal needs: the library refuses instead of silently ignoring the invariant
+    some = rng.standard_normal((n, 5))
+    with pytest.raises(NotImplementedError):
+        reach_homog_LGG09(some, X0, Phi, 50, X=inv, ctx=ctx)
+    # ... unless the normal itself is in the template
+    with_normal = np.hstack([some, -a[:, None] * 2.5])
+    plan = reach_homog_LGG09(with_normal, X0, Phi, 150, X=inv, ctx=ctx)
+    assert plan.invariant_info()["exact"]
+    assert plan.nsteps_done == LO.reach_LGG09_invariant(with_normal, X0, Phi, 150, inv, exact=True)[1]
+
+
+def test_invariant_stops_launching_device_work(ctx):
+    """Early termination is real: once a step is certified disjoint no further passes are launched."""
+    wl = W.building_c1()
+    n = wl.n
+    full = Lgg09Plan(ctx, n, wl.dirs.shape[1], wl.nsteps, time_block=64, path="gemm")
+    full.upload(wl.Phi, wl.dirs, wl.Omega0, wl.V)
+    full.run()
+    ref = full.sfmat()
+    # x_i <= b for the coordinate whose lower bound -rho(-e_i) peaks latest (Building's transient is over after ~400 of
+    # the 10^4 steps), with b between the earlier maximum and that peak: first violated shortly before the peak
+    lo = -ref[n:, :]
+    i = int(lo.argmax(axis=1).argmax())
+    kpk = int(lo[i].argmax())
+    assert kpk > 200
+    b = float(0.5 * (lo[i, :kpk - 30].max() + lo[i, kpk]))
+    lower = lo[i]
+    k_first = int(np.nonzero(lower > b)[0][0])
+    assert kpk - 30 <= k_first <= kpk
+    e = np.zeros(n)
+    e[i] = 1.0
+    plan = Lgg09Plan(ctx, n, wl.dirs.shape[1], wl.nsteps, time_block=64, path="gemm")
+    plan.upload(wl.Phi, wl.dirs, wl.Omega0, wl.V, rb.HalfSpace(e, b))
+    plan.run()
+    info = plan.invariant_info()
+    assert plan.nsteps_done == k_first and info["exact"]
+    assert info["steps_computed"] < wl.nsteps // 2                     # stopped within a few passes of the violation
+    assert info["steps_computed"] >= k_first
+    assert plan.stats()["launches"] < full.stats()["launches"] // 2
+    assert np.array_equal(plan.sfmat(), ref[:, :k_first])
+    assert np.all(plan.max_over_steps()[0] == ref[:, :k_first].max(axis=1))
+    # a violation at step 0 leaves an empty flowpipe: rho(d, fp) over nothing is -inf
+    plan0 = Lgg09Plan(ctx, n, wl.dirs.shape[1], 500, path="gemm")
+    plan0.upload(wl.Phi, wl.dirs, wl.Omega0, wl.V, rb.HalfSpace(e, float(lower[0] - 1.0)))
+    plan0.run()
+    assert plan0.nsteps_done == 0 and plan0.sfmat().shape == (2 * n, 0)
+    assert np.all(np.isneginf(plan0.max_over_steps()[0]))
