@@ -22,7 +22,8 @@
  *     from reach_last_error().  The library never aborts and has no CPU fallback: without a
  *     usable CUDA device reach_create fails.
  *   - host pointers are borrowed for the duration of the call only.
- *   - one reach_ctx per calling thread (or lock externally); a ctx owns one device + one stream.
+ *   - one reach_ctx per calling thread (or lock externally); a ctx owns one device + one stream;
+ *     reach_multi_* drives several devices from one handle (below).
  *   - time stamps (dt, dt0), TemplateReachSet / ReachSet construction and the :sfmat dictionary
  *     stay on the caller's side.
  */
@@ -139,7 +140,7 @@ typedef struct {
                              batched GEMM on the INT8 tcgen05 pipe through error-free digit planes
                              (unguarded when forced; auto picks it for large dense problems and
                              guards it against the DMMA kernel, see reach_lgg09_plan_path)      */
-    int32_t reserved[3];  /* reserved[0]: digit planes of path 3 (0 = 8; 4..8)
+    int32_t reserved[3];  /* reserved[0]: 8-bit digit planes of path 3 (0 = 7, i.e. 56 bits; 4..8)
                              reserved[1]: 1 = box output: the two rows of a direction pair (l, -l) hold
                              (lin, abs) = (centre, radius) of the box hull instead of abs +- lin
                              (what reach_box uses; Omega0 must have one alternative)            */
@@ -294,6 +295,37 @@ int reach_glgm06(reach_ctx* ctx, int n, int64_t nsteps, int nsplits, int max_ord
 int reach_reduce_order_gir05(reach_ctx* ctx, int n, int p, int max_order, const double* G,
                              double* Gred, int* pred, int32_t* sel);
 
+/* ---------------------------------------------------------------------------------------------
+ * Several GPUs behind one handle (single process, one host thread per device inside the library).
+ *
+ * The path has no inter-step exchange.  LGG09: the template directions are sharded over the devices
+ * (`Threads.@threads for j in eachindex(l)`, LGG09/reach_inhomog.jl:35-40, becomes "device r owns a contiguous block of
+ * direction chains"; l and -l stay on one device so they keep sharing (Phi')^k l); the one exchange is the all-gather of
+ * the per-device support-value blocks, done by the copy engines as strided 2-D copies that place each block's rows at
+ * their position in the caller's ndirs x nsteps matrix -- into rho_host and/or into one full device-resident copy per
+ * GPU (rho_dev[j], written through peer memory over NVLink).  GLGM06: the initial-set splits are sharded
+ * (`_solve_distributed`, Continuous/solve.jl:84-117); the shared chain is recomputed per device; no exchange.
+ * Results are bit-identical to the single-device calls.  No invariant argument: early termination is decided on
+ * all directions of a step, which no single device holds.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct reach_multi reach_multi;
+int         reach_multi_create(reach_multi** out, const int* device_ids /* NULL: 0..ndev-1 */, int ndev);
+void        reach_multi_destroy(reach_multi* m);
+int         reach_multi_ndev(const reach_multi* m);
+reach_ctx*  reach_multi_ctx(reach_multi* m, int i);               /* the i-th device's context (owned by m) */
+const char* reach_multi_last_error(const reach_multi* m);         /* m may be NULL: last create error        */
+/* rho_host: ndirs x nsteps column-major, rows in the caller's order, or NULL.  rho_dev: NULL, or ndev device pointers
+ * (entry j on device j, ndirs x nsteps doubles, NULL entries skipped) that each receive the complete matrix.
+ * ms_per_device (may be NULL, ndev entries): CUDA-event time of each device's run. */
+int reach_multi_lgg09(reach_multi* m, int n, int ndirs, int64_t nsteps, const double* Phi, const double* dirs,
+                      const reach_setexpr* Omega0, const reach_setexpr* V, const reach_lgg09_opts* opts,
+                      double* rho_host, void* const* rho_dev, double* ms_per_device);
+/* Same arguments and output layout as reach_glgm06; device r runs a contiguous, balanced block of the splits. */
+int reach_multi_glgm06(reach_multi* m, int n, int64_t nsteps, int nsplits, int max_order,
+                       const double* Phi, const double* c0, const double* G0, int p0,
+                       const double* cU, const double* GU, int pU,
+                       double* c_host, double* G_host, int gcap, int32_t* ngens_host);
+
 /* Device-side discretisation matrices (src/Discretization/Exponentiation.jl): Phi = exp(A*delta) (:168-171),
  * Phi1(A, delta) = sum_i delta^(i+1)/(i+1)! A^i (:263-291) and Phi2(A, delta) = sum_i delta^(i+2)/(i+2)! A^i
  * (:397-427), which the Forward and NoBloating models turn into (Phi, Omega0, V) (ForwardModule.jl:86-164,
@@ -308,7 +340,7 @@ int reach_discretize_phi(reach_ctx* ctx, int n, const double* A, double delta,
  * (C[m x n] = X[m x k] * Y[n x k]'), returns achieved TFLOP/s; used by bench.py beside cuBLAS. */
 int reach_dgemm_probe(reach_ctx* ctx, int m, int n, int k, int iters, double* tflops);
 
-/* The same contraction on the INT8 tcgen05 tensor pipe through `slices` (4..8) error-free 7-bit digit planes
+/* The same contraction on the INT8 tcgen05 tensor pipe through `slices` (4..8) error-free 8-bit digit planes
  * per operand (csrc/oz_gemm.cuh): C[m x n] (row-major) = X[m x k] * Y[n x k]' for row-major host matrices.
  * C_host may be NULL.  *tflops counts 2 m n k per launch (FP64-equivalent), *slice_ms the digit-plane
  * conversion of both operands.  Used by the tests (accuracy against NumPy) and by bench.py. */

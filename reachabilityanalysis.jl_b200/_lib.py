@@ -98,6 +98,17 @@ SIGNATURES = {
     "reach_glgm06": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, c_double_p, c_double_p,
                                c_double_p, C.c_int, c_double_p, c_double_p, C.c_int, c_double_p,
                                c_double_p, C.c_int, c_int32_p]),
+    "reach_multi_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int]),
+    "reach_multi_destroy": (None, [C.c_void_p]),
+    "reach_multi_ndev": (C.c_int, [C.c_void_p]),
+    "reach_multi_ctx": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "reach_multi_last_error": (C.c_char_p, [C.c_void_p]),
+    "reach_multi_lgg09": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, c_double_p, c_double_p,
+                                    C.POINTER(reach_setexpr), C.POINTER(reach_setexpr), C.POINTER(reach_lgg09_opts),
+                                    c_double_p, C.POINTER(C.c_void_p), c_double_p]),
+    "reach_multi_glgm06": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int, c_double_p, c_double_p,
+                                     c_double_p, C.c_int, c_double_p, c_double_p, C.c_int, c_double_p,
+                                     c_double_p, C.c_int, c_int32_p]),
     "reach_reduce_order_gir05": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p,
                                            C.POINTER(C.c_int), c_int32_p]),
     "reach_discretize_phi": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_double, c_double_p, c_double_p, c_double_p,
@@ -199,6 +210,81 @@ class Context:
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:
             self.lib.reach_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiContext:
+    """Several devices behind one handle (`reach_multi`): single process, directions / splits sharded inside the
+    library, the LGG09 all-gather done by peer / host 2-D copies (include/reach.h)."""
+
+    def __init__(self, device_ids):
+        self.lib = load()
+        ids = (C.c_int * len(device_ids))(*[int(d) for d in device_ids])
+        h = C.c_void_p()
+        rc = self.lib.reach_multi_create(C.byref(h), ids, len(device_ids))
+        if rc != REACH_OK:
+            raise ReachError("reach_multi_create(%s) failed (%d): %s"
+                             % (list(device_ids), rc, self.lib.reach_multi_last_error(None).decode()))
+        self.handle = h
+        self.device_ids = [int(d) for d in device_ids]
+
+    @property
+    def ndev(self):
+        return self.lib.reach_multi_ndev(self.handle)
+
+    def check(self, rc):
+        if rc == REACH_OK:
+            return
+        msg = self.lib.reach_multi_last_error(self.handle).decode()
+        if rc == REACH_EINVAL:
+            raise ValueError(msg)
+        if rc == REACH_EUNSUPPORTED:
+            raise NotImplementedError(msg)
+        raise ReachError("libreach_cuda error %d: %s" % (rc, msg))
+
+    def lgg09(self, Phi, dirs, Omega0_c, V_c, nsteps, opts=None, rho_dev=None, want_host=True):
+        """`reach_multi_lgg09`: Omega0_c / V_c are flattened programs (support_program.to_c).  Returns
+        (rho [ndirs x nsteps] or None, ms per device)."""
+        Phi, dirs = fmat(Phi), fmat(dirs)
+        n, ndirs = dirs.shape
+        out = np.empty((ndirs, int(nsteps)), order="F") if want_host else None
+        ms = np.zeros(self.ndev)
+        devp = None
+        if rho_dev is not None:
+            devp = (C.c_void_p * self.ndev)(*[C.c_void_p(int(p)) if p else None for p in rho_dev])
+        self.check(self.lib.reach_multi_lgg09(self.handle, n, ndirs, int(nsteps), dptr(Phi), dptr(dirs), Omega0_c.ptr(),
+                                              V_c.ptr() if V_c is not None else None,
+                                              C.byref(opts) if opts is not None else None, dptr(out), devp, dptr(ms)))
+        return out, ms
+
+    def glgm06(self, Phi, c0, G0, cU, GU, nsteps, max_order, gcap):
+        """`reach_multi_glgm06`: c0 [n x nsplits], G0 [n x p0 x nsplits] (Fortran order); returns (c, G, ngens) in the
+        one-shot layout of reach_glgm06."""
+        Phi = fmat(Phi)
+        n = Phi.shape[0]
+        c0 = np.asfortranarray(c0, dtype=np.float64)
+        G0 = np.asfortranarray(G0, dtype=np.float64)
+        nsplits, p0 = c0.shape[1], G0.shape[1]
+        pU = -1 if GU is None else np.asarray(GU).shape[1]
+        cUa = None if cU is None else np.ascontiguousarray(cU, dtype=np.float64)
+        GUa = None if GU is None else fmat(GU)
+        c = np.empty((n, nsplits, int(nsteps)), order="F")
+        G = np.zeros((n, gcap, nsplits, int(nsteps)), order="F")
+        ng = np.zeros((nsplits, int(nsteps)), dtype=np.int32, order="F")
+        self.check(self.lib.reach_multi_glgm06(self.handle, n, int(nsteps), nsplits, int(max_order), dptr(Phi), dptr(c0),
+                                               dptr(G0), p0, dptr(cUa), dptr(GUa), pU, dptr(c), dptr(G), int(gcap),
+                                               ng.ctypes.data_as(c_int32_p)))
+        return c, G, ng
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            self.lib.reach_multi_destroy(self.handle)
             self.handle = C.c_void_p()
 
     def __del__(self):

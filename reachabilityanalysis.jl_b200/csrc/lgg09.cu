@@ -259,7 +259,7 @@ struct reach_lgg09_plan {
     // INT8 tcgen05 digit-plane path (path == 3)
     bool use_oz = false;
     bool oz_guard = false;        // auto-selected: sampled passes are re-run on the DMMA kernel and compared
-    int oz_T = 8, oz_nkb = 0, oz_tiles_n = 0;
+    int oz_T = OZ_DEFAULT_T, oz_nkb = 0, oz_tiles_n = 0;
     DevBuf Xq, Yq, eX, eY;
     DevBuf ftot_ref, guard_val;
     // State after the last verified pass (direction block, running input sums, carried features): a failed check
@@ -640,11 +640,11 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
     // ---- INT8 tcgen05 digit-plane GEMM requested (path 3) ----
     p->use_oz = false;
     p->oz_guard = false;
-    if (!p->use_compact && p->opts.path == 0 && !p->opts.tile_m && !p->opts.tile_n && n >= 512 && n <= 32768 && p->mu >= 96 &&
+    if (!p->use_compact && p->opts.path == 0 && !p->opts.tile_m && !p->opts.tile_n && n >= 512 && n <= OZ_MAX_K && p->mu >= 96 &&
         n + p->ne >= 128 && p->nq >= 1 && p->nq <= 4 && !getenv("REACH_NO_INT8")) {
         // large dense problem: the INT8 tcgen05 digit-plane GEMM (~2x the FP64 tensor pipe), guarded: sampled passes
         // are recomputed with the DMMA kernel and the run falls back to it if they differ by more than kOzGuardTol
-        const int T = p->opts.reserved[0] ? p->opts.reserved[0] : 8;
+        const int T = p->opts.reserved[0] ? p->opts.reserved[0] : OZ_DEFAULT_T;
         if (T < 4 || T > OZ_MAX_T)
             return set_error(ctx, REACH_EINVAL, "digit planes (opts.reserved[0]) must be in 4..%d, got %d", OZ_MAX_T, T);
         p->use_oz = true;
@@ -652,12 +652,12 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
         p->oz_T = T;
     }
     if (p->opts.path == 3) {
-        const int T = p->opts.reserved[0] ? p->opts.reserved[0] : 8;
+        const int T = p->opts.reserved[0] ? p->opts.reserved[0] : OZ_DEFAULT_T;
         if (T < 4 || T > OZ_MAX_T)
             return set_error(ctx, REACH_EINVAL, "digit planes (opts.reserved[0]) must be in 4..%d, got %d", OZ_MAX_T, T);
-        if (n + p->ne < 128 || p->nq < 1 || p->nq > 4 || n > 32768)
+        if (n + p->ne < 128 || p->nq < 1 || p->nq > 4 || n > OZ_MAX_K)
             return set_error(ctx, REACH_EUNSUPPORTED,
-                             "the digit-plane GEMM path needs 128 <= n + mapped rows, n <= 32768 and 1..4 support features "
+                             "the digit-plane GEMM path needs 128 <= n + mapped rows, n <= 16384 and 1..4 support features "
                              "(n=%d, mapped rows=%d, features=%d)", n, p->ne, p->nq);
         p->use_oz = true;
         p->oz_T = T;

@@ -3,13 +3,16 @@
 //     C[m][n] = sum_k X[m][k] * Y[n][k]            (the same NT contraction as nt_dgemm.cuh)
 //
 // B200's FP64 tensor path (DMMA) tops out at ~36 TFLOP/s; its INT8 tcgen05 path is >100x faster.  Each FP64
-// operand row is scaled by a power of two and cut into T signed 7-bit digits,
-//     x = 2^e * sum_s q_s 2^(-6-7s),   q_s in [-64, 64]  (exact: every step is a scaling and an integer subtraction)
-// so that  x_i . y_j = 2^(e_i+e_j-12) * sum_d 2^(-7d) * ( sum_{s+u=d} q_s . p_u ).  The inner integer dot products
-// are exact in the INT32 accumulators (|.| <= (d+1) K 2^12 < 2^31), all (s,u) pairs of one level d accumulate
-// into the SAME tensor-memory accumulator, and only levels d < T are kept: T(T+1)/2 INT8 MMAs per k-step and a
-// truncation error below (T+1) K 2^(-7T) relative to rowmax(X) * rowmax(Y) (T = 8: ~2^-42 worst case, ~2^-50 typical:
-// on par with DGEMM's own rounding).  The result is independent of the summation order, hence deterministic.
+// operand row is scaled by a power of two and cut into T signed 8-bit digits (balanced radix 256),
+//     x = 2^(e-7) * sum_s q_s 2^(-8s),   q_s in [-128, 127]  (exact: scalings, floors and integer subtractions only)
+// so that  x_i . y_j = 2^(e_i+e_j-14) * sum_d 2^(-8d) * ( sum_{s+u=d} q_s . p_u ).  The inner integer dot products
+// are exact in the INT32 accumulators (|.| <= (d+1) K 2^14 < 2^31 for K <= 16384), all (s,u) pairs of one level d
+// accumulate into the SAME tensor-memory accumulator, and only levels d < T are kept: T(T+1)/2 INT8 MMAs per k-step and a
+// truncation error below T K 2^(-8T) relative to rowmax(X) * rowmax(Y) (T = 7: 56 bits, ~2^-42 worst case, ~2^-50
+// typical: on par with DGEMM's own rounding).  The result is independent of the summation order, hence deterministic.
+// (Rounds 1-2a used 7-bit digits in [-64, 64] from round-to-nearest: 8 planes = 36 plane pairs for the same 56 bits that
+// 7 planes = 28 pairs give with full 8-bit digits.  The kernel runs at the chip's power-limited INT8 rate, so the
+// plane-pair count is what sets its time.)
 //
 // Kernel shape (one CTA per 128 x 128 output tile, 18 warps):
 //   warp 16 producer: per 32-byte k-block two cp.async.bulk copies (the digit planes of the X tile, of the Y
@@ -33,6 +36,9 @@ constexpr int OZ_TM = 128, OZ_TN = 128, OZ_KB = 32, OZ_STAGES = 3;
 constexpr int OZ_EPI_WARPS = 16, OZ_THREADS = (OZ_EPI_WARPS + 2) * 32;
 constexpr int OZ_CPT = OZ_TN / (OZ_EPI_WARPS / 4);    // output columns per epilogue thread (32)
 constexpr int OZ_MAX_T = 8, OZ_G = 4;                  // OZ_G levels live in tensor memory at a time (4 x 128 columns)
+constexpr int OZ_DEFAULT_T = 7;                        // 7 x 8 = 56 bits below the row maximum
+constexpr int OZ_BITS = 8;                             // bits per digit; x-hat = x 2^(OZ_BITS-1-e) lies in [-127, 127]
+constexpr int OZ_MAX_K = (1 << (31 - 2 * (OZ_BITS - 1))) / OZ_MAX_T * 1;   // INT32 level sums stay exact up to this K (16384)
 constexpr int OZ_PLANE = OZ_TM * OZ_KB;                // bytes of one digit plane of a 128-row tile per k-block
 
 struct OzOperands {
@@ -43,6 +49,7 @@ struct OzOperands {
     int nkb;              // k-blocks of 32
     int tiles_m, tiles_m_total;
     int tile_n0, tiles_n, tiles_n_total;   // this launch covers Y tiles [tile_n0, tile_n0 + tiles_n)
+    int no_pair = 0;      // 1: one level per MMA (N = 128) everywhere; A/B switch for the two-level N = 256 MMAs
 };
 
 __device__ __forceinline__ uint64_t oz_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -166,9 +173,52 @@ struct OzLgg09Epi {
     }
 };
 
+// MMAs of one k-block of sweep SW (levels 4 SW .. min(4 SW + 4, TE) - 1) with everything but the ring addresses folded
+// at compile time (one thread issues them: a run-time loop nest costs more issue cycles than the MMAs take).
+// X plane sx meets the Y planes sy = d - sx of the sweep's levels d.  Two consecutive Y planes are 256 consecutive rows
+// of the shared-memory image (a plane is 16 row groups of 256 B = the SBO), and the accumulators of levels d, d + 1 are
+// 256 consecutive tensor-memory columns: ONE M = 128, N = 256 MMA does the plane pairs (sx, sy) and (sx, sy + 1) and reads
+// the X plane once instead of twice.  sx = 0 touches every level of the sweep first: at the first k-block those MMAs
+// overwrite, everything else accumulates.
+template <int TE, int SW, bool PAIR>
+__device__ __forceinline__ void oz_issue_kblock(uint32_t xs, uint32_t ys, uint32_t tmem_base, bool first_kb) {
+    // instruction descriptor: D = S32 (2<<4), A = B = signed 8-bit (1<<7, 1<<10), K-major both, N>>3 at 17, M>>4 at 24
+    constexpr uint32_t idesc1 = (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(OZ_TN >> 3) << 17) | (uint32_t(OZ_TM >> 4) << 24);
+    constexpr uint32_t idesc2 = (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t((2 * OZ_TN) >> 3) << 17) | (uint32_t(OZ_TM >> 4) << 24);
+    constexpr int d0 = SW * OZ_G, d1 = (d0 + OZ_G < TE ? d0 + OZ_G : TE) - 1;
+#pragma unroll
+    for (int sx = 0; sx <= d1; ++sx) {
+        const int lo = d0 - sx > 0 ? d0 - sx : 0, hi = d1 - sx;
+        // one digit plane of a tile: [rows/8][2 k-chunks][8 rows][16 B]: LBO = 128 B (next k-chunk), SBO = 256 B (next 8 rows)
+        const uint64_t da = oz_smem_desc(xs + sx * OZ_PLANE, 128, 256);
+        const uint32_t acc = (!first_kb || sx > 0) ? 1u : 0u;
+#pragma unroll
+        for (int j = 0; j < OZ_G / 2; ++j) {
+            const int sy = lo + 2 * j;
+            if (sy <= hi) {
+                const uint64_t db = oz_smem_desc(ys + sy * OZ_PLANE, 128, 256);
+                const bool two = PAIR && sy + 1 <= hi;
+                asm volatile(
+                    "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+                    " tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_base + uint32_t((sx + sy - d0) * OZ_TN)),
+                    "l"(da), "l"(db), "r"(two ? idesc2 : idesc1), "r"(acc)
+                    : "memory");
+                if (!two && sy + 1 <= hi) {
+                    const uint64_t db1 = oz_smem_desc(ys + (sy + 1) * OZ_PLANE, 128, 256);
+                    asm volatile(
+                        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+                        " tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_base + uint32_t((sx + sy + 1 - d0) * OZ_TN)),
+                        "l"(da), "l"(db1), "r"(idesc1), "r"(acc)
+                        : "memory");
+                }
+            }
+        }
+    }
+}
 // Two passes over K ("sweeps") when T > 4: levels 0..3 first (digit planes 0..3 of both operands, 10 MMAs per k-block),
 // then levels 4..T-1 (all planes, up to 26 MMAs).  Each sweep's level sum  sum_d 2^(-7 (d - d0)) acc_d  is EXACT in
-// FP64 (<= 47 bits), so the epilogue threads keep sweep 1 as one double per output while sweep 2 runs.
+// FP64 (<= 53 bits for K <= 8192; beyond, one rounding at 2^-53 of the sum), so the epilogue threads keep sweep 1 as one
+// double per output while sweep 2 runs.
 //
 // Persistent: CTA c walks tiles c, c + gridDim.x, ...  The epilogue warps hand the accumulators back to the MMA
 // warp as soon as they have pulled a sweep into registers (tmem_empty), so the arithmetic part of a tile's epilogue
@@ -233,8 +283,6 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzOperands
     } else if (warp == OZ_EPI_WARPS + 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            // instruction descriptor: D = S32 (2<<4), A = B = signed 8-bit (1<<7, 1<<10), K-major both, N>>3 at 17, M>>4 at 24
-            constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(OZ_TN >> 3) << 17) | (uint32_t(OZ_TM >> 4) << 24);
             int jb = 0;
             uint32_t nsweeps_done = 0;                            // sweeps issued so far (all tiles)
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
@@ -249,24 +297,12 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzOperands
                         mbar_wait(&full[s], ph);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t xs = smem_u32(ring + size_t(s) * SLOT), ys = xs + T * OZ_PLANE;
-#pragma unroll
-                        for (int dd = 0; dd < OZ_G; ++dd) {
-                            const int d = sw * OZ_G + dd;
-                            if (d >= T) break;
-#pragma unroll
-                            for (int sx = 0; sx < T; ++sx) {
-                                if (sx > d) break;
-                                const int sy = d - sx;
-                                // one digit plane of a tile: [rows/8][2 k-chunks][8 rows][16 B]: LBO = 128 B (next k-chunk), SBO = 256 B (next 8 rows)
-                                const uint64_t da = oz_smem_desc(xs + sx * OZ_PLANE, 128, 256);
-                                const uint64_t db = oz_smem_desc(ys + sy * OZ_PLANE, 128, 256);
-                                const uint32_t acc = (kb > 0 || sx > 0) ? 1u : 0u;
-                                asm volatile(
-                                    "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
-                                    " tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_base + uint32_t(dd * OZ_TN)),
-                                    "l"(da), "l"(db), "r"(idesc), "r"(acc)
-                                    : "memory");
-                            }
+                        if (g.no_pair) {
+                            if (sw == 0) oz_issue_kblock<T, 0, false>(xs, ys, tmem_base, kb == 0);
+                            else oz_issue_kblock<T, NSWEEP - 1, false>(xs, ys, tmem_base, kb == 0);
+                        } else {
+                            if (sw == 0) oz_issue_kblock<T, 0, true>(xs, ys, tmem_base, kb == 0);
+                            else oz_issue_kblock<T, NSWEEP - 1, true>(xs, ys, tmem_base, kb == 0);
                         }
                         // frees the ring slot once the MMAs above have read it (implies fence::before_thread_sync)
                         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
@@ -290,7 +326,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzOperands
             if (tid < OZ_TN) sYscale[tid] = oz_pow2(max(-1000, min(1000, g.eY[size_t(tn) * OZ_TN + tid])));
             epi.prepare(epi_smem, tn, tid);
             asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory");
-            const int ex = g.eX[size_t(tm) * OZ_TM + ml] - 12;
+            const int ex = g.eX[size_t(tm) * OZ_TM + ml] - 2 * (OZ_BITS - 1);
             typename Epi::State st;
             epi.begin(st);
             double part[OZ_CPT];
@@ -316,9 +352,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzOperands
                         double v = oz_i2d(a[nlev - 1][jj]);
 #pragma unroll
                         for (int dd = OZ_G - 2; dd >= 0; --dd)
-                            if (dd < nlev - 1) v = fma(v, 0.0078125, oz_i2d(a[dd][jj]));   // * 2^-7, exact
+                            if (dd < nlev - 1) v = fma(v, 1.0 / (1 << OZ_BITS), oz_i2d(a[dd][jj]));   // * 2^-8; exact (<= 53 bits) for K <= 8192
                         if (sw == 0) part[cc * 8 + jj] = v;
-                        else part[cc * 8 + jj] = fma(v, 3.7252902984619140625e-09, part[cc * 8 + jj]);   // 2^-28
+                        else part[cc * 8 + jj] = fma(v, 1.0 / double(1ull << (OZ_G * OZ_BITS)), part[cc * 8 + jj]);   // 2^-32
                     }
                 }
                 // the accumulators may be overwritten: the next sweep (of this tile or of the CTA's next tile) can start
@@ -368,7 +404,10 @@ inline cudaError_t launch_oz_gemm_t(const OzOperands& g, const Epi& epi, cudaStr
         if (e != cudaSuccess) return e;
     }
     const int ntiles = g.tiles_m * g.tiles_n;
-    kern<<<ntiles < sms ? ntiles : sms, OZ_THREADS, smem, stream>>>(g, epi);      // persistent: one CTA per SM
+    static const int env_no_pair = getenv("REACH_OZ_NOPAIR") ? 1 : 0;
+    OzOperands gg = g;
+    if (env_no_pair) gg.no_pair = 1;
+    kern<<<ntiles < sms ? ntiles : sms, OZ_THREADS, smem, stream>>>(gg, epi);      // persistent: one CTA per SM
     return cudaGetLastError();
 }
 
@@ -387,9 +426,14 @@ inline cudaError_t launch_oz_gemm(int T, const OzOperands& g, const Epi& epi, cu
 // ---- slicing: FP64 rows -> T digit planes in the UMMA core-matrix layout --------------------------------
 // One CTA per 8-row group and k range (gridDim.y splits the 16-wide chunks of a row: a direction block of a few hundred
 // rows would otherwise occupy a fifth of the SMs; every CTA re-derives the row maxima, 8 rows from L2).
-// Phase 1: row maxima -> exponents (2^e > max|x|).  Phase 2: thread = (row, 16-wide k chunk):
+// Phase 1: row maxima -> exponents (max|x| <= 127/128 2^e).  Phase 2: thread = (row, 16-wide k chunk):
 // 16 values -> T x 16 digits, written as T 16-byte stores (8 consecutive rows = one 128-byte core matrix).
 //   Q[((kb * tiles_total + tile) * T + s) * (TR*32) + ((g * 2 + c) * 8 + r) * 16 + b],   tile = row / TR, g = (row % TR) / 8
+// Digits of x-hat = x 2^(7-e) in [-127, 127]: q_0 = floor, then radix-256 digits of the remainder in [0, 255] (the last one
+// rounded to nearest, so it may be 256), then balanced from the last digit up: a digit >= 128 becomes digit - 256 and
+// carries 1 into the next higher one.  Every digit ends in [-128, 127] (q_0 + carry <= 127 because x-hat <= 127 + 1/2 is
+// excluded by the exponent), signs are as random as the data (no one-sided truncation bias in the dropped levels), and
+// sum_s q_s 2^(-8s) = x-hat up to the final rounding at 2^(-8(T-1)-1).
 template <int TR>
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ X, int ldx, int rows_valid, int k_valid,
                                                        int T, int nkb, int tiles_total, int8_t* __restrict__ Q,
@@ -408,7 +452,10 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if (lane == 0) {
             int e = 0;
-            if (mx > 0.0 && mx < 1.0e308) e = ilogb(mx) + 1;           // 2^(e-1) <= mx < 2^e
+            if (mx > 0.0 && mx < 1.0e308) {
+                e = ilogb(mx) + 1;                                     // 2^(e-1) <= mx < 2^e
+                if (oz_scale(mx, OZ_BITS - 1 - e) > double((1 << (OZ_BITS - 1)) - 1)) ++e;   // keep |x-hat| <= 127
+            }
             s_e[warp] = e;
             if (blockIdx.y == 0) eout[row] = e;
         }
@@ -418,31 +465,46 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
     const int nchunks = nkb * 2;
     const int per = (nchunks + gridDim.y - 1) / gridDim.y;
     const int item_lo = 8 * per * blockIdx.y, item_hi = min(8 * nchunks, item_lo + 8 * per);
+    constexpr double RADIX = double(1 << OZ_BITS);
+    constexpr int HALF = 1 << (OZ_BITS - 1);
     for (int item = item_lo + threadIdx.x; item < item_hi; item += blockDim.x) {
         const int r = item & 7, chunk = item >> 3;
         const int row = row0 + r;
         const int kb = chunk >> 1, c = chunk & 1;
         const int k0 = chunk * 16;
-        double v[16];
+        const int e = s_e[r];
+        uint32_t w[OZ_MAX_T][4];
+#pragma unroll
+        for (int s = 0; s < OZ_MAX_T; ++s) w[s][0] = w[s][1] = w[s][2] = w[s][3] = 0u;
 #pragma unroll
         for (int b = 0; b < 16; ++b) {
             const int k = k0 + b;
-            v[b] = (row < rows_valid && k < k_valid) ? X[size_t(row) * ldx + k] : 0.0;
-        }
-        const int e = s_e[r];
+            double v = (row < rows_valid && k < k_valid) ? X[size_t(row) * ldx + k] : 0.0;
+            v = oz_scale(v, OZ_BITS - 1 - e);                                  // |v| <= 127, exact
+            int q[OZ_MAX_T];
+            double f = floor(v);
+            q[0] = int(f);
+            v -= f;                                                            // [0, 1), exact
 #pragma unroll
-        for (int b = 0; b < 16; ++b) v[b] = oz_scale(v[b], 6 - e);          // |y| < 64
-        int8_t* q = Q + ((size_t(kb) * tiles_total + tile) * T) * (TR * 32) + ((gidx * 2 + c) * 8 + r) * 16;
-        for (int s = 0; s < T; ++s) {
-            uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-            for (int b = 0; b < 16; ++b) {
-                const double d = rint(v[b]);
-                v[b] = (v[b] - d) * 128.0;                                   // exact
-                w[b >> 2] |= (uint32_t(int(d)) & 0xFFu) << (8 * (b & 3));
+            for (int s = 1; s < OZ_MAX_T; ++s) {
+                q[s] = 0;
+                if (s < T) {
+                    v *= RADIX;
+                    f = (s == T - 1) ? rint(v) : floor(v);
+                    q[s] = int(f);
+                    v -= f;
+                }
             }
-            *reinterpret_cast<uint4*>(q + size_t(s) * (TR * 32)) = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+            for (int s = OZ_MAX_T - 1; s >= 1; --s)
+                if (s < T && q[s] >= HALF) { q[s] -= 2 * HALF; q[s - 1] += 1; }
+#pragma unroll
+            for (int s = 0; s < OZ_MAX_T; ++s) w[s][b >> 2] |= (uint32_t(q[s]) & 0xFFu) << (8 * (b & 3));
         }
+        int8_t* q = Q + ((size_t(kb) * tiles_total + tile) * T) * (TR * 32) + ((gidx * 2 + c) * 8 + r) * 16;
+#pragma unroll
+        for (int s = 0; s < OZ_MAX_T; ++s)
+            if (s < T) *reinterpret_cast<uint4*>(q + size_t(s) * (TR * 32)) = make_uint4(w[s][0], w[s][1], w[s][2], w[s][3]);
     }
 }
 

@@ -15,7 +15,7 @@ extern "C" int reach_ozgemm_probe(reach_ctx* ctx, int m, int n, int k, int slice
     if (!ctx) return REACH_EINVAL;
     if (m < 1 || n < 1 || k < 1 || iters < 1) return set_error(ctx, REACH_EINVAL, "probe sizes must be positive");
     if (slices < 4 || slices > OZ_MAX_T) return set_error(ctx, REACH_EINVAL, "slices must be in 4..%d", OZ_MAX_T);
-    if (k > 32768) return set_error(ctx, REACH_EINVAL, "k must be <= 32768 (INT32 accumulator headroom)");
+    if (k > OZ_MAX_K) return set_error(ctx, REACH_EINVAL, "k must be <= %d (INT32 accumulator headroom)", OZ_MAX_K);
     if (!X_host || !Y_host) return set_error(ctx, REACH_EINVAL, "X and Y must not be NULL");
     REACH_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;

@@ -54,8 +54,24 @@ class TemplateReachSet:
             ok, k = samedir(d, D[:, i])
             if ok:
                 return float(self.sf[i]) * k
-        raise NotImplementedError("ρ(d, TemplateReachSet) for a non-template direction needs an LP "
-                                  "(out of scope of the device path)")
+        # TemplateReachSet.jl:112-114: `ρ(d, set(R))`, the support function of the polyhedron the template describes --
+        # a linear program (LazySets' ρ(d, ::HPolyhedron)); host side, as in the reference
+        return lp_support(d, D, np.asarray(self.sf, dtype=np.float64))
+
+
+def lp_support(d, D, sf):
+    """ρ(d, {x : D[:, j]·x ≤ sf[j] ∀j}) = max d·x by linear programming (what LazySets' `ρ(d, P::HPolyhedron)` solves).
+    +inf when the polyhedron is unbounded in direction d; raises on an empty polyhedron, like LazySets."""
+    from scipy.optimize import linprog
+    res = linprog(-np.asarray(d, dtype=np.float64), A_ub=np.ascontiguousarray(D.T), b_ub=sf,
+                  bounds=[(None, None)] * D.shape[0], method="highs")
+    if res.status == 3:
+        return float("inf")
+    if res.status == 2:
+        raise ValueError("the support function in direction(s) %s is undefined because the polyhedron is empty" % (d,))
+    if res.status != 0:
+        raise RuntimeError("LP solver: %s" % res.message)
+    return float(-res.fun)
 
 
 def samedir(u, v):

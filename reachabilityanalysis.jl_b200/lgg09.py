@@ -114,7 +114,7 @@ class Lgg09Plan:
         opts.time_block, opts.share_negated = int(time_block), int(bool(share_negated))
         opts.tile_m, opts.tile_n = int(tile_m), int(tile_n)
         opts.path = {"auto": 0, "gemm": 1, "chain": 2, "int8": 3, "compact": 4}.get(path, path)
-        opts.reserved[0] = int(digit_planes)      # 0 = 8 planes (FP64-level accuracy); 4..8
+        opts.reserved[0] = int(digit_planes)      # 0 = 7 planes of 8 bits (FP64-level accuracy); 4..8
         self.handle = C.c_void_p()
         ctx.check(self.lib.reach_lgg09_plan_create(ctx.handle, self.n, self.ndirs, self.nsteps,
                                                    C.byref(opts), C.byref(self.handle)))
@@ -215,7 +215,11 @@ class Lgg09Plan:
             ok, k = samedir(d, D[:, i])
             if ok:
                 return float(self.max_over_steps()[0][i]) * k
-        raise NotImplementedError("ρ(d, flowpipe) for a non-template direction needs an LP")
+        # not a template direction: max over the reach-sets of ρ(d, set(R_k)), one LP per step on the fetched support
+        # values (TemplateReachSet.jl:112-114 through AbstractFlowpipe.jl:35-37) -- host side, as in the reference
+        from .flowpipe import lp_support
+        M = self.sfmat()
+        return max(lp_support(d, D, M[:, k]) for k in range(M.shape[1]))
 
     @property
     def device_rho(self):
@@ -317,7 +321,11 @@ class Lgg09BatchPlan:
             ok, k = samedir(d, D[:, i])
             if ok:
                 return float(self.max_over_steps(split)[i]) * k
-        raise NotImplementedError("ρ(d, flowpipe) for a non-template direction needs an LP")
+        # not a template direction: max over the reach-sets of ρ(d, set(R_k)), one LP per step on the fetched support
+        # values (TemplateReachSet.jl:112-114 through AbstractFlowpipe.jl:35-37) -- host side, as in the reference
+        from .flowpipe import lp_support
+        splits = range(self.nsplits) if split < 0 else [split]
+        return max(lp_support(d, D, self.sfmat(i)[:, k]) for i in splits for k in range(self.nsteps))
 
     def stats(self):
         ms, launches, chunk = C.c_double(), C.c_int64(), C.c_int64()
@@ -437,3 +445,30 @@ def post(alg, ivp, NSTEPS=None, Δt0=zeroT, ctx=None, **kwargs):
 
     ext = {"sfmat": plan.sfmat, "alg_vars": alg.vars}
     return Flowpipe(nsets, make, alg.δ, Δt0, ext, device=plan)
+
+
+def reach_homog_dir_LGG09(rho_vec, Omega0, PhiT, ell, NSTEPS, cache=True, ctx=None, **opts):
+    """`reach_homog_dir_LGG09!(ρvec_ℓ, Ω₀, Φᵀ, ℓ, NSTEPS, cache)` — the vector-output twin (reach_homog.jl:80-106):
+    ρvec_ℓ[i] = ρ((Φᵀ)^i ℓ, Ω₀), i = 0..NSTEPS-1, for ONE direction.  Note the reference passes Φ **transposed** here.
+    Same device kernels as the matrix form with ndirs = 1 (one chain; `cache` has nothing to select on the device).
+    `rho_vec` (length ≥ NSTEPS) is filled in place and returned."""
+    return reach_inhomog_dir_LGG09(rho_vec, Omega0, PhiT, None, ell, NSTEPS, cache, ctx=ctx, **opts)
+
+
+def reach_inhomog_dir_LGG09(rho_vec, Omega0, PhiT, U, ell, NSTEPS, cache=True, ctx=None, **opts):
+    """`reach_inhomog_dir_LGG09!(ρvec_ℓ, Ω₀, Φᵀ, U, ℓ, NSTEPS, cache)` (reach_inhomog.jl:98-128):
+    ρvec_ℓ[i] = ρ(r_i, Ω₀) + s_i, s_{i+1} = s_i + ρ(r_i, U), r_{i+1} = Φᵀ r_i."""
+    ctx = ctx or L.default_context()
+    PhiT = np.asarray(PhiT, dtype=np.float64)
+    ell = np.asarray(ell, dtype=np.float64).reshape(-1)
+    if PhiT.shape != (len(ell), len(ell)):
+        raise ValueError("Φᵀ is %s, the direction has length %d" % (PhiT.shape, len(ell)))
+    rho_vec = np.asarray(rho_vec) if not isinstance(rho_vec, np.ndarray) else rho_vec
+    if rho_vec.shape[0] < NSTEPS:
+        raise IndexError("ρvec_ℓ has length %d < NSTEPS = %d (BoundsError in the reference)" % (rho_vec.shape[0], NSTEPS))
+    plan = Lgg09Plan(ctx, len(ell), 1, NSTEPS, **opts)
+    plan.upload(np.ascontiguousarray(PhiT.T), ell.reshape(-1, 1), Omega0, U)
+    plan.run()
+    rho_vec[:NSTEPS] = plan.fetch(0, NSTEPS)[0]
+    plan.close()
+    return rho_vec

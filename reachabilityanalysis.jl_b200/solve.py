@@ -26,7 +26,10 @@ class IVP:
 
 
 def _nsteps(T, delta):
-    return int(math.ceil(T / delta - 1e-12))
+    """compute_nsteps (solve.jl:284-289): `ceil(Int, T / δ)` on the floating-point quotient, exactly as the
+    reference -- T = 9.3, δ = 0.3 gives 32 there (9.3 / 0.3 = 31.000000000000004) and here."""
+    assert T > 0, "the time horizon should be positive"
+    return int(math.ceil(T / delta))
 
 
 def discretize(ivp, delta, model):
@@ -78,8 +81,10 @@ def solve(ivp, T=None, alg=None, NSTEPS=None, tspan=None, algorithm=None, opC=No
     if alg is None:
         raise ValueError("an algorithm (`alg=LGG09(...)` or `alg=GLGM06(...)`) is required")
     if tspan is not None:
-        T = tspan[1] - tspan[0]
-        dt0 = zeroT + tspan[0]
+        # _get_T (solve.jl:272-282): the linear algorithms only take time spans of the form (0, T)
+        assert tspan[0] == 0, "this algorithm can only handle zero initial time"
+        T = tspan[1]
+        dt0 = zeroT
     else:
         dt0 = zeroT
     if isinstance(ivp.X0, (list, tuple)):

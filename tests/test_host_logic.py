@@ -146,3 +146,43 @@ def test_oracle_invariant_variant_stops_and_drops_the_triggering_step():
     out, k = LO.reach_LGG09_invariant(dirs, X0, Phi, 50, rb.HalfSpace(np.array([-1.0, 0.0]), -1.0))
     # x1 upper bound: 4.1 * 0.5^k ; disjoint from {x1 >= 1} once 4.1*0.5^k < 1  ->  k = 3
     assert k == 3 and out.shape == (4, 3)
+
+
+def test_nsteps_is_ceil_of_the_floating_point_quotient():
+    """compute_nsteps (src/Continuous/solve.jl:284-289): `ceil(Int, T / δ)` -- 9.3 / 0.3 = 31.000000000000004 ⇒ 32."""
+    from reach_b200.solve import _nsteps
+    assert _nsteps(9.3, 0.3) == 32
+    assert _nsteps(20.0, 0.002) == 10000
+    assert _nsteps(20.0, 6e-4) == 33334
+    with pytest.raises(AssertionError):
+        _nsteps(0.0, 0.1)
+
+
+def test_solve_rejects_nonzero_initial_time():
+    """_get_T (solve.jl:272-282): 'this algorithm can only handle zero initial time'."""
+    ivp = rb.IVP(-np.eye(2), rb.Hyperrectangle(np.zeros(2), np.ones(2)))
+    with pytest.raises(AssertionError, match="zero initial time"):
+        rb.solve(ivp, tspan=(1.0, 2.0), alg=rb.LGG09(δ=0.1, template="box", n=2))
+
+
+def test_template_reach_set_lp_fallback():
+    """ρ(d, TemplateReachSet) for a direction outside the template = ρ(d, set(R)) (TemplateReachSet.jl:112-114): an
+    LP over the template polyhedron.  Box template ⇒ the LP optimum is the box support function; an oct template is
+    tighter; a polyhedron unbounded in d gives +inf."""
+    from reach_b200.flowpipe import TemplateReachSet, zeroT, lp_support
+    from reach_b200.directions import get_template
+    box = get_template("box", 3)
+    lo, hi = np.array([-1.0, 0.5, -2.0]), np.array([2.0, 1.5, 3.0])
+    sf = np.r_[hi, -lo] if np.array_equal(box.matrix()[:, :3], np.eye(3)) else None
+    assert sf is not None
+    R = TemplateReachSet(box, sf, zeroT)
+    d = np.array([1.0, -2.0, 0.5])
+    expect = sum(di * (h if di > 0 else l) for di, l, h in zip(d, lo, hi))
+    assert abs(R.rho(d) - expect) < 1e-9
+    assert R.rho(2.0 * box.matrix()[:, 1]) == 2.0 * sf[1]              # positive multiple: no LP
+    # x <= 1 only: unbounded in y
+    assert lp_support(np.array([0.0, 1.0]), np.array([[1.0], [0.0]]), np.array([1.0])) == float("inf")
+    # octagon {|x|,|y| <= 1, |x+y| <= 1.5, |x-y| <= 2}: ρ((2,1)) is attained at the vertex (1, 0.5)
+    Doct = np.array([[1, 0], [0, 1], [-1, 0], [0, -1], [1, 1], [-1, -1], [1, -1], [-1, 1]], dtype=float).T
+    sfo = np.array([1, 1, 1, 1, 1.5, 1.5, 2, 2], dtype=float)
+    assert abs(lp_support(np.array([2.0, 1.0]), Doct, sfo) - 2.5) < 1e-9

@@ -24,11 +24,12 @@ def test_digit_plane_gemm_matches_numpy(ctx, m, n, k):
     Y = rng.standard_normal((n, k)) * np.exp(rng.uniform(-3, 3, (n, 1)))
     ref = X @ Y.T
     bound = np.abs(X).max(1)[:, None] * np.abs(Y).max(1)[None, :] * k
-    for T, tol_norm, tol_bound in ((8, 2e-14, 2.0 ** -50), (7, 2e-12, 2.0 ** -43), (6, 3e-10, 2.0 ** -36), (4, 1e-5, 2.0 ** -22)):
+    for T, tol_norm, tol_bound in ((8, 2e-14, 2.0 ** -50), (7, 2e-14, 2.0 ** -50), (6, 4e-12, 2.0 ** -44), (5, 1e-9, 2.0 ** -36),
+                                   (4, 3e-7, 2.0 ** -28)):
         Cm, _, _ = ctx.ozgemm_probe(X, Y, slices=T)
         assert np.all(np.isfinite(Cm))
         assert _rel(Cm, ref) <= tol_norm, (T, _rel(Cm, ref))
-        # the documented bound: truncation below (T+1) K 2^(-7T) of rowmax(X) rowmax(Y), per entry
+        # the documented bound: truncation below T K 2^(-8T) of rowmax(X) rowmax(Y), per entry (8-bit digits)
         assert (np.abs(Cm - ref) / bound).max() <= tol_bound, (T, (np.abs(Cm - ref) / bound).max())
 
 
@@ -78,7 +79,7 @@ def test_lgg09_int8_path_matches_oracle(ctx, n, nsteps, S):
     ref = LO.reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, wl.V)
     plan = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=S, path="int8")
     st = plan.stats()
-    assert st["path"] == "int8" and st["digit_planes"] == 8 and (st["tile_m"], st["tile_n"]) == (128, 128)
+    assert st["path"] == "int8" and st["digit_planes"] == 7 and (st["tile_m"], st["tile_n"]) == (128, 128)
     err = assert_support_parity(plan.sfmat(), ref)
     assert err <= 2e-11                          # measured ~1e-12: two decades inside the tolerance
     # same numbers on a second run (deterministic), and the DMMA path agrees

@@ -467,3 +467,59 @@ def test_invariant_stops_launching_device_work(ctx):
     plan0.run()
     assert plan0.nsteps_done == 0 and plan0.sfmat().shape == (2 * n, 0)
     assert np.all(np.isneginf(plan0.max_over_steps()[0]))
+
+
+@pytest.mark.parametrize("n", [1, 6, 48])
+def test_vector_output_twins_single_direction(ctx, n):
+    """L5: `reach_homog_dir_LGG09!` / `reach_inhomog_dir_LGG09!` with a Vector output (reach_homog.jl:80-106,
+    reach_inhomog.jl:98-128; called with n = 1, NSTEPS = 1 at test/algorithms/LGG09.jl:120-128): ONE direction
+    (ndirs = 1 on the device), Φ passed transposed as in the reference."""
+    from reach_b200.lgg09 import reach_homog_dir_LGG09, reach_inhomog_dir_LGG09
+    if n == 1:
+        # the reference's own call: X0, hcat([1.0]), [1.0], NSTEPS = 1, pre-filled vector [1.0]
+        X0 = rb.Interval(0.0, 1.0)
+        v = reach_homog_dir_LGG09(np.array([1.0]), X0, np.array([[1.0]]), [1.0], 1, cache=False, ctx=ctx)
+        assert len(v) == 1 and v[0] == 1.0                                   # ρ([1], [0,1]) = 1
+        v = reach_inhomog_dir_LGG09(np.array([1.0]), X0, np.array([[1.0]]), rb.Interval(-0.5, 0.25), [1.0], 1,
+                                    cache=True, ctx=ctx)
+        assert len(v) == 1 and v[0] == 1.0                                   # s_0 = 0
+    A, Phi = stable_system(n, 40 + n)
+    X0, U, Z = random_sets(n, 40 + n)
+    ivp = D.forward(A, X0, 0.05, U)
+    rng = np.random.default_rng(n)
+    ell = rng.standard_normal(n)
+    for nsteps in (1, 2, 37):
+        ref = LO.reach_inhomog_LGG09(ell.reshape(-1, 1), ivp.Omega0, ivp.Phi, nsteps, ivp.V)
+        out = np.full(nsteps + 2, np.nan)
+        got = reach_inhomog_dir_LGG09(out, ivp.Omega0, ivp.Phi.T, ivp.V, ell, nsteps, ctx=ctx)
+        assert got is out and np.all(np.isnan(out[nsteps:]))
+        assert_support_parity(out[:nsteps].reshape(1, -1), ref)
+        refh = LO.reach_homog_LGG09(ell.reshape(-1, 1), Z, ivp.Phi, nsteps)
+        gh = reach_homog_dir_LGG09(np.empty(nsteps), Z, ivp.Phi.T, ell, nsteps, cache=False, ctx=ctx)
+        assert_support_parity(gh.reshape(1, -1), refh)
+    with pytest.raises(IndexError):
+        reach_homog_dir_LGG09(np.empty(3), Z, ivp.Phi.T, ell, 4, ctx=ctx)
+
+
+def test_rho_of_a_non_template_direction_falls_back_to_the_polyhedron(ctx):
+    """ρ(d, fp) for d outside the template: max_k ρ(d, set(F[k])) by LP on the fetched support values
+    (TemplateReachSet.jl:112-114, AbstractFlowpipe.jl:35-37).  With a box template the LP optimum is the box hull's
+    support function, which the oracle evaluates in closed form."""
+    n, nsteps = 6, 25
+    A, _ = stable_system(n, 5)
+    X0, U, _ = random_sets(n, 5)
+    ivp = D.forward(A, X0, 0.05, U)
+    alg = rb.LGG09(δ=0.05, template="box", n=n)
+    fp = post(alg, ivp, nsteps, ctx=ctx)
+    M = fp.support_function_matrix()
+    Dm = alg.template.matrix()
+    d = np.array([1.0, -0.5, 0.0, 2.0, 0.0, -1.0])
+    best = -np.inf
+    # rows of +e_i / -e_i
+    pos = [next(j for j in range(2 * n) if np.array_equal(Dm[:, j], np.eye(n)[i])) for i in range(n)]
+    neg = [next(j for j in range(2 * n) if np.array_equal(Dm[:, j], -np.eye(n)[i])) for i in range(n)]
+    for k in range(nsteps):
+        val = sum(d[i] * (M[pos[i], k] if d[i] > 0 else -M[neg[i], k]) for i in range(n))
+        best = max(best, val)
+    assert abs(fp.rho(d) - best) <= 1e-9 * max(1.0, abs(best))
+    assert abs(fp[3].rho(d) - sum(d[i] * (M[pos[i], 3] if d[i] > 0 else -M[neg[i], 3]) for i in range(n))) <= 1e-9
