@@ -221,6 +221,7 @@ struct reach_lgg09_plan {
     // derived sizes
     int Kp = 0;            // n padded to BK
     int mu = 0, mu_pad = 0;
+    int mu_ld = 0;               // stride of the per-chain feature arrays: mu_pad * oz_J (mu_pad without pass groups)
     int ne = 0, nbe = 0;   // mapped rows, rows per stack block
     int nq = 0;
     int S = 1;
@@ -261,6 +262,15 @@ struct reach_lgg09_plan {
     bool oz_guard = false;        // auto-selected: sampled passes are re-run on the DMMA kernel and compared
     int oz_T = OZ_DEFAULT_T, oz_nkb = 0, oz_tiles_n = 0;
     DevBuf Xq, Yq, eX, eY;
+    // Pass groups (few chains, e.g. one shard of a multi-GPU run): oz_J consecutive passes become ONE pair of launches.
+    // The carry stack holds (Phi')^(jS), j = 1..oz_J; L_t x carry stack gives the direction rows of the next oz_J passes
+    // at once (Lst), and the stacked rows [L_t; L_{t+1}; ...; L_{t+J-1}] x blocks 1..S is a GEMM with oz_J times the
+    // rows -- the shape (and tensor-pipe efficiency) of the unsharded problem, and oz_J times fewer dependent launches.
+    int oz_J = 1;
+    int oz_ctiles = 0;            // 128-row tiles per carry block (round_up(n, 128) / 128)
+    DevBuf Lst;                   // [oz_J][mu_pad][Kp]: L_{t+1} .. L_{t+J}
+    DevBuf cstack;                // [oz_J][oz_ctiles*128][Kp] FP64: first n rows of block jS
+    DevBuf Yq_c, eY_c;            // digit planes / exponents of the carry stack
     DevBuf ftot_ref, guard_val;
     // State after the last verified pass (direction block, running input sums, carried features): a failed check
     // restores it and replays every pass since then on the FP64 tensor pipe.
@@ -388,8 +398,8 @@ int launch_compact(reach_ctx* ctx, int G, int ne, const Lgg09Compact& c, bool in
 // tiles lose a little to shared-memory traffic; every pass costs two launches; building the row
 // stack costs about S + 2 log2(S) passes of an n x n x n product, amortised over the run.
 double step_cost(const reach_lgg09_plan& p, const TileCfg& c, int S, int mu, int nrows, int sms) {
-    // cfg 0 is the warp-specialised kernel; cfg 4 the digit-plane GEMM (T = 8: ~2.1x the DMMA rate, less for fewer planes)
-    static const double eff[kNumCfgs] = {1.12, 0.85, 0.9, 0.92, 2.3, 0.85};
+    // cfg 0 is the warp-specialised kernel; cfg 4 the digit-plane GEMM (7 planes of 8 bits: ~3x the DMMA rate)
+    static const double eff[kNumCfgs] = {1.12, 0.85, 0.9, 0.92, 3.0, 0.85};
     const int mu_pad = round_up(mu, c.TM);
     const bool packed = (c.id == 0 || c.id == kOzCfg) && nrows >= 128;
     const int nbe = packed ? round_up(nrows, 8) : round_up(nrows, c.TN);
@@ -437,7 +447,7 @@ int choose_config(reach_lgg09_plan& p) {
             const double stack_bytes = double(S + 1) * nbe * p.Kp * 8.0;
             const double feat_bytes = double(S + 1) * (nbe / c.TN) * std::max(1, p.nq) * 2.0 * mu_pad * 8.0;
             if (S > 1 && (stack_bytes > 3e9 || feat_bytes > 1e9)) continue;
-            const double cost = step_cost(p, c, S, p.mu, nrows, ctx->sm_count);
+            const double cost = step_cost(p, c, S, p.mu * (ci == kOzCfg ? p.oz_J : 1), nrows, ctx->sm_count);
             // prefer the earlier (larger-tile, smaller-S) candidate unless clearly beaten
             if (cost < best * 0.985) { best = cost; best_cfg = ci; best_S = S; }
         }
@@ -662,6 +672,15 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
         p->use_oz = true;
         p->oz_T = T;
     }
+    p->oz_J = 1;
+    if (p->use_oz && !(inv && inv->kind != REACH_INV_NONE) && !getenv("REACH_OZ_NO_GROUPS")) {
+        // pass groups: stack passes until the GEMM has ~2048 rows (16 row tiles).  Not with an invariant: the early exit
+        // is decided pass by pass.
+        const int mu_pad128 = round_up(p->mu, OZ_TM);
+        int J = std::max(1, std::min(16, 2048 / mu_pad128));
+        if (const char* e = getenv("REACH_OZ_GROUP")) J = std::max(1, std::min(16, atoi(e)));
+        p->oz_J = J;
+    }
     REACH_TRY(choose_config(*p));
     // ---- small / sparse Phi: ELL form of Phi' (row i of Phi' = column i of Phi) ----
     std::vector<double> ell_val;
@@ -719,7 +738,8 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
     p->tpb = p->packed ? 1 : p->nbe / TN;
     const size_t slice_tiles = (size_t(S + 1) * p->nbe + TN - 1) / TN;      // row tiles of the longest launch
     p->nq_pad = round_up(n, 128);
-    const int nbe = p->nbe, mu_pad = p->mu_pad, nq = p->nq;
+    p->mu_ld = p->mu_pad * (p->use_oz ? p->oz_J : 1);
+    const int nbe = p->nbe, mu_pad = p->mu_pad, mu_ld = p->mu_ld, nq = p->nq;
 
     // ---- device buffers ----
     REACH_TRY(p->stack.alloc(ctx, (size_t(S + 1) * nbe + 256) * Kp * sizeof(double)));     // + slack rows (zero)
@@ -731,12 +751,12 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
     REACH_TRY(p->Wl.alloc(ctx, size_t(std::max(1, nq)) * nbe * sizeof(double)));
     REACH_TRY(p->Wa.alloc(ctx, size_t(std::max(1, nq)) * nbe * sizeof(double)));
     REACH_TRY(p->tile_mask.alloc(ctx, size_t(p->tpb) * sizeof(uint32_t)));
-    p->fp_stride = (p->packed ? slice_tiles * 2 : size_t(S + 1) * p->tpb) * std::max(1, nq) * 2 * mu_pad;
+    p->fp_stride = (p->packed ? slice_tiles * 2 : size_t(S + 1) * p->tpb) * std::max(1, nq) * 2 * mu_ld;
     REACH_TRY(p->featpart.alloc(ctx, 2 * p->fp_stride * sizeof(double)));
-    REACH_TRY(p->ftot.alloc(ctx, size_t(S + 1) * std::max(1, nq) * 2 * mu_pad * sizeof(double)));
-    REACH_TRY(p->carry[0].alloc(ctx, size_t(std::max(1, nq)) * 2 * mu_pad * sizeof(double)));
-    REACH_TRY(p->carry[1].alloc(ctx, size_t(std::max(1, nq)) * 2 * mu_pad * sizeof(double)));
-    REACH_TRY(p->dv.alloc(ctx, size_t(S + 2) * 2 * mu_pad * sizeof(double)));
+    REACH_TRY(p->ftot.alloc(ctx, size_t(S + 1) * std::max(1, nq) * 2 * mu_ld * sizeof(double)));
+    REACH_TRY(p->carry[0].alloc(ctx, size_t(std::max(1, nq)) * 2 * mu_ld * sizeof(double)));
+    REACH_TRY(p->carry[1].alloc(ctx, size_t(std::max(1, nq)) * 2 * mu_ld * sizeof(double)));
+    REACH_TRY(p->dv.alloc(ctx, size_t(S + 2) * 2 * mu_ld * sizeof(double)));
     REACH_TRY(p->s_pos.alloc(ctx, size_t(mu_pad) * sizeof(double)));
     REACH_TRY(p->s_neg.alloc(ctx, size_t(mu_pad) * sizeof(double)));
     REACH_TRY(p->row_pos.alloc(ctx, size_t(p->mu) * sizeof(int)));
@@ -754,8 +774,16 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
         const size_t plane_blk = size_t(p->oz_T) * OZ_PLANE;
         REACH_TRY(p->Yq.alloc(ctx, size_t(p->oz_nkb) * p->oz_tiles_n * plane_blk, false));
         REACH_TRY(p->eY.alloc(ctx, size_t(p->oz_tiles_n) * OZ_TN * sizeof(int)));
-        REACH_TRY(p->Xq.alloc(ctx, size_t(p->oz_nkb) * (mu_pad / OZ_TM) * plane_blk, false));
-        REACH_TRY(p->eX.alloc(ctx, size_t(mu_pad) * sizeof(int)));
+        REACH_TRY(p->Xq.alloc(ctx, size_t(p->oz_nkb) * (mu_ld / OZ_TM) * plane_blk, false));
+        REACH_TRY(p->eX.alloc(ctx, size_t(mu_ld) * sizeof(int)));
+        if (p->oz_J > 1) {
+            p->oz_ctiles = round_up(n, OZ_TN) / OZ_TN;
+            const size_t crows = size_t(p->oz_J) * p->oz_ctiles * OZ_TN;
+            REACH_TRY(p->Lst.alloc(ctx, size_t(p->oz_J) * mu_pad * Kp * sizeof(double)));
+            REACH_TRY(p->cstack.alloc(ctx, crows * Kp * sizeof(double)));
+            REACH_TRY(p->Yq_c.alloc(ctx, size_t(p->oz_nkb) * (crows / OZ_TN) * plane_blk, false));
+            REACH_TRY(p->eY_c.alloc(ctx, crows * sizeof(int)));
+        }
         if (p->oz_guard) {
             REACH_TRY(p->ftot_ref.alloc(ctx, p->ftot.bytes));
             REACH_TRY(p->guard_val.alloc(ctx, sizeof(unsigned long long)));
@@ -1157,6 +1185,30 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         REACH_CUDA(ctx, cudaGetLastError());
         ++p->launches;
     }
+    const int J = p->use_oz ? p->oz_J : 1;
+    const int mu_ld = p->mu_ld;
+    const int mt = mu_pad / OZ_TM;                      // row tiles of one pass's direction rows (digit-plane path)
+    if (J > 1) {
+        // carry stack: C_j = (Phi')^(jS) = first n rows of block jS, j = 1..J.  C_1 is a copy of block S, C_{j+1} = C_j x P_S
+        // with Y = Q_S = the transpose of C_1 (the same NT product as the stack build).
+        const size_t cblk = size_t(p->oz_ctiles) * OZ_TN * Kp;          // doubles per carry block
+        double* C = p->cstack.as<double>();
+        REACH_CUDA(ctx, cudaMemsetAsync(C, 0, p->cstack.bytes, st));
+        REACH_CUDA(ctx, cudaMemcpy2DAsync(C, size_t(Kp) * 8, block(S), size_t(Kp) * 8, size_t(Kp) * 8, n, cudaMemcpyDeviceToDevice, st));
+        double* QS = p->Qbuf[0].as<double>();
+        {
+            dim3 grid((n + 31) / 32, (n + 31) / 32), blk(32, 8);
+            REACH_CUDA(ctx, cudaMemsetAsync(QS, 0, p->Qbuf[0].bytes, st));
+            transpose_kernel<<<grid, blk, 0, st>>>(C, Kp, QS, Kp, n);
+            REACH_CUDA(ctx, cudaGetLastError());
+            ++p->launches;
+        }
+        for (int j = 1; j < J; ++j) REACH_TRY(plain_gemm(C + (j - 1) * cblk, n, QS, n, C + j * cblk, n));
+        oz_slice_kernel<OZ_TN><<<J * p->oz_ctiles * OZ_TN / 8, 256, 0, st>>>(C, Kp, J * p->oz_ctiles * OZ_TN, n, p->oz_T, p->oz_nkb,
+                                                                     J * p->oz_ctiles, p->Yq_c.as<int8_t>(), p->eY_c.as<int>());
+        REACH_CUDA(ctx, cudaGetLastError());
+        ++p->launches;
+    }
     OzLgg09Epi<4> oepi{};
     oepi.ldl = Kp;
     oepi.n = n;
@@ -1165,19 +1217,19 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     oepi.Wa = p->Wa.as<double>();
     oepi.nq = p->nq;
     oepi.featpart = p->featpart.as<double>();
-    oepi.mu_pad = mu_pad;
+    oepi.mu_pad = mu_ld;
     // one pass of the digit-plane GEMM: L (fp64) -> digit planes, then blocks b_lo..S of the stack
     auto oz_pass = [&](const double* Lcur, double* Lnext, int b_lo, int b_hi, int store_block, bool sample) -> int {
         // a few hundred chains are only mu_pad/8 row groups: split the k range so that ~2 CTAs per SM are in flight
         const int ksplit = std::max(1, std::min(8, (2 * ctx->sm_count) / std::max(1, mu_pad / 8)));
-        oz_slice_kernel<OZ_TM><<<dim3(mu_pad / 8, ksplit), 256, 0, st>>>(Lcur, Kp, p->mu, n, p->oz_T, p->oz_nkb, mu_pad / OZ_TM,
+        oz_slice_kernel<OZ_TM><<<dim3(mu_pad / 8, ksplit), 256, 0, st>>>(Lcur, Kp, p->mu, n, p->oz_T, p->oz_nkb, J * mt,
                                                           p->Xq.as<int8_t>(), p->eX.as<int>());
         REACH_CUDA(ctx, cudaGetLastError());
         ++p->launches;
         const int tile_lo = int((size_t(b_lo) * nbe) / OZ_TN);
         const int tile_hi = int((size_t(b_hi + 1) * nbe + OZ_TN - 1) / OZ_TN);
         OzOperands g{p->Xq.as<int8_t>(), p->Yq.as<int8_t>(), p->eX.as<int>(), p->eY.as<int>(), p->oz_nkb,
-                     mu_pad / OZ_TM, mu_pad / OZ_TM, tile_lo, tile_hi - tile_lo, p->oz_tiles_n};
+                     mt, J * mt, tile_lo, tile_hi - tile_lo, p->oz_tiles_n};
         oepi.Lnext = Lnext;
         oepi.store_block = store_block;
         if (sample) REACH_CUDA(ctx, cudaEventRecord(p->gemm_ev[2 * p->gemm_sampled], st));
@@ -1187,6 +1239,45 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
             ++p->gemm_sampled;
         }
         ++p->launches;
+        return REACH_OK;
+    };
+
+    // A group of Jg passes t .. t+Jg-1 from the direction rows L_t (see reach_lgg09_plan::oz_J): carry GEMM -> L_{t+1..t+Jg},
+    // digit planes of [L_t; ...; L_{t+Jg-1}], ONE output GEMM over blocks b_lo..S for all Jg passes (features only: nothing
+    // is carried out of it), and L_{t+Jg} becomes the plan's current direction rows.
+    auto oz_group = [&](double* Lcur, int Jg, int b_lo, bool sample) -> int {
+        const int ksplit = std::max(1, std::min(8, (2 * ctx->sm_count) / std::max(1, mu_pad / 8)));
+        oz_slice_kernel<OZ_TM><<<dim3(mu_pad / 8, ksplit), 256, 0, st>>>(Lcur, Kp, p->mu, n, p->oz_T, p->oz_nkb, J * mt,
+                                                          p->Xq.as<int8_t>(), p->eX.as<int>());
+        REACH_CUDA(ctx, cudaGetLastError());
+        OzOperands gc{p->Xq.as<int8_t>(), p->Yq_c.as<int8_t>(), p->eX.as<int>(), p->eY_c.as<int>(), p->oz_nkb,
+                      mt, J * mt, 0, Jg * p->oz_ctiles, J * p->oz_ctiles};
+        OzCarryEpi cepi{p->Lst.as<double>(), Kp, n, p->oz_ctiles, mu_pad};
+        REACH_CUDA(ctx, (launch_oz_gemm(p->oz_T, gc, cepi, st)));
+        if (Jg > 1) {
+            const int rows = (Jg - 1) * mu_pad;
+            const int ks2 = std::max(1, std::min(8, (2 * ctx->sm_count) / std::max(1, rows / 8)));
+            oz_slice_kernel<OZ_TM><<<dim3(rows / 8, ks2), 256, 0, st>>>(p->Lst.as<double>(), Kp, rows, n, p->oz_T, p->oz_nkb, J * mt,
+                                                         p->Xq.as<int8_t>(), p->eX.as<int>(), mt);
+            REACH_CUDA(ctx, cudaGetLastError());
+            ++p->launches;
+        }
+        // the next group's (or pass's) direction rows
+        REACH_CUDA(ctx, cudaMemcpyAsync(Lcur, p->Lst.as<double>() + size_t(Jg - 1) * mu_pad * Kp, size_t(mu_pad) * Kp * 8,
+                                        cudaMemcpyDeviceToDevice, st));
+        const int tile_lo = int((size_t(b_lo) * nbe) / OZ_TN);
+        const int tile_hi = int((size_t(S + 1) * nbe + OZ_TN - 1) / OZ_TN);
+        OzOperands g{p->Xq.as<int8_t>(), p->Yq.as<int8_t>(), p->eX.as<int>(), p->eY.as<int>(), p->oz_nkb,
+                     Jg * mt, J * mt, tile_lo, tile_hi - tile_lo, p->oz_tiles_n};
+        oepi.Lnext = nullptr;
+        oepi.store_block = -1;
+        if (sample) REACH_CUDA(ctx, cudaEventRecord(p->gemm_ev[2 * p->gemm_sampled], st));
+        REACH_CUDA(ctx, (launch_oz_gemm(p->oz_T, g, oepi, st)));
+        if (sample) {
+            REACH_CUDA(ctx, cudaEventRecord(p->gemm_ev[2 * p->gemm_sampled + 1], st));
+            ++p->gemm_sampled;
+        }
+        p->launches += 3;
         return REACH_OK;
     };
 
@@ -1202,7 +1293,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     epi.tile_mask = p->tile_mask.as<uint32_t>();
     epi.nq = p->nq;
     epi.featpart = p->featpart.as<double>();
-    epi.mu_pad = mu_pad;
+    epi.mu_pad = mu_ld;
 
     Lgg09PackedEpi pepi{};
     pepi.ldl = Kp;
@@ -1212,7 +1303,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     pepi.Wa = p->Wa.as<double>();
     pepi.nq = p->nq;
     pepi.featpart = p->featpart.as<double>();
-    pepi.mu_pad = mu_pad;
+    pepi.mu_pad = mu_ld;
 
     Lgg09Combine cmb{};
     cmb.prog = p->prog.dev;
@@ -1220,7 +1311,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     cmb.tile_mask = p->tile_mask.as<uint32_t>();
     cmb.tpb = p->tpb;
     cmb.nq = p->nq;
-    cmb.mu_pad = mu_pad;
+    cmb.mu_pad = mu_ld;
     cmb.mu = p->mu;
     cmb.nsteps = p->nsteps;
     cmb.s_pos = p->s_pos.as<double>();
@@ -1383,9 +1474,12 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         return REACH_OK;
     };
     const int gemm_ev_pairs = int(p->gemm_ev.size() / 2);
-    for (int64_t t = 0; t < T; ++t) {
+    // guarded digit-plane path: passes 0, 1, every 64th and the last are also run on the DMMA kernel
+    auto is_check = [&](int64_t tt) { return oz_now && p->oz_guard && (tt < 2 || (tt & 63) == 0 || tt == T - 1); };
+    int64_t npl = 0;                               // main-loop GEMM launches so far (a pass, or a group of passes)
+    for (int64_t t = 0; t < T; ++t, ++npl) {
         const int b_lo = t == 0 ? 0 : 1;
-        const int par = int(t & 1);
+        const int par = int(npl & 1);
         if (fb_pending[par]) {                     // the invariant scan of pass t-2
             REACH_CUDA(ctx, cudaEventSynchronize(p->ev_fb[par]));
             fb_pending[par] = false;
@@ -1406,9 +1500,47 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         epi.store_block = S;
         const bool sample = (t % sample_every) == 0 && p->gemm_sampled < gemm_ev_pairs;
         cmb.b_lo = b_lo; cmb.b_hi = S; cmb.has_carry = t > 0; cmb.tail = 0; cmb.k0 = t * S;
-        // guarded digit-plane path: passes 0, 1, every 64th and the last are also run on the DMMA kernel
-        const bool check = oz_now && p->oz_guard && (t < 2 || (t & 63) == 0 || t == T - 1);
+        const bool check = is_check(t);
         const bool side = overlap && !check;
+        if (oz_now && J > 1 && !check) {
+            // pass group: as many unchecked passes as fit (the checked ones stay single passes, so the guard logic below
+            // sees exactly the state it always saw)
+            int Jg = 1;
+            while (Jg < J && t + Jg < T && !is_check(t + Jg)) ++Jg;
+            if (Jg >= 2) {
+                if (side && side_busy[par]) {      // the combines of launch npl-2 have read this parity's partials
+                    REACH_CUDA(ctx, cudaStreamWaitEvent(st, p->ev_comb[par], 0));
+                    side_busy[par] = false;
+                }
+                REACH_TRY(oz_group(p->Lbuf[cur].as<double>(), Jg, b_lo, sample));
+                ++p->gemm_total;
+                cudaStream_t cs = side ? st2 : st;
+                if (side) {
+                    REACH_CUDA(ctx, cudaEventRecord(p->ev_gemm[par], st));
+                    REACH_CUDA(ctx, cudaStreamWaitEvent(st2, p->ev_gemm[par], 0));
+                }
+                for (int j = 0; j < Jg; ++j) {     // the passes of the group, in step order (running sums, carried features)
+                    Lgg09Combine c = cmb;
+                    c.featpart = cmb.featpart + size_t(j) * mu_pad;
+                    c.b_lo = (t + j == 0) ? 0 : 1; c.b_hi = S; c.has_carry = (t + j > 0); c.tail = 0; c.k0 = (t + j) * int64_t(S);
+                    REACH_TRY(combine(c, cs));
+                }
+                if (side) {
+                    REACH_CUDA(ctx, cudaEventRecord(p->ev_comb[par], st2));
+                    side_busy[par] = true;
+                }
+                if (sen_on) {                      // sentinel rows Jg passes on: x (Phi')^(Jg S), FP64, own stream
+                    const double* Cj = p->cstack.as<double>() + size_t(Jg - 1) * p->oz_ctiles * OZ_TN * Kp;
+                    GemmOperands gs{p->Lsh[sen_cur].as<double>(), Cj, Kp, Kp, Kp, 1, round_up(n, 128) / 128};
+                    StoreEpi sepi{p->Lsh[1 - sen_cur].as<double>(), Kp, nsen, n};
+                    REACH_CUDA(ctx, (launch_cfg(0, gs, sepi, st3)));
+                    ++p->launches;
+                    sen_cur ^= 1;
+                }
+                t += Jg - 1;
+                continue;
+            }
+        }
         if (check) {
             REACH_TRY(join_side());
         } else if (side && side_busy[par]) {       // the combine of pass t-2 has read this parity's partials
@@ -1430,12 +1562,12 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
             if (check) {
                 REACH_CUDA(ctx, cudaMemsetAsync(p->guard_val.p, 0, sizeof(unsigned long long), st));
                 REACH_CUDA(ctx, cudaMemsetAsync(p->drift_val.p, 0, sizeof(unsigned long long), st));
-                lgg09_guard_kernel<<<(p->mu * p->nq + 127) / 128, 128, 0, st>>>(ftot, p->ftot_ref.as<double>(), p->nq, mu_pad, p->mu,
+                lgg09_guard_kernel<<<(p->mu * p->nq + 127) / 128, 128, 0, st>>>(ftot, p->ftot_ref.as<double>(), p->nq, mu_ld, p->mu,
                                                                                1, S, p->guard_val.as<unsigned long long>());
                 REACH_CUDA(ctx, cudaGetLastError());
                 ++p->launches;
                 if (sen_on) {
-                    lgg09_guard_kernel<<<(nsen * p->nq + 127) / 128, 128, 0, st>>>(ftot, p->ftot_sen.as<double>(), p->nq, mu_pad, nsen,
+                    lgg09_guard_kernel<<<(nsen * p->nq + 127) / 128, 128, 0, st>>>(ftot, p->ftot_sen.as<double>(), p->nq, mu_ld, nsen,
                                                                                   1, S, p->drift_val.as<unsigned long long>(), sen_stride);
                     REACH_CUDA(ctx, cudaGetLastError());
                     ++p->launches;

@@ -87,6 +87,22 @@ struct OzStoreEpi {
     __device__ __forceinline__ void finish(State&, unsigned char*, int, int, int, int) const {}
 };
 
+// ---- carry epilogue (LGG09 pass groups): Y = [(Phi')^S; (Phi')^2S; ...], blocks of tiles_per_block tiles ----
+// value (chain m, row r of block j) -> out[(j * rows_per_slot + m) * ldl + r]: the direction rows of pass t + j + 1.
+struct OzCarryEpi {
+    double* out;
+    int ldl, n, tiles_per_block, rows_per_slot;
+    struct State {};
+    static constexpr size_t SMEM = 0;
+    __device__ __forceinline__ void prepare(unsigned char*, int, int) const {}
+    __device__ __forceinline__ void begin(State&) const {}
+    __device__ __forceinline__ void accept(State&, const unsigned char*, int m, int tn, int j, double v) const {
+        const int blk = tn / tiles_per_block, col = (tn - blk * tiles_per_block) * OZ_TN + j;
+        if (col < n) out[(size_t(blk) * rows_per_slot + m) * ldl + col] = v;
+    }
+    __device__ __forceinline__ void finish(State&, unsigned char*, int, int, int, int) const {}
+};
+
 // ---- fused LGG09 epilogue on the digit-plane GEMM (packed stack layout, see Lgg09PackedEpi) ---------------
 // Stack rows are addressed absolutely (tile tn covers rows [128 tn, 128 tn + 128) of the stack; block b = row / nbe).
 // A tile straddles at most one block boundary (nbe >= 128): segment 0 = rows of the tile's first block, segment 1 =
@@ -437,7 +453,8 @@ inline cudaError_t launch_oz_gemm(int T, const OzOperands& g, const Epi& epi, cu
 template <int TR>
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ X, int ldx, int rows_valid, int k_valid,
                                                        int T, int nkb, int tiles_total, int8_t* __restrict__ Q,
-                                                       int* __restrict__ eout) {
+                                                       int* __restrict__ eout, int tile0 = 0) {
+    // tile0: the rows of X are tiles tile0, tile0 + 1, ... of the plane buffer (and exponents eout[tile0 * TR ...])
     __shared__ int s_e[8];
     const int row0 = blockIdx.x * 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -457,11 +474,11 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
                 if (oz_scale(mx, OZ_BITS - 1 - e) > double((1 << (OZ_BITS - 1)) - 1)) ++e;   // keep |x-hat| <= 127
             }
             s_e[warp] = e;
-            if (blockIdx.y == 0) eout[row] = e;
+            if (blockIdx.y == 0) eout[tile0 * TR + row] = e;
         }
     }
     __syncthreads();
-    const int tile = row0 / TR, gidx = (row0 % TR) / 8;
+    const int tile = tile0 + row0 / TR, gidx = (row0 % TR) / 8;
     const int nchunks = nkb * 2;
     const int per = (nchunks + gridDim.y - 1) / gridDim.y;
     const int item_lo = 8 * per * blockIdx.y, item_hi = min(8 * nchunks, item_lo + 8 * per);
