@@ -662,7 +662,10 @@ def run_b200(args):
     if rank == 0:
         S = st["time_block"]
         gemm_ms = gemm_ms_acc / args.steps                                  # mean duration of one launch
-        flops_per_launch = 2.0 * n * n * st["nchains"] * S                  # algorithmic: 2 n^2 per chain-step
+        # algorithmic: 2 n^2 per chain-step; a launch covers S steps of every chain, or (pass groups, few chains per GPU)
+        # S steps of several consecutive passes at once -- so: all chain-steps of the run / main-loop launches of the run
+        steps_covered = -(-nsteps // S) * S
+        flops_per_launch = 2.0 * n * n * st["nchains"] * steps_covered / max(1, st["gemm_launches"])
         achieved = flops_per_launch / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None   # FP64-equivalent TFLOP/s
         traffic, ncu = None, {}
         try:

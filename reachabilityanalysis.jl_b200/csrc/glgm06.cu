@@ -324,6 +324,7 @@ extern "C" int reach_glgm06_plan_run(reach_glgm06_plan* p) {
     if (!p) return REACH_EINVAL;
     reach_ctx* ctx = p->ctx;
     if (!p->uploaded) return set_error(ctx, REACH_ESTATE, "plan_run before plan_upload");
+    NvtxRange nvtx_fn("reach_glgm06_plan_run (powers, shared chain, batched product, selection)");
     REACH_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int n = p->n, Kp = p->Kp, nb = p->nb, r = p->r, nsplits = p->nsplits;

@@ -525,6 +525,7 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
     if (!p) return REACH_EINVAL;
     reach_ctx* ctx = p->ctx;
     if (!Phi || !dirs) return set_error(ctx, REACH_EINVAL, "Phi and dirs must not be NULL");
+    NvtxRange nvtx_fn("reach_lgg09_plan_upload (flatten program, choose path, H2D)");
     REACH_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int n = p->n, Kp = p->Kp, ndirs = p->ndirs;
@@ -1047,6 +1048,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     if (!p) return REACH_EINVAL;
     reach_ctx* ctx = p->ctx;
     if (!p->uploaded) return set_error(ctx, REACH_ESTATE, "plan_run before plan_upload");
+    NvtxRange nvtx_fn("reach_lgg09_plan_run");
     REACH_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int n = p->n, Kp = p->Kp, nbe = p->nbe, S = p->S, TM = p->TM, TN = p->TN, mu_pad = p->mu_pad;
@@ -1150,6 +1152,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     REACH_CUDA(ctx, cudaMemsetAsync(p->s_neg.p, 0, p->s_neg.bytes, st));
 
     // ---- row stack: block_b = [I;E] (Phi')^b, b = 0..S.  block_0 was uploaded. ----
+    nvtxRangePushA("reach_lgg09: row stack (powers of Phi')");
     {   // Q_1 = Phi row-major: Q[k][l] = Phi(k,l) = phi_cm[k + n l]
         dim3 grid((n + 31) / 32, (n + 31) / 32), blk(32, 8);
         transpose_kernel<<<grid, blk, 0, st>>>(p->phi_cm.as<double>(), n, p->Qbuf[0].as<double>(), Kp, n);
@@ -1209,6 +1212,8 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         REACH_CUDA(ctx, cudaGetLastError());
         ++p->launches;
     }
+    nvtxRangePop();
+    NvtxRange nvtx_main("reach_lgg09: main loop (GEMM passes + combine)");
     OzLgg09Epi<4> oepi{};
     oepi.ldl = Kp;
     oepi.n = n;

@@ -11,6 +11,8 @@
 #include <vector>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges show up in Nsight Systems / ncu --nvtx, no-ops otherwise
+
 #include "../../include/reach.h"
 
 struct reach_ctx {
@@ -120,6 +122,14 @@ struct DevBuf {
         return REACH_OK;
     }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// NVTX range for the scope (phases of plan_run: upload, stack build, main loop, chain, batched product, selection ...)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
 };
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
