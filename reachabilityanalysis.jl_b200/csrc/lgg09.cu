@@ -410,7 +410,10 @@ double step_cost(const reach_lgg09_plan& p, const TileCfg& c, int S, int mu, int
         const double mem = double(c.TM + c.TN) * p.Kp * 8.0 / 40.0 * c.occ;   // ~40 B/clk/SM from L2
         return waves * (std::max(mma, mem) + (c.id == 0 || c.id == kOzCfg ? 12000.0 : 4000.0));   // prologue + epilogue
     };
-    const double launch = 60000.0;     // ~30 us per pass: GEMM + tile-sum + eval + prefix launches back to back
+    // ~30 us per pass: GEMM + tile-sum + eval + prefix launches back to back.  The persistent digit-plane kernel pays about
+    // one more tile time per launch (ring fill, the last tile's epilogue, the slice of L in front of it): measured on
+    // shards of C5, 1000 chains: S = 14 / 20 / 28 -> 901 / 880 / 855 ms.
+    const double launch = c.id == kOzCfg ? 250000.0 : 60000.0;
     double cost = (pass(double(mu_pad / c.TM) * std::ceil(double(S) * nbe / c.TN)) + launch) / S;
     // stack build by doubling (64x64 tiles, occupancy 2), amortised: one launch per product, each as many waves as its
     // row count needs (for small n a whole doubling step is a single wave -- the build is ~2 log2(S) launches, not S)
@@ -678,7 +681,9 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
         // pass groups: stack passes until the GEMM has ~2048 rows (16 row tiles).  Not with an invariant: the early exit
         // is decided pass by pass.
         const int mu_pad128 = round_up(p->mu, OZ_TM);
-        int J = std::max(1, std::min(16, 2048 / mu_pad128));
+        // measured on shards of C5 (n = 2000): 250 chains J = 8: 325 -> 247 ms, 500 chains J = 4: 484 -> 462 ms, 1000 chains
+        // J = 2: no gain over single passes (the carry GEMM costs what the fuller waves save)
+        int J = mu_pad128 <= 512 ? std::max(1, std::min(16, 2048 / mu_pad128)) : 1;
         if (const char* e = getenv("REACH_OZ_GROUP")) J = std::max(1, std::min(16, atoi(e)));
         p->oz_J = J;
     }
@@ -1463,19 +1468,31 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     }
     // features of blocks 1 and S (the first step of the pass and the block that becomes L_{k+S}) on the DMMA kernel from
     // the rows X; nothing of the run's state is touched (no store block, separate totals buffer)
-    auto dmma_features = [&](const double* X, int mtiles, int nchains, double* totals) -> int {
+    // With few chains a 128x128 launch is a fraction of one wave (250 chains: 32 CTAs of 0.3 ms each); 64x64 tiles put four
+    // times as many CTAs to work on it.  Same arithmetic (FP64 DMMA), only the tile shape differs.
+    auto dmma_features = [&](const double* X, int rows_pad, int nchains, double* totals) -> int {
+        const bool small = int64_t(rows_pad / 128) * ((nbe + 127) / 128) * 2 <= 3 * int64_t(ctx->sm_count);
+        const int tm = small ? 64 : TM, tn = small ? 64 : TN;
         for (int cb : {1, S}) {
-            GemmOperands gc{X, block(cb), Kp, Kp, Kp, mtiles, (nbe + TN - 1) / TN};
+            GemmOperands gc{X, block(cb), Kp, Kp, Kp, rows_pad / tm, (nbe + tn - 1) / tn};
             pepi.Lnext = p->Lbuf[1 - cur].as<double>(); pepi.slice_block0 = cb; pepi.store_block = -1;
-            REACH_CUDA(ctx, (launch_cfg(0, gc, pepi, st)));
+            REACH_CUDA(ctx, (launch_cfg(small ? 1 : 0, gc, pepi, st)));
             Lgg09Combine cc = cmb;
             cc.b_lo = cb; cc.b_hi = cb; cc.mu = nchains;
             dim3 grid((nchains + cthreads - 1) / cthreads, 1);
-            lgg09_tilesum_packed_kernel<<<grid, cthreads, 0, st>>>(cc, cc.featpart, totals, nbe, TN, cb);
+            lgg09_tilesum_packed_kernel<<<grid, cthreads, 0, st>>>(cc, cc.featpart, totals, nbe, tn, cb);
             REACH_CUDA(ctx, cudaGetLastError());
             p->launches += 2;
             if (S == 1) break;
         }
+        return REACH_OK;
+    };
+    // sentinel rows (<= 128) x an n x n power: 64x64 tiles (2 x n/64 CTAs instead of n/128)
+    auto sentinel_step = [&](const double* Ypow, int sen_from) -> int {
+        GemmOperands gs{p->Lsh[sen_from].as<double>(), Ypow, Kp, Kp, Kp, OZ_TM / 64, round_up(n, 64) / 64};
+        StoreEpi sepi{p->Lsh[1 - sen_from].as<double>(), Kp, nsen, n};
+        REACH_CUDA(ctx, (launch_cfg(1, gs, sepi, st3)));
+        ++p->launches;
         return REACH_OK;
     };
     const int gemm_ev_pairs = int(p->gemm_ev.size() / 2);
@@ -1535,11 +1552,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
                     side_busy[par] = true;
                 }
                 if (sen_on) {                      // sentinel rows Jg passes on: x (Phi')^(Jg S), FP64, own stream
-                    const double* Cj = p->cstack.as<double>() + size_t(Jg - 1) * p->oz_ctiles * OZ_TN * Kp;
-                    GemmOperands gs{p->Lsh[sen_cur].as<double>(), Cj, Kp, Kp, Kp, 1, round_up(n, 128) / 128};
-                    StoreEpi sepi{p->Lsh[1 - sen_cur].as<double>(), Kp, nsen, n};
-                    REACH_CUDA(ctx, (launch_cfg(0, gs, sepi, st3)));
-                    ++p->launches;
+                    REACH_TRY(sentinel_step(p->cstack.as<double>() + size_t(Jg - 1) * p->oz_ctiles * OZ_TN * Kp, sen_cur));
                     sen_cur ^= 1;
                 }
                 t += Jg - 1;
@@ -1556,9 +1569,9 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
             if (sen_on) {                          // the sentinel rows of pass t, propagated in FP64 since pass 0
                 REACH_CUDA(ctx, cudaEventRecord(p->ev_sen[1], st3));
                 REACH_CUDA(ctx, cudaStreamWaitEvent(st, p->ev_sen[1], 0));
-                REACH_TRY(dmma_features(p->Lsh[sen_cur].as<double>(), 1, nsen, p->ftot_sen.as<double>()));
+                REACH_TRY(dmma_features(p->Lsh[sen_cur].as<double>(), OZ_TM, nsen, p->ftot_sen.as<double>()));
             }
-            REACH_TRY(dmma_features(p->Lbuf[cur].as<double>(), mu_pad / TM, p->mu, p->ftot_ref.as<double>()));
+            REACH_TRY(dmma_features(p->Lbuf[cur].as<double>(), mu_pad, p->mu, p->ftot_ref.as<double>()));
         }
         if (oz_now) {
             REACH_TRY(oz_pass(p->Lbuf[cur].as<double>(), epi.Lnext, b_lo, S, S, sample));
@@ -1631,10 +1644,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
                 }
             }
             if (sen_on) {                          // sentinel rows of pass t + 1 = rows of pass t x block S, FP64, own stream
-                GemmOperands gs{p->Lsh[sen_cur].as<double>(), block(S), Kp, Kp, Kp, 1, round_up(n, 128) / 128};
-                StoreEpi sepi{p->Lsh[1 - sen_cur].as<double>(), Kp, nsen, n};
-                REACH_CUDA(ctx, (launch_cfg(0, gs, sepi, st3)));
-                ++p->launches;
+                REACH_TRY(sentinel_step(block(S), sen_cur));
                 sen_cur ^= 1;
             }
             cur ^= 1;

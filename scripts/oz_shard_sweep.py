@@ -15,11 +15,13 @@ wl = W.synthetic_c5(nsteps=nsteps)
 ref = None
 for world in worlds:
     local_dirs, rows_by_rank, mloc = shard_directions(wl.dirs, world, 0)
-    for groups in (True, False):
-        if groups:
-            os.environ.pop("REACH_OZ_NO_GROUPS", None)
-        else:
+    for groups in ([int(v) for v in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0, 1]):   # 0: auto J, 1: no groups, k: J = k
+        os.environ.pop("REACH_OZ_NO_GROUPS", None)
+        os.environ.pop("REACH_OZ_GROUP", None)
+        if groups == 1:
             os.environ["REACH_OZ_NO_GROUPS"] = "1"
+        elif groups > 1:
+            os.environ["REACH_OZ_GROUP"] = str(groups)
         for S in Ss:
             plan = Lgg09Plan(ctx, wl.n, mloc, nsteps, time_block=S)
             plan.upload(wl.Phi, local_dirs, wl.Omega0, wl.V)
