@@ -243,6 +243,15 @@ def post_batch(alg, ivp, T=None, NSTEPS=None, Δt0=zeroT, ctx=None):
             raise ValueError("the time horizon `T` (or `NSTEPS`) should be specified")
         NSTEPS = _nsteps(T, alg.δ)
     divps = [discretize(IVP(ivp.A, X0, ivp.B, ivp.U, ivp.X), alg.δ, alg.approx_model) for X0 in ivp.X0]
+    # one plan only makes sense if the splits really share Φ and the input zonotope (they do for the reference's models:
+    # neither depends on X0); checked rather than assumed
+    v0 = to_zonotope(divps[0].V) if divps[0].V is not None else None
+    for d in divps[1:]:
+        if not np.array_equal(d.Phi, divps[0].Phi):
+            raise ValueError("the splits must share Φ")
+        vd = to_zonotope(d.V) if d.V is not None else None
+        if (vd is None) != (v0 is None) or (v0 is not None and not (np.array_equal(vd[0], v0[0]) and np.array_equal(vd[1], v0[1]))):
+            raise ValueError("the splits must share the input set V")
     plan = _run_batch(alg, divps[0].Phi, [d.Omega0 for d in divps], divps[0].V, NSTEPS, ctx)
     kept = _sets_kept(plan, ivp.X)
     return MixedFlowpipe([_flowpipe_of_split(plan, s, alg, Δt0, int(kept[s])) for s in range(len(divps))],

@@ -368,6 +368,22 @@ class _SplitView:
         return self.batch.rho_flowpipe(d, self.split)
 
 
+def _same_set(X, Y):
+    """Structural equality of two (flattened) sets: same alternatives, same terms, same numbers."""
+    a, b = flatten(X, None), flatten(Y, None)
+    if len(a) != len(b) or any(len(x) != len(y) for x, y in zip(a, b)):
+        return False
+    for x, y in zip(a, b):
+        for t, u in zip(x, y):
+            if t.kind != u.kind or t.which != u.which:
+                return False
+            for name in ("M", "c", "r", "G"):
+                v, w = getattr(t, name), getattr(u, name)
+                if (v is None) != (w is None) or (v is not None and not np.array_equal(v, w)):
+                    return False
+    return True
+
+
 def post_batch(alg, ivps, NSTEPS, Δt0=zeroT, ctx=None):
     """The vector-of-initial-sets form of `solve` (src/Continuous/solve.jl:84-117) for LGG09: `ivps` are the
     discretised problems of the splits (same Φ and V, different Ω₀).  Returns a MixedFlowpipe whose flowpipes
@@ -384,6 +400,8 @@ def post_batch(alg, ivps, NSTEPS, Δt0=zeroT, ctx=None):
     for iv in ivps[1:]:
         if not np.array_equal(iv.Phi, first.Phi):
             raise ValueError("the splits must share Φ")
+        if (iv.V is None) != (first.V is None) or (first.V is not None and not _same_set(iv.V, first.V)):
+            raise ValueError("the splits must share the input set V")
     batch = Lgg09BatchPlan(ctx, first.Phi, template.matrix(), [iv.Omega0 for iv in ivps], first.V, NSTEPS)
     batch.run()
     fps = []

@@ -186,3 +186,17 @@ def test_template_reach_set_lp_fallback():
     Doct = np.array([[1, 0], [0, 1], [-1, 0], [0, -1], [1, 1], [-1, -1], [1, -1], [-1, 1]], dtype=float).T
     sfo = np.array([1, 1, 1, 1, 1.5, 1.5, 2, 2], dtype=float)
     assert abs(lp_support(np.array([2.0, 1.0]), Doct, sfo) - 2.5) < 1e-9
+
+
+def test_post_batch_rejects_splits_that_do_not_share_the_input_set():
+    """The split callers share Φ and V across the splits (`_solve_distributed`, solve.jl:84-117: same system, different
+    X0); a batch whose discretised problems differ in V must be refused, not silently run with the first one."""
+    from reach_b200 import lgg09
+    A = -np.eye(3)
+    X0 = rb.Hyperrectangle(np.zeros(3), 0.1 * np.ones(3))
+    a = D.forward(A, X0, 0.1, rb.BallInf(np.zeros(3), 0.05))
+    b = D.forward(A, X0, 0.1, rb.BallInf(np.zeros(3), 0.06))
+    alg = rb.LGG09(δ=0.1, template="box", n=3)
+    with pytest.raises(ValueError, match="share the input set"):
+        lgg09.post_batch(alg, [a, b], 5, ctx=object())
+    assert lgg09._same_set(a.V, a.V) and not lgg09._same_set(a.V, b.V)

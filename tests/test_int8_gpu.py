@@ -253,3 +253,57 @@ def test_sentinel_chains_report_the_accumulated_drift(ctx):
     assert st["path"] == "int8" and st["fallback_pass"] == -1 and st["guard_checks"] >= 5
     assert 0.0 < st["drift_max"] <= 1e-11 and st["replay_from"] == -1 and st["replayed_passes"] == 0
     assert_support_parity(plan.sfmat(), LO.reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, wl.V))
+
+
+# ---- pass groups: few chains (one shard of a multi-GPU run) -> several passes per pair of launches ----------------
+
+def _few_chains(n, nchains, nsteps, seed):
+    wl = _synthetic(n, nsteps, seed=seed)
+    dirs = np.hstack([np.eye(n)[:, :nchains], -np.eye(n)[:, :nchains]])
+    return wl, dirs
+
+
+@pytest.mark.parametrize("n,nchains,nsteps,S", [(200, 37, 29, 3), (300, 130, 64, 1), (600, 250, 41, 4), (520, 64, 90, 0)])
+def test_pass_groups_forced_int8_match_oracle_and_ungrouped_run(ctx, monkeypatch, n, nchains, nsteps, S):
+    """Unguarded INT8 path with few chains: every pass is grouped (J = 16 / 8 / 8 / 16 stacked passes, ragged last group,
+    group 0 starts at block 0).  Same numbers as the oracle, and as the run without groups up to the reassociation through
+    (Phi')^(jS)."""
+    wl, dirs = _few_chains(n, nchains, nsteps, seed=n + nchains)
+    rng = np.random.default_rng(1)
+    if nchains == 37:                                     # custom directions too: an odd number of chains without negation
+        dirs = np.hstack([dirs, rng.standard_normal((n, 3))])
+    ref = LO.reach_inhomog_LGG09(dirs, wl.Omega0, wl.Phi, nsteps, wl.V)
+    plan = reach_inhomog_LGG09(dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=S, path="int8")
+    st = plan.stats()
+    assert st["path"] == "int8"
+    passes = -(-(nsteps - 1 + 1) // st["time_block"])     # Forward model: features of r_{k+1} are needed
+    assert st["gemm_launches"] < passes, (st["gemm_launches"], passes)       # grouped
+    assert_support_parity(plan.sfmat(), ref)
+    monkeypatch.setenv("REACH_OZ_NO_GROUPS", "1")
+    single = reach_inhomog_LGG09(dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=S, path="int8")
+    monkeypatch.delenv("REACH_OZ_NO_GROUPS")
+    assert single.stats()["gemm_launches"] >= passes
+    assert_support_parity(plan.sfmat(), single.sfmat(), tol=1e-11)
+
+
+def test_pass_groups_with_the_guard_and_a_trip_inside_a_grouped_run(ctx, monkeypatch):
+    """Auto path (guarded) with 120 chains: checked passes 0, 1, 64, 128, last stay single, the passes between them run in
+    groups of up to 16.  A failed check at pass 64 restores the state kept after pass 1 and redoes passes 2..64 on the
+    FP64 tensor pipe -- the grouped INT8 passes in between leave nothing behind."""
+    n, nchains, nsteps = 520, 120, 333
+    wl, dirs = _few_chains(n, nchains, nsteps, seed=11)
+    ref = LO.reach_inhomog_LGG09(dirs, wl.Omega0, wl.Phi, nsteps, wl.V)
+    plan = reach_inhomog_LGG09(dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=2)
+    st = plan.stats()
+    assert st["path"] == "int8" and st["fallback_pass"] == -1 and st["guard_checks"] == 5, st
+    assert st["gemm_launches"] <= 5 + 2 + 11, st          # 5 single checked passes + ceil(62/16) + ceil(63/16) + ceil(36/16) groups
+    assert 0.0 < st["guard_max"] <= 1e-12 and 0.0 < st["drift_max"] <= 1e-11
+    assert_support_parity(plan.sfmat(), ref)
+    monkeypatch.setenv("REACH_OZ_TRIP_AT", "3")
+    trip = reach_inhomog_LGG09(dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=2)
+    monkeypatch.delenv("REACH_OZ_TRIP_AT")
+    st = trip.stats()
+    assert st["fallback_pass"] == 64 and st["replay_from"] == 2 and st["replayed_passes"] == 63, st
+    assert_support_parity(trip.sfmat(), ref)
+    dmma = reach_inhomog_LGG09(dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=2, path="gemm")
+    assert_support_parity(trip.sfmat()[:, 4:], dmma.sfmat()[:, 4:], tol=1e-12)     # steps of passes >= 2: FP64 pipe output
