@@ -558,18 +558,24 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
         index.reserve(size_t(ndirs) * 2);
         for (int j = 0; j < ndirs; ++j) {
             const double* d = dirs + size_t(j) * n;
+            // canonical orientation first (sign of the first non-zero entry), then an FNV-style hash of sign * d in four
+            // independent lanes (one dependent multiply per element was ~10 ms for 4000 x 2000 directions)
             double sign = 1.0;
-            bool seen = false;
-            uint64_t h = 1469598103934665603ull;
+            if (p->opts.share_negated)
+                for (int i = 0; i < n; ++i)
+                    if (d[i] != 0.0) { sign = d[i] < 0 ? -1.0 : 1.0; break; }
+            uint64_t hl[4] = {1469598103934665603ull, 0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull};
+            bool finite = true;
             for (int i = 0; i < n; ++i) {
                 const double v = d[i];
-                if (!std::isfinite(v)) return set_error(ctx, REACH_EINVAL, "direction %d is not finite", j);
-                if (!seen && v != 0.0 && p->opts.share_negated) { sign = v < 0 ? -1.0 : 1.0; seen = true; }
-                const double cv = sign * v + 0.0;                 // zeros before the first non-zero hash as +0
+                finite &= std::isfinite(v);
+                const double cv = sign * v + 0.0;                 // -0 hashes as +0
                 uint64_t bits;
                 std::memcpy(&bits, &cv, 8);
-                h = (h ^ bits) * 1099511628211ull;
+                hl[i & 3] = (hl[i & 3] ^ bits) * 1099511628211ull;
             }
+            if (!finite) return set_error(ctx, REACH_EINVAL, "direction %d is not finite", j);
+            const uint64_t h = ((hl[0] * 31 + hl[1]) * 31 + hl[2]) * 31 + hl[3];
             int c = -1;
             if (p->opts.share_negated) {
                 auto range = index.equal_range(h);

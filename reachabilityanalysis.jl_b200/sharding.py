@@ -46,24 +46,36 @@ def shard_directions(dirs, world, rank):
     return local, rows_by_rank, mloc
 
 
+_gather_cache = {}
+
+
 def gather_support_values(local_T, rows_by_rank, ndirs, group=None):
     """All-gather the per-rank blocks and place the rows.
 
     local_T: torch tensor [nsteps, mloc] (i.e. the column-major mloc × nsteps block the device
     path produced).  Returns a tensor [nsteps, ndirs] == column-major ndirs × nsteps, the
-    reference's ρℓ layout."""
+    reference's ρℓ layout.  The per-rank row indices are built once per (sharding, device) and kept on the
+    device, and the gather / output buffers are reused between calls (the returned tensor is overwritten by
+    the next call)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
     nsteps, mloc = local_T.shape
-    flat = torch.empty((world * nsteps, mloc), dtype=local_T.dtype, device=local_T.device)
-    dist.all_gather_into_tensor(flat, local_T.contiguous(), group=group)
-    gathered = flat.view(world, nsteps, mloc)
-    out = torch.empty((nsteps, ndirs), dtype=local_T.dtype, device=local_T.device)
-    for r in range(world):
-        rows = torch.as_tensor(rows_by_rank[r], device=local_T.device)
+    key = (id(rows_by_rank), str(local_T.device), nsteps, mloc, ndirs, local_T.dtype)
+    ent = _gather_cache.get(key)
+    if ent is None:
+        ent = {"rows": [torch.as_tensor(np.asarray(rows_by_rank[r], dtype=np.int64), device=local_T.device) for r in range(world)],
+               "flat": torch.empty((world, nsteps, mloc), dtype=local_T.dtype, device=local_T.device),
+               "out": torch.empty((nsteps, ndirs), dtype=local_T.dtype, device=local_T.device),
+               "rows_by_rank": rows_by_rank}                       # keeps id() stable while cached
+        _gather_cache.clear()
+        _gather_cache[key] = ent
+    flat, out = ent["flat"], ent["out"]
+    dist.all_gather_into_tensor(flat.view(world * nsteps, mloc), local_T.contiguous(), group=group)
+    for r in range(world):                                         # out[:, rows_r] = block of rank r (its valid columns)
+        rows = ent["rows"][r]
         if len(rows):
-            out.index_copy_(1, rows, gathered[r, :, :len(rows)])
+            out.index_copy_(1, rows, flat[r, :, :len(rows)])
     return out
 
 
