@@ -347,6 +347,11 @@ int reach_dgemm_probe(reach_ctx* ctx, int m, int n, int k, int iters, double* tf
 int reach_ozgemm_probe(reach_ctx* ctx, int m, int n, int k, int slices, const double* X_host,
                        const double* Y_host, double* C_host, int iters, double* tflops, double* slice_ms);
 
+/* The same probe through the residue path (csrc/crt_gemm.cuh): `moduli` (8..16) INT8 GEMMs per FP64 product, one per
+ * pairwise coprime modulus <= 256, rebuilt with the Chinese remainder theorem; 2-CTA tcgen05 MMAs. */
+int reach_crtgemm_probe(reach_ctx* ctx, int m, int n, int k, int moduli, const double* X_host,
+                        const double* Y_host, double* C_host, int iters, double* tflops, double* slice_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,8 @@ SIGNATURES = {
     "reach_dgemm_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p]),
     "reach_ozgemm_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p,
                                      c_double_p, C.c_int, c_double_p, c_double_p]),
+    "reach_crtgemm_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p,
+                                      c_double_p, C.c_int, c_double_p, c_double_p]),
 }
 
 _lib = None
@@ -205,6 +207,19 @@ class Context:
         tf, sl = C.c_double(), C.c_double()
         self.check(self.lib.reach_ozgemm_probe(self.handle, m, n, k, slices, dptr(X), dptr(Y), dptr(Cm), iters,
                                                C.byref(tf), C.byref(sl)))
+        return Cm, tf.value, sl.value
+
+    def crtgemm_probe(self, X, Y, moduli=14, iters=1, want_result=True):
+        """C = X @ Y.T through the INT8-tcgen05 residue (CRT) GEMM; returns (C or None, TFLOP/s, residue conversion ms)."""
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        m, k = X.shape
+        n = Y.shape[0]
+        assert Y.shape[1] == k
+        Cm = np.empty((m, n)) if want_result else None
+        tf, sl = C.c_double(), C.c_double()
+        self.check(self.lib.reach_crtgemm_probe(self.handle, m, n, k, moduli, dptr(X), dptr(Y), dptr(Cm), iters,
+                                                C.byref(tf), C.byref(sl)))
         return Cm, tf.value, sl.value
 
     def close(self):

@@ -1,0 +1,512 @@
+// crt_gemm.cuh -- FP64-accurate GEMM on the INT8 tcgen05 tensor pipe through residue arithmetic ("Ozaki scheme II":
+// Ozaki, Uchino, Imamura 2025, integer modular technique), with 2-CTA (cta_group::2) MMAs.
+//
+//     C[m][n] = sum_k X[m][k] * Y[n][k]            (the same NT contraction as nt_dgemm.cuh / oz_gemm.cuh)
+//
+// oz_gemm.cuh cuts every operand into T = 7 digit planes and needs T(T+1)/2 = 28 INT8 products per FP64 product.  The
+// kernel runs at the chip's power / L2-to-SM limit, so the number of INT8 products is what sets its time.  Here each
+// operand row is scaled by a power of two and rounded to an integer vector of 2-norm <= 2^alpha (resp. 2^beta),
+//     x' = rint(x 2^sx),  y' = rint(y 2^sy),      |sum_k x'_k y'_k| <= ||x'|| ||y'|| <= 2^(alpha+beta) < P/4
+// and the integer dot product C' is computed EXACTLY from its residues modulo N pairwise coprime moduli p_i <= 256
+// (P = prod p_i): the residues of x', y' fit signed bytes, one INT8 GEMM per modulus gives C'_i = X_i Y_i' with INT32
+// accumulators (exact for K <= 65472), and the Chinese remainder theorem rebuilds C' from u_i = C'_i mod p_i:
+//     C'/P = frac( sum_i u_i w_i / P ),   w_i = (P/p_i) ((P/p_i)^-1 mod p_i)
+// The fractions f_i = w_i/P are split f_i = f1_i + f2_i with f1_i a multiple of 2^-40: sum_i u_i f1_i is exact in FP64,
+// its integer part drops out, and sum_i u_i f2_i (< 2^-29) is accurate to 2^-80.  N = 14 moduli (P ~ 2^110, alpha = beta = 54)
+// round each operand element at 2^-54 of its row NORM -- below FP64's own rounding of the products -- with 14 INT8
+// products instead of 28; N = 13 matches the digit-plane path's accuracy.  The result does not depend on summation order.
+//
+// Kernel shape: CTA pairs (cluster of 2, cta_group::2).  A pair owns a 256 x 256 output tile: CTA r holds rows
+// [128 r, 128 r + 128) of X and of Y in its shared memory (8 KB + 8 KB per 64-byte k-block: half the L2 -> SM bytes
+// per MAC of a 128 x 256 one-CTA tile), the leader issues M = 256, N = 256, K = 32 MMAs, and each CTA's tensor memory
+// holds its 128 rows x 256 columns, double buffered (2 x 256 columns), so modulus i+1 is multiplied while modulus i is
+// drained.  Per tile the pair loops over the moduli; the epilogue warps reduce every INT32 accumulator mod p_i to a signed
+// byte and park it in a per-thread global scratch (L2 resident), then rebuild the FP64 values from the N residues
+// and hand them to the same epilogue functors as oz_gemm.cuh (plain store, carry rows, fused LGG09 support features).
+//   warp 16   producer: per k-block two cp.async.bulk copies (own X rows, own Y rows) into a 10-stage ring
+//   warp 17   leader: one thread issues the MMAs and commits (multicast) to both CTAs' barriers;
+//             peer: one thread relays "my stage is full" to the leader's barrier (a bulk copy can only signal an
+//             mbarrier of the CTA it writes to)
+//   warps 0-15 epilogue (thread = output row x 32 columns of each 128-column half)
+#pragma once
+
+#include "oz_gemm.cuh"
+
+namespace reach {
+
+constexpr int CRT_TM = 128, CRT_TN = 256, CRT_KB = 64, CRT_STAGES = 10;
+constexpr int CRT_MAX_N = 16, CRT_MIN_N = 8, CRT_DEFAULT_N = 14;
+constexpr int CRT_IMG = CRT_TM * CRT_KB;                  // bytes of one 128-row residue image per k-block (8 KB)
+constexpr int CRT_SLOT = 2 * CRT_IMG;                     // X rows then Y rows
+constexpr int CRT_MAX_K = 65472;                          // K 2^14 < 2^30
+constexpr int CRT_SCR_WORDS = 2 * 8 * (OZ_EPI_WARPS * 32);   // u32 words of scratch per modulus and CTA
+
+// pairwise coprime, largest first (256 = 2^8, 255 = 3 5 17, 253 = 11 23, 247 = 13 19, 217 = 7 31, the rest prime)
+__host__ __device__ constexpr int crt_modulus(int i) {
+    constexpr int m[CRT_MAX_N] = {256, 255, 253, 251, 247, 241, 239, 233, 229, 227, 223, 217, 211, 199, 197, 193};
+    return m[i];
+}
+
+struct CrtConsts {
+    int N = 0;
+    int alpha = 0, beta = 0;       // 2-norm budgets of the X and Y rows (bits)
+    double Pd = 0.0;               // P rounded to FP64
+    uint32_t p[CRT_MAX_N];
+    uint32_t magic[CRT_MAX_N];     // floor(2^32 / p)
+    uint32_t off[CRT_MAX_N];       // multiple of p, >= 2^30: makes the INT32 accumulators non-negative
+    double f1[CRT_MAX_N], f2[CRT_MAX_N];
+};
+
+inline CrtConsts crt_make_consts(int N) {
+    CrtConsts c{};
+    c.N = N;
+    unsigned __int128 P = 1;
+    for (int i = 0; i < N; ++i) P *= (unsigned)crt_modulus(i);
+    int lp = 0;
+    for (unsigned __int128 t = P; t > 1; t >>= 1) ++lp;               // floor(log2 P)
+    const int tot = lp - 2;                                           // ||x'|| ||y'|| <= 2^tot <= P/4
+    c.alpha = (tot + 1) / 2;
+    c.beta = tot - c.alpha;
+    c.Pd = (double)P;
+    for (int i = 0; i < N; ++i) {
+        const unsigned p = (unsigned)crt_modulus(i);
+        const unsigned __int128 Mi = P / p;
+        unsigned inv = 0;
+        const unsigned mi = (unsigned)(Mi % p);
+        for (unsigned t = 1; t < p; ++t)
+            if ((mi * t) % p == 1) { inv = t; break; }
+        const unsigned __int128 w = Mi * inv;                         // < P
+        // binary expansion of w / P: bits 1..40 -> f1, bits 41..120 -> f2 (rounded to FP64)
+        unsigned __int128 r = w;
+        double f1 = 0.0, f2 = 0.0;
+        for (int b = 1; b <= 120; ++b) {
+            r <<= 1;
+            int bit = 0;
+            if (r >= P) { r -= P; bit = 1; }
+            if (bit) {
+                if (b <= 40) f1 += ldexp(1.0, -b);
+                else f2 += ldexp(1.0, -b);                            // exact while the partial sum spans <= 53 bits, rounded after
+            }
+        }
+        c.p[i] = p;
+        c.magic[i] = (uint32_t)((((uint64_t)1) << 32) / p);
+        c.off[i] = (uint32_t)(((((uint64_t)1) << 30) / p + 1) * p);
+        c.f1[i] = f1;
+        c.f2[i] = f2;
+    }
+    return c;
+}
+
+struct CrtOperands {
+    const int8_t* Xr;     // [N][tiles_m_total][nkb][16 row groups][4 k-chunks][8][16]
+    const int8_t* Yr;     // [N][tiles_n_total][nkb][...]            (128-row tiles)
+    const int* eX;        // [tiles_m_total*128]: value = C' 2^(eX[m] + eY[n])
+    const int* eY;
+    int nkb;              // k-blocks of 64
+    int tiles_m, tiles_m_total;
+    int tile_n0, tiles_n, tiles_n_total;   // this launch covers 128-row Y tiles [tile_n0, tile_n0 + tiles_n)
+    uint32_t* scratch;    // [gridDim.x][N][CRT_SCR_WORDS]
+    CrtConsts c;
+    int32_t* dbg = nullptr;   // debug: raw accumulators of modulus dbg_mod of the first tile of pair 0, [2][128][256]
+    int dbg_mod = 0;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n .reg .b32 ra;\n mapa.shared::cluster.u32 ra, %0, %1;\n"
+        " mbarrier.arrive.shared::cluster.b64 _, [ra];\n}" ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+// wait on a barrier the peer CTA arrives on.  Default (CTA-scope) semantics as in CUTLASS' ClusterBarrier: the operands
+// travel through the async proxy only (bulk copy -> shared memory -> MMA), and a cluster-scope acquire / release per
+// k-block costs a memory fence each (measured: 1.1 us per k-block instead of 0.15)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, bool sleep) {
+    uint32_t ok = 0, spins = 0;
+    const uint32_t a = smem_u32(bar);
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (!ok) {
+            if (sleep) __nanosleep(256);
+            if (++spins > (1u << (sleep ? 24 : 27))) __trap();
+        }
+    } while (!ok);
+}
+
+// c mod p in the symmetric range [-(p/2), (p-1)/2], for |c| < 2^30
+__device__ __forceinline__ uint32_t crt_mod_sym(uint32_t c, uint32_t p, uint32_t magic, uint32_t off, uint32_t hi) {
+    const uint32_t cu = c + off;                      // in (0, 2^31 + 2^30): residue unchanged (off is a multiple of p)
+    const uint32_t q = __umulhi(cu, magic);           // floor(cu / p) or one less
+    uint32_t r = cu - q * p;                          // [0, 2p)
+    r = min(r, r - p);                                // unsigned: r - p wraps unless r >= p
+    return r > hi ? r - p : r;                        // two's complement byte of the symmetric residue
+}
+
+__device__ __forceinline__ double crt_sext_i2d(uint32_t word, int e) {
+    // signed byte e of word -> double, no conversion pipe: one PRMT sign-extends (selector nibble 8|e replicates the sign
+    // of byte e; __byte_perm masks that bit away, hence the PTX), and 2^52 + 2^31 + x has x in its low mantissa bits
+    const uint32_t sel = e == 0 ? 0x8880u : e == 1 ? 0x9991u : e == 2 ? 0xAAA2u : 0xBBB3u;
+    uint32_t x;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(x) : "r"(word), "r"(0u), "r"(sel));
+    return oz_i2d(x);
+}
+
+template <class Epi>
+__global__ void __launch_bounds__(OZ_THREADS, 1) crt_gemm_kernel(const CrtOperands g, const Epi epi) {
+    extern __shared__ __align__(1024) unsigned char crt_smem[];
+    unsigned char* ring = crt_smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(crt_smem + size_t(CRT_STAGES) * CRT_SLOT);
+    uint64_t* pfull = full + CRT_STAGES;              // leader: the peer's stage is full
+    uint64_t* empty = pfull + CRT_STAGES;
+    uint64_t* tmem_full = empty + CRT_STAGES;         // [2]
+    uint64_t* tmem_empty = tmem_full + 2;             // [2] (leader's are waited on)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    double* sYscale = reinterpret_cast<double*>(tmem_empty + 3);      // [128]
+    unsigned char* epi_smem = reinterpret_cast<unsigned char*>(sYscale + OZ_TN);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int N = g.c.N;
+    const int n2_lo = g.tile_n0 >> 1, n2_hi = (g.tile_n0 + g.tiles_n + 1) >> 1;
+    const int mgroups = (g.tiles_m + 1) >> 1;
+    const int ngroups = mgroups * (n2_hi - n2_lo);
+
+    if (tid == 0) {
+        for (int s = 0; s < CRT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&pfull[s], 1); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 2 * OZ_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == OZ_EPI_WARPS + 1) {   // warp 17 of both CTAs allocates the pair's tensor memory (all 512 columns)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();               // both CTAs' barriers are initialised and both allocations are done
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == OZ_EPI_WARPS) {
+        // ===== producer (both CTAs): own 128 rows of X and own 128 rows of the pair's 256 Y rows =====
+        if (lane == 0) {
+            const size_t img_stride = size_t(CRT_IMG);
+            uint32_t jb = 0;
+            for (int grp = pair; grp < ngroups; grp += npairs) {
+                int tm = (grp % mgroups) * 2 + int(rank);
+                if (tm >= g.tiles_m) tm = 0;                             // odd tile count: the peer multiplies a dummy tile
+                int tn = (n2_lo + grp / mgroups) * 2 + int(rank);
+                if (tn >= g.tiles_n_total) tn = g.tiles_n_total - 1;     // odd tile count at the end of the stack
+                for (int i = 0; i < N; ++i) {
+                    const int8_t* gx = g.Xr + (size_t(i) * g.tiles_m_total + tm) * g.nkb * img_stride;
+                    const int8_t* gy = g.Yr + (size_t(i) * g.tiles_n_total + tn) * g.nkb * img_stride;
+                    for (int kb = 0; kb < g.nkb; ++kb, ++jb) {
+                        const int s = jb % CRT_STAGES;
+                        const uint32_t ph = (jb / CRT_STAGES) & 1;
+                        mbar_wait_cluster(&empty[s], ph ^ 1, false);
+                        mbar_expect_tx(&full[s], CRT_SLOT);
+                        unsigned char* dst = ring + size_t(s) * CRT_SLOT;
+                        bulk_copy_g2s(dst, gx + size_t(kb) * img_stride, CRT_IMG, &full[s]);
+                        bulk_copy_g2s(dst + CRT_IMG, gy + size_t(kb) * img_stride, CRT_IMG, &full[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == OZ_EPI_WARPS + 1) {
+        if (lane == 0 && rank == 0) {
+            // ===== MMA issuer (leader) =====
+            // instruction descriptor: D = S32, A = B = signed 8-bit, K-major both, N = 256, M = 256 (128 rows per CTA)
+            constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(CRT_TN >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+            uint32_t jb = 0, u = 0;
+            for (int grp = pair; grp < ngroups; grp += npairs) {
+                for (int i = 0; i < N; ++i, ++u) {
+                    const uint32_t buf = u & 1, use = u >> 1;
+                    if (use > 0) {                                     // both CTAs have pulled the buffer's previous contents
+                        mbar_wait_cluster(&tmem_empty[buf], (use - 1) & 1, false);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    const uint32_t dcol = tmem_base + buf * uint32_t(CRT_TN);
+                    for (int kb = 0; kb < g.nkb; ++kb, ++jb) {
+                        const int s = jb % CRT_STAGES;
+                        const uint32_t ph = (jb / CRT_STAGES) & 1;
+                        mbar_wait(&full[s], ph);
+                        mbar_wait_cluster(&pfull[s], ph, false);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t xs = smem_u32(ring + size_t(s) * CRT_SLOT), ys = xs + CRT_IMG;
+#pragma unroll
+                        for (int h = 0; h < CRT_KB / 32; ++h) {
+                            // image: [16 row groups][4 k-chunks][8 rows][16 B]: LBO = 128 B (next k-chunk), SBO = 512 B (next 8 rows)
+                            const uint64_t da = oz_smem_desc(xs + h * 256, 128, 512);
+                            const uint64_t db = oz_smem_desc(ys + h * 256, 128, 512);
+                            const uint32_t acc = (kb > 0 || h > 0) ? 1u : 0u;
+                            asm volatile(
+                                "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+                                " tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(dcol), "l"(da), "l"(db), "r"(idesc), "r"(acc)
+                                : "memory");
+                        }
+                        // frees the ring slot in both CTAs once the MMAs above have read it
+                        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                     ::"r"(smem_u32(&empty[s])), "h"(uint16_t(3)) : "memory");
+                    }
+                    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                                 ::"r"(smem_u32(&tmem_full[buf])), "h"(uint16_t(3)) : "memory");
+                }
+            }
+        } else if (lane == 0) {
+            // ===== relay (peer): stage s of my ring is full -> the leader's pfull[s] =====
+            uint32_t jb = 0;
+            for (int grp = pair; grp < ngroups; grp += npairs)
+                for (int i = 0; i < N; ++i)
+                    for (int kb = 0; kb < g.nkb; ++kb, ++jb) {
+                        const int s = jb % CRT_STAGES;
+                        mbar_wait(&full[s], (jb / CRT_STAGES) & 1);
+                        mbar_arrive_remote(&pfull[s], 0);
+                    }
+        }
+    } else {
+        // ===== epilogue warps 0..15: thread = (output row, 32-column group of each 128-column half) =====
+        const int quarter = warp & 3, cgrp = warp >> 2;
+        const int ml = quarter * 32 + lane;
+        const uint32_t tlane = tmem_base + (uint32_t(quarter * 32) << 16);
+        uint32_t* scr = g.scratch + size_t(blockIdx.x) * N * CRT_SCR_WORDS + tid;
+        uint32_t u = 0;
+        for (int grp = pair; grp < ngroups; grp += npairs) {
+            const int tm = (grp % mgroups) * 2 + int(rank);
+            const int tn2 = n2_lo + grp / mgroups;
+            // ---- residues of the N accumulators ----
+            for (int i = 0; i < N; ++i, ++u) {
+                const uint32_t buf = u & 1, use = u >> 1;
+                const uint32_t p = g.c.p[i], magic = g.c.magic[i], off = g.c.off[i], hi = (p - 1) >> 1;
+                mbar_wait_cluster(&tmem_full[buf], use & 1, true);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t a[32];
+                    const uint32_t taddr = tlane + buf * uint32_t(CRT_TN) + uint32_t(h * OZ_TN + cgrp * OZ_CPT);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]),
+                          "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]),
+                          "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]),
+                          "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (g.dbg && grp == 0 && i == g.dbg_mod) {
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj)
+                            g.dbg[(size_t(rank) * 128 + ml) * 256 + h * OZ_TN + cgrp * OZ_CPT + jj] = int32_t(a[jj]);
+                    }
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        uint32_t word = 0;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) word |= (crt_mod_sym(a[4 * w + e], p, magic, off, hi) & 0xFFu) << (8 * e);
+                        __stcg(scr + size_t((i * 2 + h) * 8 + w) * (OZ_EPI_WARPS * 32), word);
+                    }
+                }
+                // the accumulator may be overwritten: modulus i + 2 (or the pair's next tile) can start
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(&tmem_empty[buf], 0);
+            }
+            if (tm >= g.tiles_m) continue;                               // dummy tile of an odd tile count (whole CTA)
+            // ---- Chinese remainder reconstruction + the fused epilogue, one 128-column half at a time ----
+            const int m = tm * OZ_TM + ml;
+            const int ex = g.eX[size_t(tm) * OZ_TM + ml];
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const int tn = tn2 * 2 + h;
+                if (tn < g.tile_n0 || tn >= g.tile_n0 + g.tiles_n) continue;     // uniform over the CTA
+                asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory");
+                if (tid < OZ_TN) sYscale[tid] = oz_pow2(max(-1000, min(1000, g.eY[size_t(tn) * OZ_TN + tid])));
+                epi.prepare(epi_smem, tn, tid);
+                asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory");
+                typename Epi::State st;
+                epi.begin(st);
+#pragma unroll 1
+                for (int w = 0; w < 8; ++w) {
+                    double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 4
+                    for (int i = 0; i < N; ++i) {
+                        const uint32_t word = __ldcg(scr + size_t((i * 2 + h) * 8 + w) * (OZ_EPI_WARPS * 32));
+                        const double f1 = g.c.f1[i], f2 = g.c.f2[i];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const double ud = crt_sext_i2d(word, e);
+                            s1[e] = fma(ud, f1, s1[e]);                  // exact: multiples of 2^-40 below 2^11
+                            s2[e] = fma(ud, f2, s2[e]);
+                        }
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const double r1 = (s1[e] + 6755399441055744.0) - 6755399441055744.0;   // nearest integer (|s1| < 2^51)
+                        const double t = (s1[e] - r1) + s2[e];           // C'/P in (-1/4, 1/4)
+                        const int j = cgrp * OZ_CPT + w * 4 + e;
+                        epi.accept(st, epi_smem, m, tn, j, oz_scale((t * g.c.Pd) * sYscale[j], ex));
+                    }
+                }
+                epi.finish(st, epi_smem, tm, tn, ml, cgrp);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    cluster_sync_all();               // the peer may still signal this CTA's barriers / read its shared memory until here
+    if (warp == OZ_EPI_WARPS + 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+template <class Epi>
+struct CrtShape {
+    static constexpr size_t SMEM = size_t(CRT_STAGES) * CRT_SLOT + (3 * CRT_STAGES + 6) * sizeof(uint64_t) + OZ_TN * sizeof(double) + Epi::SMEM;
+};
+
+// number of CTAs (2 per pair) a launch over `ntiles_m` x `ntiles_n` 128-row tiles uses, and the scratch it needs
+inline int crt_grid(int tiles_m, int tiles_n, int sm_count) {
+    const int groups = ((tiles_m + 1) / 2) * ((tiles_n + 2) / 2);
+    const int pairs = std::max(1, std::min(sm_count / 2, groups));
+    return 2 * pairs;
+}
+inline size_t crt_scratch_bytes(int N, int sm_count) { return size_t(sm_count) * N * CRT_SCR_WORDS * sizeof(uint32_t); }
+
+template <class Epi>
+inline cudaError_t launch_crt_gemm(const CrtOperands& g, const Epi& epi, cudaStream_t stream) {
+    auto kern = crt_gemm_kernel<Epi>;
+    constexpr size_t smem = CrtShape<Epi>::SMEM;
+    static thread_local int configured_dev = -1;
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (configured_dev != dev) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (e != cudaSuccess) return e;
+        configured_dev = dev;
+    }
+    if (g.tiles_m <= 0 || g.tiles_n <= 0) return cudaSuccess;
+    static thread_local int sms = 0;
+    if (sms == 0) {
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+    }
+    const int n2 = ((g.tile_n0 + g.tiles_n + 1) >> 1) - (g.tile_n0 >> 1);
+    const int groups = ((g.tiles_m + 1) / 2) * n2;
+    const int pairs = std::max(1, std::min(sms / 2, groups));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(OZ_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, g, epi);
+}
+
+// ---- residues: FP64 rows -> N signed-byte residue images in the UMMA core-matrix layout -------------------
+// One CTA per 8-row group and k range (as oz_slice_kernel).  Phase 1: row maximum and sum of squares -> the scale s with
+// ||rint(x 2^s)||_2 <= 2^bits.  Phase 2: thread = (row, 16-wide k chunk): x' = rint(x 2^s) as a 64-bit integer, its
+// residue modulo every p_i (compile-time moduli: the divisions become multiplications), written as N 16-byte stores.
+//   Q[((i * tiles_total + tile) * nkb + kb) * (128*64) + ((g * 4 + c) * 8 + r) * 16 + b],  g = (row % 128) / 8, c = k-chunk % 4
+template <int NMAX>
+__global__ void __launch_bounds__(256) crt_slice_kernel(const double* __restrict__ X, int ldx, int rows_valid, int k_valid, int N,
+                                                        int bits, int nkb, int tiles_total, int8_t* __restrict__ Q,
+                                                        int* __restrict__ eout, int tile0 = 0) {
+    __shared__ int s_s[8];
+    const int row0 = blockIdx.x * 8;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {   // phase 1: warp w scans row row0 + w
+        const int row = row0 + warp;
+        double mx = 0.0;
+        if (row < rows_valid) {
+            const double* x = X + size_t(row) * ldx;
+            for (int k = lane; k < k_valid; k += 32) mx = fmax(mx, fabs(x[k]));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        int s = 0;
+        if (mx > 0.0 && mx < 1.0e308) {
+            const int em = ilogb(mx);                                  // 2^em <= mx < 2^(em+1)
+            double ss = 0.0;
+            const double* x = X + size_t(row) * ldx;
+            for (int k = lane; k < k_valid; k += 32) {
+                const double v = oz_scale(x[k], -em);                  // |v| < 2
+                ss = fma(v, v, ss);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            // ||x|| = 2^em sqrt(ss) < 2^(em + en),  en = ilogb(sqrt(ss) (1 + 2^-20)) + 1
+            const int en = ilogb(sqrt(ss) * 1.000001) + 1;
+            s = bits - (em + en);
+        }
+        if (lane == 0) {
+            s_s[warp] = s;
+            if (blockIdx.y == 0) eout[tile0 * 128 + row] = -s;
+        }
+    }
+    __syncthreads();
+    const int tile = tile0 + row0 / 128, gidx = (row0 % 128) / 8;
+    const int nchunks = nkb * 4;
+    const int per = (nchunks + gridDim.y - 1) / gridDim.y;
+    const int item_lo = 8 * per * blockIdx.y, item_hi = min(8 * nchunks, item_lo + 8 * per);
+    for (int item = item_lo + threadIdx.x; item < item_hi; item += blockDim.x) {
+        const int r = item & 7, chunk = item >> 3;
+        const int row = row0 + r;
+        const int kb = chunk >> 2, c = chunk & 3;
+        const int k0 = chunk * 16;
+        const int s = s_s[r];
+        uint32_t w[NMAX][4];
+#pragma unroll
+        for (int i = 0; i < NMAX; ++i) w[i][0] = w[i][1] = w[i][2] = w[i][3] = 0u;
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+            const int k = k0 + b;
+            const double v = (row < rows_valid && k < k_valid) ? X[size_t(row) * ldx + k] : 0.0;
+            const long long xi = __double2ll_rn(oz_scale(v, s));      // |xi| <= 2^bits (1 + eps): exact
+            const unsigned long long ax = xi < 0 ? (unsigned long long)(-xi) : (unsigned long long)xi;
+            const uint32_t lo = uint32_t(ax), hi = uint32_t(ax >> 32);
+#pragma unroll
+            for (int i = 0; i < NMAX; ++i) {
+                constexpr uint32_t dummy = 0;
+                (void)dummy;
+                const uint32_t p = uint32_t(crt_modulus(i));
+                const uint32_t two32 = uint32_t((uint64_t(1) << 32) % p);
+                uint32_t rr = ((hi % p) * two32 + (lo % p)) % p;       // < p; (p-1)(p-1) + p-1 < 2^16
+                int sr = xi < 0 ? -int(rr) : int(rr);                  // (-p, p)
+                const int hs = int(p - 1) >> 1;
+                if (sr > hs) sr -= int(p);
+                if (sr < -int(p >> 1)) sr += int(p);
+                w[i][b >> 2] |= (uint32_t(sr) & 0xFFu) << (8 * (b & 3));
+            }
+        }
+        int8_t* q = Q + (size_t(tile) * nkb + kb) * CRT_IMG + ((gidx * 4 + c) * 8 + r) * 16;
+        const size_t mstride = size_t(tiles_total) * nkb * CRT_IMG;
+#pragma unroll
+        for (int i = 0; i < NMAX; ++i)
+            if (i < N) *reinterpret_cast<uint4*>(q + size_t(i) * mstride) = make_uint4(w[i][0], w[i][1], w[i][2], w[i][3]);
+    }
+}
+
+inline void launch_crt_slice(const double* X, int ldx, int rows_valid, int rows_padded, int k_valid, const CrtConsts& c, bool is_y, int nkb,
+                             int tiles_total, int8_t* Q, int* eout, int tile0, int ksplit, cudaStream_t st) {
+    crt_slice_kernel<CRT_MAX_N><<<dim3(rows_padded / 8, ksplit), 256, 0, st>>>(X, ldx, rows_valid, k_valid, c.N, is_y ? c.beta : c.alpha, nkb,
+                                                                             tiles_total, Q, eout, tile0);
+}
+
+}  // namespace reach

@@ -2,8 +2,10 @@
 // tests and bench.py.  The LGG09 main loop launches the same kernels from lgg09.cu.
 #include "reach_common.cuh"
 #include "oz_gemm.cuh"
+#include "crt_gemm.cuh"
 
 #include <vector>
+#include <stdlib.h>
 
 using namespace reach;
 
@@ -67,5 +69,75 @@ extern "C" int reach_ozgemm_probe(reach_ctx* ctx, int m, int n, int k, int slice
     cudaEventDestroy(e2);
     if (tflops) *tflops = 2.0 * m * double(n) * k * iters / (ms * 1e-3) / 1e12;
     if (C_host) REACH_CUDA(ctx, cudaMemcpy(C_host, C.p, size_t(m) * n * 8, cudaMemcpyDeviceToHost));
+    return REACH_OK;
+}
+
+// The same product through the residue (Chinese remainder) path of crt_gemm.cuh with `moduli` INT8 GEMMs per FP64 product.
+// *tflops counts 2 m n k per launch (FP64-equivalent), *slice_ms the residue conversion.
+extern "C" int reach_crtgemm_probe(reach_ctx* ctx, int m, int n, int k, int moduli, const double* X_host,
+                                   const double* Y_host, double* C_host, int iters, double* tflops, double* slice_ms) {
+    if (!ctx) return REACH_EINVAL;
+    if (m < 1 || n < 1 || k < 1 || iters < 1) return set_error(ctx, REACH_EINVAL, "probe sizes must be positive");
+    if (moduli < CRT_MIN_N || moduli > CRT_MAX_N) return set_error(ctx, REACH_EINVAL, "moduli must be in %d..%d", CRT_MIN_N, CRT_MAX_N);
+    if (k > CRT_MAX_K) return set_error(ctx, REACH_EINVAL, "k must be <= %d (INT32 accumulator headroom)", CRT_MAX_K);
+    if (!X_host || !Y_host) return set_error(ctx, REACH_EINVAL, "X and Y must not be NULL");
+    REACH_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const CrtConsts cc = crt_make_consts(moduli);
+    const int tiles_m = (m + 127) / 128, tiles_n = (n + 127) / 128, nkb = (k + CRT_KB - 1) / CRT_KB;
+    DevBuf X, Y, C, Xr, Yr, eX, eY, scr;
+    REACH_TRY(X.alloc(ctx, size_t(m) * k * 8, false));
+    REACH_TRY(Y.alloc(ctx, size_t(n) * k * 8, false));
+    REACH_TRY(C.alloc(ctx, size_t(m) * n * 8));
+    REACH_TRY(Xr.alloc(ctx, size_t(moduli) * tiles_m * nkb * CRT_IMG));
+    REACH_TRY(Yr.alloc(ctx, size_t(moduli) * tiles_n * nkb * CRT_IMG));
+    REACH_TRY(eX.alloc(ctx, size_t(tiles_m) * 128 * 4));
+    REACH_TRY(eY.alloc(ctx, size_t(tiles_n) * 128 * 4));
+    REACH_TRY(scr.alloc(ctx, crt_scratch_bytes(moduli, ctx->sm_count), false));
+    REACH_CUDA(ctx, cudaMemcpyAsync(X.p, X_host, size_t(m) * k * 8, cudaMemcpyHostToDevice, st));
+    REACH_CUDA(ctx, cudaMemcpyAsync(Y.p, Y_host, size_t(n) * k * 8, cudaMemcpyHostToDevice, st));
+    cudaEvent_t e0, e1, e2;
+    REACH_CUDA(ctx, cudaEventCreate(&e0));
+    REACH_CUDA(ctx, cudaEventCreate(&e1));
+    REACH_CUDA(ctx, cudaEventCreate(&e2));
+    auto slice_both = [&]() {
+        launch_crt_slice(X.as<double>(), k, m, tiles_m * 128, k, cc, false, nkb, tiles_m, Xr.as<int8_t>(), eX.as<int>(), 0, 1, st);
+        launch_crt_slice(Y.as<double>(), k, n, tiles_n * 128, k, cc, true, nkb, tiles_n, Yr.as<int8_t>(), eY.as<int>(), 0, 1, st);
+    };
+    slice_both();
+    REACH_CUDA(ctx, cudaGetLastError());
+    CrtOperands g{Xr.as<int8_t>(), Yr.as<int8_t>(), eX.as<int>(), eY.as<int>(), nkb, tiles_m, tiles_m, 0, tiles_n, tiles_n,
+                  scr.as<uint32_t>(), cc};
+    OzStoreEpi epi{C.as<double>(), n, m, n};
+    DevBuf dbg;
+    const char* dbg_env = getenv("REACH_CRT_DEBUG");           // "<modulus index>": raw accumulators -> <C_host as int32 [2][128][256]>
+    if (dbg_env && size_t(m) * n * 8 >= size_t(2) * 128 * 256 * 4) {
+        REACH_TRY(dbg.alloc(ctx, size_t(2) * 128 * 256 * 4));
+        g.dbg = dbg.as<int32_t>();
+        g.dbg_mod = atoi(dbg_env);
+    }
+    REACH_CUDA(ctx, (launch_crt_gemm(g, epi, st)));            // warm-up (also the result)
+    REACH_CUDA(ctx, cudaStreamSynchronize(st));
+    REACH_CUDA(ctx, cudaEventRecord(e1, st));
+    for (int i = 0; i < iters; ++i) REACH_CUDA(ctx, (launch_crt_gemm(g, epi, st)));
+    REACH_CUDA(ctx, cudaEventRecord(e2, st));
+    REACH_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    REACH_CUDA(ctx, cudaEventElapsedTime(&ms, e1, e2));
+    if (slice_ms) {
+        REACH_CUDA(ctx, cudaEventRecord(e0, st));
+        slice_both();
+        REACH_CUDA(ctx, cudaEventRecord(e1, st));
+        REACH_CUDA(ctx, cudaStreamSynchronize(st));
+        float s = 0.f;
+        REACH_CUDA(ctx, cudaEventElapsedTime(&s, e0, e1));
+        *slice_ms = s;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    if (tflops) *tflops = 2.0 * m * double(n) * k * iters / (ms * 1e-3) / 1e12;
+    if (C_host) REACH_CUDA(ctx, cudaMemcpy(C_host, C.p, size_t(m) * n * 8, cudaMemcpyDeviceToHost));
+    if (C_host && g.dbg) REACH_CUDA(ctx, cudaMemcpy(C_host, dbg.p, size_t(2) * 128 * 256 * 4, cudaMemcpyDeviceToHost));
     return REACH_OK;
 }
