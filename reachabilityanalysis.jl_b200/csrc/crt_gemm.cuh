@@ -12,34 +12,45 @@
 // accumulators (exact for K <= 65472), and the Chinese remainder theorem rebuilds C' from u_i = C'_i mod p_i:
 //     C'/P = frac( sum_i u_i w_i / P ),   w_i = (P/p_i) ((P/p_i)^-1 mod p_i)
 // The fractions f_i = w_i/P are split f_i = f1_i + f2_i with f1_i a multiple of 2^-40: sum_i u_i f1_i is exact in FP64,
-// its integer part drops out, and sum_i u_i f2_i (< 2^-29) is accurate to 2^-80.  N = 14 moduli (P ~ 2^110, alpha = beta = 54)
+// its integer part drops out, and sum_i u_i f2_i (< 2^-28) is accurate to 2^-80.  N = 14 moduli (P ~ 2^110, alpha = beta = 54)
 // round each operand element at 2^-54 of its row NORM -- below FP64's own rounding of the products -- with 14 INT8
 // products instead of 28; N = 13 matches the digit-plane path's accuracy.  The result does not depend on summation order.
 //
 // Kernel shape: CTA pairs (cluster of 2, cta_group::2).  A pair owns a 256 x 256 output tile: CTA r holds rows
-// [128 r, 128 r + 128) of X and of Y in its shared memory (8 KB + 8 KB per 64-byte k-block: half the L2 -> SM bytes
-// per MAC of a 128 x 256 one-CTA tile), the leader issues M = 256, N = 256, K = 32 MMAs, and each CTA's tensor memory
-// holds its 128 rows x 256 columns, double buffered (2 x 256 columns), so modulus i+1 is multiplied while modulus i is
-// drained.  Per tile the pair loops over the moduli; the epilogue warps reduce every INT32 accumulator mod p_i to a signed
-// byte and park it in a per-thread global scratch (L2 resident), then rebuild the FP64 values from the N residues
-// and hand them to the same epilogue functors as oz_gemm.cuh (plain store, carry rows, fused LGG09 support features).
-//   warp 16   producer: per k-block two cp.async.bulk copies (own X rows, own Y rows) into a 10-stage ring
+// [128 r, 128 r + 128) of X and of Y in its shared memory (16 KB + 16 KB per 128-byte k-block, SWIZZLE_128B images: half
+// the L2 -> SM bytes per MAC of a 128 x 256 one-CTA tile; an unswizzled core-matrix layout ran the 2-CTA MMAs at a quarter
+// of their rate), the leader issues M = 256, N = 256, K = 32 MMAs, and each CTA's tensor memory holds its 128 rows x 256
+// columns, double buffered (2 x 256 columns), so modulus i+1 is multiplied while modulus i is drained.  Per tile the pair
+// loops over the moduli.
+//   warp 16   producer: per k-block two cp.async.bulk copies (own X rows, own Y rows) into a 4-stage ring
 //   warp 17   leader: one thread issues the MMAs and commits (multicast) to both CTAs' barriers;
 //             peer: one thread relays "my stage is full" to the leader's barrier (a bulk copy can only signal an
 //             mbarrier of the CTA it writes to)
-//   warps 0-15 epilogue (thread = output row x 32 columns of each 128-column half)
+//   warps 0-7 drain: tcgen05.ld, every INT32 accumulator reduced mod p_i to a byte, parked in a global scratch (two
+//             halves per CTA, thread = output row x 2 x 32 columns of each 128-column half)
+//   warps 8-15 reconstruction of the pair's PREVIOUS tile from the other scratch half + the same epilogue functors as
+//             oz_gemm.cuh (plain store, carry rows, fused LGG09 support features): off the accumulator hand-over path (with
+//             all 16 warps doing both, the MMAs waited for the FP64 work: 2.6 ms per launch of C5 against 1.86 ms without
+//             reconstruction)
+//   warp 18   one thread streams the scratch back into a 4-stage shared-memory ring, one bulk copy per slice (the N
+//             residue words of 4 outputs of each thread), so the reconstruction warps never wait for an L2 / DRAM round trip
 #pragma once
 
 #include "oz_gemm.cuh"
 
 namespace reach {
 
-constexpr int CRT_TM = 128, CRT_TN = 256, CRT_KB = 64, CRT_STAGES = 10;
-constexpr int CRT_MAX_N = 16, CRT_MIN_N = 8, CRT_DEFAULT_N = 14;
-constexpr int CRT_IMG = CRT_TM * CRT_KB;                  // bytes of one 128-row residue image per k-block (8 KB)
+constexpr int CRT_TM = 128, CRT_TN = 256, CRT_KB = 128, CRT_STAGES = 4;
+constexpr int CRT_MAX_N = 16, CRT_MIN_N = 10, CRT_DEFAULT_N = 14;
+constexpr int CRT_IMG = CRT_TM * CRT_KB;                  // bytes of one 128-row residue image per k-block (16 KB)
 constexpr int CRT_SLOT = 2 * CRT_IMG;                     // X rows then Y rows
 constexpr int CRT_MAX_K = 65472;                          // K 2^14 < 2^30
-constexpr int CRT_SCR_WORDS = 2 * 8 * (OZ_EPI_WARPS * 32);   // u32 words of scratch per modulus and CTA
+constexpr int CRT_EPI_HALF = OZ_EPI_WARPS * 32 / 2;       // threads that drain, threads that reconstruct (256 each)
+constexpr int CRT_THREADS = OZ_THREADS + 32;              // + the scratch prefetch warp
+constexpr int CRT_SCR_WORDS = 4 * 8 * CRT_EPI_HALF;       // u32 words of scratch per modulus and CTA (4 x 32 columns x 128 rows)
+constexpr int CRT_SLICES = 32;                            // slices of a tile: (half, column group of the pair, word) = 2 x 2 x 8
+constexpr int CRT_SCR_STAGES = 4;                         // shared-memory ring of slices
+constexpr int CRT_SLICE_BYTES = CRT_MAX_N * CRT_EPI_HALF * 4;   // ring stage (N KB are used)
 
 // pairwise coprime, largest first (256 = 2^8, 255 = 3 5 17, 253 = 11 23, 247 = 13 19, 217 = 7 31, the rest prime)
 __host__ __device__ constexpr int crt_modulus(int i) {
@@ -98,17 +109,18 @@ inline CrtConsts crt_make_consts(int N) {
 }
 
 struct CrtOperands {
-    const int8_t* Xr;     // [N][tiles_m_total][nkb][16 row groups][4 k-chunks][8][16]
+    const int8_t* Xr;     // [N][tiles_m_total][nkb][16 row groups][8 rows][128 B, 16-byte chunks swizzled]
     const int8_t* Yr;     // [N][tiles_n_total][nkb][...]            (128-row tiles)
     const int* eX;        // [tiles_m_total*128]: value = C' 2^(eX[m] + eY[n])
     const int* eY;
-    int nkb;              // k-blocks of 64
+    int nkb;              // k-blocks of 128
     int tiles_m, tiles_m_total;
     int tile_n0, tiles_n, tiles_n_total;   // this launch covers 128-row Y tiles [tile_n0, tile_n0 + tiles_n)
-    uint32_t* scratch;    // [gridDim.x][N][CRT_SCR_WORDS]
+    uint32_t* scratch;    // [gridDim.x][2 halves][32 slices][N][256 threads]
     CrtConsts c;
     int32_t* dbg = nullptr;   // debug: raw accumulators of modulus dbg_mod of the first tile of pair 0, [2][128][256]
     int dbg_mod = 0;
+    int flags = 0;            // debug / timing experiments: 1 = no reconstruction, 2 = no residue reduction (drain only)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -142,36 +154,69 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     } while (!ok);
 }
 
-// c mod p in the symmetric range [-(p/2), (p-1)/2], for |c| < 2^30
-__device__ __forceinline__ uint32_t crt_mod_sym(uint32_t c, uint32_t p, uint32_t magic, uint32_t off, uint32_t hi) {
+// c mod p in [0, p), for |c| < 2^30 (negp = -p)
+__device__ __forceinline__ uint32_t crt_mod(uint32_t c, uint32_t negp, uint32_t magic, uint32_t off) {
     const uint32_t cu = c + off;                      // in (0, 2^31 + 2^30): residue unchanged (off is a multiple of p)
     const uint32_t q = __umulhi(cu, magic);           // floor(cu / p) or one less
-    uint32_t r = cu - q * p;                          // [0, 2p)
-    r = min(r, r - p);                                // unsigned: r - p wraps unless r >= p
-    return r > hi ? r - p : r;                        // two's complement byte of the symmetric residue
+    const uint32_t r = cu + q * negp;                 // [0, 2p)
+    return min(r, r + negp);                          // unsigned: r - p wraps unless r >= p
+}
+// scratch stores: L2 only (read back through the async proxy by the prefetch thread)
+__device__ __forceinline__ void crt_st_scratch(uint32_t* p, uint32_t v) {
+    asm volatile("st.global.cg.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-__device__ __forceinline__ double crt_sext_i2d(uint32_t word, int e) {
-    // signed byte e of word -> double, no conversion pipe: one PRMT sign-extends (selector nibble 8|e replicates the sign
-    // of byte e; __byte_perm masks that bit away, hence the PTX), and 2^52 + 2^31 + x has x in its low mantissa bits
-    const uint32_t sel = e == 0 ? 0x8880u : e == 1 ? 0x9991u : e == 2 ? 0xAAA2u : 0xBBB3u;
-    uint32_t x;
-    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(x) : "r"(word), "r"(0u), "r"(sel));
-    return oz_i2d(x);
+// SWIZZLE_128B K-major shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart, 16-byte chunk c
+// of row r stored at chunk c ^ (r % 8).  start >> 4 at [0,14), LBO (unused) = 1 at [16,30), SBO >> 4 at [32,46), version 1 at
+// [46,48), layout type 2 = SWIZZLE_128B at [61,64).  The k-th 32-byte slice of the rows starts 32 k bytes further.
+__device__ __forceinline__ uint64_t crt_smem_desc(uint32_t saddr) {
+    return uint64_t((saddr & 0x3FFFF) >> 4) | (uint64_t(1) << 16) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) |
+           (uint64_t(2) << 61);
+}
+
+__device__ __forceinline__ double crt_byte_i2d(uint32_t word, int e) {
+    // unsigned byte e of word -> double without the conversion pipe: 2^52 + u has u in its low mantissa bits
+    const uint32_t u = __byte_perm(word, 0u, 0x4440u | uint32_t(e));
+    return __hiloint2double(0x43300000, int(u)) - 4503599627370496.0;
+}
+
+// s1[e] = sum_k u_k f1_k (exact), s2[e] = sum_k u_k f2_k for the 4 outputs whose residue bytes are in word k of the slice
+template <int NN>
+__device__ __forceinline__ void crt_slice_sums(const uint32_t* sw, const CrtConsts& c, double (&s1)[4], double (&s2)[4]) {
+    uint32_t wq[NN];
+#pragma unroll
+    for (int k = 0; k < NN; ++k) wq[k] = sw[k * CRT_EPI_HALF];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s1[e] = s2[e] = 0.0;
+#pragma unroll
+    for (int k = 0; k < NN; ++k) {
+        const double f1 = c.f1[k], f2 = c.f2[k];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const double ud = crt_byte_i2d(wq[k], e);
+            s1[e] = fma(ud, f1, s1[e]);                       // exact: multiples of 2^-40 below 2^12
+            s2[e] = fma(ud, f2, s2[e]);
+        }
+    }
 }
 
 template <class Epi>
-__global__ void __launch_bounds__(OZ_THREADS, 1) crt_gemm_kernel(const CrtOperands g, const Epi epi) {
+__global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOperands g, const Epi epi) {
     extern __shared__ __align__(1024) unsigned char crt_smem[];
     unsigned char* ring = crt_smem;
-    uint64_t* full = reinterpret_cast<uint64_t*>(crt_smem + size_t(CRT_STAGES) * CRT_SLOT);
+    uint32_t* sring = reinterpret_cast<uint32_t*>(crt_smem + size_t(CRT_STAGES) * CRT_SLOT);          // scratch slices
+    uint64_t* full = reinterpret_cast<uint64_t*>(crt_smem + size_t(CRT_STAGES) * CRT_SLOT + size_t(CRT_SCR_STAGES) * CRT_SLICE_BYTES);
     uint64_t* pfull = full + CRT_STAGES;              // leader: the peer's stage is full
     uint64_t* empty = pfull + CRT_STAGES;
     uint64_t* tmem_full = empty + CRT_STAGES;         // [2]
     uint64_t* tmem_empty = tmem_full + 2;             // [2] (leader's are waited on)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    double* sYscale = reinterpret_cast<double*>(tmem_empty + 3);      // [128]
-    unsigned char* epi_smem = reinterpret_cast<unsigned char*>(sYscale + OZ_TN);
+    uint64_t* scr_ready = tmem_empty + 2;             // [2] drain warps -> prefetch thread: the tile's residues are in the scratch half
+    uint64_t* scr_free = scr_ready + 2;               // [2] reconstruction -> drain warps: the half may be overwritten
+    uint64_t* sfull = scr_free + 2;                   // [CRT_SCR_STAGES] slice ring
+    uint64_t* sempty = sfull + CRT_SCR_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + CRT_SCR_STAGES);
+    int* sYexp = reinterpret_cast<int*>(sempty + CRT_SCR_STAGES + 1);    // [128] (+ 128 unused: keeps the epilogue data 8-byte aligned)
+    unsigned char* epi_smem = reinterpret_cast<unsigned char*>(sYexp + 2 * OZ_TN);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
@@ -183,7 +228,13 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) crt_gemm_kernel(const CrtOperan
 
     if (tid == 0) {
         for (int s = 0; s < CRT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&pfull[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 2 * OZ_EPI_WARPS); }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full[b], 1);
+            mbar_init(&tmem_empty[b], OZ_EPI_WARPS);            // 8 drain warps of each CTA
+            mbar_init(&scr_ready[b], CRT_EPI_HALF);
+            mbar_init(&scr_free[b], CRT_EPI_HALF + 1);          // the reconstruction threads and the prefetch thread
+        }
+        for (int s = 0; s < CRT_SCR_STAGES; ++s) { mbar_init(&sfull[s], 1); mbar_init(&sempty[s], OZ_EPI_WARPS / 2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -196,6 +247,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) crt_gemm_kernel(const CrtOperan
     cluster_sync_all();               // both CTAs' barriers are initialised and both allocations are done
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    uint32_t* const scr_cta = g.scratch + size_t(blockIdx.x) * 2 * N * CRT_SCR_WORDS;
 
     if (warp == OZ_EPI_WARPS) {
         // ===== producer (both CTAs): own 128 rows of X and own 128 rows of the pair's 256 Y rows =====
@@ -245,9 +297,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) crt_gemm_kernel(const CrtOperan
                         const uint32_t xs = smem_u32(ring + size_t(s) * CRT_SLOT), ys = xs + CRT_IMG;
 #pragma unroll
                         for (int h = 0; h < CRT_KB / 32; ++h) {
-                            // image: [16 row groups][4 k-chunks][8 rows][16 B]: LBO = 128 B (next k-chunk), SBO = 512 B (next 8 rows)
-                            const uint64_t da = oz_smem_desc(xs + h * 256, 128, 512);
-                            const uint64_t db = oz_smem_desc(ys + h * 256, 128, 512);
+                            const uint64_t da = crt_smem_desc(xs + h * 32);
+                            const uint64_t db = crt_smem_desc(ys + h * 32);
                             const uint32_t acc = (kb > 0 || h > 0) ? 1u : 0u;
                             asm volatile(
                                 "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
@@ -273,90 +324,139 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) crt_gemm_kernel(const CrtOperan
                         mbar_arrive_remote(&pfull[s], 0);
                     }
         }
-    } else {
-        // ===== epilogue warps 0..15: thread = (output row, 32-column group of each 128-column half) =====
-        const int quarter = warp & 3, cgrp = warp >> 2;
-        const int ml = quarter * 32 + lane;
-        const uint32_t tlane = tmem_base + (uint32_t(quarter * 32) << 16);
-        uint32_t* scr = g.scratch + size_t(blockIdx.x) * N * CRT_SCR_WORDS + tid;
-        uint32_t u = 0;
-        for (int grp = pair; grp < ngroups; grp += npairs) {
-            const int tm = (grp % mgroups) * 2 + int(rank);
-            const int tn2 = n2_lo + grp / mgroups;
-            // ---- residues of the N accumulators ----
-            for (int i = 0; i < N; ++i, ++u) {
-                const uint32_t buf = u & 1, use = u >> 1;
-                const uint32_t p = g.c.p[i], magic = g.c.magic[i], off = g.c.off[i], hi = (p - 1) >> 1;
-                mbar_wait_cluster(&tmem_full[buf], use & 1, true);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t a[32];
-                    const uint32_t taddr = tlane + buf * uint32_t(CRT_TN) + uint32_t(h * OZ_TN + cgrp * OZ_CPT);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-                        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                        : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]),
-                          "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]),
-                          "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]),
-                          "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
-                        : "r"(taddr));
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (g.dbg && grp == 0 && i == g.dbg_mod) {
-#pragma unroll
-                        for (int jj = 0; jj < 32; ++jj)
-                            g.dbg[(size_t(rank) * 128 + ml) * 256 + h * OZ_TN + cgrp * OZ_CPT + jj] = int32_t(a[jj]);
-                    }
-#pragma unroll
-                    for (int w = 0; w < 8; ++w) {
-                        uint32_t word = 0;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) word |= (crt_mod_sym(a[4 * w + e], p, magic, off, hi) & 0xFFu) << (8 * e);
-                        __stcg(scr + size_t((i * 2 + h) * 8 + w) * (OZ_EPI_WARPS * 32), word);
-                    }
+    } else if (warp == OZ_EPI_WARPS + 2) {
+        // ===== scratch prefetch: slice by slice from the global scratch half into the shared-memory ring =====
+        if (lane == 0) {
+            uint32_t js = 0, nt = 0;
+            for (int grp = pair; grp < ngroups; grp += npairs, ++nt) {
+                const uint32_t par = nt & 1;
+                const int tm = (grp % mgroups) * 2 + int(rank);
+                const int tn2 = n2_lo + grp / mgroups;
+                mbar_wait_sleep(&scr_ready[par], (nt >> 1) & 1, 128);     // all 256 drain threads have written the tile's residues
+                asm volatile("fence.proxy.async;" ::: "memory");          // generic-proxy stores -> async-proxy (bulk copy) reads
+                if (tm >= g.tiles_m || (g.flags & 1)) { mbar_arrive(&scr_free[par]); continue; }
+                const uint32_t* half = scr_cta + size_t(par) * N * CRT_SCR_WORDS;
+                for (int sl = 0; sl < CRT_SLICES; ++sl) {
+                    const int tn = tn2 * 2 + (sl >> 4);
+                    if (tn < g.tile_n0 || tn >= g.tile_n0 + g.tiles_n) continue;
+                    const int s = js % CRT_SCR_STAGES;
+                    mbar_wait(&sempty[s], ((js / CRT_SCR_STAGES) & 1) ^ 1);
+                    const uint32_t bytes = uint32_t(N) * CRT_EPI_HALF * 4;
+                    mbar_expect_tx(&sfull[s], bytes);
+                    bulk_copy_g2s(sring + size_t(s) * (CRT_SLICE_BYTES / 4), half + size_t(sl) * N * CRT_EPI_HALF, bytes, &sfull[s]);
+                    ++js;
                 }
-                // the accumulator may be overwritten: modulus i + 2 (or the pair's next tile) can start
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(&tmem_empty[buf], 0);
+                mbar_arrive(&scr_free[par]);      // (the half is free once the reconstruction threads have arrived as well)
             }
-            if (tm >= g.tiles_m) continue;                               // dummy tile of an odd tile count (whole CTA)
-            // ---- Chinese remainder reconstruction + the fused epilogue, one 128-column half at a time ----
-            const int m = tm * OZ_TM + ml;
-            const int ex = g.eX[size_t(tm) * OZ_TM + ml];
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                const int tn = tn2 * 2 + h;
-                if (tn < g.tile_n0 || tn >= g.tile_n0 + g.tiles_n) continue;     // uniform over the CTA
-                asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory");
-                if (tid < OZ_TN) sYscale[tid] = oz_pow2(max(-1000, min(1000, g.eY[size_t(tn) * OZ_TN + tid])));
-                epi.prepare(epi_smem, tn, tid);
-                asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory");
-                typename Epi::State st;
-                epi.begin(st);
-#pragma unroll 1
-                for (int w = 0; w < 8; ++w) {
-                    double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 4
-                    for (int i = 0; i < N; ++i) {
-                        const uint32_t word = __ldcg(scr + size_t((i * 2 + h) * 8 + w) * (OZ_EPI_WARPS * 32));
-                        const double f1 = g.c.f1[i], f2 = g.c.f2[i];
+        }
+    } else {
+        // ===== epilogue: warps 0..7 drain the accumulators, warps 8..15 rebuild the previous tile's outputs =====
+        // Both groups map a thread to (output row = tensor-memory lane, two of the four 32-column groups of each 128-column
+        // half): drain thread d and reconstruction thread 256 + d own the same outputs.
+        // Scratch half: [slice = (half h, column group c2 of the pair, word w)][modulus][256 threads].
+        const bool is_drain = warp < OZ_EPI_WARPS / 2;
+        const int etid = tid & (CRT_EPI_HALF - 1);                       // 0..255 inside the group
+        const int quarter = warp & 3, grp2 = (warp >> 2) & 1;            // lane quarter, pair of column groups
+        const int ml = quarter * 32 + lane;
+        if (is_drain) {
+            const uint32_t tlane = tmem_base + (uint32_t(quarter * 32) << 16);
+            uint32_t u = 0, nt = 0;
+            for (int grp = pair; grp < ngroups; grp += npairs, ++nt) {
+                const uint32_t par = nt & 1;
+                if (nt >= 2) mbar_wait(&scr_free[par], ((nt >> 1) - 1) & 1);     // tile nt - 2 has been rebuilt from this half
+                uint32_t* scr = scr_cta + size_t(par) * N * CRT_SCR_WORDS + etid;
+                for (int i = 0; i < N; ++i, ++u) {
+                    const uint32_t buf = u & 1, use = u >> 1;
+                    const uint32_t p = g.c.p[i], negp = 0u - p, magic = g.c.magic[i], off = g.c.off[i];
+                    mbar_wait_cluster(&tmem_full[buf], use & 1, false);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const double ud = crt_sext_i2d(word, e);
-                            s1[e] = fma(ud, f1, s1[e]);                  // exact: multiples of 2^-40 below 2^11
-                            s2[e] = fma(ud, f2, s2[e]);
+                    for (int hc = 0; hc < 4; ++hc) {                 // (half, column group of the pair)
+                        if (g.flags & 2) break;
+                        const int h = hc >> 1, cg = grp2 * 2 + (hc & 1);
+                        uint32_t a[32];
+                        const uint32_t taddr = tlane + buf * uint32_t(CRT_TN) + uint32_t(h * OZ_TN + cg * OZ_CPT);
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                            "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                            : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]),
+                              "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]), "=r"(a[16]),
+                              "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]), "=r"(a[24]),
+                              "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
+                            : "r"(taddr));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (g.dbg && grp == 0 && i == g.dbg_mod) {
+#pragma unroll
+                            for (int jj = 0; jj < 32; ++jj)
+                                g.dbg[(size_t(rank) * 128 + ml) * 256 + h * OZ_TN + cg * OZ_CPT + jj] = int32_t(a[jj]);
+                        }
+#pragma unroll
+                        for (int w = 0; w < 8; ++w) {
+                            const uint32_t r0 = crt_mod(a[4 * w], negp, magic, off), r1 = crt_mod(a[4 * w + 1], negp, magic, off);
+                            const uint32_t r2 = crt_mod(a[4 * w + 2], negp, magic, off), r3 = crt_mod(a[4 * w + 3], negp, magic, off);
+                            const uint32_t word = __byte_perm(__byte_perm(r0, r1, 0x0040), __byte_perm(r2, r3, 0x0040), 0x5410);
+                            crt_st_scratch(scr + (size_t(hc * 8 + w) * N + i) * CRT_EPI_HALF, word);
                         }
                     }
+                    // the accumulator may be overwritten: modulus i + 2 (or the pair's next tile) can start
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_remote(&tmem_empty[buf], 0);
+                }
+                asm volatile("fence.proxy.async;" ::: "memory");        // the residues are read back by bulk copies (async proxy)
+                mbar_arrive(&scr_ready[par]);                         // release: this thread's residues of the tile are written
+            }
+        } else {
+            uint32_t js = 0, nt = 0;
+            typename Epi::State st;
+            for (int grp = pair; grp < ngroups; grp += npairs, ++nt) {
+                const uint32_t par = nt & 1;
+                const int tm = (grp % mgroups) * 2 + int(rank);
+                const int tn2 = n2_lo + grp / mgroups;
+                if (tm < g.tiles_m && !(g.flags & 1)) {                // not the dummy tile of an odd tile count
+                    const int m = tm * OZ_TM + ml;
+                    const int ex = g.eX[size_t(tm) * OZ_TM + ml];
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        const int tn = tn2 * 2 + h;
+                        if (tn < g.tile_n0 || tn >= g.tile_n0 + g.tiles_n) continue;     // uniform over the CTA
+                        asm volatile("bar.sync 2, %0;" ::"n"(CRT_EPI_HALF) : "memory");
+                        if (etid < OZ_TN) sYexp[etid] = g.eY[size_t(tn) * OZ_TN + etid];
+                        epi.prepare(epi_smem, tn, etid);
+                        asm volatile("bar.sync 2, %0;" ::"n"(CRT_EPI_HALF) : "memory");
+                        epi.begin(st);
+#pragma unroll 1
+                        for (int sl = 0; sl < 16; ++sl, ++js) {
+                            const int c2 = sl >> 3, w = sl & 7, cg = grp2 * 2 + c2;
+                            const int s = js % CRT_SCR_STAGES;
+                            mbar_wait(&sfull[s], (js / CRT_SCR_STAGES) & 1);
+                            const uint32_t* sw = sring + size_t(s) * (CRT_SLICE_BYTES / 4) + etid;
+                            double s1[4], s2[4];
+                            switch (N) {                                 // compile-time trip counts: all loads first, no branches
+                                case 10: crt_slice_sums<10>(sw, g.c, s1, s2); break;
+                                case 11: crt_slice_sums<11>(sw, g.c, s1, s2); break;
+                                case 12: crt_slice_sums<12>(sw, g.c, s1, s2); break;
+                                case 13: crt_slice_sums<13>(sw, g.c, s1, s2); break;
+                                case 14: crt_slice_sums<14>(sw, g.c, s1, s2); break;
+                                case 15: crt_slice_sums<15>(sw, g.c, s1, s2); break;
+                                default: crt_slice_sums<16>(sw, g.c, s1, s2); break;
+                            }
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&sempty[s]);      // the slice has been read into registers
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const double r1 = (s1[e] + 6755399441055744.0) - 6755399441055744.0;   // nearest integer (|s1| < 2^51)
-                        const double t = (s1[e] - r1) + s2[e];           // C'/P in (-1/4, 1/4)
-                        const int j = cgrp * OZ_CPT + w * 4 + e;
-                        epi.accept(st, epi_smem, m, tn, j, oz_scale((t * g.c.Pd) * sYscale[j], ex));
+                            for (int e = 0; e < 4; ++e) {
+                                const double r1 = (s1[e] + 6755399441055744.0) - 6755399441055744.0;   // nearest integer (|s1| < 2^51)
+                                const double t = (s1[e] - r1) + s2[e];   // C'/P in (-1/4, 1/4)
+                                const int j = cg * OZ_CPT + w * 4 + e;
+                                epi.accept(st, epi_smem, m, tn, j, oz_scale(t * g.c.Pd, ex + sYexp[j]));   // any exponent
+                            }
+                        }
+                        epi.template finish_g<2, 2>(st, epi_smem, tm, tn, ml, grp2);
                     }
                 }
-                epi.finish(st, epi_smem, tm, tn, ml, cgrp);
+                // a tile without reconstruction (dummy tile of an odd tile count): stay in step with the drain warps
+                if (tm >= g.tiles_m || (g.flags & 1)) mbar_wait_sleep(&scr_ready[par], (nt >> 1) & 1, 128);
+                mbar_arrive(&scr_free[par]);      // every slice of the tile has left the global scratch half
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -371,16 +471,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) crt_gemm_kernel(const CrtOperan
 
 template <class Epi>
 struct CrtShape {
-    static constexpr size_t SMEM = size_t(CRT_STAGES) * CRT_SLOT + (3 * CRT_STAGES + 6) * sizeof(uint64_t) + OZ_TN * sizeof(double) + Epi::SMEM;
+    static constexpr size_t SMEM = size_t(CRT_STAGES) * CRT_SLOT + size_t(CRT_SCR_STAGES) * CRT_SLICE_BYTES +
+                                   (3 * CRT_STAGES + 2 * CRT_SCR_STAGES + 10) * sizeof(uint64_t) + OZ_TN * sizeof(double) + Epi::SMEM;
 };
 
-// number of CTAs (2 per pair) a launch over `ntiles_m` x `ntiles_n` 128-row tiles uses, and the scratch it needs
-inline int crt_grid(int tiles_m, int tiles_n, int sm_count) {
-    const int groups = ((tiles_m + 1) / 2) * ((tiles_n + 2) / 2);
-    const int pairs = std::max(1, std::min(sm_count / 2, groups));
-    return 2 * pairs;
-}
-inline size_t crt_scratch_bytes(int N, int sm_count) { return size_t(sm_count) * N * CRT_SCR_WORDS * sizeof(uint32_t); }
+inline size_t crt_scratch_bytes(int N, int sm_count) { return size_t(sm_count) * 2 * N * CRT_SCR_WORDS * sizeof(uint32_t); }
 
 template <class Epi>
 inline cudaError_t launch_crt_gemm(const CrtOperands& g, const Epi& epi, cudaStream_t stream) {
@@ -406,7 +501,7 @@ inline cudaError_t launch_crt_gemm(const CrtOperands& g, const Epi& epi, cudaStr
     const int pairs = std::max(1, std::min(sms / 2, groups));
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(OZ_THREADS);
+    cfg.blockDim = dim3(CRT_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -423,7 +518,8 @@ inline cudaError_t launch_crt_gemm(const CrtOperands& g, const Epi& epi, cudaStr
 // One CTA per 8-row group and k range (as oz_slice_kernel).  Phase 1: row maximum and sum of squares -> the scale s with
 // ||rint(x 2^s)||_2 <= 2^bits.  Phase 2: thread = (row, 16-wide k chunk): x' = rint(x 2^s) as a 64-bit integer, its
 // residue modulo every p_i (compile-time moduli: the divisions become multiplications), written as N 16-byte stores.
-//   Q[((i * tiles_total + tile) * nkb + kb) * (128*64) + ((g * 4 + c) * 8 + r) * 16 + b],  g = (row % 128) / 8, c = k-chunk % 4
+//   Q[((i * tiles_total + tile) * nkb + kb) * (128*128) + g * 1024 + r * 128 + ((c ^ r) * 16) + b],  g = (row % 128) / 8,
+//   r = row % 8, c = 16-byte chunk of the k-block: the SWIZZLE_128B image the MMA descriptors expect
 template <int NMAX>
 __global__ void __launch_bounds__(256) crt_slice_kernel(const double* __restrict__ X, int ldx, int rows_valid, int k_valid, int N,
                                                         int bits, int nkb, int tiles_total, int8_t* __restrict__ Q,
@@ -462,13 +558,13 @@ __global__ void __launch_bounds__(256) crt_slice_kernel(const double* __restrict
     }
     __syncthreads();
     const int tile = tile0 + row0 / 128, gidx = (row0 % 128) / 8;
-    const int nchunks = nkb * 4;
+    const int nchunks = nkb * 8;
     const int per = (nchunks + gridDim.y - 1) / gridDim.y;
     const int item_lo = 8 * per * blockIdx.y, item_hi = min(8 * nchunks, item_lo + 8 * per);
     for (int item = item_lo + threadIdx.x; item < item_hi; item += blockDim.x) {
         const int r = item & 7, chunk = item >> 3;
         const int row = row0 + r;
-        const int kb = chunk >> 2, c = chunk & 3;
+        const int kb = chunk >> 3, c = chunk & 7;
         const int k0 = chunk * 16;
         const int s = s_s[r];
         uint32_t w[NMAX][4];
@@ -495,7 +591,7 @@ __global__ void __launch_bounds__(256) crt_slice_kernel(const double* __restrict
                 w[i][b >> 2] |= (uint32_t(sr) & 0xFFu) << (8 * (b & 3));
             }
         }
-        int8_t* q = Q + (size_t(tile) * nkb + kb) * CRT_IMG + ((gidx * 4 + c) * 8 + r) * 16;
+        int8_t* q = Q + (size_t(tile) * nkb + kb) * CRT_IMG + gidx * 1024 + r * 128 + ((c ^ r) * 16);
         const size_t mstride = size_t(tiles_total) * nkb * CRT_IMG;
 #pragma unroll
         for (int i = 0; i < NMAX; ++i)

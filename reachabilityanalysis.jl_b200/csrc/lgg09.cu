@@ -9,6 +9,7 @@
 #include "reach_common.cuh"
 #include "lgg09_kernels.cuh"
 #include "oz_gemm.cuh"
+#include "crt_gemm.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -261,6 +262,11 @@ struct reach_lgg09_plan {
     bool use_oz = false;
     bool oz_guard = false;        // auto-selected: sampled passes are re-run on the DMMA kernel and compared
     int oz_T = OZ_DEFAULT_T, oz_nkb = 0, oz_tiles_n = 0;
+    // residue (Chinese remainder) form of the same path (crt_gemm.cuh): oz_crt moduli = INT8 products per FP64 product
+    // (0: digit planes).  Same launches, guard and pass groups; Xq / Yq hold residue images instead of digit planes.
+    int oz_crt = 0;
+    CrtConsts crt{};
+    DevBuf crt_scr;               // per-CTA residue scratch of the kernel
     DevBuf Xq, Yq, eX, eY;
     // Pass groups (few chains, e.g. one shard of a multi-GPU run): oz_J consecutive passes become ONE pair of launches.
     // The carry stack holds (Phi')^(jS), j = 1..oz_J; L_t x carry stack gives the direction rows of the next oz_J passes
@@ -664,23 +670,35 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
         n + p->ne >= 128 && p->nq >= 1 && p->nq <= 4 && !getenv("REACH_NO_INT8")) {
         // large dense problem: the INT8 tcgen05 digit-plane GEMM (~2x the FP64 tensor pipe), guarded: sampled passes
         // are recomputed with the DMMA kernel and the run falls back to it if they differ by more than kOzGuardTol
-        const int T = p->opts.reserved[0] ? p->opts.reserved[0] : OZ_DEFAULT_T;
-        if (T < 4 || T > OZ_MAX_T)
-            return set_error(ctx, REACH_EINVAL, "digit planes (opts.reserved[0]) must be in 4..%d, got %d", OZ_MAX_T, T);
         p->use_oz = true;
         p->oz_guard = true;
-        p->oz_T = T;
     }
     if (p->opts.path == 3) {
-        const int T = p->opts.reserved[0] ? p->opts.reserved[0] : OZ_DEFAULT_T;
-        if (T < 4 || T > OZ_MAX_T)
-            return set_error(ctx, REACH_EINVAL, "digit planes (opts.reserved[0]) must be in 4..%d, got %d", OZ_MAX_T, T);
         if (n + p->ne < 128 || p->nq < 1 || p->nq > 4 || n > OZ_MAX_K)
             return set_error(ctx, REACH_EUNSUPPORTED,
-                             "the digit-plane GEMM path needs 128 <= n + mapped rows, n <= 16384 and 1..4 support features "
+                             "the INT8 GEMM path needs 128 <= n + mapped rows, n <= 16384 and 1..4 support features "
                              "(n=%d, mapped rows=%d, features=%d)", n, p->ne, p->nq);
         p->use_oz = true;
-        p->oz_T = T;
+    }
+    p->oz_crt = 0;
+    if (p->use_oz) {
+        // opts.reserved[0]: 0 = default (residues modulo CRT_DEFAULT_N moduli), 4..8 = that many 8-bit digit planes,
+        // 10..16 = residues modulo that many moduli
+        int sel = p->opts.reserved[0];
+        if (sel == 0) {
+            sel = getenv("REACH_NO_CRT") ? OZ_DEFAULT_T : CRT_DEFAULT_N;
+            if (const char* e = getenv("REACH_CRT_MODULI")) sel = atoi(e);
+        }
+        if (sel >= 4 && sel <= OZ_MAX_T) {
+            p->oz_T = sel;
+        } else if (sel >= 10 && sel <= CRT_MAX_N) {
+            p->oz_crt = sel;
+            p->oz_T = sel;
+            p->crt = crt_make_consts(sel);
+        } else {
+            return set_error(ctx, REACH_EINVAL, "opts.reserved[0] must be 0, 4..%d (digit planes) or 10..%d (moduli), got %d", OZ_MAX_T,
+                             CRT_MAX_N, sel);
+        }
     }
     p->oz_J = 1;
     if (p->use_oz && !(inv && inv->kind != REACH_INV_NONE) && !getenv("REACH_OZ_NO_GROUPS")) {
@@ -781,9 +799,12 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
     }
 
     if (p->use_oz) {
-        p->oz_nkb = (n + OZ_KB - 1) / OZ_KB;
+        const int kblock = p->oz_crt ? CRT_KB : OZ_KB;
+        p->oz_nkb = (n + kblock - 1) / kblock;
         p->oz_tiles_n = int((size_t(S + 1) * nbe + OZ_TN - 1) / OZ_TN);
-        const size_t plane_blk = size_t(p->oz_T) * OZ_PLANE;
+        // bytes of all planes (digit planes or residue images) of one 128-row tile and one k-block
+        const size_t plane_blk = p->oz_crt ? size_t(p->oz_crt) * CRT_IMG : size_t(p->oz_T) * OZ_PLANE;
+        if (p->oz_crt) REACH_TRY(p->crt_scr.alloc(ctx, crt_scratch_bytes(p->oz_crt, ctx->sm_count), false));
         REACH_TRY(p->Yq.alloc(ctx, size_t(p->oz_nkb) * p->oz_tiles_n * plane_blk, false));
         REACH_TRY(p->eY.alloc(ctx, size_t(p->oz_tiles_n) * OZ_TN * sizeof(int)));
         REACH_TRY(p->Xq.alloc(ctx, size_t(p->oz_nkb) * (mu_ld / OZ_TM) * plane_blk, false));
@@ -1193,9 +1214,27 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         qcur ^= 1;
     }
 
+    // digit planes (oz_gemm.cuh) or residue images (crt_gemm.cuh) of FP64 rows; the GEMM over them
+    auto oz_slice = [&](const double* X, int rows_valid, int rows_padded, int ksplit, int tiles_total, int8_t* Q, int* e, int tile0,
+                        bool is_y) {
+        if (p->oz_crt)
+            launch_crt_slice(X, Kp, rows_valid, rows_padded, n, p->crt, is_y, p->oz_nkb, tiles_total, Q, e, tile0, ksplit, st);
+        else
+            oz_slice_kernel<OZ_TM><<<dim3(rows_padded / 8, ksplit), 256, 0, st>>>(X, Kp, rows_valid, n, p->oz_T, p->oz_nkb, tiles_total, Q,
+                                                                               e, tile0);
+    };
+    auto oz_launch = [&](const OzOperands& g, const auto& e) -> cudaError_t {
+        if (p->oz_crt) {
+            CrtOperands c{g.Xq, g.Yq, g.eX, g.eY, g.nkb, g.tiles_m, g.tiles_m_total, g.tile_n0, g.tiles_n, g.tiles_n_total,
+                          p->crt_scr.as<uint32_t>(), p->crt};
+            static const int dbg_flags = getenv("REACH_CRT_FLAGS") ? atoi(getenv("REACH_CRT_FLAGS")) : 0;   // timing experiments
+            c.flags = dbg_flags;
+            return launch_crt_gemm(c, e, st);
+        }
+        return launch_oz_gemm(p->oz_T, g, e, st);
+    };
     if (p->use_oz) {   // digit planes of the whole row stack (once per run)
-        oz_slice_kernel<OZ_TN><<<p->oz_tiles_n * OZ_TN / 8, 256, 0, st>>>(stack, Kp, (S + 1) * nbe, n, p->oz_T, p->oz_nkb,
-                                                                      p->oz_tiles_n, p->Yq.as<int8_t>(), p->eY.as<int>());
+        oz_slice(stack, (S + 1) * nbe, p->oz_tiles_n * OZ_TN, 1, p->oz_tiles_n, p->Yq.as<int8_t>(), p->eY.as<int>(), 0, true);
         REACH_CUDA(ctx, cudaGetLastError());
         ++p->launches;
     }
@@ -1218,8 +1257,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
             ++p->launches;
         }
         for (int j = 1; j < J; ++j) REACH_TRY(plain_gemm(C + (j - 1) * cblk, n, QS, n, C + j * cblk, n));
-        oz_slice_kernel<OZ_TN><<<J * p->oz_ctiles * OZ_TN / 8, 256, 0, st>>>(C, Kp, J * p->oz_ctiles * OZ_TN, n, p->oz_T, p->oz_nkb,
-                                                                     J * p->oz_ctiles, p->Yq_c.as<int8_t>(), p->eY_c.as<int>());
+        oz_slice(C, J * p->oz_ctiles * OZ_TN, J * p->oz_ctiles * OZ_TN, 1, J * p->oz_ctiles, p->Yq_c.as<int8_t>(), p->eY_c.as<int>(), 0, true);
         REACH_CUDA(ctx, cudaGetLastError());
         ++p->launches;
     }
@@ -1238,8 +1276,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     auto oz_pass = [&](const double* Lcur, double* Lnext, int b_lo, int b_hi, int store_block, bool sample) -> int {
         // a few hundred chains are only mu_pad/8 row groups: split the k range so that ~2 CTAs per SM are in flight
         const int ksplit = std::max(1, std::min(8, (2 * ctx->sm_count) / std::max(1, mu_pad / 8)));
-        oz_slice_kernel<OZ_TM><<<dim3(mu_pad / 8, ksplit), 256, 0, st>>>(Lcur, Kp, p->mu, n, p->oz_T, p->oz_nkb, J * mt,
-                                                          p->Xq.as<int8_t>(), p->eX.as<int>());
+        oz_slice(Lcur, p->mu, mu_pad, ksplit, J * mt, p->Xq.as<int8_t>(), p->eX.as<int>(), 0, false);
         REACH_CUDA(ctx, cudaGetLastError());
         ++p->launches;
         const int tile_lo = int((size_t(b_lo) * nbe) / OZ_TN);
@@ -1249,7 +1286,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         oepi.Lnext = Lnext;
         oepi.store_block = store_block;
         if (sample) REACH_CUDA(ctx, cudaEventRecord(p->gemm_ev[2 * p->gemm_sampled], st));
-        REACH_CUDA(ctx, (launch_oz_gemm(p->oz_T, g, oepi, st)));
+        REACH_CUDA(ctx, (oz_launch(g, oepi)));
         if (sample) {
             REACH_CUDA(ctx, cudaEventRecord(p->gemm_ev[2 * p->gemm_sampled + 1], st));
             ++p->gemm_sampled;
@@ -1263,18 +1300,16 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     // is carried out of it), and L_{t+Jg} becomes the plan's current direction rows.
     auto oz_group = [&](double* Lcur, int Jg, int b_lo, bool sample) -> int {
         const int ksplit = std::max(1, std::min(8, (2 * ctx->sm_count) / std::max(1, mu_pad / 8)));
-        oz_slice_kernel<OZ_TM><<<dim3(mu_pad / 8, ksplit), 256, 0, st>>>(Lcur, Kp, p->mu, n, p->oz_T, p->oz_nkb, J * mt,
-                                                          p->Xq.as<int8_t>(), p->eX.as<int>());
+        oz_slice(Lcur, p->mu, mu_pad, ksplit, J * mt, p->Xq.as<int8_t>(), p->eX.as<int>(), 0, false);
         REACH_CUDA(ctx, cudaGetLastError());
         OzOperands gc{p->Xq.as<int8_t>(), p->Yq_c.as<int8_t>(), p->eX.as<int>(), p->eY_c.as<int>(), p->oz_nkb,
                       mt, J * mt, 0, Jg * p->oz_ctiles, J * p->oz_ctiles};
         OzCarryEpi cepi{p->Lst.as<double>(), Kp, n, p->oz_ctiles, mu_pad};
-        REACH_CUDA(ctx, (launch_oz_gemm(p->oz_T, gc, cepi, st)));
+        REACH_CUDA(ctx, (oz_launch(gc, cepi)));
         if (Jg > 1) {
             const int rows = (Jg - 1) * mu_pad;
             const int ks2 = std::max(1, std::min(8, (2 * ctx->sm_count) / std::max(1, rows / 8)));
-            oz_slice_kernel<OZ_TM><<<dim3(rows / 8, ks2), 256, 0, st>>>(p->Lst.as<double>(), Kp, rows, n, p->oz_T, p->oz_nkb, J * mt,
-                                                         p->Xq.as<int8_t>(), p->eX.as<int>(), mt);
+            oz_slice(p->Lst.as<double>(), rows, rows, ks2, J * mt, p->Xq.as<int8_t>(), p->eX.as<int>(), mt, false);
             REACH_CUDA(ctx, cudaGetLastError());
             ++p->launches;
         }
@@ -1288,7 +1323,7 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         oepi.Lnext = nullptr;
         oepi.store_block = -1;
         if (sample) REACH_CUDA(ctx, cudaEventRecord(p->gemm_ev[2 * p->gemm_sampled], st));
-        REACH_CUDA(ctx, (launch_oz_gemm(p->oz_T, g, oepi, st)));
+        REACH_CUDA(ctx, (oz_launch(g, oepi)));
         if (sample) {
             REACH_CUDA(ctx, cudaEventRecord(p->gemm_ev[2 * p->gemm_sampled + 1], st));
             ++p->gemm_sampled;

@@ -85,6 +85,8 @@ struct OzStoreEpi {
         if (m < m_valid && n < n_valid) out[size_t(m) * ldc + n] = v;
     }
     __device__ __forceinline__ void finish(State&, unsigned char*, int, int, int, int) const {}
+    template <int NG, int BAR>
+    __device__ __forceinline__ void finish_g(State&, unsigned char*, int, int, int, int) const {}
 };
 
 // ---- carry epilogue (LGG09 pass groups): Y = [(Phi')^S; (Phi')^2S; ...], blocks of tiles_per_block tiles ----
@@ -101,6 +103,8 @@ struct OzCarryEpi {
         if (col < n) out[(size_t(blk) * rows_per_slot + m) * ldl + col] = v;
     }
     __device__ __forceinline__ void finish(State&, unsigned char*, int, int, int, int) const {}
+    template <int NG, int BAR>
+    __device__ __forceinline__ void finish_g(State&, unsigned char*, int, int, int, int) const {}
 };
 
 // ---- fused LGG09 epilogue on the digit-plane GEMM (packed stack layout, see Lgg09PackedEpi) ---------------
@@ -163,11 +167,16 @@ struct OzLgg09Epi {
         }
     }
     __device__ __forceinline__ void finish(State& st, unsigned char* sm, int tm, int tn, int ml, int cgrp) const {
-        // red[q][seg][part][128 rows] after the staged weights: the four column groups of a row add their partials in
-        // fixed order (group 0 stores, 1..3 add), one named barrier between the phases -> deterministic
+        finish_g<OZ_EPI_WARPS / 4, 1>(st, sm, tm, tn, ml, cgrp);
+    }
+    // NG threads per output row (column groups 0..NG-1, 128 NG threads in all) meet on named barrier BAR
+    template <int NG, int BAR>
+    __device__ __forceinline__ void finish_g(State& st, unsigned char* sm, int tm, int tn, int ml, int cgrp) const {
+        // red[q][seg][part][128 rows] after the staged weights: the column groups of a row add their partials in
+        // fixed order (group 0 stores, 1.. add), one named barrier between the phases -> deterministic
         double* red = reinterpret_cast<double*>(sm + size_t(OZ_TN) * (2 * NQ) * sizeof(double) + size_t(OZ_TN) * sizeof(int));
 #pragma unroll
-        for (int c = 0; c < OZ_EPI_WARPS / 4; ++c) {
+        for (int c = 0; c < NG; ++c) {
             if (cgrp == c) {
 #pragma unroll
                 for (int q = 0; q < NQ; ++q)
@@ -179,10 +188,10 @@ struct OzLgg09Epi {
                         else { *rl += st.lin[q][sg]; *ra += st.ab[q][sg]; }
                     }
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NG * OZ_TM) : "memory");
         }
         const int t = cgrp * OZ_TM + ml;
-        for (int idx = t; idx < nq * 4 * OZ_TM; idx += OZ_EPI_WARPS * 32) {
+        for (int idx = t; idx < nq * 4 * OZ_TM; idx += NG * OZ_TM) {
             const int r = idx % OZ_TM, part = (idx / OZ_TM) & 1, sg = (idx / (2 * OZ_TM)) & 1, q = idx / (4 * OZ_TM);
             featpart[((((size_t(tn) * 2 + sg) * nq + q) * 2) + part) * mu_pad + tm * OZ_TM + r] = red[((q * 2 + sg) * 2 + part) * OZ_TM + r];
         }

@@ -116,6 +116,7 @@ extern "C" int reach_crtgemm_probe(reach_ctx* ctx, int m, int n, int k, int modu
         g.dbg = dbg.as<int32_t>();
         g.dbg_mod = atoi(dbg_env);
     }
+    if (getenv("REACH_CRT_FLAGS")) g.flags = atoi(getenv("REACH_CRT_FLAGS"));
     REACH_CUDA(ctx, (launch_crt_gemm(g, epi, st)));            // warm-up (also the result)
     REACH_CUDA(ctx, cudaStreamSynchronize(st));
     REACH_CUDA(ctx, cudaEventRecord(e1, st));

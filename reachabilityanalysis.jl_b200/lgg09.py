@@ -114,7 +114,7 @@ class Lgg09Plan:
         opts.time_block, opts.share_negated = int(time_block), int(bool(share_negated))
         opts.tile_m, opts.tile_n = int(tile_m), int(tile_n)
         opts.path = {"auto": 0, "gemm": 1, "chain": 2, "int8": 3, "compact": 4}.get(path, path)
-        opts.reserved[0] = int(digit_planes)      # 0 = 7 planes of 8 bits (FP64-level accuracy); 4..8
+        opts.reserved[0] = int(digit_planes)      # 0 = residues modulo 14 moduli (default); 4..8 digit planes; 10..16 moduli
         self.handle = C.c_void_p()
         ctx.check(self.lib.reach_lgg09_plan_create(ctx.handle, self.n, self.ndirs, self.nsteps,
                                                    C.byref(opts), C.byref(self.handle)))

@@ -69,21 +69,66 @@ def test_digit_plane_gemm_rejects_bad_arguments(ctx):
         ctx.ozgemm_probe(X, X, slices=9)
 
 
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (100, 64, 37), (300, 200, 1000), (384, 640, 130), (129, 257, 513)])
+@pytest.mark.parametrize("moduli", [12, 14, 16])
+def test_residue_gemm_matches_exact_products(ctx, m, n, k, moduli):
+    """crt_gemm.cuh: one INT8 GEMM per modulus + Chinese remainder reconstruction.  Error model: every operand element is
+    rounded at 2^-bits of its ROW NORM (bits = 46 / 54 / 61 for 12 / 14 / 16 moduli), nothing else is inexact."""
+    rng = np.random.default_rng(m + n + k)
+    X = rng.standard_normal((m, k)) * np.exp(rng.uniform(-3, 3, (m, 1)))
+    Y = rng.standard_normal((n, k)) * np.exp(rng.uniform(-3, 3, (n, 1)))
+    ref = (X.astype(np.longdouble) @ Y.T.astype(np.longdouble)).astype(np.float64)
+    Cm, _, _ = ctx.crtgemm_probe(X, Y, moduli=moduli)
+    scale = np.sqrt((X * X).sum(1))[:, None] * np.sqrt((Y * Y).sum(1))[None, :]
+    bits = {12: 46, 14: 54, 16: 61}[moduli]
+    tol = max(2.0 ** -(bits - 2), 2.0 ** -51)          # 2^-51: the rounding of the FP64 result itself
+    assert (np.abs(Cm - ref) / scale).max() <= tol
+
+
+def test_residue_gemm_is_deterministic_and_handles_zero_and_tiny_rows(ctx):
+    rng = np.random.default_rng(7)
+    X = rng.standard_normal((260, 300))
+    Y = rng.standard_normal((140, 300))
+    X[5] = 0.0
+    X[9] *= 1e-290
+    Y[3] = 0.0
+    Y[11] *= 1e250
+    X[17, :] = 0.0
+    X[17, 4] = 3.0                                   # a single entry: the row norm equals the row maximum
+    C1, _, _ = ctx.crtgemm_probe(X, Y)
+    C2, _, _ = ctx.crtgemm_probe(X, Y)
+    assert np.array_equal(C1, C2)
+    ref = X @ Y.T
+    assert np.all(C1[5] == 0.0) and np.all(C1[:, 3] == 0.0)
+    scale = np.sqrt((X * X).sum(1))[:, None] * np.sqrt((Y * Y).sum(1))[None, :]
+    ok = scale > 0
+    assert (np.abs(C1 - ref)[ok] / scale[ok]).max() <= 2.0 ** -50
+
+
+def test_residue_gemm_rejects_bad_arguments(ctx):
+    X = np.ones((4, 4))
+    with pytest.raises(ValueError):
+        ctx.crtgemm_probe(X, X, moduli=9)
+    with pytest.raises(ValueError):
+        ctx.crtgemm_probe(X, X, moduli=17)
+
+
 def _synthetic(n, nsteps, seed=0):
     return W.synthetic_c5(n=n, nsteps=nsteps, seed=seed)
 
 
+@pytest.mark.parametrize("planes,expect", [(0, 14), (7, 7), (13, 13)])   # default = residues mod 14 moduli; 7 digit planes; 13 moduli
 @pytest.mark.parametrize("n,nsteps,S", [(130, 30, 1), (200, 48, 3), (333, 40, 0), (600, 24, 5)])
-def test_lgg09_int8_path_matches_oracle(ctx, n, nsteps, S):
+def test_lgg09_int8_path_matches_oracle(ctx, n, nsteps, S, planes, expect):
     wl = _synthetic(n, nsteps, seed=n)
     ref = LO.reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, wl.V)
-    plan = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=S, path="int8")
+    plan = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=S, path="int8", digit_planes=planes)
     st = plan.stats()
-    assert st["path"] == "int8" and st["digit_planes"] == 7 and (st["tile_m"], st["tile_n"]) == (128, 128)
+    assert st["path"] == "int8" and st["digit_planes"] == expect and (st["tile_m"], st["tile_n"]) == (128, 128)
     err = assert_support_parity(plan.sfmat(), ref)
     assert err <= 2e-11                          # measured ~1e-12: two decades inside the tolerance
     # same numbers on a second run (deterministic), and the DMMA path agrees
-    again = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=S, path="int8")
+    again = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=S, path="int8", digit_planes=planes)
     assert np.array_equal(again.sfmat(), plan.sfmat())
     dmma = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=S, path="gemm")
     assert dmma.stats()["path"] == "gemm"
@@ -114,8 +159,9 @@ def test_lgg09_int8_path_unsupported_shapes_raise(ctx):
     with pytest.raises(NotImplementedError):     # n + mapped rows < 128
         reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, 10, None, wl.V, ctx=ctx, path="int8")
     wl = _synthetic(160, 10)
-    with pytest.raises(ValueError):              # digit planes outside 4..8
-        reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, 10, None, wl.V, ctx=ctx, path="int8", digit_planes=3)
+    for bad in (3, 9, 17):                       # neither 4..8 digit planes nor 10..16 moduli
+        with pytest.raises(ValueError):
+            reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, 10, None, wl.V, ctx=ctx, path="int8", digit_planes=bad)
 
 
 def test_auto_selects_guarded_int8_and_keeps_it_on_a_well_scaled_problem(ctx):
