@@ -121,6 +121,7 @@ struct CrtOperands {
     int32_t* dbg = nullptr;   // debug: raw accumulators of modulus dbg_mod of the first tile of pair 0, [2][128][256]
     int dbg_mod = 0;
     int flags = 0;            // debug / timing experiments: 1 = no reconstruction, 2 = no residue reduction (drain only)
+    unsigned long long* tim = nullptr;   // debug: [gridDim.x][16] cycle counters of the warp roles (REACH_CRT_TIMING)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -138,19 +139,19 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
         "{\n .reg .b32 ra;\n mapa.shared::cluster.u32 ra, %0, %1;\n"
         " mbarrier.arrive.shared::cluster.b64 _, [ra];\n}" ::"r"(smem_u32(bar)), "r"(rank) : "memory");
 }
-// wait on a barrier the peer CTA arrives on.  Default (CTA-scope) semantics as in CUTLASS' ClusterBarrier: the operands
-// travel through the async proxy only (bulk copy -> shared memory -> MMA), and a cluster-scope acquire / release per
-// k-block costs a memory fence each (measured: 1.1 us per k-block instead of 0.15)
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, bool sleep) {
+// Every wait of this kernel: try_wait with a suspend-time hint (SASS: TRYWAIT, NANOSLEEP.SYNCS, re-check), so a waiting warp
+// sleeps until the barrier's phase completes instead of spinning.  (Spinning waits of the 8 drain warps, which idle ~70 % of
+// the time, took 40 % of all issued instructions and starved the reconstruction warps on the same schedulers.)
+// Default (CTA-scope) semantics as in CUTLASS' ClusterBarrier also where the peer CTA arrives: the operands travel through
+// the async proxy only (bulk copy -> shared memory -> MMA), and a cluster-scope acquire / release per k-block costs a
+// memory fence each (measured: 1.1 us per k-block instead of 0.15).
+__device__ __forceinline__ void crt_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok = 0, spins = 0;
     const uint32_t a = smem_u32(bar);
     do {
-        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
-        if (!ok) {
-            if (sleep) __nanosleep(256);
-            if (++spins > (1u << (sleep ? 24 : 27))) __trap();
-        }
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity), "r"(20000u) : "memory");
+        if (!ok && ++spins > (1u << 20)) __trap();     // a protocol error must fail, not hang the GPU
     } while (!ok);
 }
 
@@ -200,6 +201,9 @@ __device__ __forceinline__ void crt_slice_sums(const uint32_t* sw, const CrtCons
     }
 }
 
+#define CRT_T0() (timing ? clock64() : 0ll)
+#define CRT_ACC(slot, t0) do { if (timing) tacc[slot] += clock64() - (t0); } while (0)
+
 template <class Epi>
 __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOperands g, const Epi epi) {
     extern __shared__ __align__(1024) unsigned char crt_smem[];
@@ -216,7 +220,7 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
     uint64_t* sempty = sfull + CRT_SCR_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sempty + CRT_SCR_STAGES);
     int* sYexp = reinterpret_cast<int*>(sempty + CRT_SCR_STAGES + 1);    // [128] (+ 128 unused: keeps the epilogue data 8-byte aligned)
-    unsigned char* epi_smem = reinterpret_cast<unsigned char*>(sYexp + 2 * OZ_TN);
+    unsigned char* epi_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sYexp + 2 * OZ_TN) + 15) & ~uintptr_t(15));   // 16-byte loads
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
@@ -225,6 +229,9 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
     const int n2_lo = g.tile_n0 >> 1, n2_hi = (g.tile_n0 + g.tiles_n + 1) >> 1;
     const int mgroups = (g.tiles_m + 1) >> 1;
     const int ngroups = mgroups * (n2_hi - n2_lo);
+    const bool timing = g.tim != nullptr;
+    long long tacc[4] = {0, 0, 0, 0};
+    const long long t_begin = CRT_T0();
 
     if (tid == 0) {
         for (int s = 0; s < CRT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&pfull[s], 1); mbar_init(&empty[s], 1); }
@@ -265,7 +272,7 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
                     for (int kb = 0; kb < g.nkb; ++kb, ++jb) {
                         const int s = jb % CRT_STAGES;
                         const uint32_t ph = (jb / CRT_STAGES) & 1;
-                        mbar_wait_cluster(&empty[s], ph ^ 1, false);
+                        crt_wait(&empty[s], ph ^ 1);
                         mbar_expect_tx(&full[s], CRT_SLOT);
                         unsigned char* dst = ring + size_t(s) * CRT_SLOT;
                         bulk_copy_g2s(dst, gx + size_t(kb) * img_stride, CRT_IMG, &full[s]);
@@ -284,15 +291,21 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
                 for (int i = 0; i < N; ++i, ++u) {
                     const uint32_t buf = u & 1, use = u >> 1;
                     if (use > 0) {                                     // both CTAs have pulled the buffer's previous contents
-                        mbar_wait_cluster(&tmem_empty[buf], (use - 1) & 1, false);
+                        const long long t0 = CRT_T0();
+                        crt_wait(&tmem_empty[buf], (use - 1) & 1);
+                        CRT_ACC(0, t0);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
                     const uint32_t dcol = tmem_base + buf * uint32_t(CRT_TN);
                     for (int kb = 0; kb < g.nkb; ++kb, ++jb) {
                         const int s = jb % CRT_STAGES;
                         const uint32_t ph = (jb / CRT_STAGES) & 1;
-                        mbar_wait(&full[s], ph);
-                        mbar_wait_cluster(&pfull[s], ph, false);
+                        const long long t1 = CRT_T0();
+                        crt_wait(&full[s], ph);
+                        CRT_ACC(1, t1);
+                        const long long t2 = CRT_T0();
+                        crt_wait(&pfull[s], ph);
+                        CRT_ACC(2, t2);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t xs = smem_u32(ring + size_t(s) * CRT_SLOT), ys = xs + CRT_IMG;
 #pragma unroll
@@ -300,6 +313,7 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
                             const uint64_t da = crt_smem_desc(xs + h * 32);
                             const uint64_t db = crt_smem_desc(ys + h * 32);
                             const uint32_t acc = (kb > 0 || h > 0) ? 1u : 0u;
+                            if (g.flags & 16) continue;                  // timing experiment: no tensor work
                             asm volatile(
                                 "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
                                 " tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(dcol), "l"(da), "l"(db), "r"(idesc), "r"(acc)
@@ -313,6 +327,8 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
                                  ::"r"(smem_u32(&tmem_full[buf])), "h"(uint16_t(3)) : "memory");
                 }
             }
+            if (timing) { g.tim[blockIdx.x * 16 + 0] = tacc[0]; g.tim[blockIdx.x * 16 + 1] = tacc[1]; g.tim[blockIdx.x * 16 + 2] = tacc[2];
+                          g.tim[blockIdx.x * 16 + 3] = clock64() - t_begin; }
         } else if (lane == 0) {
             // ===== relay (peer): stage s of my ring is full -> the leader's pfull[s] =====
             uint32_t jb = 0;
@@ -320,7 +336,7 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
                 for (int i = 0; i < N; ++i)
                     for (int kb = 0; kb < g.nkb; ++kb, ++jb) {
                         const int s = jb % CRT_STAGES;
-                        mbar_wait(&full[s], (jb / CRT_STAGES) & 1);
+                        crt_wait(&full[s], (jb / CRT_STAGES) & 1);
                         mbar_arrive_remote(&pfull[s], 0);
                     }
         }
@@ -332,7 +348,7 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
                 const uint32_t par = nt & 1;
                 const int tm = (grp % mgroups) * 2 + int(rank);
                 const int tn2 = n2_lo + grp / mgroups;
-                mbar_wait_sleep(&scr_ready[par], (nt >> 1) & 1, 128);     // all 256 drain threads have written the tile's residues
+                crt_wait(&scr_ready[par], (nt >> 1) & 1);     // all 256 drain threads have written the tile's residues
                 asm volatile("fence.proxy.async;" ::: "memory");          // generic-proxy stores -> async-proxy (bulk copy) reads
                 if (tm >= g.tiles_m || (g.flags & 1)) { mbar_arrive(&scr_free[par]); continue; }
                 const uint32_t* half = scr_cta + size_t(par) * N * CRT_SCR_WORDS;
@@ -340,7 +356,7 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
                     const int tn = tn2 * 2 + (sl >> 4);
                     if (tn < g.tile_n0 || tn >= g.tile_n0 + g.tiles_n) continue;
                     const int s = js % CRT_SCR_STAGES;
-                    mbar_wait(&sempty[s], ((js / CRT_SCR_STAGES) & 1) ^ 1);
+                    crt_wait(&sempty[s], ((js / CRT_SCR_STAGES) & 1) ^ 1);
                     const uint32_t bytes = uint32_t(N) * CRT_EPI_HALF * 4;
                     mbar_expect_tx(&sfull[s], bytes);
                     bulk_copy_g2s(sring + size_t(s) * (CRT_SLICE_BYTES / 4), half + size_t(sl) * N * CRT_EPI_HALF, bytes, &sfull[s]);
@@ -363,12 +379,17 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
             uint32_t u = 0, nt = 0;
             for (int grp = pair; grp < ngroups; grp += npairs, ++nt) {
                 const uint32_t par = nt & 1;
-                if (nt >= 2) mbar_wait(&scr_free[par], ((nt >> 1) - 1) & 1);     // tile nt - 2 has been rebuilt from this half
+                { const long long t0 = CRT_T0();
+                if (nt >= 2) crt_wait(&scr_free[par], ((nt >> 1) - 1) & 1);     // tile nt - 2 has been rebuilt from this half
+                CRT_ACC(0, t0); }
                 uint32_t* scr = scr_cta + size_t(par) * N * CRT_SCR_WORDS + etid;
                 for (int i = 0; i < N; ++i, ++u) {
                     const uint32_t buf = u & 1, use = u >> 1;
                     const uint32_t p = g.c.p[i], negp = 0u - p, magic = g.c.magic[i], off = g.c.off[i];
-                    mbar_wait_cluster(&tmem_full[buf], use & 1, false);
+                    const long long t1 = CRT_T0();
+                    crt_wait(&tmem_full[buf], use & 1);
+                    CRT_ACC(1, t1);
+                    const long long t2 = CRT_T0();
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
                     for (int hc = 0; hc < 4; ++hc) {                 // (half, column group of the pair)
@@ -402,10 +423,12 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive_remote(&tmem_empty[buf], 0);
+                    CRT_ACC(2, t2);
                 }
                 asm volatile("fence.proxy.async;" ::: "memory");        // the residues are read back by bulk copies (async proxy)
                 mbar_arrive(&scr_ready[par]);                         // release: this thread's residues of the tile are written
             }
+            if (timing && tid == 0) { g.tim[blockIdx.x * 16 + 4] = tacc[0]; g.tim[blockIdx.x * 16 + 5] = tacc[1]; g.tim[blockIdx.x * 16 + 6] = tacc[2]; }
         } else {
             uint32_t js = 0, nt = 0;
             typename Epi::State st;
@@ -421,18 +444,30 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
                         const int tn = tn2 * 2 + h;
                         if (tn < g.tile_n0 || tn >= g.tile_n0 + g.tiles_n) continue;     // uniform over the CTA
                         asm volatile("bar.sync 2, %0;" ::"n"(CRT_EPI_HALF) : "memory");
-                        if (etid < OZ_TN) sYexp[etid] = g.eY[size_t(tn) * OZ_TN + etid];
+                        if (etid == 0) sYexp[OZ_TN] = 1;                 // all column exponents of the half within +-450
+                        asm volatile("bar.sync 2, %0;" ::"n"(CRT_EPI_HALF) : "memory");
+                        if (etid < OZ_TN) {
+                            const int ey = g.eY[size_t(tn) * OZ_TN + etid];
+                            sYexp[etid] = ey;
+                            if (ey < -450 || ey > 450) sYexp[OZ_TN] = 0;
+                        }
                         epi.prepare(epi_smem, tn, etid);
                         asm volatile("bar.sync 2, %0;" ::"n"(CRT_EPI_HALF) : "memory");
-                        epi.begin(st);
+                        epi.begin(st, tn);
+                        // |ex + eY| <= 900: 2^(ex + eY) is a normal number and t P 2^(ex + eY) cannot overflow early (P < 2^126)
+                        const bool fast = sYexp[OZ_TN] != 0 && ex >= -450 && ex <= 450;
 #pragma unroll 1
                         for (int sl = 0; sl < 16; ++sl, ++js) {
                             const int c2 = sl >> 3, w = sl & 7, cg = grp2 * 2 + c2;
                             const int s = js % CRT_SCR_STAGES;
-                            mbar_wait(&sfull[s], (js / CRT_SCR_STAGES) & 1);
+                            const long long t0 = CRT_T0();
+                            crt_wait(&sfull[s], (js / CRT_SCR_STAGES) & 1);
+                            CRT_ACC(0, t0);
+                            const long long t1 = CRT_T0();
                             const uint32_t* sw = sring + size_t(s) * (CRT_SLICE_BYTES / 4) + etid;
                             double s1[4], s2[4];
-                            switch (N) {                                 // compile-time trip counts: all loads first, no branches
+                            if (g.flags & 8) { s1[0] = s1[1] = s1[2] = s1[3] = 0.25; s2[0] = s2[1] = s2[2] = s2[3] = double(sw[0]) * 1e-30; }
+                            else switch (N) {                                 // compile-time trip counts: all loads first, no branches
                                 case 10: crt_slice_sums<10>(sw, g.c, s1, s2); break;
                                 case 11: crt_slice_sums<11>(sw, g.c, s1, s2); break;
                                 case 12: crt_slice_sums<12>(sw, g.c, s1, s2); break;
@@ -443,21 +478,32 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
                             }
                             __syncwarp();
                             if (lane == 0) mbar_arrive(&sempty[s]);      // the slice has been read into registers
+                            CRT_ACC(1, t1);
+                            const long long t2 = CRT_T0();
+                            double v[4];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const double r1 = (s1[e] + 6755399441055744.0) - 6755399441055744.0;   // nearest integer (|s1| < 2^51)
                                 const double t = (s1[e] - r1) + s2[e];   // C'/P in (-1/4, 1/4)
-                                const int j = cg * OZ_CPT + w * 4 + e;
-                                epi.accept(st, epi_smem, m, tn, j, oz_scale(t * g.c.Pd, ex + sYexp[j]));   // any exponent
+                                // value = t P 2^(ex + eY[j]); one exponent-field add unless an exponent is far out of range
+                                const int et = ex + sYexp[cg * OZ_CPT + w * 4 + e];
+                                v[e] = fast ? (t * g.c.Pd) * oz_pow2(et) : oz_scale(t * g.c.Pd, et);
                             }
+                            if (!(g.flags & 4)) epi.accept4(st, epi_smem, m, tn, cg * OZ_CPT + w * 4, v);
+                            else if (v[0] == 0.123) sYexp[0] = 1;
+                            CRT_ACC(2, t2);
                         }
+                        { const long long t3 = CRT_T0();
                         epi.template finish_g<2, 2>(st, epi_smem, tm, tn, ml, grp2);
+                        CRT_ACC(3, t3); }
                     }
                 }
                 // a tile without reconstruction (dummy tile of an odd tile count): stay in step with the drain warps
-                if (tm >= g.tiles_m || (g.flags & 1)) mbar_wait_sleep(&scr_ready[par], (nt >> 1) & 1, 128);
+                if (tm >= g.tiles_m || (g.flags & 1)) crt_wait(&scr_ready[par], (nt >> 1) & 1);
                 mbar_arrive(&scr_free[par]);      // every slice of the tile has left the global scratch half
             }
+            if (timing && etid == 0) { g.tim[blockIdx.x * 16 + 8] = tacc[0]; g.tim[blockIdx.x * 16 + 9] = tacc[1]; g.tim[blockIdx.x * 16 + 10] = tacc[2];
+                                       g.tim[blockIdx.x * 16 + 11] = tacc[3]; g.tim[blockIdx.x * 16 + 12] = clock64() - t_begin; }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
@@ -472,7 +518,7 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
 template <class Epi>
 struct CrtShape {
     static constexpr size_t SMEM = size_t(CRT_STAGES) * CRT_SLOT + size_t(CRT_SCR_STAGES) * CRT_SLICE_BYTES +
-                                   (3 * CRT_STAGES + 2 * CRT_SCR_STAGES + 10) * sizeof(uint64_t) + OZ_TN * sizeof(double) + Epi::SMEM;
+                                   (3 * CRT_STAGES + 2 * CRT_SCR_STAGES + 10) * sizeof(uint64_t) + OZ_TN * sizeof(double) + 16 + Epi::SMEM;
 };
 
 inline size_t crt_scratch_bytes(int N, int sm_count) { return size_t(sm_count) * 2 * N * CRT_SCR_WORDS * sizeof(uint32_t); }

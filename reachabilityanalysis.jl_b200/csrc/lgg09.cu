@@ -1229,6 +1229,29 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
                           p->crt_scr.as<uint32_t>(), p->crt};
             static const int dbg_flags = getenv("REACH_CRT_FLAGS") ? atoi(getenv("REACH_CRT_FLAGS")) : 0;   // timing experiments
             c.flags = dbg_flags;
+            static const bool want_tim = getenv("REACH_CRT_TIMING") != nullptr;
+            if (want_tim) {      // cycle counters of the warp roles of this launch, printed after a blocking copy (debug only)
+                static unsigned long long* tim = nullptr;
+                if (!tim) cudaMalloc(&tim, size_t(256) * 16 * 8);
+                cudaMemsetAsync(tim, 0, size_t(256) * 16 * 8, st);
+                c.tim = tim;
+                cudaError_t le = launch_crt_gemm(c, e, st);
+                std::vector<unsigned long long> h(size_t(256) * 16);
+                cudaMemcpyAsync(h.data(), tim, h.size() * 8, cudaMemcpyDeviceToHost, st);
+                cudaStreamSynchronize(st);
+                double a[16] = {0};
+                int nb = 0;
+                for (int b = 0; b < 256; b += 2) {       // leaders only
+                    if (!h[size_t(b) * 16 + 12]) continue;
+                    ++nb;
+                    for (int k = 0; k < 16; ++k) a[k] += double(h[size_t(b) * 16 + k]);
+                }
+                for (int k = 0; k < 16; ++k) a[k] /= std::max(1, nb) * 1e3;
+                fprintf(stderr, "[crt timing, kcycles avg over %d leader CTAs] mma: wait tmem_empty %.0f, wait full %.0f, wait pfull %.0f, total %.0f | "
+                        "drain(t0): wait scr_free %.0f, wait tmem_full %.0f, work %.0f | recon(t256): wait slice %.0f, sums %.0f, accept %.0f, finish %.0f, total %.0f\n",
+                        nb, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[8], a[9], a[10], a[11], a[12]);
+                return le;
+            }
             return launch_crt_gemm(c, e, st);
         }
         return launch_oz_gemm(p->oz_T, g, e, st);

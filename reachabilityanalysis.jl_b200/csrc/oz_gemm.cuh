@@ -78,11 +78,15 @@ struct OzStoreEpi {
     struct State {};
     static constexpr size_t SMEM = 0;
     __device__ __forceinline__ void prepare(unsigned char*, int, int) const {}
-    __device__ __forceinline__ void begin(State&) const {}
+    __device__ __forceinline__ void begin(State&, int) const {}
     // value of output (row m, column j of tile tn)
     __device__ __forceinline__ void accept(State&, const unsigned char*, int m, int tn, int j, double v) const {
         const int n = tn * OZ_TN + j;
         if (m < m_valid && n < n_valid) out[size_t(m) * ldc + n] = v;
+    }
+    __device__ __forceinline__ void accept4(State& st, const unsigned char* sm, int m, int tn, int j0, const double (&v)[4]) const {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) accept(st, sm, m, tn, j0 + e, v[e]);
     }
     __device__ __forceinline__ void finish(State&, unsigned char*, int, int, int, int) const {}
     template <int NG, int BAR>
@@ -97,10 +101,14 @@ struct OzCarryEpi {
     struct State {};
     static constexpr size_t SMEM = 0;
     __device__ __forceinline__ void prepare(unsigned char*, int, int) const {}
-    __device__ __forceinline__ void begin(State&) const {}
+    __device__ __forceinline__ void begin(State&, int) const {}
     __device__ __forceinline__ void accept(State&, const unsigned char*, int m, int tn, int j, double v) const {
         const int blk = tn / tiles_per_block, col = (tn - blk * tiles_per_block) * OZ_TN + j;
         if (col < n) out[(size_t(blk) * rows_per_slot + m) * ldl + col] = v;
+    }
+    __device__ __forceinline__ void accept4(State& st, const unsigned char* sm, int m, int tn, int j0, const double (&v)[4]) const {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) accept(st, sm, m, tn, j0 + e, v[e]);
     }
     __device__ __forceinline__ void finish(State&, unsigned char*, int, int, int, int) const {}
     template <int NG, int BAR>
@@ -122,12 +130,12 @@ struct OzLgg09Epi {
     int nq;
     double* featpart;           // [tiles_n_total][2 segments][nq][2][mu_pad]
     int mu_pad;
-    struct State { double lin[NQ][2], ab[NQ][2]; };
+    struct State { double lin[NQ][2], ab[NQ][2]; int bnd; };
     static constexpr size_t SMEM = size_t(OZ_TN) * (2 * NQ) * sizeof(double) + size_t(OZ_TN) * sizeof(int) +
                                    size_t(NQ) * 4 * OZ_TM * sizeof(double);      // staged weights, row info, reduction buffer
 
     __device__ __forceinline__ void prepare(unsigned char* sm, int tn, int tid) const {
-        double* sw = reinterpret_cast<double*>(sm);                      // [2*NQ][128]: wl_q then wa_q
+        double* sw = reinterpret_cast<double*>(sm);                      // [128 rows][2*NQ]: wl_0, wa_0, wl_1, wa_1, ... of the row
         int* srib = reinterpret_cast<int*>(sw + size_t(2 * NQ) * OZ_TN); // row in block | store flag << 30
         if (tid < OZ_TN) {
             const int row = tn * OZ_TN + tid;
@@ -135,34 +143,82 @@ struct OzLgg09Epi {
             srib[tid] = rib | (blk == store_block ? (1 << 30) : 0);
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                sw[(2 * q) * OZ_TN + tid] = q < nq ? Wl[size_t(q) * nbe + rib] : 0.0;
-                sw[(2 * q + 1) * OZ_TN + tid] = q < nq ? Wa[size_t(q) * nbe + rib] : 0.0;
+                sw[tid * (2 * NQ) + 2 * q] = q < nq ? Wl[size_t(q) * nbe + rib] : 0.0;
+                sw[tid * (2 * NQ) + 2 * q + 1] = q < nq ? Wa[size_t(q) * nbe + rib] : 0.0;
             }
         }
     }
-    __device__ __forceinline__ void begin(State& st) const {
+    __device__ __forceinline__ void begin(State& st, int tn) const {
 #pragma unroll
         for (int q = 0; q < NQ; ++q) st.lin[q][0] = st.lin[q][1] = st.ab[q][0] = st.ab[q][1] = 0.0;
+        const int row0 = tn * OZ_TN;
+        st.bnd = (row0 / nbe + 1) * nbe - row0;                          // tile-local row where the next block starts
     }
-    __device__ __forceinline__ void accept(State& st, const unsigned char* sm, int m, int tn, int j, double v) const {
-        const double* sw = reinterpret_cast<const double*>(sm);
-        const int* srib = reinterpret_cast<const int*>(sw + size_t(2 * NQ) * OZ_TN);
+    __device__ __forceinline__ void accept(State& st, const unsigned char* sm, int m, int, int j, double v) const {
+        const double2* sw = reinterpret_cast<const double2*>(sm) + j * NQ;           // (wl_q, wa_q) of row j: NQ 16-byte loads
+        const int* srib = reinterpret_cast<const int*>(sm + size_t(2 * NQ) * OZ_TN * sizeof(double));
         const int info = srib[j], rib = info & 0x3FFFFFFF;
         if ((info >> 30) && rib < n) Lnext[size_t(m) * ldl + rib] = v;
-        const int row0 = tn * OZ_TN;
-        const int bnd = (row0 / nbe + 1) * nbe - row0;                   // tile-local row where the next block starts
         const double av = fabs(v);
-        if (j < bnd) {
+        if (j < st.bnd) {
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                st.lin[q][0] = fma(sw[(2 * q) * OZ_TN + j], v, st.lin[q][0]);
-                st.ab[q][0] = fma(sw[(2 * q + 1) * OZ_TN + j], av, st.ab[q][0]);
+                const double2 w = sw[q];
+                st.lin[q][0] = fma(w.x, v, st.lin[q][0]);
+                st.ab[q][0] = fma(w.y, av, st.ab[q][0]);
             }
         } else {
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                st.lin[q][1] = fma(sw[(2 * q) * OZ_TN + j], v, st.lin[q][1]);
-                st.ab[q][1] = fma(sw[(2 * q + 1) * OZ_TN + j], av, st.ab[q][1]);
+                const double2 w = sw[q];
+                st.lin[q][1] = fma(w.x, v, st.lin[q][1]);
+                st.ab[q][1] = fma(w.y, av, st.ab[q][1]);
+            }
+        }
+    }
+    // four consecutive columns j0 .. j0 + 3 (j0 a multiple of 4): when they lie on one side of the block boundary -- always,
+    // except in the one slice that straddles it -- all shared-memory loads are issued before the first FMA (the tensor pipe's
+    // operand reads keep the shared memory busy: a load per dependent FMA pair costs hundreds of cycles each)
+    __device__ __forceinline__ void accept4(State& st, const unsigned char* sm, int m, int tn, int j0, const double (&v)[4]) const {
+        if (j0 < st.bnd && j0 + 3 >= st.bnd) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) accept(st, sm, m, tn, j0 + e, v[e]);
+            return;
+        }
+        const double2* sw = reinterpret_cast<const double2*>(sm) + j0 * NQ;
+        const int4 info = *reinterpret_cast<const int4*>(sm + size_t(2 * NQ) * OZ_TN * sizeof(double) + size_t(j0) * sizeof(int));
+        const int inf[4] = {info.x, info.y, info.z, info.w};
+        if ((inf[0] | inf[3]) >> 30) {                                   // rows of the block that is carried to the next pass
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int rib = inf[e] & 0x3FFFFFFF;
+                if ((inf[e] >> 30) && rib < n) Lnext[size_t(m) * ldl + rib] = v[e];
+            }
+        }
+        const bool seg0 = j0 < st.bnd;
+#pragma unroll
+        for (int e2 = 0; e2 < 4; e2 += 2) {                              // two columns at a time: 8 independent 16-byte loads
+            double2 w[2][NQ];
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) w[e][q] = sw[(e2 + e) * NQ + q];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double x = v[e2 + e], av = fabs(x);
+                if (seg0) {
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        st.lin[q][0] = fma(w[e][q].x, x, st.lin[q][0]);
+                        st.ab[q][0] = fma(w[e][q].y, av, st.ab[q][0]);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        st.lin[q][1] = fma(w[e][q].x, x, st.lin[q][1]);
+                        st.ab[q][1] = fma(w[e][q].y, av, st.ab[q][1]);
+                    }
+                }
             }
         }
     }
@@ -262,7 +318,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzOperands
     uint64_t* tmem_empty = tmem_full + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
     double* sYscale = reinterpret_cast<double*>(tmem_empty + 2);      // [128] 2^eY of the tile's columns
-    unsigned char* epi_smem = reinterpret_cast<unsigned char*>(sYscale + OZ_TN);
+    unsigned char* epi_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sYscale + OZ_TN) + 15) & ~uintptr_t(15));   // 16-byte loads
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = g.tiles_m * g.tiles_n;
@@ -353,7 +409,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzOperands
             asm volatile("bar.sync 1, %0;" ::"n"(OZ_EPI_WARPS * 32) : "memory");
             const int ex = g.eX[size_t(tm) * OZ_TM + ml] - 2 * (OZ_BITS - 1);
             typename Epi::State st;
-            epi.begin(st);
+            epi.begin(st, tn);
             double part[OZ_CPT];
 #pragma unroll
             for (int sw = 0; sw < NSWEEP; ++sw, ++nfull) {
@@ -406,7 +462,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const OzOperands
 template <int T, class Epi>
 struct OzShape {
     static constexpr size_t SLOT = size_t(2) * T * OZ_PLANE;
-    static constexpr size_t SMEM = OZ_STAGES * SLOT + (2 * OZ_STAGES + 4) * sizeof(uint64_t) + OZ_TN * sizeof(double) + Epi::SMEM;
+    static constexpr size_t SMEM = OZ_STAGES * SLOT + (2 * OZ_STAGES + 4) * sizeof(uint64_t) + OZ_TN * sizeof(double) + 16 + Epi::SMEM;
 };
 
 template <int T, class Epi>
