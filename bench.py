@@ -683,15 +683,19 @@ def run_b200(args):
         share = st["gemm_launches"] * gemm_ms / (total_ms / args.steps)
         if st["path"] == "int8":
             T = st["digit_planes"]
-            pairs = T * (T + 1) // 2
+            # digit planes (4..8): T(T+1)/2 plane pairs per FP64 product; residue path (10..16): one INT8 product per modulus
+            crt = T >= 10
+            pairs = T if crt else T * (T + 1) // 2
             int8_ops = flops_per_launch * pairs                              # INT8 MMA work actually issued
             ach_int8 = int8_ops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
             bf16 = peaks.get("bf16_tflops_sustained")
             peak_int8 = 2.0 * bf16 if bf16 else int8_sustained              # dense INT8 tensor rate = 2 x dense bf16
             roofline = {
                 "bound": "tensor",
-                "kernel": "oz_gemm_kernel<%d, OzLgg09Epi> (INT8 tcgen05 digit-plane GEMM, FP64 by error-free slicing, "
-                          "fused support epilogue)" % T,
+                "kernel": ("crt_gemm_kernel<OzLgg09Epi> (INT8 tcgen05 2-CTA GEMM per modulus, %d coprime moduli, FP64 by Chinese "
+                           "remainder reconstruction, fused support epilogue)" % T) if crt else
+                          ("oz_gemm_kernel<%d, OzLgg09Epi> (INT8 tcgen05 digit-plane GEMM, FP64 by error-free slicing, "
+                           "fused support epilogue)" % T),
                 "achieved": ach_int8, "peak": peak_int8, "unit": "TOP/s (INT8 tensor)",
                 "frac": (ach_int8 / peak_int8) if ach_int8 and peak_int8 else None,
                 "peak_source": ("2 x MEASURED_PEAKS.json bf16_tflops_sustained (%.1f): dense INT8 tcgen05 rate is twice the bf16 "
@@ -702,7 +706,8 @@ def run_b200(args):
                                           "cublaslt_sustained_tops": int8_sustained, "cublaslt_burst_tops": int8_burst,
                                           "how": "torch._int_mm 8192^3 measured in this run"},
                 "ncu": ncu,
-                "int8_ops_per_launch": int8_ops, "plane_pairs": pairs, "digit_planes": T,
+                "int8_ops_per_launch": int8_ops, "int8_products_per_fp64_product": pairs,
+                "scheme": "residues (Ozaki II)" if crt else "digit planes (Ozaki I)", "moduli_or_digit_planes": T,
                 "fp64_equivalent": {"achieved_tflops": achieved, "cublas_dgemm_tflops": peak_tf,
                                     "ratio": (achieved / peak_tf) if achieved and peak_tf else None,
                                     "note": "algorithmic 2 n^2 flop per chain-step; cuBLAS DGEMM 8192^3 measured in this run"},

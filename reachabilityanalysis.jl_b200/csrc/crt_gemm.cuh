@@ -49,7 +49,7 @@ constexpr int CRT_EPI_HALF = OZ_EPI_WARPS * 32 / 2;       // threads that drain,
 constexpr int CRT_THREADS = OZ_THREADS + 32;              // + the scratch prefetch warp
 constexpr int CRT_SCR_WORDS = 4 * 8 * CRT_EPI_HALF;       // u32 words of scratch per modulus and CTA (4 x 32 columns x 128 rows)
 constexpr int CRT_SLICES = 32;                            // slices of a tile: (half, column group of the pair, word) = 2 x 2 x 8
-constexpr int CRT_SCR_STAGES = 4;                         // shared-memory ring of slices
+constexpr int CRT_SCR_STAGES = 4;                         // shared-memory ring of slices (5 operand + 2 slice stages: same time)
 constexpr int CRT_SLICE_BYTES = CRT_MAX_N * CRT_EPI_HALF * 4;   // ring stage (N KB are used)
 
 // pairwise coprime, largest first (256 = 2^8, 255 = 3 5 17, 253 = 11 23, 247 = 13 19, 217 = 7 31, the rest prime)
@@ -128,6 +128,16 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+// bulk copy global -> the same shared-memory offset of every CTA in ctaMask; each destination's mbarrier (same offset) gets the bytes
+__device__ __forceinline__ void bulk_copy_g2s_mc(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -223,18 +233,23 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
     unsigned char* epi_smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sYexp + 2 * OZ_TN) + 15) & ~uintptr_t(15));   // 16-byte loads
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t rank = cluster_ctarank();
-    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    // Cluster = NQ CTA pairs (NQ = 1 or 2) that share the pair's 256 Y rows and own consecutive 256-row blocks of X: CTA
+    // (pair q, rank r in the pair) fetches 1/NQ of the Y rows r needs and multicasts it to the CTAs with the same r.
+    const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+    const uint32_t rank = crank & 1, cq = crank >> 1, NQ = csize >> 1;
+    const uint32_t lead = crank & ~1u;                // cluster rank of this pair's leader
+    const int pair = blockIdx.x / int(csize), npairs = gridDim.x / int(csize);     // cluster index / number of clusters
     const int N = g.c.N;
     const int n2_lo = g.tile_n0 >> 1, n2_hi = (g.tile_n0 + g.tiles_n + 1) >> 1;
-    const int mgroups = (g.tiles_m + 1) >> 1;
+    const int mstep = 2 * int(NQ);                    // 128-row X tiles per cluster
+    const int mgroups = (g.tiles_m + mstep - 1) / mstep;
     const int ngroups = mgroups * (n2_hi - n2_lo);
     const bool timing = g.tim != nullptr;
     long long tacc[4] = {0, 0, 0, 0};
     const long long t_begin = CRT_T0();
 
     if (tid == 0) {
-        for (int s = 0; s < CRT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&pfull[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < CRT_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&pfull[s], 1); mbar_init(&empty[s], NQ); }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full[b], 1);
             mbar_init(&tmem_empty[b], OZ_EPI_WARPS);            // 8 drain warps of each CTA
@@ -260,9 +275,11 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
         // ===== producer (both CTAs): own 128 rows of X and own 128 rows of the pair's 256 Y rows =====
         if (lane == 0) {
             const size_t img_stride = size_t(CRT_IMG);
+            uint16_t ymask = 0;
+            for (uint32_t q = 0; q < NQ; ++q) ymask |= uint16_t(1u << (2 * q + rank));
             uint32_t jb = 0;
             for (int grp = pair; grp < ngroups; grp += npairs) {
-                int tm = (grp % mgroups) * 2 + int(rank);
+                int tm = (grp % mgroups) * mstep + int(cq) * 2 + int(rank);
                 if (tm >= g.tiles_m) tm = 0;                             // odd tile count: the peer multiplies a dummy tile
                 int tn = (n2_lo + grp / mgroups) * 2 + int(rank);
                 if (tn >= g.tiles_n_total) tn = g.tiles_n_total - 1;     // odd tile count at the end of the stack
@@ -276,7 +293,12 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
                         mbar_expect_tx(&full[s], CRT_SLOT);
                         unsigned char* dst = ring + size_t(s) * CRT_SLOT;
                         bulk_copy_g2s(dst, gx + size_t(kb) * img_stride, CRT_IMG, &full[s]);
-                        bulk_copy_g2s(dst + CRT_IMG, gy + size_t(kb) * img_stride, CRT_IMG, &full[s]);
+                        if (NQ == 1) {
+                            bulk_copy_g2s(dst + CRT_IMG, gy + size_t(kb) * img_stride, CRT_IMG, &full[s]);
+                        } else {                      // my part of the Y rows, to every CTA of the cluster with my rank in its pair
+                            const uint32_t part = CRT_IMG / NQ;
+                            bulk_copy_g2s_mc(dst + CRT_IMG + cq * part, gy + size_t(kb) * img_stride + cq * part, part, &full[s], ymask);
+                        }
                     }
                 }
             }
@@ -286,6 +308,7 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
             // ===== MMA issuer (leader) =====
             // instruction descriptor: D = S32, A = B = signed 8-bit, K-major both, N = 256, M = 256 (128 rows per CTA)
             constexpr uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(CRT_TN >> 3) << 17) | (uint32_t(256 >> 4) << 24);
+            const uint16_t allmask = uint16_t((1u << csize) - 1), pairmask = uint16_t(3u << lead);
             uint32_t jb = 0, u = 0;
             for (int grp = pair; grp < ngroups; grp += npairs) {
                 for (int i = 0; i < N; ++i, ++u) {
@@ -321,10 +344,10 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
                         }
                         // frees the ring slot in both CTAs once the MMAs above have read it
                         asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                                     ::"r"(smem_u32(&empty[s])), "h"(uint16_t(3)) : "memory");
+                                     ::"r"(smem_u32(&empty[s])), "h"(allmask) : "memory");
                     }
                     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                                 ::"r"(smem_u32(&tmem_full[buf])), "h"(uint16_t(3)) : "memory");
+                                 ::"r"(smem_u32(&tmem_full[buf])), "h"(pairmask) : "memory");
                 }
             }
             if (timing) { g.tim[blockIdx.x * 16 + 0] = tacc[0]; g.tim[blockIdx.x * 16 + 1] = tacc[1]; g.tim[blockIdx.x * 16 + 2] = tacc[2];
@@ -337,7 +360,7 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
                     for (int kb = 0; kb < g.nkb; ++kb, ++jb) {
                         const int s = jb % CRT_STAGES;
                         crt_wait(&full[s], (jb / CRT_STAGES) & 1);
-                        mbar_arrive_remote(&pfull[s], 0);
+                        mbar_arrive_remote(&pfull[s], lead);
                     }
         }
     } else if (warp == OZ_EPI_WARPS + 2) {
@@ -346,7 +369,7 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
             uint32_t js = 0, nt = 0;
             for (int grp = pair; grp < ngroups; grp += npairs, ++nt) {
                 const uint32_t par = nt & 1;
-                const int tm = (grp % mgroups) * 2 + int(rank);
+                const int tm = (grp % mgroups) * mstep + int(cq) * 2 + int(rank);
                 const int tn2 = n2_lo + grp / mgroups;
                 crt_wait(&scr_ready[par], (nt >> 1) & 1);     // all 256 drain threads have written the tile's residues
                 asm volatile("fence.proxy.async;" ::: "memory");          // generic-proxy stores -> async-proxy (bulk copy) reads
@@ -422,7 +445,7 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
                     // the accumulator may be overwritten: modulus i + 2 (or the pair's next tile) can start
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_remote(&tmem_empty[buf], 0);
+                    if (lane == 0) mbar_arrive_remote(&tmem_empty[buf], lead);
                     CRT_ACC(2, t2);
                 }
                 asm volatile("fence.proxy.async;" ::: "memory");        // the residues are read back by bulk copies (async proxy)
@@ -434,7 +457,7 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
             typename Epi::State st;
             for (int grp = pair; grp < ngroups; grp += npairs, ++nt) {
                 const uint32_t par = nt & 1;
-                const int tm = (grp % mgroups) * 2 + int(rank);
+                const int tm = (grp % mgroups) * mstep + int(cq) * 2 + int(rank);
                 const int tn2 = n2_lo + grp / mgroups;
                 if (tm < g.tiles_m && !(g.flags & 1)) {                // not the dummy tile of an odd tile count
                     const int m = tm * OZ_TM + ml;
@@ -543,20 +566,30 @@ inline cudaError_t launch_crt_gemm(const CrtOperands& g, const Epi& epi, cudaStr
         if (e != cudaSuccess) return e;
     }
     const int n2 = ((g.tile_n0 + g.tiles_n + 1) >> 1) - (g.tile_n0 >> 1);
-    const int groups = ((g.tiles_m + 1) / 2) * n2;
-    const int pairs = std::max(1, std::min(sms / 2, groups));
+    // REACH_CRT_CLUSTER=4: two pairs per cluster, Y rows multicast (3/4 of the L2 -> SM bytes, but only 132 of 148 SMs host such clusters)
+    static const int env_cs = getenv("REACH_CRT_CLUSTER") ? atoi(getenv("REACH_CRT_CLUSTER")) : 0;
+    const int cs = env_cs == 4 && g.tiles_m >= 3 ? 4 : 2;     // (measured on C5: 2.37 ms with 33 clusters of 4 against 2.22 ms with 74 pairs)
+    const int groups = ((g.tiles_m + cs - 1) / cs) * n2;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(CRT_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    static thread_local int max_clusters[5] = {0, 0, 0, 0, 0};           // co-resident clusters of this kernel, by cluster size
+    if (max_clusters[cs] == 0) {
+        cfg.gridDim = dim3(cs * (sms / cs));
+        int nc = 0;
+        e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+        if (e != cudaSuccess) return e;
+        max_clusters[cs] = std::max(1, nc);
+    }
+    cfg.gridDim = dim3(cs * std::max(1, std::min(max_clusters[cs], groups)));
     return cudaLaunchKernelEx(&cfg, kern, g, epi);
 }
 
@@ -622,14 +655,14 @@ __global__ void __launch_bounds__(256) crt_slice_kernel(const double* __restrict
             const double v = (row < rows_valid && k < k_valid) ? X[size_t(row) * ldx + k] : 0.0;
             const long long xi = __double2ll_rn(oz_scale(v, s));      // |xi| <= 2^bits (1 + eps): exact
             const unsigned long long ax = xi < 0 ? (unsigned long long)(-xi) : (unsigned long long)xi;
-            const uint32_t lo = uint32_t(ax), hi = uint32_t(ax >> 32);
+            // |x'| < 2^62 in three limbs a 2^40 + b 2^20 + c: a c40 + b c20 + c < 2^31 is congruent to it (c40 = 2^40 mod p,
+            // c20 = 2^20 mod p), so every modulus costs two multiply-adds and ONE reduction by a compile-time constant
+            const uint32_t la = uint32_t(ax >> 40), lb = uint32_t(ax >> 20) & 0xFFFFFu, lc = uint32_t(ax) & 0xFFFFFu;
 #pragma unroll
             for (int i = 0; i < NMAX; ++i) {
-                constexpr uint32_t dummy = 0;
-                (void)dummy;
                 const uint32_t p = uint32_t(crt_modulus(i));
-                const uint32_t two32 = uint32_t((uint64_t(1) << 32) % p);
-                uint32_t rr = ((hi % p) * two32 + (lo % p)) % p;       // < p; (p-1)(p-1) + p-1 < 2^16
+                const uint32_t c20 = uint32_t((uint64_t(1) << 20) % p), c40 = uint32_t((uint64_t(1) << 40) % p);
+                const uint32_t rr = (la * c40 + lb * c20 + lc) % p;    // la < 2^22: < 2^30 + 2^28 + 2^20
                 int sr = xi < 0 ? -int(rr) : int(rr);                  // (-p, p)
                 const int hs = int(p - 1) >> 1;
                 if (sr > hs) sr -= int(p);
@@ -647,8 +680,23 @@ __global__ void __launch_bounds__(256) crt_slice_kernel(const double* __restrict
 
 inline void launch_crt_slice(const double* X, int ldx, int rows_valid, int rows_padded, int k_valid, const CrtConsts& c, bool is_y, int nkb,
                              int tiles_total, int8_t* Q, int* eout, int tile0, int ksplit, cudaStream_t st) {
-    crt_slice_kernel<CRT_MAX_N><<<dim3(rows_padded / 8, ksplit), 256, 0, st>>>(X, ldx, rows_valid, k_valid, c.N, is_y ? c.beta : c.alpha, nkb,
-                                                                             tiles_total, Q, eout, tile0);
+    // the residues cost ~20 integer operations per element and modulus: split the k range until ~8 CTAs per SM are in flight
+    // (a CTA then still has >= 256 (row, 16-byte chunk) items), and only instantiate the moduli in use
+    int sms = 148;
+    {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int groups = rows_padded / 8;
+    ksplit = std::max(ksplit, std::min(std::max(1, nkb * 8 * 8 / 256), (8 * sms + groups - 1) / std::max(1, groups)));
+    const dim3 grid(groups, ksplit);
+    const int bits = is_y ? c.beta : c.alpha;
+#define CRT_SLICE_CASE(NN) case NN: crt_slice_kernel<NN><<<grid, 256, 0, st>>>(X, ldx, rows_valid, k_valid, c.N, bits, nkb, tiles_total, Q, eout, tile0); break
+    switch (c.N) {
+        CRT_SLICE_CASE(10); CRT_SLICE_CASE(11); CRT_SLICE_CASE(12); CRT_SLICE_CASE(13); CRT_SLICE_CASE(14); CRT_SLICE_CASE(15);
+        default: crt_slice_kernel<CRT_MAX_N><<<grid, 256, 0, st>>>(X, ldx, rows_valid, k_valid, c.N, bits, nkb, tiles_total, Q, eout, tile0);
+    }
+#undef CRT_SLICE_CASE
 }
 
 }  // namespace reach
