@@ -292,6 +292,8 @@ __global__ void __launch_bounds__(CRT_THREADS, 1) crt_gemm_kernel(const CrtOpera
                         crt_wait(&empty[s], ph ^ 1);
                         mbar_expect_tx(&full[s], CRT_SLOT);
                         unsigned char* dst = ring + size_t(s) * CRT_SLOT;
+                        // (L2 eviction hints -- evict_last for X, which every tile re-reads, evict_first for the Y stream -- measured: no
+                        // gain resp. 6 % slower)
                         bulk_copy_g2s(dst, gx + size_t(kb) * img_stride, CRT_IMG, &full[s]);
                         if (NQ == 1) {
                             bulk_copy_g2s(dst + CRT_IMG, gy + size_t(kb) * img_stride, CRT_IMG, &full[s]);
