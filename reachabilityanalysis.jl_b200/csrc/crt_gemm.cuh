@@ -651,10 +651,23 @@ __global__ void __launch_bounds__(256) crt_slice_kernel(const double* __restrict
         uint32_t w[NMAX][4];
 #pragma unroll
         for (int i = 0; i < NMAX; ++i) w[i][0] = w[i][1] = w[i][2] = w[i][3] = 0u;
+        // the thread's 16 values: eight 16-byte loads when the chunk is whole and aligned (all loads in flight at once)
+        double xv[16];
+        const double* xrow = X + size_t(row) * ldx + k0;
+        if (row < rows_valid && k0 + 16 <= k_valid && (ldx & 1) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const double2 t = reinterpret_cast<const double2*>(xrow)[b];
+                xv[2 * b] = t.x;
+                xv[2 * b + 1] = t.y;
+            }
+        } else {
+#pragma unroll
+            for (int b = 0; b < 16; ++b) xv[b] = (row < rows_valid && k0 + b < k_valid) ? xrow[b] : 0.0;
+        }
 #pragma unroll
         for (int b = 0; b < 16; ++b) {
-            const int k = k0 + b;
-            const double v = (row < rows_valid && k < k_valid) ? X[size_t(row) * ldx + k] : 0.0;
+            const double v = xv[b];
             const long long xi = __double2ll_rn(oz_scale(v, s));      // |xi| <= 2^bits (1 + eps): exact
             const unsigned long long ax = xi < 0 ? (unsigned long long)(-xi) : (unsigned long long)xi;
             // |x'| < 2^62 in three limbs a 2^40 + b 2^20 + c: a c40 + b c20 + c < 2^31 is congruent to it (c40 = 2^40 mod p,
