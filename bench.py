@@ -671,6 +671,10 @@ def run_b200(args):
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "lgg09_main_kernel_traffic.json")))
             ent = tj.get(st["path"])
+            if st["path"] == "int8" and ent and ent.get("moduli", ent.get("digit_planes")) != st.get("digit_planes"):
+                ent = tj.get("int8_digit_planes")            # the capture must be of the kernel that ran
+                if ent and ent.get("digit_planes") != st.get("digit_planes"):
+                    ent = None
             if ent and ent.get("n") == n and ent.get("chains") == st["nchains"]:
                 # DRAM bytes of one launch from the ncu --set full capture; only rescaled if the capture's time block differs
                 traffic = ent["dram_bytes_per_launch"] * (S / float(ent["time_block"]))

@@ -140,7 +140,11 @@ typedef struct {
                              batched GEMM on the INT8 tcgen05 pipe through error-free digit planes
                              (unguarded when forced; auto picks it for large dense problems and
                              guards it against the DMMA kernel, see reach_lgg09_plan_path)      */
-    int32_t reserved[3];  /* reserved[0]: 8-bit digit planes of path 3 (0 = 7, i.e. 56 bits; 4..8)
+    int32_t reserved[3];  /* reserved[0]: FP64 emulation of path 3.  0 = default: residues modulo 14 pairwise
+                             coprime moduli, 14 INT8 products per FP64 product (csrc/crt_gemm.cuh);
+                             10..16 = that many moduli (13 matches the digit planes' accuracy, 12 is
+                             below it); 4..8 = that many 8-bit digit planes (csrc/oz_gemm.cuh, 7 = 56 bits,
+                             28 INT8 products per FP64 product).  Anything else: REACH_EINVAL.
                              reserved[1]: 1 = box output: the two rows of a direction pair (l, -l) hold
                              (lin, abs) = (centre, radius) of the box hull instead of abs +- lin
                              (what reach_box uses; Omega0 must have one alternative)            */
@@ -185,7 +189,8 @@ int  reach_lgg09_plan_stats(reach_lgg09_plan* p, double* ms, int64_t* launches,
                             int32_t* time_block, int32_t* tile_m, int32_t* tile_n,
                             int32_t* nchains, double* gemm_ms, int64_t* gemm_launches);
 /* Which main-loop kernel the plan uses / used: *path = 1 FP64 tensor-core (DMMA) GEMM, 2 persistent chain kernel,
- * 3 INT8 tcgen05 digit-plane GEMM (FP64 emulation by error-free slicing, csrc/oz_gemm.cuh) with *digit_planes planes.
+ * 3 INT8 tcgen05 GEMM with FP64 results: *digit_planes = 10..16 moduli of the residue path (csrc/crt_gemm.cuh) or
+ * 4..8 digit planes of the error-free slicing path (csrc/oz_gemm.cuh).
  * When path 3 was chosen automatically it is guarded: *guard_checks sampled passes were recomputed on the DMMA kernel,
  * *guard_max is the largest relative feature difference seen, and *fallback_pass >= 0 is the pass whose check failed
  * (-1: never): the run was then redone on the DMMA kernel from the last verified pass on (reach_lgg09_plan_guard).
