@@ -613,7 +613,14 @@ __global__ void __launch_bounds__(256) crt_slice_kernel(const double* __restrict
         double mx = 0.0;
         if (row < rows_valid) {
             const double* x = X + size_t(row) * ldx;
-            for (int k = lane; k < k_valid; k += 32) mx = fmax(mx, fabs(x[k]));
+            double m4[4] = {0.0, 0.0, 0.0, 0.0};                       // four loads in flight (the scans are L2 round trips)
+            int k = lane;
+            for (; k + 96 < k_valid; k += 128) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) m4[u] = fmax(m4[u], fabs(x[k + 32 * u]));
+            }
+            for (; k < k_valid; k += 32) m4[0] = fmax(m4[0], fabs(x[k]));
+            mx = fmax(fmax(m4[0], m4[1]), fmax(m4[2], m4[3]));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -622,10 +629,20 @@ __global__ void __launch_bounds__(256) crt_slice_kernel(const double* __restrict
             const int em = ilogb(mx);                                  // 2^em <= mx < 2^(em+1)
             double ss = 0.0;
             const double* x = X + size_t(row) * ldx;
-            for (int k = lane; k < k_valid; k += 32) {
-                const double v = oz_scale(x[k], -em);                  // |v| < 2
-                ss = fma(v, v, ss);
+            double s4[4] = {0.0, 0.0, 0.0, 0.0};
+            int k = lane;
+            for (; k + 96 < k_valid; k += 128) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double v = oz_scale(x[k + 32 * u], -em);     // |v| < 2
+                    s4[u] = fma(v, v, s4[u]);
+                }
             }
+            for (; k < k_valid; k += 32) {
+                const double v = oz_scale(x[k], -em);
+                s4[0] = fma(v, v, s4[0]);
+            }
+            ss = (s4[0] + s4[1]) + (s4[2] + s4[3]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
             // ||x|| = 2^em sqrt(ss) < 2^(em + en),  en = ilogb(sqrt(ss) (1 + 2^-20)) + 1

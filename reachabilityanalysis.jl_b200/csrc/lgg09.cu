@@ -419,8 +419,18 @@ double step_cost(const reach_lgg09_plan& p, const TileCfg& c, int S, int mu, int
     // ~30 us per pass: GEMM + tile-sum + eval + prefix launches back to back.  The persistent digit-plane kernel pays about
     // one more tile time per launch (ring fill, the last tile's epilogue, the slice of L in front of it): measured on
     // shards of C5, 1000 chains: S = 14 / 20 / 28 -> 901 / 880 / 855 ms.
-    const double launch = c.id == kOzCfg ? 250000.0 : 60000.0;
-    double cost = (pass(double(mu_pad / c.TM) * std::ceil(double(S) * nbe / c.TN)) + launch) / S;
+    // (the residue kernel: + the 0.11 ms residue conversion of L in front of every launch and a longer tail -- measured on C5, 10^4
+    // steps: S = 20 / 32 / 40 / 48 / 64 / 80 -> 1398 / 1369 / 1357 / 1334 / 1362 / 1369 ms)
+    const double launch = c.id == kOzCfg ? (p.oz_crt ? 450000.0 : 250000.0) : 60000.0;
+    double gemm_pass = pass(double(mu_pad / c.TM) * std::ceil(double(S) * nbe / c.TN));
+    if (c.id == kOzCfg && p.oz_crt) {
+        // residue kernel: CTA pairs on 256 x 256 tiles, one pair per two SMs -- whole waves of those
+        const double pair_tiles = std::ceil(mu_pad / 256.0) * (std::floor(double(S) * nbe / 256.0) + 1.0);
+        const double waves = std::ceil(pair_tiles / std::max(1, sms / 2));
+        const double mma = 128.0 * 128.0 * p.Kp / (55.0 * eff[c.id]);
+        gemm_pass = waves * (4.0 * mma + 12000.0);
+    }
+    double cost = (gemm_pass + launch) / S;
     // stack build by doubling (64x64 tiles, occupancy 2), amortised: one launch per product, each as many waves as its
     // row count needs (for small n a whole doubling step is a single wave -- the build is ~2 log2(S) launches, not S)
     auto product = [&](double rows) {

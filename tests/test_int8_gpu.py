@@ -85,6 +85,19 @@ def test_residue_gemm_matches_exact_products(ctx, m, n, k, moduli):
     assert (np.abs(Cm - ref) / scale).max() <= tol
 
 
+@pytest.mark.parametrize("m,n,k", [(100, 30000, 96), (384, 40000, 64), (640, 20000, 200)])
+def test_residue_gemm_many_tiles_per_cta_pair_and_odd_row_tile_counts(ctx, m, n, k):
+    """More 256 x 256 tiles than CTA pairs (each pair walks several tiles: both scratch halves, the slice ring and the
+    accumulator hand-over wrap around), with 1 / 3 / 5 row tiles: the second CTA of the last pair multiplies a dummy tile."""
+    rng = np.random.default_rng(m + k)
+    X = rng.standard_normal((m, k)) * np.exp(rng.uniform(-2, 2, (m, 1)))
+    Y = rng.standard_normal((n, k)) * np.exp(rng.uniform(-2, 2, (n, 1)))
+    Cm, _, _ = ctx.crtgemm_probe(X, Y)
+    ref = X @ Y.T
+    scale = np.sqrt((X * X).sum(1))[:, None] * np.sqrt((Y * Y).sum(1))[None, :]
+    assert (np.abs(Cm - ref) / scale).max() <= 2.0 ** -49
+
+
 def test_residue_gemm_is_deterministic_and_handles_zero_and_tiny_rows(ctx):
     rng = np.random.default_rng(7)
     X = rng.standard_normal((260, 300))
