@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--n", type=int, default=2000, help="state dimension of the synthetic workload")
     ap.add_argument("--nsteps", type=int, default=10000, help="time steps per pass")
     ap.add_argument("--time-block", type=int, default=0)
+    ap.add_argument("--no-dist-stack", action="store_true",
+                    help="N > 1: every rank builds the whole row stack itself (default: the ranks share the build)")
     ap.add_argument("--path", default="auto", choices=["auto", "gemm", "int8"],
                     help="main-loop kernel: auto (INT8 digit-plane GEMM guarded by DMMA passes), gemm (FP64 DMMA), int8 (unguarded)")
     ap.add_argument("--cpu-sample-steps", type=int, default=0, help="time steps of the CPU sample (0: auto)")
@@ -544,7 +546,7 @@ def run_b200(args):
     import reach_b200  # noqa: F401
     from reach_b200 import _lib, workloads as W
     from reach_b200.lgg09 import Lgg09Plan
-    from reach_b200.sharding import shard_directions, gather_support_values
+    from reach_b200.sharding import shard_directions, gather_support_values, build_stack_distributed
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -564,6 +566,12 @@ def run_b200(args):
 
     ctx = _lib.Context(local_rank)
     wl = W.synthetic_c5(n=args.n, nsteps=args.nsteps)
+    if world > 1:
+        # one problem for all ranks: expm on the hosts of two ranks can differ in the last bit (BLAS threading), and the ranks
+        # build ONE row stack together -- every rank must hold rank 0's Phi, Omega0 and V
+        box = [wl if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        wl = box[0]
     n, ndirs, nsteps = wl.n, wl.dirs.shape[1], args.nsteps
     local_dirs, rows_by_rank, mloc = shard_directions(wl.dirs, world, rank)
 
@@ -573,14 +581,29 @@ def run_b200(args):
     plan.set_output(out_T.data_ptr())
     plan.upload(wl.Phi, local_dirs, wl.Omega0, wl.V)
     flush = torch.empty(512 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")
+    dist_stack = world > 1 and not args.no_dist_stack
+    if dist_stack:
+        try:
+            plan.stack_info()                     # GEMM paths only (a chain-kernel plan has no row stack)
+        except NotImplementedError:
+            dist_stack = False
 
     def one_pass():
         """Whole hot path, inputs resident in HBM: recurrence on this rank's chains + all-gather."""
         flush.zero_()
         barrier()
+        build_ms = 0.0
+        if dist_stack:
+            # the row stack is built once per run by all ranks together (row ranges of every doubling step + in-place
+            # all-gathers over NVLink) instead of once per rank; its time is part of the step
+            t0 = time.perf_counter()
+            build_stack_distributed(plan)
+            torch.cuda.synchronize()
+            build_ms = (time.perf_counter() - t0) * 1e3
         plan.run(sync=True)
         st = plan.stats()
-        ms = st["ms"]
+        ms = st["ms"] + build_ms
+        st["stack_build_ms"] = build_ms
         full = None
         if world > 1:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -656,6 +679,7 @@ def run_b200(args):
     e2e_value = ndirs * nsteps * len(e2e_t) / e2e_s
     # e2e result must be the same numbers as the device-resident run
     same = bool(np.array_equal(rho_h, out_T.cpu().numpy()))
+    e2e_maxdiff = float(np.abs(rho_h - out_T.cpu().numpy()).max())
 
     glgm06 = None if args.no_glgm06 else glgm06_leg(args, ctx, torch, dist, world, rank, peak_tf)
 
@@ -746,14 +770,16 @@ def run_b200(args):
                        "ndirs_per_gpu": mloc, "chains_per_gpu": st["nchains"], "time_block": S,
                        "tile": "%dx%d" % (st["tile_m"], st["tile_n"]), "main_kernel": st["path"],
                        "sharding": "template directions",
-                       "collective": "all-gather of per-rank rho blocks" if world > 1 else "none",
+                       "collective": ("all-gather of per-rank rho blocks" + ("; in-place all-gathers of the row stack's doubling steps "
+                                      "(each rank builds 1/N of the stack: %.1f ms per run incl. the gathers)" % st.get("stack_build_ms", 0.0)
+                                      if dist_stack else "")) if world > 1 else "none",
                        "l2": "working set (row stack %d MB + rho %d MB) exceeds the 126 MB L2; 512 MB flush "
                              "between passes" % ((S + 1) * 2048 * n * 8 * (2 if st["path"] == "int8" else 1) >> 20,
                                                  mloc * nsteps * 8 >> 20)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "timer": "host wall clock around reach_lgg09(host buffers), max over ranks",
-                    "bit_identical_to_device_resident_run": same},
+                    "bit_identical_to_device_resident_run": same, "max_abs_diff_to_device_resident_run": e2e_maxdiff},
             "gpu_launches": launches,
             "wall_s_timed_region": wall,
             "roofline": roofline,

@@ -176,6 +176,17 @@ int  reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, const doubl
  * column-major) instead of the plan's own; lets a caller hand in memory it will feed to NCCL. */
 int  reach_lgg09_plan_set_output(reach_lgg09_plan* p, void* rho_device);
 int  reach_lgg09_plan_run(reach_lgg09_plan* p);            /* asynchronous on the ctx stream  */
+/* The row stack [I;E](Phi')^b, b = 0..S, of a GEMM-path plan in steps, for callers that split its rows over several GPUs
+ * (one plan per GPU, same Phi and time block): step 0 is block 1, step j >= 1 the doubling step s = 2^(j-1).  With
+ * row_lo < 0 the call only reports the step's output rows (*step_rows, 0 past the last step) and where they start in the
+ * stack (*dest_row); otherwise it computes rows [row_lo, row_hi) of them (asynchronously on the ctx stream).  Every caller
+ * takes every step in order, all-gathers the rows in place (plan_stack_info: device buffer, rows per block, leading
+ * dimension in doubles; at most 256 rows past the step's rows may be overwritten) and calls plan_stack_ready; the next
+ * plan_run then skips its own stack build.  Same products in the same order as plan_run: bit-identical results. */
+int  reach_lgg09_plan_stack_info(reach_lgg09_plan* p, void** stack_device, int64_t* rows_per_block, int64_t* ld, int32_t* S);
+int  reach_lgg09_plan_stack_step(reach_lgg09_plan* p, int32_t step, int64_t row_lo, int64_t row_hi, int64_t* step_rows,
+                                 int64_t* dest_row);
+int  reach_lgg09_plan_stack_ready(reach_lgg09_plan* p);
 int  reach_lgg09_plan_sync(reach_lgg09_plan* p);           /* waits; reports device faults    */
 int  reach_lgg09_plan_fetch(reach_lgg09_plan* p, int64_t step0, int64_t nsteps, double* rho_host);
 int  reach_lgg09_plan_nsteps_done(reach_lgg09_plan* p, int64_t* out);

@@ -62,6 +62,11 @@ SIGNATURES = {
                                           C.POINTER(reach_setexpr), C.POINTER(reach_invariant)]),
     "reach_lgg09_plan_set_output": (C.c_int, [C.c_void_p, C.c_void_p]),
     "reach_lgg09_plan_run": (C.c_int, [C.c_void_p]),
+    "reach_lgg09_plan_stack_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                              C.POINTER(C.c_int32)]),
+    "reach_lgg09_plan_stack_step": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.POINTER(C.c_int64),
+                                              C.POINTER(C.c_int64)]),
+    "reach_lgg09_plan_stack_ready": (C.c_int, [C.c_void_p]),
     "reach_lgg09_plan_sync": (C.c_int, [C.c_void_p]),
     "reach_lgg09_plan_fetch": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_double_p]),
     "reach_lgg09_plan_nsteps_done": (C.c_int, [C.c_void_p, c_int64_p]),

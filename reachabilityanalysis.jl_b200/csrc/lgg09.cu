@@ -229,6 +229,10 @@ struct reach_lgg09_plan {
     int cfg = 0, TM = 0, TN = 0, tpb = 0;
     int nq_pad = 0;        // rows of the Q (row-major power) buffers
     bool uploaded = false, ran = false;
+    // row stack built from outside in steps (reach_lgg09_plan_stack_step): the ranks of a sharded run split the rows of
+    // every doubling step and all-gather them instead of every rank building the whole stack
+    bool stack_ready = false;
+    int stack_steps_done = 0;
     Program prog;
 
     DevBuf stack;          // [(S+1)*nbe][Kp]
@@ -1195,7 +1199,12 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
 
     // ---- row stack: block_b = [I;E] (Phi')^b, b = 0..S.  block_0 was uploaded. ----
     nvtxRangePushA("reach_lgg09: row stack (powers of Phi')");
-    {   // Q_1 = Phi row-major: Q[k][l] = Phi(k,l) = phi_cm[k + n l]
+    const bool stack_prebuilt = p->stack_ready;          // built by reach_lgg09_plan_stack_step calls since the last run
+    p->stack_ready = false;
+    p->stack_steps_done = 0;
+    if (stack_prebuilt)                                  // the gathered row chunks may have spilled into the slack rows
+        REACH_CUDA(ctx, cudaMemsetAsync(block(S + 1), 0, size_t(256) * Kp * sizeof(double), st));
+    if (!stack_prebuilt) {   // Q_1 = Phi row-major: Q[k][l] = Phi(k,l) = phi_cm[k + n l]
         dim3 grid((n + 31) / 32, (n + 31) / 32), blk(32, 8);
         transpose_kernel<<<grid, blk, 0, st>>>(p->phi_cm.as<double>(), n, p->Qbuf[0].as<double>(), Kp, n);
         REACH_CUDA(ctx, cudaGetLastError());
@@ -1212,9 +1221,9 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
         return REACH_OK;
     };
     // block_1 = block_0 * P_1   (Y[k][l] = P_1[l][k] = Phi(k,l) = Q_1)
-    REACH_TRY(plain_gemm(block(0), nbe, p->Qbuf[0].as<double>(), n, block(1), nbe));
+    if (!stack_prebuilt) REACH_TRY(plain_gemm(block(0), nbe, p->Qbuf[0].as<double>(), n, block(1), nbe));
     int qcur = 0;
-    for (int s = 1; s < S; s *= 2) {
+    for (int s = 1; s < S && !stack_prebuilt; s *= 2) {
         const int cnt = std::min(s, S - s);              // blocks s+1 .. s+cnt
         // Q_{2s} = Q_s Q_s : X = Q_s rows, Y[b][l] = Q_s[l][b] = P_s[b][l] = first n rows of block_s
         if (2 * s < S)
@@ -1756,6 +1765,100 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     if (p->nchecks > 0 && T == 0) REACH_TRY(disjoint_scan(0, p->nsteps, st));
     REACH_CUDA(ctx, cudaEventRecord(p->ev1, st));
     p->ran = true;
+    return REACH_OK;
+}
+
+// ---- the row stack in steps, driven from outside -----------------------------------------------------------------
+// Step 0 is block 1 = block_0 x P_1; step j >= 1 is the doubling step s = 2^(j-1): blocks s+1 .. s+min(s, S-s) = (blocks
+// 1..) x P_s, after Q_{2s} = Q_s Q_s (an n x n x n product every caller repeats).  A caller computes rows [row_lo, row_hi)
+// of the step's `*step_rows` output rows, which start at stack row `*dest_row`; the ranks of a sharded run take disjoint row
+// ranges and all-gather them in place (reach_lgg09_plan_stack_info gives the device buffer), so each builds 1/N of the
+// stack.  The products and their order are those of reach_lgg09_plan_run: the stack is bit-identical.
+extern "C" int reach_lgg09_plan_stack_info(reach_lgg09_plan* p, void** stack, int64_t* rows_per_block, int64_t* ld, int32_t* S) {
+    if (!p) return REACH_EINVAL;
+    reach_ctx* ctx = p->ctx;
+    if (!p->uploaded) return set_error(ctx, REACH_ESTATE, "plan_stack_info before plan_upload");
+    if (p->use_compact || p->use_chain)
+        return set_error(ctx, REACH_EUNSUPPORTED, "this plan runs a chain kernel: it has no row stack");
+    if (stack) *stack = p->stack.p;
+    if (rows_per_block) *rows_per_block = p->nbe;
+    if (ld) *ld = p->Kp;
+    if (S) *S = p->S;
+    return REACH_OK;
+}
+
+extern "C" int reach_lgg09_plan_stack_step(reach_lgg09_plan* p, int32_t step, int64_t row_lo, int64_t row_hi, int64_t* step_rows,
+                                           int64_t* dest_row) {
+    if (!p) return REACH_EINVAL;
+    reach_ctx* ctx = p->ctx;
+    if (!p->uploaded) return set_error(ctx, REACH_ESTATE, "plan_stack_step before plan_upload");
+    if (p->use_compact || p->use_chain)
+        return set_error(ctx, REACH_EUNSUPPORTED, "this plan runs a chain kernel: it has no row stack");
+    if (step < 0 || step > 30) return set_error(ctx, REACH_EINVAL, "stack step %d out of range", step);
+    const int n = p->n, Kp = p->Kp, nbe = p->nbe, S = p->S;
+    int64_t rows = 0, dest = 0;
+    int s = 0;
+    if (step == 0) {
+        rows = nbe;
+        dest = nbe;
+    } else {
+        s = 1 << (step - 1);
+        if (s < S) {
+            rows = int64_t(std::min(s, S - s)) * nbe;
+            dest = int64_t(s + 1) * nbe;
+        }
+    }
+    if (step_rows) *step_rows = rows;
+    if (dest_row) *dest_row = dest;
+    if (row_lo < 0 || rows == 0) return REACH_OK;                      // query only / past the last step
+    if (row_lo > row_hi || row_hi > rows)
+        return set_error(ctx, REACH_EINVAL, "rows [%lld, %lld) outside the step's %lld rows", (long long)row_lo, (long long)row_hi,
+                         (long long)rows);
+    // in order; a step may be called several times with different row ranges (its n x n x n product is done once)
+    const bool first_call = step == p->stack_steps_done;
+    if (!first_call && step != p->stack_steps_done - 1)
+        return set_error(ctx, REACH_ESTATE, "stack steps must be taken in order (expected %d, got %d)", p->stack_steps_done, step);
+    REACH_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    double* stack = p->stack.as<double>();
+    const bool big = (p->packed || nbe % 128 == 0) && n >= 512;
+    auto plain_gemm = [&](const double* X, int mrows, const double* Y, int yrows, double* out, int m_valid) -> int {
+        const int t = big ? 128 : 64;
+        GemmOperands g{X, Y, Kp, Kp, Kp, round_up(mrows, t) / t, round_up(yrows, t) / t};
+        StoreEpi epi{out, Kp, m_valid, n};
+        REACH_CUDA(ctx, (launch_cfg(big ? 0 : 1, g, epi, st)));
+        return REACH_OK;
+    };
+    const int nrows = int(row_hi - row_lo);
+    if (step == 0) {
+        if (first_call) {
+            dim3 grid((n + 31) / 32, (n + 31) / 32), blk(32, 8);
+            transpose_kernel<<<grid, blk, 0, st>>>(p->phi_cm.as<double>(), n, p->Qbuf[0].as<double>(), Kp, n);
+            REACH_CUDA(ctx, cudaGetLastError());
+        }
+        if (nrows > 0)
+            REACH_TRY(plain_gemm(stack + size_t(row_lo) * Kp, nrows, p->Qbuf[0].as<double>(), n, stack + size_t(dest + row_lo) * Kp, nrows));
+    } else {
+        const int qcur = (step - 1) & 1;                 // Q_s ping-pongs between the two buffers from step 1 on
+        if (first_call && 2 * s < S)      // needs the whole block s: the caller has gathered the previous step
+            REACH_TRY(plain_gemm(p->Qbuf[qcur].as<double>(), n, stack + size_t(s) * nbe * Kp, n, p->Qbuf[1 - qcur].as<double>(), n));
+        if (nrows > 0)
+            REACH_TRY(plain_gemm(stack + size_t(nbe + row_lo) * Kp, nrows, p->Qbuf[qcur].as<double>(), n,
+                                 stack + size_t(dest + row_lo) * Kp, nrows));
+    }
+    p->stack_steps_done = step + 1;
+    return REACH_OK;
+}
+
+// every step has been taken (and gathered): the next reach_lgg09_plan_run uses the stack as it is
+extern "C" int reach_lgg09_plan_stack_ready(reach_lgg09_plan* p) {
+    if (!p) return REACH_EINVAL;
+    reach_ctx* ctx = p->ctx;
+    int need = 1;
+    for (int s = 1; s < p->S; s *= 2) ++need;
+    if (p->stack_steps_done != need)
+        return set_error(ctx, REACH_ESTATE, "%d of %d stack steps taken", p->stack_steps_done, need);
+    p->stack_ready = true;
     return REACH_OK;
 }
 

@@ -150,6 +150,24 @@ class Lgg09Plan:
     def set_output(self, device_ptr):
         self.ctx.check(self.lib.reach_lgg09_plan_set_output(self.handle, C.c_void_p(int(device_ptr))))
 
+    # ---- the row stack in steps (reach_lgg09_plan_stack_*): the ranks of a sharded run split its rows ----
+    def stack_info(self):
+        """(device pointer, rows per block, leading dimension in doubles, time block S) of the plan's row stack."""
+        ptr, nbe, ld, S = C.c_void_p(), C.c_int64(), C.c_int64(), C.c_int32()
+        self.ctx.check(self.lib.reach_lgg09_plan_stack_info(self.handle, C.byref(ptr), C.byref(nbe), C.byref(ld), C.byref(S)))
+        return ptr.value, nbe.value, ld.value, S.value
+
+    def stack_step(self, step, row_lo=-1, row_hi=-1):
+        """Rows [row_lo, row_hi) of build step `step` (asynchronous); returns (rows of the step, first stack row they go to).
+        With row_lo < 0 nothing is computed."""
+        rows, dest = C.c_int64(), C.c_int64()
+        self.ctx.check(self.lib.reach_lgg09_plan_stack_step(self.handle, int(step), int(row_lo), int(row_hi), C.byref(rows),
+                                                            C.byref(dest)))
+        return rows.value, dest.value
+
+    def stack_ready(self):
+        self.ctx.check(self.lib.reach_lgg09_plan_stack_ready(self.handle))
+
     def run(self, sync=True):
         self.ctx.check(self.lib.reach_lgg09_plan_run(self.handle))
         self._sfmat = None

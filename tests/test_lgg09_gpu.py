@@ -523,3 +523,41 @@ def test_rho_of_a_non_template_direction_falls_back_to_the_polyhedron(ctx):
         best = max(best, val)
     assert abs(fp.rho(d) - best) <= 1e-9 * max(1.0, abs(best))
     assert abs(fp[3].rho(d) - sum(d[i] * (M[pos[i], 3] if d[i] > 0 else -M[neg[i], 3]) for i in range(n))) <= 1e-9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,nsteps,S,pieces,path", [(130, 60, 7, 3, "gemm"), (200, 90, 20, 8, "gemm"), (520, 48, 6, 2, "int8")])
+def test_row_stack_built_in_steps_by_row_ranges_is_bit_identical(ctx, n, nsteps, S, pieces, path):
+    """reach_lgg09_plan_stack_step: what the ranks of a sharded run do (sharding.build_stack_distributed), here with the row
+    ranges of all `pieces` ranks taken one after the other on one GPU -- same products in the same order as plan_run's
+    own build, so the support values must be bit-identical; steps out of order and runs without every step are refused."""
+    from reach_b200 import workloads as W
+    from reach_b200.lgg09 import Lgg09Plan
+    from reach_b200.sharding import stack_row_split
+    wl = W.synthetic_c5(n=n, nsteps=nsteps, seed=n)
+    ref = Lgg09Plan(ctx, n, wl.dirs.shape[1], nsteps, time_block=S, path=path)
+    ref.upload(wl.Phi, wl.dirs, wl.Omega0, wl.V)
+    want = ref.run().sfmat().copy()
+    plan = Lgg09Plan(ctx, n, wl.dirs.shape[1], nsteps, time_block=S, path=path)
+    plan.upload(wl.Phi, wl.dirs, wl.Omega0, wl.V)
+    ptr, nbe, ld, S_ = plan.stack_info()
+    assert S_ == S and ptr and ld >= n and nbe >= n
+    with pytest.raises(rb._lib.ReachError):
+        plan.stack_step(1, 0, 8)                         # step 1 before step 0
+    step = 0
+    while True:
+        rows, dest = plan.stack_step(step)
+        if rows == 0:
+            break
+        assert dest == (nbe if step == 0 else ((1 << (step - 1)) + 1) * nbe)
+        for r in range(pieces):
+            chunk, lo, hi = stack_row_split(rows, pieces, r)
+            plan.stack_step(step, lo, hi)
+        step += 1
+    plan.stack_ready()
+    got = plan.run().sfmat()
+    assert np.array_equal(got, want)
+    assert np.array_equal(plan.run().sfmat(), want)      # the flag is consumed: this run builds the stack itself
+    plan.stack_step(0, 0, nbe)
+    with pytest.raises(rb._lib.ReachError):
+        plan.stack_ready()                               # not every step taken
