@@ -200,3 +200,23 @@ def test_post_batch_rejects_splits_that_do_not_share_the_input_set():
     with pytest.raises(ValueError, match="share the input set"):
         lgg09.post_batch(alg, [a, b], 5, ctx=object())
     assert lgg09._same_set(a.V, a.V) and not lgg09._same_set(a.V, b.V)
+
+
+def test_stack_row_split_partitions_every_step_and_stays_inside_the_slack_rows():
+    """sharding.stack_row_split: the row ranges the ranks of a sharded run take from one doubling step of the row stack
+    (reach_lgg09_plan_stack_step) -- disjoint, complete, chunks of a multiple of 8 rows, and the in-place all-gather of
+    world equal chunks overruns the step's rows by fewer than the 256 slack rows the stack buffer ends with."""
+    from reach_b200.sharding import stack_row_split
+    for world in (1, 2, 3, 4, 8):
+        for rows in (8, 48, 270, 2000, 2001, 16000, 52 * 2000):
+            covered = []
+            chunks = set()
+            for r in range(world):
+                chunk, lo, hi = stack_row_split(rows, world, r)
+                chunks.add(chunk)
+                assert chunk % 8 == 0 and 0 <= lo <= hi <= rows and hi - lo <= chunk
+                assert lo == min(rows, r * chunk)
+                covered.extend(range(lo, hi))
+            assert covered == list(range(rows))
+            assert len(chunks) == 1
+            assert world * chunks.pop() - rows < 256
