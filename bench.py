@@ -658,8 +658,18 @@ def run_b200(args):
     def e2e_pass():
         barrier()
         t0 = time.perf_counter()
-        ctx.check(ctx.lib.reach_lgg09(ctx.handle, n, mloc, nsteps, _lib.dptr(Phi_h), _lib.dptr(dirs_h), om.ptr(),
-                                      v.ptr(), None, C.byref(opts), _lib.dptr(rho_h), None))
+        if dist_stack:
+            # the same C-ABI calls the one-shot reach_lgg09 makes (plan create, upload from host buffers, run, fetch to the
+            # host, destroy), with the row stack built by the ranks together in between (reach_lgg09_plan_stack_*)
+            p2 = Lgg09Plan(ctx, n, mloc, nsteps, time_block=args.time_block, path=args.path)
+            ctx.check(ctx.lib.reach_lgg09_plan_upload(p2.handle, _lib.dptr(Phi_h), _lib.dptr(dirs_h), om.ptr(), v.ptr(), None))
+            build_stack_distributed(p2)
+            p2.run(sync=True)
+            ctx.check(ctx.lib.reach_lgg09_plan_fetch(p2.handle, 0, nsteps, _lib.dptr(rho_h)))
+            p2.close()
+        else:
+            ctx.check(ctx.lib.reach_lgg09(ctx.handle, n, mloc, nsteps, _lib.dptr(Phi_h), _lib.dptr(dirs_h), om.ptr(),
+                                          v.ptr(), None, C.byref(opts), _lib.dptr(rho_h), None))
         if world > 1:
             # the only exchange: all-gather of the per-rank blocks; rank 0 lands the full matrix on its host
             loc = torch.from_numpy(rho_h).cuda(non_blocking=True)
@@ -778,7 +788,9 @@ def run_b200(args):
                                                  mloc * nsteps * 8 >> 20)},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "timer": "host wall clock around reach_lgg09(host buffers), max over ranks",
+                    "timer": ("host wall clock around reach_lgg09_plan_create / _upload(host buffers) / shared stack build / _run / "
+                              "_fetch(host buffer) / _destroy + the all-gather, max over ranks") if dist_stack else
+                             "host wall clock around reach_lgg09(host buffers), max over ranks",
                     "bit_identical_to_device_resident_run": same, "max_abs_diff_to_device_resident_run": e2e_maxdiff},
             "gpu_launches": launches,
             "wall_s_timed_region": wall,
