@@ -701,7 +701,7 @@ def run_b200(args):
         steps_covered = -(-nsteps // S) * S
         flops_per_launch = 2.0 * n * n * st["nchains"] * steps_covered / max(1, st["gemm_launches"])
         achieved = flops_per_launch / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None   # FP64-equivalent TFLOP/s
-        traffic, ncu = None, {}
+        traffic, ncu, l2sm = None, {}, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "lgg09_main_kernel_traffic.json")))
             ent = tj.get(st["path"])
@@ -712,6 +712,9 @@ def run_b200(args):
             if ent and ent.get("n") == n and ent.get("chains") == st["nchains"]:
                 # DRAM bytes of one launch from the ncu --set full capture; only rescaled if the capture's time block differs
                 traffic = ent["dram_bytes_per_launch"] * (S / float(ent["time_block"]))
+                if ent.get("l2_to_sm_bytes_per_launch") and tj.get("l2_to_sm_peak"):
+                    l2sm = {"bytes_per_launch": ent["l2_to_sm_bytes_per_launch"] * (S / float(ent["time_block"])),
+                            "peak_tbs": tj["l2_to_sm_peak"]["tbs"], "peak_source": tj["l2_to_sm_peak"]["source"]}
                 ncu = {"time_block_of_capture": ent["time_block"], "source": ent.get("source"),
                        "pipe_tensor_active_pct": ent.get("pipe_tensor_active_pct"),
                        "tc_shared_operand_feed_pct": ent.get("tc_shared_operand_feed_pct")}
@@ -757,6 +760,14 @@ def run_b200(args):
                 "launches_per_step": st["gemm_launches"],
                 "gemm_share_of_step": share,
                 "traffic": traffic}
+            if l2sm and gemm_ms > 0 and crt and world == 1:
+                # what actually bounds the residue kernel: the residue images delivered from L2 to the SMs' shared memory
+                tbs = l2sm["bytes_per_launch"] / (gemm_ms * 1e-3) / 1e12
+                roofline["operand_delivery_l2_to_sm"] = {
+                    "achieved_tbs": tbs, "peak_tbs": l2sm["peak_tbs"], "frac": tbs / l2sm["peak_tbs"],
+                    "bytes_per_launch": l2sm["bytes_per_launch"], "peak_source": l2sm["peak_source"],
+                    "note": "bytes from the ncu capture (l1tex__m_xbar2l1tex_read_bytes), duration live; the tensor pipe waits for "
+                            "operand stages 37 % of a launch (per-role cycle counters, profiles/r2b_lgg09_crt_gemm_ncu_full_s20.md)"}
         else:
             roofline = {
                 "bound": "tensor", "kernel": "nt_dgemm_ws_kernel<...,Lgg09PackedEpi> (FP64 DMMA + fused support epilogue)",
