@@ -332,7 +332,9 @@ reach_ctx*  reach_multi_ctx(reach_multi* m, int i);               /* the i-th de
 const char* reach_multi_last_error(const reach_multi* m);         /* m may be NULL: last create error        */
 /* rho_host: ndirs x nsteps column-major, rows in the caller's order, or NULL.  rho_dev: NULL, or ndev device pointers
  * (entry j on device j, ndirs x nsteps doubles, NULL entries skipped) that each receive the complete matrix.
- * ms_per_device (may be NULL, ndev entries): CUDA-event time of each device's run. */
+ * ms_per_device (may be NULL, ndev entries): CUDA-event time of each device's run.  On the GEMM paths the devices build the
+ * row stack together (row ranges of every doubling step, peer copies) when their plans agree on the time block, else each
+ * builds its own; the results are bit-identical either way (REACH_MULTI_NO_SHARED_STACK=1 forces the per-device build). */
 int reach_multi_lgg09(reach_multi* m, int n, int ndirs, int64_t nsteps, const double* Phi, const double* dirs,
                       const reach_setexpr* Omega0, const reach_setexpr* V, const reach_lgg09_opts* opts,
                       double* rho_host, void* const* rho_dev, double* ms_per_device);

@@ -147,20 +147,91 @@ extern "C" int reach_multi_lgg09(reach_multi* m, int n, int ndirs, int64_t nstep
         const int mloc = int(rows[r].size());
         std::vector<double> local(size_t(n) * mloc);
         for (int l = 0; l < mloc; ++l) std::memcpy(&local[size_t(l) * n], dirs + size_t(rows[r][l]) * n, sizeof(double) * n);
-        int e = reach_lgg09_plan_create(c, n, mloc, nsteps, opts, &plans[r]);
-        if (e == REACH_OK) e = reach_lgg09_plan_upload(plans[r], Phi, local.data(), Omega0, V, nullptr);
+        int e = REACH_OK;
+        if (!plans[r]) {                                     // (not created by the shared stack build below)
+            e = reach_lgg09_plan_create(c, n, mloc, nsteps, opts, &plans[r]);
+            if (e == REACH_OK) e = reach_lgg09_plan_upload(plans[r], Phi, local.data(), Omega0, V, nullptr);
+        }
         if (e == REACH_OK) e = reach_lgg09_plan_run(plans[r]);
         if (e == REACH_OK) e = reach_lgg09_plan_sync(plans[r]);
         if (e == REACH_OK && ms_per_device)
             e = reach_lgg09_plan_stats(plans[r], &ms_per_device[r], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
         if (e != REACH_OK) fail(r, e);
     };
-    {
+    // phase 0 (GEMM paths, >= 2 devices with work): the row stack [I;E](Phi')^b is the same on every device, so the devices
+    // build it together -- each computes a row range of every doubling step (reach_lgg09_plan_stack_step) and pushes it to
+    // the others by peer copies -- instead of each repeating the whole build (the largest per-device fixed cost of a sharded
+    // run).  Same products in the same order: bit-identical to the per-device build.  Any irregularity (a chain-kernel
+    // plan, different time blocks) falls back to the per-device build inside plan_run.
+    auto shared_stack = [&]() {
+        int nwork = 0;
+        for (int r = 0; r < ndev; ++r) nwork += rows[r].empty() ? 0 : 1;
+        if (nwork < 2 || nwork != ndev || getenv("REACH_MULTI_NO_SHARED_STACK")) return;
+        auto create_device = [&](int r) {
+            reach_ctx* c = m->ctx[r];
+            const int mloc = int(rows[r].size());
+            std::vector<double> local(size_t(n) * mloc);
+            for (int l = 0; l < mloc; ++l) std::memcpy(&local[size_t(l) * n], dirs + size_t(rows[r][l]) * n, sizeof(double) * n);
+            int e = reach_lgg09_plan_create(c, n, mloc, nsteps, opts, &plans[r]);
+            if (e == REACH_OK) e = reach_lgg09_plan_upload(plans[r], Phi, local.data(), Omega0, V, nullptr);
+            if (e != REACH_OK) fail(r, e);
+        };
+        {
+            std::vector<std::thread> th;
+            for (int r = 0; r < ndev; ++r) th.emplace_back(create_device, r);
+            for (auto& t : th) t.join();
+        }
+        if (!std::all_of(rc.begin(), rc.end(), [](int v) { return v == REACH_OK; })) return;
+        std::vector<double*> stack(ndev, nullptr);
+        int64_t nbe0 = 0, ld0 = 0;
+        int32_t S0 = 0;
+        for (int r = 0; r < ndev; ++r) {
+            void* sp = nullptr;
+            int64_t nbe = 0, ld = 0;
+            int32_t S = 0;
+            if (reach_lgg09_plan_stack_info(plans[r], &sp, &nbe, &ld, &S) != REACH_OK) return;      // chain kernel: nothing to share
+            if (r == 0) { nbe0 = nbe; ld0 = ld; S0 = S; }
+            else if (nbe != nbe0 || ld != ld0 || S != S0) return;                                    // different time blocks
+            stack[r] = static_cast<double*>(sp);
+        }
+        for (int step = 0;; ++step) {
+            int64_t srows = 0, dest = 0;
+            if (reach_lgg09_plan_stack_step(plans[0], step, -1, -1, &srows, &dest) != REACH_OK) return;
+            if (srows == 0) break;
+            int64_t chunk = (srows + ndev - 1) / ndev;
+            chunk = (chunk + 7) / 8 * 8;
+            for (int r = 0; r < ndev; ++r) {
+                const int64_t lo = std::min(srows, r * chunk), hi = std::min(srows, (r + 1) * chunk);
+                const int e = reach_lgg09_plan_stack_step(plans[r], step, lo, hi, nullptr, nullptr);
+                if (e != REACH_OK) { fail(r, e); return; }
+            }
+            for (int r = 0; r < ndev; ++r) reach_synchronize(m->ctx[r]);
+            for (int r = 0; r < ndev; ++r) {                 // device r pushes its rows into every other device's stack
+                const int64_t lo = std::min(srows, r * chunk), hi = std::min(srows, (r + 1) * chunk);
+                if (hi <= lo) continue;
+                cudaSetDevice(m->dev[r]);
+                cudaStream_t st = static_cast<cudaStream_t>(reach_stream(m->ctx[r]));
+                const size_t off = size_t(dest + lo) * size_t(ld0), bytes = size_t(hi - lo) * size_t(ld0) * sizeof(double);
+                for (int j = 0; j < ndev; ++j)
+                    if (j != r && cudaMemcpyPeerAsync(stack[j] + off, m->dev[j], stack[r] + off, m->dev[r], bytes, st) != cudaSuccess) {
+                        rc[r] = REACH_ECUDA;
+                        msg[r] = "peer copy of the row stack failed";
+                        return;
+                    }
+            }
+            for (int r = 0; r < ndev; ++r) reach_synchronize(m->ctx[r]);
+        }
+        for (int r = 0; r < ndev; ++r)
+            if (reach_lgg09_plan_stack_ready(plans[r]) != REACH_OK) return;     // (plan_run then builds the stack itself)
+    };
+    shared_stack();
+    bool ok = std::all_of(rc.begin(), rc.end(), [](int v) { return v == REACH_OK; });
+    if (ok) {
         std::vector<std::thread> th;
         for (int r = 0; r < ndev; ++r) th.emplace_back(run_device, r);
         for (auto& t : th) t.join();
     }
-    bool ok = std::all_of(rc.begin(), rc.end(), [](int v) { return v == REACH_OK; });
+    ok = std::all_of(rc.begin(), rc.end(), [](int v) { return v == REACH_OK; });
 
     // phase 2: the all-gather.  Device r pushes its rows into the host matrix and into every device's full copy.
     auto gather_device = [&](int r) {

@@ -39,7 +39,7 @@ def test_multi_handle_basics(multi2):
         multi2.lgg09(np.eye(2), np.eye(2), to_c(flatten(rb.Hyperrectangle([0, 0], [1, 1]), None), 2), None, 0)
 
 
-@pytest.mark.parametrize("n,ndirs_extra,nsteps,ndev", [(6, 0, 40, 2), (48, 5, 120, 2), (48, 3, 64, 3), (130, 0, 33, 2)])
+@pytest.mark.parametrize("n,ndirs_extra,nsteps,ndev", [(6, 0, 40, 2), (48, 5, 120, 2), (48, 3, 64, 3), (130, 0, 33, 2), (520, 0, 30, 2)])
 def test_multi_lgg09_is_bit_identical_to_one_device(ctx, n, ndirs_extra, nsteps, ndev):
     rng = np.random.default_rng(n + ndirs_extra)
     A = -np.eye(n) + (0.5 / np.sqrt(n)) * rng.standard_normal((n, n))
