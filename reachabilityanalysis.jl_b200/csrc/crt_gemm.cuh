@@ -712,15 +712,11 @@ __global__ void __launch_bounds__(256) crt_slice_kernel(const double* __restrict
 
 inline void launch_crt_slice(const double* X, int ldx, int rows_valid, int rows_padded, int k_valid, const CrtConsts& c, bool is_y, int nkb,
                              int tiles_total, int8_t* Q, int* eout, int tile0, int ksplit, cudaStream_t st) {
-    // the residues cost ~20 integer operations per element and modulus: split the k range until ~8 CTAs per SM are in flight
-    // (a CTA then still has >= 256 (row, 16-byte chunk) items), and only instantiate the moduli in use
-    int sms = 148;
-    {
-        int dev = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    // only instantiate the moduli in use.  The k split is the caller's (enough CTAs for few rows): every CTA of a row group
+    // repeats the two scans of its 8 rows, so splitting further costs more than it fills -- 2 x 2048 rows x 2000 columns:
+    // k split 1 / 2 / 4 / 8 -> 0.156 / 0.178 / 0.222 / 0.336 ms (REACH_CRT_KSPLIT overrides for experiments)
     const int groups = rows_padded / 8;
-    ksplit = std::max(ksplit, std::min(std::max(1, nkb * 8 * 8 / 256), (8 * sms + groups - 1) / std::max(1, groups)));
+    if (const char* e = getenv("REACH_CRT_KSPLIT")) ksplit = std::max(1, atoi(e));
     const dim3 grid(groups, ksplit);
     const int bits = is_y ? c.beta : c.alpha;
 #define CRT_SLICE_CASE(NN) case NN: crt_slice_kernel<NN><<<grid, 256, 0, st>>>(X, ldx, rows_valid, k_valid, c.N, bits, nkb, tiles_total, Q, eout, tile0); break
