@@ -705,17 +705,21 @@ def run_b200(args):
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "lgg09_main_kernel_traffic.json")))
             ent = tj.get(st["path"])
+            nscale = 1.0
             if st["path"] == "int8" and ent and ent.get("moduli", ent.get("digit_planes")) != st.get("digit_planes"):
-                ent = tj.get("int8_digit_planes")            # the capture must be of the kernel that ran
-                if ent and ent.get("digit_planes") != st.get("digit_planes"):
-                    ent = None
+                if ent.get("moduli") and st.get("digit_planes", 0) >= 10:
+                    nscale = st["digit_planes"] / float(ent["moduli"])     # same kernel, other modulus count: bytes scale with it
+                else:
+                    ent = tj.get("int8_digit_planes")        # the capture must be of the kernel that ran
+                    if ent and ent.get("digit_planes") != st.get("digit_planes"):
+                        ent = None
             if ent and ent.get("n") == n and ent.get("chains") == st["nchains"]:
                 # DRAM bytes of one launch from the ncu --set full capture; only rescaled if the capture's time block differs
-                traffic = ent["dram_bytes_per_launch"] * (S / float(ent["time_block"]))
+                traffic = ent["dram_bytes_per_launch"] * (S / float(ent["time_block"])) * nscale
                 if ent.get("l2_to_sm_bytes_per_launch") and tj.get("l2_to_sm_peak"):
-                    l2sm = {"bytes_per_launch": ent["l2_to_sm_bytes_per_launch"] * (S / float(ent["time_block"])),
+                    l2sm = {"bytes_per_launch": ent["l2_to_sm_bytes_per_launch"] * (S / float(ent["time_block"])) * nscale,
                             "peak_tbs": tj["l2_to_sm_peak"]["tbs"], "peak_source": tj["l2_to_sm_peak"]["source"]}
-                ncu = {"time_block_of_capture": ent["time_block"], "source": ent.get("source"),
+                ncu = {"time_block_of_capture": ent["time_block"], "moduli_of_capture": ent.get("moduli"), "source": ent.get("source"),
                        "pipe_tensor_active_pct": ent.get("pipe_tensor_active_pct"),
                        "tc_shared_operand_feed_pct": ent.get("tc_shared_operand_feed_pct")}
         except Exception:

@@ -140,8 +140,10 @@ typedef struct {
                              batched GEMM on the INT8 tcgen05 pipe through error-free digit planes
                              (unguarded when forced; auto picks it for large dense problems and
                              guards it against the DMMA kernel, see reach_lgg09_plan_path)      */
-    int32_t reserved[3];  /* reserved[0]: FP64 emulation of path 3.  0 = default: residues modulo 14 pairwise
-                             coprime moduli, 14 INT8 products per FP64 product (csrc/crt_gemm.cuh);
+    int32_t reserved[3];  /* reserved[0]: FP64 emulation of path 3.  0 = default: residues modulo pairwise coprime
+                             moduli, one INT8 product per modulus and FP64 product (csrc/crt_gemm.cuh): 14 moduli
+                             when path 3 is forced; on the guarded auto path 13, and the run restarts at pass 0
+                             with 14 if the first guard check exceeds 2.5e-13 (REACH_CRT_NO_ADAPT=1: always 14);
                              10..16 = that many moduli (13 matches the digit planes' accuracy, 12 is
                              below it); 4..8 = that many 8-bit digit planes (csrc/oz_gemm.cuh, 7 = 56 bits,
                              28 INT8 products per FP64 product).  Anything else: REACH_EINVAL.

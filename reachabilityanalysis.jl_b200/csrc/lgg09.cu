@@ -269,6 +269,8 @@ struct reach_lgg09_plan {
     // residue (Chinese remainder) form of the same path (crt_gemm.cuh): oz_crt moduli = INT8 products per FP64 product
     // (0: digit planes).  Same launches, guard and pass groups; Xq / Yq hold residue images instead of digit planes.
     int oz_crt = 0;
+    int crt_lo = 0, crt_hi = 0;    // guarded auto path: start with crt_lo moduli, go to crt_hi if the first guard check is marginal
+    double crt_escalated_at = 0.0; // the pass-0 guard value that made the run switch to crt_hi (0: it did not)
     CrtConsts crt{};
     DevBuf crt_scr;               // per-CTA residue scratch of the kernel
     DevBuf Xq, Yq, eX, eY;
@@ -699,9 +701,17 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
         // opts.reserved[0]: 0 = default (residues modulo CRT_DEFAULT_N moduli), 4..8 = that many 8-bit digit planes,
         // 10..16 = residues modulo that many moduli
         int sel = p->opts.reserved[0];
+        p->crt_lo = p->crt_hi = 0;
         if (sel == 0) {
             sel = getenv("REACH_NO_CRT") ? OZ_DEFAULT_T : CRT_DEFAULT_N;
             if (const char* e = getenv("REACH_CRT_MODULI")) sel = atoi(e);
+            else if (sel == CRT_DEFAULT_N && p->oz_guard && !getenv("REACH_CRT_NO_ADAPT")) {
+                // guarded: one modulus fewer (the digit planes' accuracy class, 7 % less work) unless the first guard check
+                // says the problem needs the full count -- then the run restarts at pass 0 with CRT_DEFAULT_N moduli
+                p->crt_lo = CRT_DEFAULT_N - 1;
+                p->crt_hi = CRT_DEFAULT_N;
+                sel = p->crt_lo;
+            }
         }
         if (sel >= 4 && sel <= OZ_MAX_T) {
             p->oz_T = sel;
@@ -817,8 +827,9 @@ extern "C" int reach_lgg09_plan_upload(reach_lgg09_plan* p, const double* Phi, c
         p->oz_nkb = (n + kblock - 1) / kblock;
         p->oz_tiles_n = int((size_t(S + 1) * nbe + OZ_TN - 1) / OZ_TN);
         // bytes of all planes (digit planes or residue images) of one 128-row tile and one k-block
-        const size_t plane_blk = p->oz_crt ? size_t(p->oz_crt) * CRT_IMG : size_t(p->oz_T) * OZ_PLANE;
-        if (p->oz_crt) REACH_TRY(p->crt_scr.alloc(ctx, crt_scratch_bytes(p->oz_crt, ctx->sm_count), false));
+        const int crt_alloc = std::max(p->oz_crt, p->crt_hi);           // room for the escalated modulus count
+        const size_t plane_blk = p->oz_crt ? size_t(crt_alloc) * CRT_IMG : size_t(p->oz_T) * OZ_PLANE;
+        if (p->oz_crt) REACH_TRY(p->crt_scr.alloc(ctx, crt_scratch_bytes(crt_alloc, ctx->sm_count), false));
         REACH_TRY(p->Yq.alloc(ctx, size_t(p->oz_nkb) * p->oz_tiles_n * plane_blk, false));
         REACH_TRY(p->eY.alloc(ctx, size_t(p->oz_tiles_n) * OZ_TN * sizeof(int)));
         REACH_TRY(p->Xq.alloc(ctx, size_t(p->oz_nkb) * (mu_ld / OZ_TM) * plane_blk, false));
@@ -1490,6 +1501,8 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
     p->oz_checks = 0;
     constexpr double kOzGuardTol = 1e-12;      // one pass, INT8 against DMMA from the same direction rows
     constexpr double kOzDriftTol = 1e-11;      // accumulated since pass 0, INT8 chain against the FP64 sentinel chain
+    // first check with crt_lo moduli: above this the run switches to crt_hi (C5: 1.0e-13 with 13 moduli, 6e-15 with 14)
+    const double crt_escalate_tol = getenv("REACH_CRT_ESCALATE_TOL") ? atof(getenv("REACH_CRT_ESCALATE_TOL")) : 2.5e-13;
     // test hook: the first check at a pass >= REACH_OZ_TRIP_AT is treated as failed (exercises the replay path)
     const char* trip_env = getenv("REACH_OZ_TRIP_AT");
     int64_t trip_at = trip_env ? atoll(trip_env) : -1;
@@ -1688,6 +1701,33 @@ extern "C" int reach_lgg09_plan_run(reach_lgg09_plan* p) {
                 if (drift > p->oz_drift_max) p->oz_drift_max = drift;
                 bool ok = worst <= kOzGuardTol && drift <= kOzDriftTol;          // NaN fails
                 if (trip_at >= 0 && t >= trip_at) { ok = false; trip_at = -1; }
+                if (t == 0 && p->crt_hi > p->oz_crt && !(worst <= crt_escalate_tol)) {
+                    // marginal (or failed) with crt_lo moduli: take crt_hi from here on.  Nothing has been emitted that is kept:
+                    // new residue images of the stack, state back to the start of pass 0 (the sentinel chains have not moved yet)
+                    p->crt_escalated_at = worst;
+                    p->oz_crt = p->oz_T = p->crt_hi;
+                    p->crt = crt_make_consts(p->crt_hi);
+                    p->oz_guard_max = 0.0;
+                    p->oz_drift_max = 0.0;
+                    oz_slice(stack, (S + 1) * nbe, p->oz_tiles_n * OZ_TN, 1, p->oz_tiles_n, p->Yq.as<int8_t>(), p->eY.as<int>(), 0, true);
+                    if (J > 1)
+                        oz_slice(p->cstack.as<double>(), J * p->oz_ctiles * OZ_TN, J * p->oz_ctiles * OZ_TN, 1, J * p->oz_ctiles,
+                                 p->Yq_c.as<int8_t>(), p->eY_c.as<int>(), 0, true);
+                    REACH_CUDA(ctx, cudaGetLastError());
+                    p->launches += 2;
+                    REACH_CUDA(ctx, cudaMemcpyAsync(p->Lbuf[0].p, p->L0.p, size_t(mu_pad) * Kp * 8, cudaMemcpyDeviceToDevice, st));
+                    REACH_CUDA(ctx, cudaMemsetAsync(p->s_pos.p, 0, p->s_pos.bytes, st));
+                    REACH_CUDA(ctx, cudaMemsetAsync(p->s_neg.p, 0, p->s_neg.bytes, st));
+                    cur = 0;
+                    carry_cur = 0;
+                    if (p->nchecks > 0) {
+                        REACH_CUDA(ctx, cudaMemsetAsync(p->first_bad.p, 0xFF, sizeof(unsigned long long), st));
+                        fb_pending[0] = fb_pending[1] = false;
+                        p->fb_host[0] = p->fb_host[1] = ~0ull;
+                    }
+                    t = -1;                        // the loop increment makes it 0
+                    continue;
+                }
                 if (ok) {
                     // verified: keep the state at the start of pass t + 1 (L_{t+1}, running sums, carried features)
                     REACH_CUDA(ctx, cudaMemcpyAsync(p->L_snap.p, p->Lbuf[1 - cur].p, size_t(mu_pad) * Kp * 8, cudaMemcpyDeviceToDevice, st));

@@ -366,3 +366,28 @@ def test_pass_groups_with_the_guard_and_a_trip_inside_a_grouped_run(ctx, monkeyp
     assert_support_parity(trip.sfmat(), ref)
     dmma = reach_inhomog_LGG09(dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=2, path="gemm")
     assert_support_parity(trip.sfmat()[:, 4:], dmma.sfmat()[:, 4:], tol=1e-12)     # steps of passes >= 2: FP64 pipe output
+
+
+def test_guarded_residue_path_starts_with_13_moduli_and_escalates_on_a_marginal_first_check(ctx, monkeypatch):
+    """Auto path: 13 moduli (the digit planes' accuracy class) unless the first guard check is above the escalation
+    threshold; then the run restarts at pass 0 with 14 moduli -- no DMMA fallback, same results within the tolerance."""
+    n, nsteps = 520, 40
+    wl = _synthetic(n, nsteps, seed=5)
+    ref = LO.reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, wl.V)
+    plan = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=4)
+    st = plan.stats()
+    assert st["path"] == "int8" and st["digit_planes"] == 13 and st["fallback_pass"] == -1 and st["guard_max"] < 2.5e-13
+    assert_support_parity(plan.sfmat(), ref)
+    monkeypatch.setenv("REACH_CRT_ESCALATE_TOL", "1e-30")            # every first check is "marginal"
+    esc = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=4)
+    se = esc.stats()
+    assert se["path"] == "int8" and se["digit_planes"] == 14 and se["fallback_pass"] == -1
+    assert se["guard_max"] < st["guard_max"]                         # the guard statistics are those of the 14-modulus run
+    assert_support_parity(esc.sfmat(), ref)
+    again = esc.run().sfmat()                                        # the plan stays at 14 moduli: same numbers
+    assert np.array_equal(again, esc.sfmat()) and esc.stats()["digit_planes"] == 14
+    monkeypatch.delenv("REACH_CRT_ESCALATE_TOL")
+    monkeypatch.setenv("REACH_CRT_NO_ADAPT", "1")
+    fixed = reach_inhomog_LGG09(wl.dirs, wl.Omega0, wl.Phi, nsteps, None, wl.V, ctx=ctx, time_block=4)
+    assert fixed.stats()["digit_planes"] == 14
+    assert np.array_equal(fixed.sfmat(), esc.sfmat())                # an escalated run equals a run that started with 14
