@@ -372,6 +372,12 @@ int reach_ozgemm_probe(reach_ctx* ctx, int m, int n, int k, int slices, const do
 int reach_crtgemm_probe(reach_ctx* ctx, int m, int n, int k, int moduli, const double* X_host,
                         const double* Y_host, double* C_host, int iters, double* tflops, double* slice_ms);
 
+/* Host-only: the constants of the residue path for `moduli` (10..16) moduli -- the moduli, the split fractions
+ * f_i = f1_i + f2_i of w_i / P (w_i the Chinese-remainder weights, f1_i a multiple of 2^-40), P rounded to FP64 and the
+ * 2-norm budgets 2^alpha / 2^beta of the integer X / Y rows (2^(alpha+beta) <= P/4).  Arrays hold `moduli` entries; any
+ * pointer may be NULL.  tests/test_crt_host.py pins them against exact integer arithmetic without a GPU. */
+int reach_crt_constants(int moduli, int32_t* p, double* f1, double* f2, double* P, int32_t* alpha, int32_t* beta);
+
 #ifdef __cplusplus
 }
 #endif

@@ -123,6 +123,7 @@ SIGNATURES = {
                                      c_double_p, C.c_int, c_double_p, c_double_p]),
     "reach_crtgemm_probe": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_double_p, c_double_p,
                                       c_double_p, C.c_int, c_double_p, c_double_p]),
+    "reach_crt_constants": (C.c_int, [C.c_int, c_int32_p, c_double_p, c_double_p, c_double_p, c_int32_p, c_int32_p]),
 }
 
 _lib = None

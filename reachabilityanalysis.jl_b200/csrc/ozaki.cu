@@ -142,3 +142,20 @@ extern "C" int reach_crtgemm_probe(reach_ctx* ctx, int m, int n, int k, int modu
     if (C_host && g.dbg) REACH_CUDA(ctx, cudaMemcpy(C_host, dbg.p, size_t(2) * 128 * 256 * 4, cudaMemcpyDeviceToHost));
     return REACH_OK;
 }
+
+// Host-only: the constants of the residue path for `moduli` moduli (crt_make_consts), so that a CPU test can pin them
+// against exact integer arithmetic: the moduli p_i, the split fractions f_i = f1_i + f2_i of w_i / P, P rounded to FP64 and the
+// norm budgets 2^alpha, 2^beta of the X and Y rows.  Arrays hold `moduli` entries.  No CUDA call is made.
+extern "C" int reach_crt_constants(int moduli, int32_t* p, double* f1, double* f2, double* P, int32_t* alpha, int32_t* beta) {
+    if (moduli < CRT_MIN_N || moduli > CRT_MAX_N) return REACH_EINVAL;
+    const CrtConsts c = crt_make_consts(moduli);
+    for (int i = 0; i < moduli; ++i) {
+        if (p) p[i] = int32_t(c.p[i]);
+        if (f1) f1[i] = c.f1[i];
+        if (f2) f2[i] = c.f2[i];
+    }
+    if (P) *P = c.Pd;
+    if (alpha) *alpha = c.alpha;
+    if (beta) *beta = c.beta;
+    return REACH_OK;
+}
