@@ -108,23 +108,27 @@ def stack_row_split(rows, world, rank):
     return chunk, lo, hi
 
 
-def build_stack_distributed(plan, group=None):
+def build_stack_distributed(plan, group=None, stack=None):
     """Build the row stack [I;E](Φᵀ)^b of `plan` (GEMM paths) with the ranks of `group` sharing the work: every doubling step's
     output rows are split over the ranks (`reach_lgg09_plan_stack_step`) and all-gathered in place over NVLink, instead of
     every rank repeating the whole build (the largest per-rank fixed cost of a sharded LGG09 run: `profiles/`).  All ranks
     must hold plans with the same Φ, mapped rows and time block.  The next `plan.run()` uses the stack as it is; the
     products and their order are those of a single-GPU run, so the results are bit-identical.  Returns the number of
-    steps taken."""
+    steps taken.
+
+    `stack` (tests): a [rows, ld] tensor over the plan's stack memory; by default a zero-copy CUDA view of
+    `plan.stack_info()`'s device pointer."""
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     ptr, nbe, ld, S = plan.stack_info()
-    dev = torch.cuda.current_device()
+    if stack is None:
+        dev = torch.cuda.current_device()
 
-    class _Holder:                                            # the whole stack buffer (+ its 256 slack rows) as [rows, ld] float64
-        __cuda_array_interface__ = {"shape": ((S + 1) * nbe + 256, ld), "typestr": "<f8", "data": (int(ptr), False),
-                                    "version": 3, "strides": None}
-    stack = torch.as_tensor(_Holder(), device=torch.device("cuda", dev))
+        class _Holder:                                        # the whole stack buffer (+ its 256 slack rows) as [rows, ld] float64
+            __cuda_array_interface__ = {"shape": ((S + 1) * nbe + 256, ld), "typestr": "<f8", "data": (int(ptr), False),
+                                        "version": 3, "strides": None}
+        stack = torch.as_tensor(_Holder(), device=torch.device("cuda", dev))
     step = 0
     while True:
         rows, dest = plan.stack_step(step)
@@ -134,8 +138,10 @@ def build_stack_distributed(plan, group=None):
         plan.stack_step(step, lo, hi)
         plan.ctx.synchronize()                                # the library's stream -> torch's (NCCL) stream
         region = stack[dest:dest + world * chunk]
-        dist.all_gather_into_tensor(region, region[rank * chunk:(rank + 1) * chunk], group=group)
-        torch.cuda.current_stream().synchronize()             # the next step reads the gathered rows on the library's stream
+        dist.all_gather_into_tensor(region, region[rank * chunk:(rank + 1) * chunk].clone() if not stack.is_cuda
+                                    else region[rank * chunk:(rank + 1) * chunk], group=group)
+        if stack.is_cuda:
+            torch.cuda.current_stream().synchronize()         # the next step reads the gathered rows on the library's stream
         step += 1
     plan.stack_ready()
     return step

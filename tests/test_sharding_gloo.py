@@ -119,3 +119,101 @@ def test_shard_splits_is_a_balanced_partition():
             parts = [list(sharding.shard_splits(nsplits, world, r)) for r in range(world)]
             assert sorted(i for p in parts for i in p) == list(range(nsplits))
             assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+
+
+class _HostPlan:
+    """Stands in for a GEMM-path `Lgg09Plan` in the CPU test of `sharding.build_stack_distributed`: the same stepwise row-stack
+    build as `reach_lgg09_plan_stack_step` (step 0: block 1 = block 0 x P; step j: blocks s+1.. = blocks 1.. x P^s with
+    s = 2^(j-1), after Q_{2s} = Q_s Q_s), in NumPy on a host tensor."""
+
+    class _Ctx:
+        def synchronize(self):
+            pass
+
+    def __init__(self, Phi, E, S):
+        n = Phi.shape[0]
+        self.n, self.S = n, S
+        self.nbe = -(-(n + E.shape[0]) // 8) * 8
+        self.stack = torch.zeros(((S + 1) * self.nbe + 256, n), dtype=torch.float64)
+        self.stack[:n, :n] = torch.eye(n, dtype=torch.float64)
+        self.stack[n:n + E.shape[0]] = torch.from_numpy(E)
+        self.P = {1: Phi.T.copy()}                            # row r of block b = row r of block 0 times (Phi')^b
+        self.ctx = self._Ctx()
+        self.steps_done, self.ready, self.calls = 0, False, []
+
+    def stack_info(self):
+        return 0, self.nbe, self.n, self.S
+
+    def stack_step(self, step, lo=-1, hi=-1):
+        s = 0 if step == 0 else 1 << (step - 1)
+        if step > 0 and s >= self.S:
+            return 0, 0
+        rows = self.nbe if step == 0 else min(s, self.S - s) * self.nbe
+        dest = self.nbe if step == 0 else (s + 1) * self.nbe
+        if lo < 0:
+            return rows, dest
+        assert step in (self.steps_done, self.steps_done - 1) and 0 <= lo <= hi <= rows
+        if step > 0 and 2 * s not in self.P:
+            self.P[2 * s] = self.P[s] @ self.P[s]
+        src0 = 0 if step == 0 else self.nbe
+        X = self.stack[src0 + lo:src0 + hi].numpy()
+        self.stack[dest + lo:dest + hi] = torch.from_numpy(X @ self.P[max(s, 1)])
+        self.calls.append((step, lo, hi))
+        self.steps_done = step + 1
+        return rows, dest
+
+    def stack_ready(self):
+        need = 1
+        s = 1
+        while s < self.S:
+            need, s = need + 1, s * 2
+        assert self.steps_done == need
+        self.ready = True
+
+
+def _stack_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(11)
+    n, S = 13, 11
+    Phi = 0.9 * np.eye(n) + 0.05 * rng.standard_normal((n, n))
+    E = rng.standard_normal((3, n))
+    plan = _HostPlan(Phi, E, S)
+    steps = sharding.build_stack_distributed(plan, stack=plan.stack)
+    q.put((rank, steps, plan.ready, plan.stack[:(S + 1) * plan.nbe].numpy().copy(), plan.calls))
+    dist.destroy_process_group()
+
+
+def test_two_ranks_build_the_row_stack_together():
+    """`sharding.build_stack_distributed` on gloo: each rank computes its row range of every doubling step, the in-place
+    all-gathers complete the stack on both, and the result equals the powers computed directly."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stack_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    rng = np.random.default_rng(11)
+    n, S = 13, 11
+    Phi = 0.9 * np.eye(n) + 0.05 * rng.standard_normal((n, n))
+    E = rng.standard_normal((3, n))
+    nbe = 16
+    B0 = np.zeros((nbe, n))
+    B0[:n] = np.eye(n)
+    B0[n:n + 3] = E
+    for rank, steps, ready, stack, calls in results:
+        assert ready and steps == 5                          # block 1, then s = 1, 2, 4, 8
+        for b in range(S + 1):
+            want = B0 @ np.linalg.matrix_power(Phi.T, b)
+            assert np.allclose(stack[b * nbe:(b + 1) * nbe], want, rtol=1e-12, atol=1e-14)
+    assert np.array_equal(results[0][3], results[1][3])      # both ranks hold the same stack, bit for bit
+    # the ranks took disjoint row ranges of every step
+    for st in range(5):
+        r0 = [(lo, hi) for s_, lo, hi in results[0][4] if s_ == st]
+        r1 = [(lo, hi) for s_, lo, hi in results[1][4] if s_ == st]
+        assert len(r0) == 1 and len(r1) == 1 and r0[0][1] <= r1[0][0]
