@@ -4,7 +4,7 @@ The device path lives in libreach_cuda.so (csrc/, C ABI in include/reach.h); thi
 host-side mirror of the reference's operator interface for that path."""
 from . import sets  # noqa: F401
 from .sets import *  # noqa: F401,F403
-from .directions import BoxDirections, OctDirections, CustomDirections  # noqa: F401
+from .directions import BoxDirections, OctDirections, CustomDirections, PolarDirections  # noqa: F401
 from .flowpipe import (Flowpipe, MixedFlowpipe, ReachSolution, TemplateReachSet, ReachSet,  # noqa: F401
                        TimeInterval, zeroT, rho)
 from .lgg09 import LGG09, Forward, NoBloating, FirstOrderZonotope, Lgg09Plan  # noqa: F401

@@ -20,9 +20,27 @@ class AbstractDirections:
     def dim(self):
         return self.n
 
+    def __eq__(self, other):
+        """Templates compare by value (`alg0 == alg1 == alg2`, test/algorithms/LGG09.jl:158-159)."""
+        if not isinstance(other, AbstractDirections):
+            return NotImplemented
+        if type(self) is type(other) and type(self) in (BoxDirections, OctDirections, PolarDirections):
+            return self._key() == other._key()
+        return self.n == other.n and np.array_equal(self.matrix(), other.matrix())
+
+    __hash__ = None
+
+    def _key(self):
+        return self.n
+
 
 class BoxDirections(AbstractDirections):
-    """+e₁..+e_n then −e₁..−e_n (LGG09.jl:112)."""
+    """+e₁..+e_n then −e₁..−e_n (LGG09.jl:112).
+
+    The rows of ρℓ follow the iteration order of the template.  The device path itself is order-agnostic (it takes
+    the direction matrix), and the Julia wrapper passes `collect(template)`, i.e. LazySets' own order, which for the
+    negative half is believed to be −e_n..−e₁ ([MEM]; LazySets is not vendored in the reference tree and no
+    reference test pins it).  This mirror and the oracle use the order stated here."""
 
     def __init__(self, n):
         self.n = int(n)
@@ -50,6 +68,24 @@ class OctDirections(AbstractDirections):
                     cols.append(d)
         D = np.array(cols).T if cols else np.zeros((n, 0))
         return np.hstack([D, BoxDirections(n).matrix()])
+
+
+class PolarDirections(AbstractDirections):
+    """`PolarDirections(Nφ)` of LazySets ([MEM]): the Nφ planar unit vectors (cos φ_i, sin φ_i) with
+    φ = range(0, 2π, length = Nφ + 1)[1:Nφ] (test/algorithms/LGG09.jl:184-188 runs LGG09 over `PolarDirections(40)`)."""
+
+    def __init__(self, Nphi):
+        if int(Nphi) <= 0:
+            raise ValueError("Nφ = %s is invalid; it should be at least 1" % (Nphi,))
+        self.Nphi = int(Nphi)
+        self.n = 2
+
+    def matrix(self):
+        phi = np.linspace(0.0, 2.0 * np.pi, self.Nphi + 1)[: self.Nphi]
+        return np.vstack([np.cos(phi), np.sin(phi)])
+
+    def _key(self):
+        return self.Nphi
 
 
 class CustomDirections(AbstractDirections):

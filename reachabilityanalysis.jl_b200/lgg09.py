@@ -22,21 +22,33 @@ from .flowpipe import Flowpipe, TemplateReachSet, zeroT, samedir
 from .support_program import flatten, to_c, invariant_to_c
 
 
-class Forward:
+class _ApproxModel:
+    """Approximation models are plain option records and compare by value, like the reference's structs."""
+
+    def __eq__(self, other):
+        return type(self) is type(other) and vars(self) == vars(other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        return "%s(%s)" % (self.name, ", ".join("%s=%r" % kv for kv in vars(self).items()))
+
+
+class Forward(_ApproxModel):
     name = "Forward"
 
     def __init__(self, sih="concrete", exp="base", setops="lazy"):
         self.sih, self.exp, self.setops = sih, exp, setops
 
 
-class NoBloating:
+class NoBloating(_ApproxModel):
     name = "NoBloating"
 
     def __init__(self, exp="base", setops="lazy"):
         self.exp, self.setops = exp, setops
 
 
-class FirstOrderZonotope:
+class FirstOrderZonotope(_ApproxModel):
     name = "FirstOrderZonotope"
 
     def __init__(self, exp="base"):
