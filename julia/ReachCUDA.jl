@@ -12,6 +12,8 @@
 module ReachCUDA
 
 using LazySets, LinearAlgebra
+using LazySets: set
+using IntervalArithmetic.Symbols: (..)                       # as src/Initialization/init.jl:40, LGG09Module.jl:11
 import LazySets: ρ, dim
 import ..ReachabilityAnalysis: TemplateReachSet, ReachSet, Flowpipe, MixedFlowpipe, AbstractFlowpipe, TimeInterval, zeroT,
                                _collect, _isdisjoint, support_function_matrix, tspan
@@ -126,7 +128,7 @@ end
 function reach_inhomog_LGG09_cuda!(F::Vector{RT}, dirs, Ω₀::LazySet{N}, Φ::AbstractMatrix{N}, NSTEPS::Integer,
                                    δ::N, X::LazySet, U::Union{LazySet,Nothing}, Δt0::TimeInterval;
                                    ctx::Ctx=Ctx()) where {N,RT<:TemplateReachSet}
-    ℓ = reduce(hcat, _collect(dirs))                           # n × ndirs, column-major
+    ℓ = Matrix{Float64}(reduce(hcat, _collect(dirs)))          # n × ndirs, column-major, dense
     n, ndirs = size(ℓ)
     ρℓ = Matrix{N}(undef, ndirs, NSTEPS)                       # same layout the reference allocates (:21)
     keep = Any[]
@@ -183,8 +185,8 @@ mutable struct DeviceTemplateFlowpipe{N,VN,TN} <: AbstractFlowpipe
 end
 
 function post_LGG09_cuda(dirs, Ω₀::LazySet{N}, Φ::AbstractMatrix{N}, NSTEPS::Integer, δ::N, X::LazySet,
-                         U::Union{LazySet,Nothing}, Δt0::TimeInterval; ctx::Ctx=Ctx()) where {N}
-    ℓ = reduce(hcat, _collect(dirs))
+                         U::Union{LazySet,Nothing}, Δt0::TimeInterval=zeroT; ctx::Ctx=Ctx()) where {N}
+    ℓ = Matrix{Float64}(reduce(hcat, _collect(dirs)))
     n, ndirs = size(ℓ)
     plan = LGG09Plan(ctx, n, ndirs, NSTEPS)
     keep = Any[]
@@ -251,16 +253,16 @@ end
 # per split; returns the MixedFlowpipe the reference builds at solve.jl:116 plus the ρℓ matrices.
 function solve_distributed_LGG09_cuda(dirs, Ω₀s::Vector{<:LazySet{N}}, Φ::AbstractMatrix{N}, NSTEPS::Integer, δ::N,
                                       U::Union{LazySet,Nothing}, Δt0::TimeInterval; ctx::Ctx=Ctx()) where {N}
-    ℓ = reduce(hcat, _collect(dirs))
+    ℓ = Matrix{Float64}(reduce(hcat, _collect(dirs)))
     n, ndirs = size(ℓ)
     m = length(Ω₀s)
     keep = Any[]
     Φd = Matrix{Float64}(Φ)
     oms = ReachSetExpr[setexpr(flatten_Ω₀(Ω₀, Φd), keep)[] for Ω₀ in Ω₀s]
     v = U === nothing ? C_NULL : setexpr(flatten_V(U), keep)
-    ρ = Array{N}(undef, ndirs, NSTEPS, m)                      # split i: ρ[:, :, i], the reference's ρℓ layout
+    ρs = Array{N}(undef, ndirs, NSTEPS, m)                      # split i: ρs[:, :, i], the reference's ρℓ layout
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve keep Φd ℓ oms ρ begin
+    GC.@preserve keep Φd ℓ oms ρs begin
         check(ctx, ccall((:reach_lgg09_batch_create, lib), Cint,
                          (Ptr{Cvoid}, Cint, Cint, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{ReachSetExpr},
                           Ptr{ReachSetExpr}, Ref{Ptr{Cvoid}}), ctx.h, n, ndirs, NSTEPS, m, Φd, ℓ, oms, v, h))
@@ -268,22 +270,22 @@ function solve_distributed_LGG09_cuda(dirs, Ω₀s::Vector{<:LazySet{N}}, Φ::Ab
             check(ctx, ccall((:reach_lgg09_batch_run, lib), Cint, (Ptr{Cvoid},), h[]))
             for i in 1:m
                 check(ctx, ccall((:reach_lgg09_batch_fetch, lib), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ptr{Float64}),
-                                 h[], i - 1, 0, NSTEPS, pointer(ρ, (i - 1) * ndirs * NSTEPS + 1)))
+                                 h[], i - 1, 0, NSTEPS, pointer(ρs, (i - 1) * ndirs * NSTEPS + 1)))
             end
         finally
             ccall((:reach_lgg09_batch_destroy, lib), Cvoid, (Ptr{Cvoid},), h[])
         end
     end
-    RT = TemplateReachSet{N,eltype(dirs),typeof(dirs),typeof(view(ρ, :, 1, 1))}
+    RT = TemplateReachSet{N,eltype(dirs),typeof(dirs),typeof(view(ρs, :, 1, 1))}
     fps = Vector{Flowpipe{N,RT,Vector{RT}}}(undef, m)
     for i in 1:m
         F = Vector{RT}(undef, NSTEPS)
         Δt = (zero(N) .. δ) + Δt0
         @inbounds for k in 1:NSTEPS
-            F[k] = TemplateReachSet(dirs, view(ρ, :, k, i), Δt)
+            F[k] = TemplateReachSet(dirs, view(ρs, :, k, i), Δt)
             Δt += δ
         end
-        fps[i] = Flowpipe(F, Dict{Symbol,Any}(:sfmat => view(ρ, :, :, i)))
+        fps[i] = Flowpipe(F, Dict{Symbol,Any}(:sfmat => view(ρs, :, :, i)))
     end
     return MixedFlowpipe(fps)
 end
@@ -385,7 +387,7 @@ end
 
 function reach_inhomog_LGG09_cuda!(F::Vector{RT}, dirs, Ω₀::LazySet{N}, Φ::AbstractMatrix{N}, NSTEPS::Integer, δ::N,
                                    ::Universe, U::Union{LazySet,Nothing}, Δt0::TimeInterval, multi::MultiCtx) where {N,RT<:TemplateReachSet}
-    ℓ = reduce(hcat, _collect(dirs))
+    ℓ = Matrix{Float64}(reduce(hcat, _collect(dirs)))
     n, ndirs = size(ℓ)
     ρℓ = Matrix{N}(undef, ndirs, NSTEPS)
     keep = Any[]

@@ -114,3 +114,63 @@ def _split_top_level(text):
     if cur.strip():
         parts.append(cur)
     return parts
+
+
+def _julia_code_only(s):
+    """Julia source with string literals emptied and comments removed."""
+    out, i, n = [], 0, len(s)
+    while i < n:
+        if s.startswith('"""', i):
+            j = s.find('"""', i + 3)
+            i = j + 3 if j >= 0 else n
+            out.append('""')
+        elif s[i] == '"':
+            j = i + 1
+            while j < n and s[j] != '"':
+                j += 2 if s[j] == "\\" else 1
+            i = j + 1
+            out.append('""')
+        elif s.startswith("#=", i):
+            j = s.find("=#", i + 2)
+            i = j + 2 if j >= 0 else n
+        elif s[i] == "#":
+            j = s.find("\n", i)
+            i = j if j >= 0 else n
+        else:
+            out.append(s[i])
+            i += 1
+    return "".join(out)
+
+
+def test_julia_wrapper_blocks_and_brackets_balance():
+    """No julia binary here: at least every block opener has its `end`, brackets nest, the module closes, and every
+    name the wrapper takes from ReachabilityAnalysis / LazySets in a qualified import is one it uses."""
+    code = _julia_code_only(open(os.path.join(ROOT, "julia", "ReachCUDA.jl")).read())
+    openers = {"function", "if", "for", "while", "let", "begin", "struct", "module", "do", "try", "quote", "macro"}
+    closing = {"(": ")", "[": "]", "{": "}"}
+    blocks, brackets, line = [], [], 1
+    for m in re.finditer(r":?[^\W\d][\w!]*|[\[\](){}]|\n", code):
+        w = m.group(0)
+        if w == "\n":
+            line += 1
+        elif w in closing:
+            brackets.append((w, line))
+        elif w in closing.values():
+            assert brackets, "line %d: unmatched %s" % (line, w)
+            o, l = brackets.pop()
+            assert closing[o] == w, "line %d: %s closes the %s of line %d" % (line, w, o, l)
+        elif w in openers:
+            if brackets and w in ("for", "if"):        # comprehension / generator: no `end`
+                continue
+            blocks.append((w, line))
+        elif w == "end":
+            if brackets and brackets[-1][0] == "[":    # indexing: x[end]
+                continue
+            assert blocks, "line %d: `end` without an open block" % line
+            blocks.pop()
+    assert not brackets, "unclosed brackets: %s" % brackets
+    assert not blocks, "unclosed blocks: %s" % blocks
+    for m in re.finditer(r"^import [\w.]+:\s*((?:[^\n,]+,\s*\n?)*[^\n,]+)$", code, flags=re.M):
+        for name in re.split(r"[,\s]+", m.group(1).strip()):
+            assert len(re.findall(r"(?<![\w.])%s(?![\w!])" % re.escape(name), code)) >= 2, \
+                "ReachCUDA.jl imports %s and never uses it" % name
