@@ -86,7 +86,7 @@ def samedir(u, v):
 
 
 class ReachSet:
-    """(set, Δt) with set a Zonotope (GLGM06) or a Hyperrectangle (BOX)."""
+    """(set, Δt) with set a Zonotope (GLGM06), a Hyperrectangle (BOX) or an Interval (`to_intervals`)."""
 
     def __init__(self, Z, dt):
         self.set, self.dt = Z, dt
@@ -100,6 +100,8 @@ class ReachSet:
         if hasattr(self.set, "generators"):
             c, G = self.set.center, self.set.generators
             return float(d @ c + np.abs(G.T @ d).sum())
+        if hasattr(self.set, "lo") and hasattr(self.set, "hi") and not hasattr(self.set, "radius"):     # Interval
+            return float(d[0] * (self.set.hi if d[0] > 0 else self.set.lo))
         return float(d @ self.set.center + np.abs(d) @ self.set.radius)      # Hyperrectangle (BOX)
 
 
@@ -128,6 +130,14 @@ class Flowpipe:
                 dt = dt + self.delta
             self._t = (lo, hi)
         return self._t
+
+    def shift(self, t0):
+        """`shift(fp, t0)` (Flowpipe.jl:153-169, ReachSet.jl:52-54): every reach-set keeps its set and gets the time
+        span `tspan(R) + t0`; the device-resident data and `ext` are shared, nothing is copied or recomputed."""
+        lo, hi = self._times()
+        out = Flowpipe(self._n, self._make, self.delta, self.dt0, self.ext, self.device)
+        out._t = (lo + float(t0), hi + float(t0))
+        return out
 
     def __len__(self):
         return self._n
@@ -228,6 +238,16 @@ class MixedFlowpipe:
                 pass
         return max(fp.rho(d) for fp in self.flowpipes)
 
+    def numrsets(self):
+        """MixedFlowpipe.jl:36."""
+        return sum(len(fp) for fp in self.flowpipes)
+
+    def tspan(self, i=None):
+        """MixedFlowpipe.jl:40-43: the time span of a mixed flowpipe is only defined per flowpipe (0-based i)."""
+        if i is None:
+            raise ValueError("for mixed flowpipes you should specify the index, as in `tspan(fp, i)`")
+        return self.flowpipes[i].tspan
+
 
 class ReachSolution:
     """(F, alg, ext) (Flowpipes/solutions.jl:60-64); forwards the flowpipe interface."""
@@ -249,6 +269,15 @@ class ReachSolution:
 
     def __call__(self, t):
         return self.F(t)
+
+    def shift(self, t0):
+        """solutions.jl:131-133."""
+        return ReachSolution(self.F.shift(t0), self.alg, self.ext)
+
+
+def shift(X, t0):
+    """`shift(fp | sol, t0)` as a free function, like the reference's."""
+    return X.shift(t0)
 
 
 def rho(d, X):

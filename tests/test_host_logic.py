@@ -220,3 +220,46 @@ def test_stack_row_split_partitions_every_step_and_stays_inside_the_slack_rows()
             assert covered == list(range(rows))
             assert len(chunks) == 1
             assert world * chunks.pop() - rows < 256
+
+
+def _host_flowpipe(n=5, delta=0.1, dt0=None):
+    from reach_b200.flowpipe import Flowpipe, ReachSet, zeroT
+    from reach_b200.sets import Interval
+    return Flowpipe(n, lambda k, dt: ReachSet(Interval(float(k), k + 1.0), dt), delta, dt0 if dt0 is not None else zeroT)
+
+
+def test_flowpipe_shift_and_time_evaluation_flowpipe_jl_97_169():
+    """`tspan(shift(sol, 1.0)) == tspan(sol) + 1.0` (test/algorithms/GLGM06.jl:85); fp(t) returns the set(s) whose time
+    span contains t and throws outside (Flowpipe.jl:97-112)."""
+    from reach_b200.flowpipe import ReachSolution, shift
+    fp = _host_flowpipe()
+    sh = shift(fp, 1.0)
+    assert tuple(sh.tspan) == (fp.tspan[0] + 1.0, fp.tspan[1] + 1.0)
+    assert len(sh) == len(fp) and sh.ext is fp.ext
+    for k in range(len(fp)):
+        assert tuple(sh[k].dt) == (fp[k].dt[0] + 1.0, fp[k].dt[1] + 1.0)
+        assert sh[k].set.lo == fp[k].set.lo                     # the sets themselves are untouched
+    assert tuple(fp.tspan) == (0.0, fp[len(fp) - 1].dt[1])       # the original is not modified
+    sol = ReachSolution(fp, "alg")
+    assert tuple(shift(sol, 2.0).tspan) == (2.0, fp.tspan[1] + 2.0) and shift(sol, 2.0).alg == "alg"
+    inner = fp(0.25)
+    assert not isinstance(inner, list) and tuple(inner.dt)[0] <= 0.25 <= tuple(inner.dt)[1]
+    edge = fp(fp[1].dt[1])                                       # a shared end point belongs to two reach-sets
+    assert isinstance(edge, list) and len(edge) == 2
+    with pytest.raises(ValueError):
+        fp(fp.tspan[1] + 1.0)
+    assert len(fp((0.05, 0.25))) == 3
+    with pytest.raises(ValueError):
+        fp((9.0, 10.0))
+
+
+def test_mixed_flowpipe_interface_mixedflowpipe_jl_31_68():
+    from reach_b200.flowpipe import MixedFlowpipe
+    a, b = _host_flowpipe(3), _host_flowpipe(4, dt0=rb.TimeInterval(1.0, 1.0))
+    mfp = MixedFlowpipe([a, b])
+    assert len(mfp) == 2 and mfp.numrsets() == 7 and mfp[1] is b
+    with pytest.raises(ValueError):
+        mfp.tspan()
+    assert tuple(mfp.tspan(1)) == tuple(b.tspan)
+    d = np.array([1.0])
+    assert mfp.rho(d) == max(a.rho(d), b.rho(d)) == 4.0          # MixedFlowpipe.jl:66-68
