@@ -6,7 +6,7 @@ from . import sets  # noqa: F401
 from .sets import *  # noqa: F401,F403
 from .directions import BoxDirections, OctDirections, CustomDirections, PolarDirections  # noqa: F401
 from .flowpipe import (Flowpipe, MixedFlowpipe, ReachSolution, TemplateReachSet, ReachSet,  # noqa: F401
-                       TimeInterval, zeroT, rho)
+                       TimeInterval, zeroT, rho, sigma, shift)
 from .lgg09 import LGG09, Forward, NoBloating, FirstOrderZonotope, Lgg09Plan  # noqa: F401
 from .glgm06 import GLGM06, Glgm06Plan, reduce_order  # noqa: F401
 from .box import BOX  # noqa: F401

@@ -58,20 +58,28 @@ class TemplateReachSet:
         # a linear program (LazySets' ρ(d, ::HPolyhedron)); host side, as in the reference
         return lp_support(d, D, np.asarray(self.sf, dtype=np.float64))
 
+    def sigma(self, d):
+        """σ(d, R) = σ(d, set(R)): a maximiser of d·x over the template polyhedron (LazySets' σ(d, ::HPolyhedron) is
+        the same linear program as its ρ); host side, like the LP fallback of `rho`."""
+        return lp_support(d, self.dirs.matrix(), np.asarray(self.sf, dtype=np.float64), argmax=True)
 
-def lp_support(d, D, sf):
+
+def lp_support(d, D, sf, argmax=False):
     """ρ(d, {x : D[:, j]·x ≤ sf[j] ∀j}) = max d·x by linear programming (what LazySets' `ρ(d, P::HPolyhedron)` solves).
-    +inf when the polyhedron is unbounded in direction d; raises on an empty polyhedron, like LazySets."""
+    +inf when the polyhedron is unbounded in direction d; raises on an empty polyhedron, like LazySets.
+    `argmax=True` returns the maximiser instead (raises when unbounded)."""
     from scipy.optimize import linprog
     res = linprog(-np.asarray(d, dtype=np.float64), A_ub=np.ascontiguousarray(D.T), b_ub=sf,
                   bounds=[(None, None)] * D.shape[0], method="highs")
     if res.status == 3:
+        if argmax:
+            raise ValueError("the support vector in direction %s is undefined because the polyhedron is unbounded" % (d,))
         return float("inf")
     if res.status == 2:
         raise ValueError("the support function in direction(s) %s is undefined because the polyhedron is empty" % (d,))
     if res.status != 0:
         raise RuntimeError("LP solver: %s" % res.message)
-    return float(-res.fun)
+    return np.array(res.x) if argmax else float(-res.fun)
 
 
 def samedir(u, v):
@@ -103,6 +111,16 @@ class ReachSet:
         if hasattr(self.set, "lo") and hasattr(self.set, "hi") and not hasattr(self.set, "radius"):     # Interval
             return float(d[0] * (self.set.hi if d[0] > 0 else self.set.lo))
         return float(d @ self.set.center + np.abs(d) @ self.set.radius)      # Hyperrectangle (BOX)
+
+    def sigma(self, d):
+        """Support vector of the set: c + Σ_j sign(g_j·d) g_j for a zonotope, the vertex c + sign(d)·r for a box."""
+        d = np.asarray(d, dtype=np.float64)
+        if hasattr(self.set, "generators"):
+            c, G = self.set.center, self.set.generators
+            return c + G @ np.sign(G.T @ d)
+        if hasattr(self.set, "lo") and hasattr(self.set, "hi") and not hasattr(self.set, "radius"):     # Interval
+            return np.array([self.set.hi if d[0] > 0 else self.set.lo])
+        return self.set.center + np.sign(d) * self.set.radius
 
 
 class Flowpipe:
@@ -212,6 +230,22 @@ class Flowpipe:
             return self.device.rho_flowpipe(d)
         return max(R.rho(d) for R in self)
 
+    def argmax_rho(self, d):
+        """Index of the first reach-set attaining ρ(d, fp).  With a device-resident flowpipe the per-step support
+        values come from one device reduction and only the index travels."""
+        if self.device is not None and hasattr(self.device, "rho_per_step"):
+            return int(np.argmax(self.device.rho_per_step(d)))
+        if self.device is not None and hasattr(self.device, "argmax_over_steps"):
+            k = self.device.argmax_over_steps(d)
+            if k is not None and 0 <= k < self._n:
+                return k
+        return int(np.argmax([R.rho(d) for R in self]))
+
+    def sigma(self, d):
+        """σ(d, fp) (AbstractFlowpipe.jl:56-58): the flowpipe behaves like the union of its reach-sets, so this is the
+        support vector of a reach-set attaining the maximum; only that one set is materialised."""
+        return self[self.argmax_rho(d)].sigma(d)
+
 
 class MixedFlowpipe:
     """Vector of flowpipes, one per initial-set split (MixedFlowpipe.jl:20-23); ρ = max (:66-68)."""
@@ -283,3 +317,8 @@ def shift(X, t0):
 def rho(d, X):
     """ρ(d, ·) for reach-sets, flowpipes and solutions."""
     return X.rho(d)
+
+
+def sigma(d, X):
+    """σ(d, ·) for reach-sets, flowpipes and solutions."""
+    return X.sigma(d)

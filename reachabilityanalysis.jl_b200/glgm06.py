@@ -160,6 +160,11 @@ class _SplitView:
             self.plan._support_cache[key] = self.plan.support(d)
         return float(self.plan._support_cache[key][self.split][:self.nsets].max())
 
+    def rho_per_step(self, d):
+        """ρ(d, Z_k) of every step of this split (one device pass over all zonotopes, cached per direction)."""
+        self.rho_flowpipe(d)
+        return self.plan._support_cache[np.asarray(d, dtype=np.float64).tobytes()][self.split][:self.nsets]
+
 
 def _flowpipe_of_split(plan, split, alg, dt0, nsets=None):
     def make(k, dt):

@@ -251,6 +251,16 @@ class Lgg09Plan:
         M = self.sfmat()
         return max(lp_support(d, D, M[:, k]) for k in range(M.shape[1]))
 
+    def argmax_over_steps(self, d):
+        """Step index attaining ρ(d, fp) for (a positive multiple of) a template direction, from the same device
+        reduction as `rho_flowpipe`; None for any other direction."""
+        d = np.asarray(d, dtype=np.float64)
+        D = self._dirs
+        for i in range(D.shape[1]):
+            if np.array_equal(d, D[:, i]) or samedir(d, D[:, i])[0]:
+                return int(self.max_over_steps()[1][i])
+        return None
+
     @property
     def device_rho(self):
         return self.lib.reach_lgg09_plan_device_rho(self.handle)

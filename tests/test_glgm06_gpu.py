@@ -40,6 +40,7 @@ def test_flowpipes_jl_43_44_on_the_device(ctx):
     Zk = sol[k].set
     sigma = Zk.center + Zk.generators @ np.sign(Zk.generators.T @ d)
     np.testing.assert_allclose(sigma, [0.7502062459270877, 0.6989729206916551], rtol=1e-12)
+    np.testing.assert_allclose(rb.sigma(d, sol), [0.7502062459270877, 0.6989729206916551], rtol=1e-12)   # σ(d, fp) itself
 
 
 def test_flowpipes_jl_56_70_projectile_inclusion_on_the_device(ctx):

@@ -263,3 +263,21 @@ def test_mixed_flowpipe_interface_mixedflowpipe_jl_31_68():
     assert tuple(mfp.tspan(1)) == tuple(b.tspan)
     d = np.array([1.0])
     assert mfp.rho(d) == max(a.rho(d), b.rho(d)) == 4.0          # MixedFlowpipe.jl:66-68
+
+
+def test_support_vector_of_reach_sets_and_flowpipes_abstractflowpipe_jl_56_58():
+    from reach_b200.flowpipe import Flowpipe, ReachSet, TemplateReachSet, zeroT
+    Z = [rb.Zonotope(np.array([0.1 * k, 0.0]), np.array([[1.0, 0.2], [0.0, 0.5]])) for k in range(4)]
+    fp = Flowpipe(4, lambda k, dt: ReachSet(Z[k], dt), 0.1)
+    d = np.ones(2)
+    assert fp.argmax_rho(d) == 3 and rb.rho(d, fp) == pytest.approx(2.0)
+    np.testing.assert_allclose(rb.sigma(d, fp), [1.5, 0.5])
+    assert d @ rb.sigma(d, fp) == pytest.approx(rb.rho(d, fp))
+    H = ReachSet(rb.Hyperrectangle([1.0, 2.0], [0.5, 0.25]), zeroT)
+    np.testing.assert_array_equal(H.sigma(np.array([1.0, -1.0])), [1.5, 1.75])
+    T = TemplateReachSet(rb.BoxDirections(2), np.array([1.0, 2.0, 0.5, 0.0]), zeroT)      # [-0.5, 1] x [0, 2]
+    np.testing.assert_allclose(T.sigma(np.array([1.0, 1.0])), [1.0, 2.0])
+    np.testing.assert_allclose(T.sigma(np.array([-1.0, 0.5])), [-0.5, 2.0])
+    unbounded = TemplateReachSet(rb.CustomDirections([[1.0, 0.0]]), np.array([1.0]), zeroT)
+    with pytest.raises(ValueError):
+        unbounded.sigma(np.array([0.0, 1.0]))
