@@ -28,9 +28,11 @@ def stable(n, seed, delta):
 
 
 def test_flowpipes_jl_43_44_on_the_device(ctx):
-    """test/flowpipes/flowpipes.jl:40-44 through solve(): default-style GLGM06, δ = 0.2."""
+    """test/flowpipes/flowpipes.jl:40-44 through solve() exactly as the reference calls it: `solve(prob; tspan=dt)`
+    with no algorithm => the default GLGM06 with δ = diam(tspan) / 100 = 0.2 (solve.jl:326-352)."""
     A = np.array([[0.0, 1.0], [-1.0, 0.0]])
-    sol = rb.solve(rb.IVP(A, rb.Singleton([1.0, 0.0])), T=20.0, alg=rb.GLGM06(δ=0.2), ctx=ctx)
+    sol = rb.solve(rb.IVP(A, rb.Singleton([1.0, 0.0])), tspan=(0.0, 20.0), ctx=ctx)
+    assert isinstance(sol.alg, rb.GLGM06) and sol.alg.δ == 0.2
     assert len(sol) == 100
     d = np.ones(2)
     assert rb.rho(d, sol) < 2.0

@@ -281,3 +281,40 @@ def test_support_vector_of_reach_sets_and_flowpipes_abstractflowpipe_jl_56_58():
     unbounded = TemplateReachSet(rb.CustomDirections([[1.0, 0.0]]), np.array([1.0]), zeroT)
     with pytest.raises(ValueError):
         unbounded.sigma(np.array([0.0, 1.0]))
+
+
+def test_solve_argument_handling_solve_jl_195_352():
+    """test/continuous/solve.jl:80-125 (ways to give the time span, T and tspan together => ArgumentError) and
+    :5-21 (default algorithm) against the pure argument helpers of the mirror -- no device call."""
+    from reach_b200.solve import _get_tspan, _get_cpost, _default_cpost, _promote_tspan
+    for given in ((0.0, 2.0), [0.0, 2.0], np.array([0.0, 2.0]), rb.Interval(0.0, 2.0), rb.TimeInterval(0.0, 2.0), 2.0, 2):
+        assert tuple(_promote_tspan(given)) == (0.0, 2.0)
+        assert tuple(_get_tspan((), tspan=given)) == (0.0, 2.0)
+        assert tuple(_get_tspan((given,))) == (0.0, 2.0)              # solve(p, (0.0, 2.0)), solve(p, 2.0)
+    assert tuple(_get_tspan((), T=2.0)) == (0.0, 2.0)
+    assert _get_tspan((), NSTEPS=10) is None                          # "defined a posteriori"
+    for kw in ({"T": 1.0, "tspan": (0.0, 2.0)}, {"tspan": (0.0, 2.0), "NSTEPS": 3}, {"T": 1.0, "NSTEPS": 3}):
+        with pytest.raises(ValueError):                               # solve.jl:220-229
+            _get_tspan((), **kw)
+    with pytest.raises(ValueError):
+        _get_tspan(())                                                # solve.jl:257-261
+    with pytest.raises(ValueError):
+        _promote_tspan([0.0, 1.0, 2.0])                               # solve.jl:208-210
+    a = rb.GLGM06(δ=0.1)
+    assert _get_cpost((), alg=a) is a and _get_cpost((), algorithm=a) is a and _get_cpost((), opC=a) is a
+    assert _get_cpost((a,)) is a and _get_cpost(((0.0, 1.0), a)) is a and _get_cpost(((0.0, 1.0),)) is None
+    with pytest.raises(ValueError):
+        _get_cpost((1.0, 2.0, 3.0))
+    A = -np.eye(8)
+    d = _default_cpost(rb.IVP(A, rb.Hyperrectangle(np.zeros(8), np.ones(8))), rb.TimeInterval(0.0, 0.001))
+    assert isinstance(d, rb.GLGM06) and d.δ == 0.001 / 100 and isinstance(d.approx_model, rb.FirstOrderZonotope)
+    assert d.static is False and d.max_order == 5                    # test/continuous/solve.jl:5-9
+    assert _default_cpost(rb.IVP(A, rb.Singleton(np.ones(8))), rb.TimeInterval(0.0, 1.0), static=True).static is True
+    lazy = rb.ConvexHull(rb.BallInf(np.zeros(8), 1.0), rb.BallInf(np.ones(8), 1.0))
+    assert isinstance(_default_cpost(rb.IVP(A, lazy), rb.TimeInterval(0.0, 1.0)).approx_model, rb.Forward)
+    assert _default_cpost(rb.IVP(A, lazy), rb.TimeInterval(0.0, 1.0), δ=0.25).δ == 0.25
+    assert _default_cpost(rb.IVP(A, lazy), rb.TimeInterval(0.0, 1.0), N=50).δ == 1.0 / 50
+    with pytest.raises(NotImplementedError):                          # statedim 1 => INT in the reference
+        _default_cpost(rb.IVP(-np.eye(1), rb.Interval(0.0, 1.0)), rb.TimeInterval(0.0, 1.0))
+    with pytest.raises(ValueError):                                   # both given: refused before any device work
+        rb.solve(rb.IVP(A, rb.Singleton(np.ones(8))), T=1.0, tspan=(0.0, 2.0), alg=a)
