@@ -7,10 +7,29 @@ matrix / the zonotope generators live in device memory (the plan object) and are
 to the host when asked for; `rho(d, fp)` over a template direction is a device reduction.
 Time stamps stay on the host exactly as in the reference (`Δt += δ`, reach_homog.jl:26-30).
 """
+import math
+
 import numpy as np
 
 
+def _add_rounded(a, b, up):
+    """a + b rounded towards +inf (`up`) or -inf: the rounded-to-nearest sum moved one ulp outwards when the exact
+    error of the addition (Knuth's TwoSum) has that sign.  Works on floats and on arrays."""
+    s = a + b
+    bb = s - a
+    err = (a - (s - bb)) + (b - bb)
+    if isinstance(s, np.ndarray):
+        return np.where(err > 0, np.nextafter(s, np.inf), s) if up else np.where(err < 0, np.nextafter(s, -np.inf), s)
+    if up:
+        return math.nextafter(s, math.inf) if err > 0 else s
+    return math.nextafter(s, -math.inf) if err < 0 else s
+
+
 class TimeInterval(tuple):
+    """`TimeInterval` (an IntervalArithmetic interval in the reference, TimeInterval.jl:54-56): sums round outwards,
+    lower bound down and upper bound up, so that repeated `Δt += δ` never loses a time point -- `F(1.0) == F[end]`
+    holds for δ = 0.1 although ten rounded-to-nearest additions of 0.1 stop below 1 (test/continuous/solve.jl:66)."""
+
     def __new__(cls, lo, hi):
         return super().__new__(cls, (float(lo), float(hi)))
 
@@ -19,8 +38,9 @@ class TimeInterval(tuple):
 
     def __add__(self, other):
         if isinstance(other, TimeInterval):
-            return TimeInterval(self[0] + other[0], self[1] + other[1])
-        return TimeInterval(self[0] + other, self[1] + other)
+            return TimeInterval(_add_rounded(self[0], other[0], False), _add_rounded(self[1], other[1], True))
+        other = float(other)
+        return TimeInterval(_add_rounded(self[0], other, False), _add_rounded(self[1], other, True))
 
     def __contains__(self, t):
         return self[0] <= t <= self[1]
@@ -42,6 +62,12 @@ class TemplateReachSet:
 
     def support_functions(self, i=None):
         return self.sf if i is None else self.sf[i]
+
+    def __eq__(self, other):
+        return (isinstance(other, TemplateReachSet) and tuple(self.dt) == tuple(other.dt) and self.dirs == other.dirs
+                and np.array_equal(np.asarray(self.sf), np.asarray(other.sf)))
+
+    __hash__ = None
 
     def rho(self, d):
         """TemplateReachSet.jl:97-115: exact match, then positive multiple; no LP fallback."""
@@ -82,6 +108,28 @@ def lp_support(d, D, sf, argmax=False):
     return np.array(res.x) if argmax else float(-res.fun)
 
 
+def _same_value(a, b):
+    """Value equality of sets / arrays / plain fields (the host set types are frozen records holding arrays)."""
+    if type(a) is not type(b):
+        return False
+    if isinstance(a, np.ndarray):
+        return a.shape == b.shape and bool(np.array_equal(a, b))
+    if hasattr(a, "__dataclass_fields__"):
+        return all(_same_value(getattr(a, f), getattr(b, f)) for f in a.__dataclass_fields__)
+    if isinstance(a, (list, tuple)):
+        return len(a) == len(b) and all(_same_value(x, y) for x, y in zip(a, b))
+    return a == b
+
+
+class FlowpipeSlice(list):
+    """`F[i:j]`, `F(Δt)`: a run of reach-sets with the time-span interface of the reference's views
+    (`tstart(F[1:3])`, `tspan(F(0.05 .. 1.05))`, test/continuous/solve.jl:43-75)."""
+
+    tstart = property(lambda s: min(R.tstart for R in s))
+    tend = property(lambda s: max(R.tend for R in s))
+    tspan = property(lambda s: TimeInterval(s.tstart, s.tend))
+
+
 def samedir(u, v):
     """(True, k) iff u = k·v with k > 0."""
     nz = np.flatnonzero(v)
@@ -102,6 +150,17 @@ class ReachSet:
     tspan = property(lambda s: s.dt)
     tstart = property(lambda s: s.dt.lo)
     tend = property(lambda s: s.dt.hi)
+
+    @property
+    def dim(self):
+        from .sets import dim
+        return dim(self.set)
+
+    def __eq__(self, other):
+        """Same set (by value) over the same time span, like `==` of the reference's immutable structs."""
+        return isinstance(other, ReachSet) and tuple(self.dt) == tuple(other.dt) and _same_value(self.set, other.set)
+
+    __hash__ = None
 
     def rho(self, d):
         d = np.asarray(d, dtype=np.float64)
@@ -154,7 +213,7 @@ class Flowpipe:
         span `tspan(R) + t0`; the device-resident data and `ext` are shared, nothing is copied or recomputed."""
         lo, hi = self._times()
         out = Flowpipe(self._n, self._make, self.delta, self.dt0, self.ext, self.device)
-        out._t = (lo + float(t0), hi + float(t0))
+        out._t = (_add_rounded(lo, float(t0), False), _add_rounded(hi, float(t0), True))
         return out
 
     def __len__(self):
@@ -162,7 +221,7 @@ class Flowpipe:
 
     def __getitem__(self, k):
         if isinstance(k, slice):
-            return [self[i] for i in range(*k.indices(self._n))]
+            return FlowpipeSlice(self[i] for i in range(*k.indices(self._n)))
         if k < 0:
             k += self._n
         if not 0 <= k < self._n:
@@ -172,6 +231,13 @@ class Flowpipe:
 
     def __iter__(self):
         return (self[k] for k in range(self._n))
+
+    @property
+    def dim(self):
+        """AbstractFlowpipe.jl:71-75: the dimension of the first reach-set; undefined for an empty flowpipe."""
+        if self._n == 0:
+            raise ValueError("the dimension is not defined because this flowpipe is empty")
+        return self[0].dim
 
     @property
     def tstart(self):
@@ -192,13 +258,16 @@ class Flowpipe:
             idx = np.flatnonzero((lo <= t) & (t <= hi))
             if len(idx) == 0:
                 raise ValueError("time %s does not belong to the time span %s" % (t, tuple(self.tspan)))
-            sets = [self[i] for i in idx]
+            sets = FlowpipeSlice(self[i] for i in idx[:2])      # the first occurrence and, on a border, its successor
             return sets[0] if len(sets) == 1 else sets
+        if hasattr(t, "lo") and hasattr(t, "hi") and not isinstance(t, tuple):
+            t = (t.lo, t.hi)                                    # a LazySets-style Interval
         t0, t1 = t
         idx = np.flatnonzero((hi >= t0) & (lo <= t1))
         if len(idx) == 0:
-            raise ValueError("time interval %s does not intersect the time span" % (t,))
-        return [self[i] for i in idx]
+            raise ValueError("the time interval %s does not intersect the time span %s of the given flowpipe"
+                             % (tuple(t), tuple(self.tspan)))
+        return FlowpipeSlice(self[i] for i in idx)
 
     def support_function_matrix(self):
         """Flowpipe.jl:304-306."""

@@ -234,14 +234,14 @@ def test_flowpipe_shift_and_time_evaluation_flowpipe_jl_97_169():
     from reach_b200.flowpipe import ReachSolution, shift
     fp = _host_flowpipe()
     sh = shift(fp, 1.0)
-    assert tuple(sh.tspan) == (fp.tspan[0] + 1.0, fp.tspan[1] + 1.0)
+    assert tuple(sh.tspan) == tuple(fp.tspan + 1.0)                 # interval addition (outward rounding)
     assert len(sh) == len(fp) and sh.ext is fp.ext
     for k in range(len(fp)):
-        assert tuple(sh[k].dt) == (fp[k].dt[0] + 1.0, fp[k].dt[1] + 1.0)
+        assert tuple(sh[k].dt) == tuple(fp[k].dt + 1.0)
         assert sh[k].set.lo == fp[k].set.lo                     # the sets themselves are untouched
     assert tuple(fp.tspan) == (0.0, fp[len(fp) - 1].dt[1])       # the original is not modified
     sol = ReachSolution(fp, "alg")
-    assert tuple(shift(sol, 2.0).tspan) == (2.0, fp.tspan[1] + 2.0) and shift(sol, 2.0).alg == "alg"
+    assert tuple(shift(sol, 2.0).tspan) == tuple(fp.tspan + 2.0) and shift(sol, 2.0).alg == "alg"
     inner = fp(0.25)
     assert not isinstance(inner, list) and tuple(inner.dt)[0] <= 0.25 <= tuple(inner.dt)[1]
     edge = fp(fp[1].dt[1])                                       # a shared end point belongs to two reach-sets
@@ -318,3 +318,40 @@ def test_solve_argument_handling_solve_jl_195_352():
         _default_cpost(rb.IVP(-np.eye(1), rb.Interval(0.0, 1.0)), rb.TimeInterval(0.0, 1.0))
     with pytest.raises(ValueError):                                   # both given: refused before any device work
         rb.solve(rb.IVP(A, rb.Singleton(np.ones(8))), T=1.0, tspan=(0.0, 2.0), alg=a)
+
+
+def test_flowpipe_interface_solve_jl_24_80():
+    """The assertions of test/continuous/solve.jl:33-80 on a host flowpipe with δ = 0.1 over [0, 1]: time spans of
+    reach-sets and slices, the callable forms, the border case, the dimension.  They need the outward rounding of
+    the time stamps: ten rounded-to-nearest additions of 0.1 end below 1.0."""
+    F = _host_flowpipe(10, 0.1)
+    δ = 0.1
+    assert F.tstart == 0.0 and F.tend == pytest.approx(1.0) and F.tend >= 1.0
+    assert F[0].tstart == 0.0 and F[0].tend == pytest.approx(0.1)
+    assert F[-1].tstart == pytest.approx(0.9) and F[-1].tend == pytest.approx(1.0)
+    assert F[0:3].tstart == pytest.approx(0.0) and F[0:3].tend == pytest.approx(3 * δ)
+    assert tuple(F[0:3].tspan) == pytest.approx((0.0, 3 * δ))
+    assert F((0.0, 1.0)) == F[0:]                                 # :64
+    assert F(0.05) == F[0]                                        # :65
+    assert F(1.0) == F[-1]                                        # :66
+    assert F((0.05, 0.15)) == F[0:2]                              # :67
+    assert F(rb.Interval(0.05, 0.15)) == F[0:2]
+    assert tuple(F((0.05, 1.05)).tspan) == tuple(F.tspan)         # :70
+    with pytest.raises(ValueError):                               # :73
+        F((2, 3))
+    assert F(0.1) == F[0:2]                                       # :77 two reach-sets on the border
+    assert F.dim == 1                                             # :80
+    assert F[2] == F[2] and F[2] != F[3]                          # same set, different time span
+
+
+def test_time_interval_addition_rounds_outwards():
+    from reach_b200.flowpipe import TimeInterval
+    from fractions import Fraction
+    dt = TimeInterval(0.0, 0.1)
+    lo, hi = Fraction(0), Fraction(0.1)
+    for _ in range(1000):
+        dt = dt + 0.1
+        lo, hi = lo + Fraction(0.1), hi + Fraction(0.1)
+        assert Fraction(dt.lo) <= lo and hi <= Fraction(dt.hi)    # encloses the exact sums of the float 0.1
+    assert dt.hi - dt.lo < 0.1 + 1e-10                            # and stays tight: at most one ulp per addition
+    assert tuple(TimeInterval(1.0, 2.0) + TimeInterval(0.5, 0.25)) == (1.5, 2.25)    # exact sums are not widened
