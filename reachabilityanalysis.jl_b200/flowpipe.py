@@ -59,6 +59,14 @@ class TemplateReachSet:
     tstart = property(lambda s: s.dt.lo)
     tend = property(lambda s: s.dt.hi)
     dim = property(lambda s: s.dirs.n)
+    vars = property(lambda s: tuple(range(1, s.dirs.n + 1)))          # TemplateReachSet.jl:71, 1-based like the reference
+    directions = property(lambda s: s.dirs)                          # :73
+
+    @property
+    def set(self):
+        """`set(R)` (TemplateReachSet.jl:57-60): the polyhedron {x : d_i·x ≤ sf_i ∀i} as a list of half-spaces."""
+        from .sets import HPolyhedron, HalfSpace
+        return HPolyhedron([HalfSpace(d, float(self.sf[i])) for i, d in enumerate(self.dirs)])
 
     def support_functions(self, i=None):
         return self.sf if i is None else self.sf[i]

@@ -355,3 +355,20 @@ def test_time_interval_addition_rounds_outwards():
         assert Fraction(dt.lo) <= lo and hi <= Fraction(dt.hi)    # encloses the exact sums of the float 0.1
     assert dt.hi - dt.lo < 0.1 + 1e-10                            # and stays tight: at most one ulp per addition
     assert tuple(TimeInterval(1.0, 2.0) + TimeInterval(0.5, 0.25)) == (1.5, 2.25)    # exact sums are not widened
+
+
+def test_template_reach_set_interface_templatereachset_jl_57_115():
+    from reach_b200.flowpipe import TemplateReachSet, TimeInterval
+    R = TemplateReachSet(rb.BoxDirections(2), np.array([1.0, 2.0, 0.5, 0.0]), TimeInterval(0.0, 1.0))
+    assert R.dim == 2 and R.vars == (1, 2) and R.directions is R.dirs
+    assert tuple(R.tspan) == (0.0, 1.0) and R.tstart == 0.0 and R.tend == 1.0
+    assert R.support_functions(1) == 2.0 and list(R.support_functions()) == [1.0, 2.0, 0.5, 0.0]
+    P = R.set                                                     # HPolyhedron of one half-space per direction
+    assert len(P.constraints) == 4 and rb.dim(P) == 2
+    for c, d, b in zip(P.constraints, R.dirs, R.sf):
+        np.testing.assert_array_equal(c.a, d)
+        assert c.b == b
+    assert R.rho(np.array([0.0, 3.0])) == 6.0                     # positive multiple of a template direction
+    assert R.rho(np.array([1.0, 1.0])) == pytest.approx(3.0)      # anything else: the LP over set(R)
+    assert R == TemplateReachSet(rb.BoxDirections(2), np.array([1.0, 2.0, 0.5, 0.0]), TimeInterval(0.0, 1.0))
+    assert R != TemplateReachSet(rb.BoxDirections(2), np.array([1.0, 2.0, 0.5, 0.1]), TimeInterval(0.0, 1.0))
