@@ -16,7 +16,7 @@ using LazySets: set
 using IntervalArithmetic.Symbols: (..)                       # as src/Initialization/init.jl:40, LGG09Module.jl:11
 import LazySets: ρ, dim
 import ..ReachabilityAnalysis: TemplateReachSet, ReachSet, Flowpipe, MixedFlowpipe, AbstractFlowpipe, TimeInterval, zeroT,
-                               _collect, _isdisjoint, support_function_matrix, tspan
+                               _collect, _isdisjoint, support_function_matrix, tspan, array
 
 const lib = "libreach_cuda"
 
@@ -181,6 +181,7 @@ mutable struct DeviceTemplateFlowpipe{N,VN,TN} <: AbstractFlowpipe
     δ::N
     Δt0::TimeInterval
     sfmat::Union{Nothing,Matrix{N}}          # filled by the first support_function_matrix call
+    Xk::Union{Nothing,Vector}                # filled by the first `array(fp)` call
     ext::Dict{Symbol,Any}
 end
 
@@ -203,7 +204,7 @@ function post_LGG09_cuda(dirs, Ω₀::LazySet{N}, Φ::AbstractMatrix{N}, NSTEPS:
     check(ctx, ccall((:reach_lgg09_plan_run, lib), Cint, (Ptr{Cvoid},), plan.h))
     check(ctx, ccall((:reach_lgg09_plan_sync, lib), Cint, (Ptr{Cvoid},), plan.h))
     check(ctx, ccall((:reach_lgg09_plan_nsteps_done, lib), Cint, (Ptr{Cvoid}, Ptr{Int64}), plan.h, done))
-    return DeviceTemplateFlowpipe{N,eltype(dirs),typeof(dirs)}(plan, dirs, ℓ, done[], δ, Δt0, nothing, Dict{Symbol,Any}())
+    return DeviceTemplateFlowpipe{N,eltype(dirs),typeof(dirs)}(plan, dirs, ℓ, done[], δ, Δt0, nothing, nothing, Dict{Symbol,Any}())
 end
 
 Base.length(fp::DeviceTemplateFlowpipe) = fp.nsets
@@ -226,6 +227,23 @@ function Base.getindex(fp::DeviceTemplateFlowpipe{N}, k::Integer) where {N}
         Δt += fp.δ                                              # repeated addition, as the fill loop does
     end
     return TemplateReachSet(fp.dirs, view(M, :, k), Δt)
+end
+
+# The generic AbstractFlowpipe interface (iterate, first / last, eachindex, set, tstart / tend, vars, dim, σ:
+# AbstractFlowpipe.jl:56-216) goes through `array(fp)`: the reach-sets are materialised once, on demand, as views
+# into the fetched matrix with the time stamps of the fill loop (reach_homog.jl:26-30).
+function array(fp::DeviceTemplateFlowpipe{N}) where {N}
+    if fp.Xk === nothing
+        M = support_function_matrix(fp)
+        Δt = (zero(N) .. fp.δ) + fp.Δt0
+        Xk = Vector{TemplateReachSet}(undef, fp.nsets)
+        for k in 1:fp.nsets
+            Xk[k] = TemplateReachSet(fp.dirs, view(M, :, k), Δt)
+            Δt += fp.δ
+        end
+        fp.Xk = Xk
+    end
+    return fp.Xk
 end
 
 # ρ(d, fp) = max_k ρ(d, F[k]) (AbstractFlowpipe.jl:35-37); TemplateReachSet.jl:97-115: exact template direction, then a
