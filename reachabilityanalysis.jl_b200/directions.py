@@ -39,23 +39,29 @@ class BoxDirections(AbstractDirections):
 
     The rows of ρℓ follow the iteration order of the template.  The device path itself is order-agnostic (it takes
     the direction matrix), and the Julia wrapper passes `collect(template)`, i.e. LazySets' own order, which for the
-    negative half is believed to be −e_n..−e₁ ([MEM]; LazySets is not vendored in the reference tree and no
-    reference test pins it).  This mirror and the oracle use the order stated here."""
+    negative half is believed to be −e_n..−e₁ ([MEM]: LazySets is not vendored in the reference tree and no reference
+    test pins it).  This mirror and the oracle default to the order stated in the first line; `lazysets_order=True`
+    gives +e₁..+e_n, −e_n..−e₁ for callers that need the rows to line up with a Julia run."""
 
-    def __init__(self, n):
+    def __init__(self, n, lazysets_order=False):
         self.n = int(n)
+        self.lazysets_order = bool(lazysets_order)
 
     def matrix(self):
         I = np.eye(self.n)
-        return np.hstack([I, -I])
+        return np.hstack([I, -I[:, ::-1]]) if self.lazysets_order else np.hstack([I, -I])
+
+    def _key(self):
+        return (self.n, self.lazysets_order)
 
 
 class OctDirections(AbstractDirections):
     """±e_i ± e_j for i < j, pair by pair in the order (+,+), (+,−), (−,+), (−,−), followed by the
-    box directions (LazySets' iteration order; LGG09.jl:113)."""
+    box directions (LazySets' iteration order; LGG09.jl:113).  `lazysets_order` is passed to the box part."""
 
-    def __init__(self, n):
+    def __init__(self, n, lazysets_order=False):
         self.n = int(n)
+        self.lazysets_order = bool(lazysets_order)
 
     def matrix(self):
         n = self.n
@@ -67,7 +73,10 @@ class OctDirections(AbstractDirections):
                     d[i], d[j] = si, sj
                     cols.append(d)
         D = np.array(cols).T if cols else np.zeros((n, 0))
-        return np.hstack([D, BoxDirections(n).matrix()])
+        return np.hstack([D, BoxDirections(n, self.lazysets_order).matrix()])
+
+    def _key(self):
+        return (self.n, self.lazysets_order)
 
 
 class PolarDirections(AbstractDirections):

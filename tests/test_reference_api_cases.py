@@ -127,3 +127,17 @@ def test_box_struct_box_jl_5_27():
     assert rb.BOX(δ=0.01, recursive=True).recursive is True        # :83
     with pytest.raises(TypeError):
         rb.BOX()
+
+
+def test_box_and_oct_templates_in_lazysets_iteration_order():
+    """Opt-in row order for callers that compare with a Julia run ([MEM]: BoxDirections(2) collects to
+    [1,0], [0,1], [0,-1], [-1,0]); the default order of the mirror and of the oracle is unchanged."""
+    np.testing.assert_array_equal(rb.BoxDirections(2, lazysets_order=True).matrix().T, [[1, 0], [0, 1], [0, -1], [-1, 0]])
+    np.testing.assert_array_equal(rb.BoxDirections(2).matrix().T, [[1, 0], [0, 1], [-1, 0], [0, -1]])
+    M = rb.OctDirections(3, lazysets_order=True).matrix()
+    assert M.shape == (3, 18)
+    np.testing.assert_array_equal(M[:, :4].T, [[1, 1, 0], [1, -1, 0], [-1, 1, 0], [-1, -1, 0]])
+    np.testing.assert_array_equal(M[:, 12:], rb.BoxDirections(3, lazysets_order=True).matrix())
+    a, b = rb.BoxDirections(4, lazysets_order=True).matrix(), rb.BoxDirections(4).matrix()
+    assert sorted(map(tuple, a.T)) == sorted(map(tuple, b.T))          # the same set of directions
+    assert rb.BoxDirections(3) != rb.BoxDirections(3, lazysets_order=True)
