@@ -10,7 +10,9 @@ import itertools
 
 import numpy as np
 import pytest
-from hypothesis import given, settings, strategies as st
+
+pytest.importorskip("hypothesis")           # collection must never fail on a box without it
+from hypothesis import given, settings, strategies as st  # noqa: E402
 
 import reach_b200 as rb
 from oracle import lgg09_oracle as LO, glgm06_oracle as GO, lazysets_oracle as Z
