@@ -2,8 +2,9 @@
 # discrete `post` of LGG09 / GLGM06 runs on libreach_cuda.so (C ABI: include/reach.h).
 #
 # NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no `julia` binary, so this file is an UNTESTED SKETCH until
-# it is run under Julia.  What is checked here: every `ccall` names a symbol of include/reach.h and passes as many
-# argument types and values as the C prototype has parameters (tests/test_abi.py).  The same ABI is exercised call for
+# it is run under Julia.  What is checked here: every `ccall` names a symbol of include/reach.h, passes as many
+# argument types and values as the C prototype has parameters and layout-compatible types (Cint / Int64 / Ptr{Float64} /
+# handles / mirrored structs), blocks and brackets balance (tests/test_abi.py).  The same ABI is exercised call for
 # call by the Python ctypes binding (reachabilityanalysis.jl_b200/_lib.py) and from plain C (tests/c_consumer).
 #
 # Intended placement: src/Algorithms/LGG09/reach_cuda.jl and src/Algorithms/GLGM06/reach_cuda.jl,

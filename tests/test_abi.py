@@ -174,3 +174,81 @@ def test_julia_wrapper_blocks_and_brackets_balance():
         for name in re.split(r"[,\s]+", m.group(1).strip()):
             assert len(re.findall(r"(?<![\w.])%s(?![\w!])" % re.escape(name), code)) >= 2, \
                 "ReachCUDA.jl imports %s and never uses it" % name
+
+
+def _c_prototypes():
+    """name -> (return type, [parameter types]) from include/reach.h, parameter names and qualifiers stripped."""
+    src = open(os.path.join(ROOT, "include", "reach.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"(?:^|[;}\n])\s*((?:const\s+)?[A-Za-z_][\w]*(?:\s*\*+)?)\s*\b(reach_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        params = []
+        if args not in ("", "void"):
+            for a in args.split(","):
+                a = re.sub(r"\bconst\b", "", a).strip()
+                stars = a.count("*")
+                base = re.sub(r"\*", " ", a).split()
+                base = base[0] if len(base) == 1 else " ".join(base[:-1])      # drop the parameter name
+                params.append(base.strip() + "*" * stars)
+        out[name] = (re.sub(r"\bconst\b", "", ret).replace(" ", ""), params)
+    return out
+
+
+_JULIA_SCALARS = {"int": {"Cint", "Int32"}, "int32_t": {"Cint", "Int32"}, "int64_t": {"Int64", "Clonglong"},
+                  "size_t": {"Csize_t"}, "double": {"Cdouble", "Float64"}}
+_JULIA_STRUCTS = {"reach_setexpr": "ReachSetExpr", "reach_invariant": "ReachInvariant", "reach_lgg09_opts": "ReachLGG09Opts",
+                  "reach_term": "ReachTerm"}
+
+
+def _julia_types_for(ctype):
+    """The Julia ccall argument types that are layout-compatible with a C parameter type."""
+    stars = ctype.count("*")
+    base = ctype.rstrip("*")
+    if stars == 0:
+        return _JULIA_SCALARS[base]
+    if base in _JULIA_STRUCTS:
+        inner = {_JULIA_STRUCTS[base]}
+    elif base in _JULIA_SCALARS:
+        inner = set(_JULIA_SCALARS[base])
+    elif base in ("void", "char") or base.startswith("reach_"):
+        inner = {"Cvoid"} if base != "char" else {"UInt8", "Cchar"}
+    else:
+        raise AssertionError("unmapped C type %r" % ctype)
+    for _ in range(stars - 1):
+        inner = {"Ptr{%s}" % t for t in inner}
+    out = {"Ptr{%s}" % t for t in inner} | {"Ref{%s}" % t for t in inner}
+    if base == "char" and stars == 1:
+        out |= {"Cstring"}
+    return out
+
+
+def test_julia_wrapper_ccall_types_match_the_header():
+    """Beyond arity: every ccall's return type and each argument type in julia/ReachCUDA.jl is layout-compatible
+    with the C prototype (int <-> Cint, int64_t <-> Int64, double* <-> Ptr{Float64}, opaque handles <-> Ptr{Cvoid},
+    handle out-parameters <-> Ref{Ptr{Cvoid}}, the mirrored structs by name)."""
+    protos = _c_prototypes()
+    assert len(protos) >= 30 and protos["reach_lgg09"][1][3] == "int64_t"
+    src = _julia_code_only(open(os.path.join(ROOT, "julia", "ReachCUDA.jl")).read())
+    checked = 0
+    for m in re.finditer(r"ccall\(\(:(reach_[a-z0-9_]+),\s*lib\),\s*(\w+),\s*\(", src):
+        name, jret = m.group(1), m.group(2)
+        cret, cparams = protos[name]
+        if cret == "void":
+            assert jret == "Cvoid", name
+        elif cret == "int":
+            assert jret == "Cint", name
+        elif cret == "char*":
+            assert jret == "Cstring", name
+        else:
+            assert jret in _julia_types_for(cret), (name, jret, cret)
+        i, depth = m.end(), 1
+        while depth:
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+        jtypes = [t.strip() for t in _split_top_level(src[m.end():i - 1].strip().rstrip(","))]
+        assert len(jtypes) == len(cparams), name
+        for k, (jt, ct) in enumerate(zip(jtypes, cparams)):
+            assert jt in _julia_types_for(ct), "%s argument %d: Julia %s against C %s" % (name, k + 1, jt, ct)
+        checked += 1
+    assert checked >= 20
