@@ -252,3 +252,43 @@ def test_julia_wrapper_ccall_types_match_the_header():
             assert jt in _julia_types_for(ct), "%s argument %d: Julia %s against C %s" % (name, k + 1, jt, ct)
         checked += 1
     assert checked >= 20
+
+
+def _ctypes_for(ctype):
+    """The ctypes argument types that are layout-compatible with a C parameter type."""
+    stars = ctype.count("*")
+    base = ctype.rstrip("*")
+    scalars = {"int": {ctypes.c_int, ctypes.c_int32}, "int32_t": {ctypes.c_int, ctypes.c_int32},
+               "int64_t": {ctypes.c_int64, ctypes.c_longlong}, "size_t": {ctypes.c_size_t}, "double": {ctypes.c_double}}
+    structs = {"reach_setexpr": _lib.reach_setexpr, "reach_invariant": _lib.reach_invariant,
+               "reach_lgg09_opts": _lib.reach_lgg09_opts, "reach_term": _lib.reach_term}
+    if stars == 0:
+        return scalars[base]
+    if base == "char" and stars == 1:
+        return {ctypes.c_char_p}
+    if base in structs:
+        return {ctypes.POINTER(structs[base])}
+    if base in scalars and stars == 1:
+        return {ctypes.POINTER(t) for t in scalars[base]} | {ctypes.c_void_p}
+    if base == "void" or base.startswith("reach_"):                 # opaque handle / raw device pointer
+        return {ctypes.c_void_p} if stars == 1 else {ctypes.POINTER(ctypes.c_void_p)}
+    if base in scalars and stars == 2:
+        return {ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.POINTER(next(iter(scalars[base]))))}
+    raise AssertionError("unmapped C type %r" % ctype)
+
+
+def test_ctypes_signatures_match_the_header_types():
+    """Width and kind of every bound argument and return type against the C prototype: a c_int where the header has
+    int64_t would pass the arity check and corrupt the call."""
+    protos = _c_prototypes()
+    assert sorted(protos) == sorted(_lib.SIGNATURES)
+    for name, (res, argtypes) in _lib.SIGNATURES.items():
+        cret, cparams = protos[name]
+        if cret == "void":
+            assert res is None, name
+        elif cret == "char*":
+            assert res is ctypes.c_char_p, name
+        else:
+            assert res in _ctypes_for(cret), (name, res, cret)
+        for k, (a, ct) in enumerate(zip(argtypes, cparams)):
+            assert a in _ctypes_for(ct), "%s argument %d: ctypes %s against C %s" % (name, k + 1, a, ct)
