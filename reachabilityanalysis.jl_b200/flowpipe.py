@@ -164,6 +164,10 @@ class ReachSet:
         from .sets import dim
         return dim(self.set)
 
+    @property
+    def vars(self):
+        return tuple(range(1, self.dim + 1))
+
     def __eq__(self, other):
         """Same set (by value) over the same time span, like `==` of the reference's immutable structs."""
         return isinstance(other, ReachSet) and tuple(self.dt) == tuple(other.dt) and _same_value(self.set, other.set)
@@ -239,6 +243,26 @@ class Flowpipe:
 
     def __iter__(self):
         return (self[k] for k in range(self._n))
+
+    def numrsets(self):
+        """Flowpipe.jl: the number of reach-sets (== len(fp), test/flowpipes/flowpipes.jl:24)."""
+        return self._n
+
+    def set_of(self, k=None):
+        """`set(fp, k)` (AbstractFlowpipe.jl:108-140): the set of reach-set k; a list of sets for a slice / index list;
+        every set for `set(fp)` (the reference wraps those in a UnionSetArray)."""
+        if k is None:
+            return [R.set for R in self]
+        if isinstance(k, slice):
+            return [R.set for R in self[k]]
+        if isinstance(k, (list, tuple, range, np.ndarray)):
+            return [self[int(i)].set for i in k]
+        return self[k].set
+
+    @property
+    def vars(self):
+        """AbstractFlowpipe.jl:211: the variables of the first reach-set (1-based, like the reference)."""
+        return self[0].vars
 
     @property
     def dim(self):

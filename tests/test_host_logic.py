@@ -372,3 +372,16 @@ def test_template_reach_set_interface_templatereachset_jl_57_115():
     assert R.rho(np.array([1.0, 1.0])) == pytest.approx(3.0)      # anything else: the LP over set(R)
     assert R == TemplateReachSet(rb.BoxDirections(2), np.array([1.0, 2.0, 0.5, 0.0]), TimeInterval(0.0, 1.0))
     assert R != TemplateReachSet(rb.BoxDirections(2), np.array([1.0, 2.0, 0.5, 0.1]), TimeInterval(0.0, 1.0))
+
+
+def test_abstract_flowpipe_interface_flowpipes_jl_5_37():
+    """Indexing, counts, sets, time domain and variables as test/flowpipes/flowpipes.jl:20-36 asserts them."""
+    from reach_b200.flowpipe import Flowpipe, ReachSet
+    Zs = [rb.Zonotope(np.array([0.1 * k, 1.0]), np.eye(2)) for k in range(6)]
+    fp = Flowpipe(6, lambda k, dt: ReachSet(Zs[k], dt), 0.5)
+    assert fp.dim == 2 and fp.vars == (1, 2)                       # :17, :36
+    assert fp[0] == next(iter(fp)) and fp[-1] == fp[len(fp) - 1]   # first / last
+    assert len(fp) == fp.numrsets() == 6                           # :24
+    assert fp.set_of(2) is Zs[2] and fp[2].set is Zs[2]            # :25
+    assert fp.set_of(slice(2, 5)) == Zs[2:5] and len(fp.set_of()) == 6 and fp.set_of([0, 5]) == [Zs[0], Zs[5]]
+    assert fp.tstart == 0.0 and fp.tend == pytest.approx(3.0) and tuple(fp.tspan) == pytest.approx((0.0, 3.0))
