@@ -38,3 +38,24 @@ def test_reference_arm_line_has_the_contract_keys():
 def test_reference_arm_under_a_multi_rank_launch_only_rank_zero_prints():
     env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
     assert _run("--gpus", "2", env=env) == []                         # the other ranks exit 0 without work
+
+
+def test_committed_gpu_bench_line_has_the_contract_keys():
+    """The GPU arm cannot run here; the committed line of the final build (profiles/r2b_bench_n1.json, unedited output of
+    `python bench.py` on a B200) is checked for the keys the measurement contract names."""
+    d = json.load(open(os.path.join(ROOT, "profiles", "r2b_bench_n1.json")))
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["gpu_launches"] > 0 and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("C5") and "l2" in d["config"]
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "tensor") and r["unit"] in ("GB/s", "TFLOP/s", "TOP/s (INT8 tensor)")
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and "traffic" in r
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] == 4000 * 10000 * 8 and 0 < e["value"] <= d["value"] * 1.02
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["sample"] and cb["unit"] == d["unit"]
+    c = d["clocks"]
+    assert c["sm_mhz"] > 0 and c["sm_max_mhz"] >= c["sm_mhz"]
+    assert not set(c["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
